@@ -1,0 +1,552 @@
+// bb_api.cu — C ABI of libbadread_b200.so (see include/badread_b200.h): context, one-time uploads, batch
+// orchestration. All hot-path work is done by the kernels in bb_kernels.cuh; there is no CPU path here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "bb_kernels.cuh"
+
+namespace {
+
+struct DevBuf {  // grow-only device allocation
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+const char *kStageNames[BB_N_STAGES] = {"build_fragments", "error_loop", "host_scan", "join",
+                                        "final_align", "qscores", "compact", "total"};
+
+}  // namespace
+
+struct bb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    uint64_t seed = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // reference + models
+    DevBuf ref; int64_t ref_len = 0;
+    bool have_em = false, have_qm = false;
+    BBErrorModelDev em{}; DevBuf em_k2r, em_rowoff, em_cum, em_flags, em_slots, em_pool;
+    BBQScoreModelDev qm{}; DevBuf qm_hkeys, qm_hvals, qm_rowoff, qm_scores, qm_cum;
+
+    // batch
+    int n_reads = 0;
+    bool uploaded = false, ran = false;
+    std::vector<BBReadDev> h_reads;
+    std::vector<int32_t> h_inlen;
+    int64_t frag_total = 0, seq_total = 0, out_total = 0;
+    DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_reads;
+    DevBuf d_frag, d_state, d_seq, d_ops, d_dcnt, d_qual, d_out_seq, d_out_qual, d_counter;
+
+    // scratch
+    int n_warps = 0;
+    BBScratchPool pool{};
+    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf;
+
+    cudaEvent_t ev[BB_N_STAGES + 1] = {};
+    float stage_ms[BB_N_STAGES] = {};
+};
+
+static thread_local std::string g_create_error;
+
+#define BB_CUDA(ctx, call)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return BB_ERR_CUDA;                                                                              \
+        }                                                                                                    \
+    } while (0)
+
+static int set_err(bb_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+extern "C" const char *bb_version(void) { return "badread_b200 0.1.0 (sm_100a)"; }
+
+extern "C" const char *bb_last_error(const bb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" const char *bb_stage_name(int stage) {
+    return (stage >= 0 && stage < BB_N_STAGES) ? kStageNames[stage] : "";
+}
+
+extern "C" int64_t bb_launch_count(const bb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
+    if (!out) return BB_ERR_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev <= 0) {
+        g_create_error = std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                         " (badread_b200 has no CPU path)";
+        return BB_ERR_CUDA;
+    }
+    if (device < 0 || device >= n_dev) { g_create_error = "invalid device ordinal"; return BB_ERR_ARG; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return BB_ERR_CUDA; }
+    bb_ctx *ctx = new bb_ctx();
+    ctx->device = device;
+    ctx->seed = seed;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    // misc.REV_COMP_DICT (misc.py:56-61); anything else complements to 'N' (misc.py:64-68)
+    uint8_t comp[256];
+    std::memset(comp, 'N', sizeof(comp));
+    const char *from = "ATGCatgcRYSWKMBVDHNryswkmbvdhn.-?";
+    const char *to = "TACGtacgYRSWMKVBHDNyrswmkvbhdn.-?";
+    for (int i = 0; from[i]; i++) comp[(uint8_t)from[i]] = (uint8_t)to[i];
+    e = cudaMemcpyToSymbol(bb_c_comp, comp, 256);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
+    // persistent warps: 4 CTAs of 4 warps per SM for the warp-per-read kernels
+    ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
+    *out = ctx;
+    return BB_OK;
+}
+
+extern "C" int bb_destroy(bb_ctx *ctx) {
+    if (!ctx) return BB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->ref, &ctx->em_k2r, &ctx->em_rowoff, &ctx->em_cum, &ctx->em_flags, &ctx->em_slots,
+                      &ctx->em_pool, &ctx->qm_hkeys, &ctx->qm_hvals, &ctx->qm_rowoff, &ctx->qm_scores, &ctx->qm_cum,
+                      &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order,
+                      &ctx->d_reads, &ctx->d_frag, &ctx->d_state, &ctx->d_seq, &ctx->d_ops, &ctx->d_dcnt,
+                      &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
+                      &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return BB_OK;
+}
+
+template <typename T>
+static int upload(bb_ctx *ctx, DevBuf &buf, const T *src, size_t count) {
+    BB_CUDA(ctx, buf.ensure(std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) BB_CUDA(ctx, cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return BB_OK;
+}
+
+extern "C" int bb_upload_reference(bb_ctx *ctx, const uint8_t *bases, int64_t n_bases) {
+    if (!ctx || n_bases < 0 || (n_bases && !bases)) return set_err(ctx, BB_ERR_ARG, "bb_upload_reference: bad arguments");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = upload(ctx, ctx->ref, bases, (size_t)n_bases);
+    if (rc) return rc;
+    BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ref_len = n_bases;
+    return BB_OK;
+}
+
+extern "C" int bb_upload_error_model(bb_ctx *ctx, int k, int type, const int32_t *kmer_to_row, int64_t n_index,
+                                     int32_t n_rows, const int32_t *row_off, const double *cum, const uint8_t *flags,
+                                     const uint32_t *slots, const uint8_t *pool, int64_t pool_len) {
+    if (!ctx) return BB_ERR_ARG;
+    if (k < 1 || k > 12 || (type != 0 && type != 1)) return set_err(ctx, BB_ERR_ARG, "error model: k must be 1..12");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->em = BBErrorModelDev{};
+    ctx->em.k = k; ctx->em.type = type;
+    if (type == 1) {
+        if (!kmer_to_row || !row_off || !cum || !flags || !slots || n_rows <= 0 || n_index != (1ll << (2 * k)))
+            return set_err(ctx, BB_ERR_ARG, "error model: missing tables");
+        const int64_t ne = row_off[n_rows];
+        int rc;
+        if ((rc = upload(ctx, ctx->em_k2r, kmer_to_row, (size_t)n_index))) return rc;
+        if ((rc = upload(ctx, ctx->em_rowoff, row_off, (size_t)n_rows + 1))) return rc;
+        if ((rc = upload(ctx, ctx->em_cum, cum, (size_t)ne))) return rc;
+        if ((rc = upload(ctx, ctx->em_flags, flags, (size_t)ne))) return rc;
+        if ((rc = upload(ctx, ctx->em_slots, slots, (size_t)ne * k))) return rc;
+        if ((rc = upload(ctx, ctx->em_pool, pool, (size_t)pool_len))) return rc;
+        ctx->em.kmer_to_row = ctx->em_k2r.as<int32_t>(); ctx->em.row_off = ctx->em_rowoff.as<int32_t>();
+        ctx->em.cum = ctx->em_cum.as<double>(); ctx->em.flags = ctx->em_flags.as<uint8_t>();
+        ctx->em.slots = ctx->em_slots.as<uint32_t>(); ctx->em.pool = ctx->em_pool.as<uint8_t>();
+    }
+    BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_em = true;
+    ctx->uploaded = false;
+    return BB_OK;
+}
+
+extern "C" int bb_upload_qscore_model(bb_ctx *ctx, int kmer_size, int32_t n_keys, const uint64_t *keys,
+                                      const int32_t *row_off, const uint8_t *scores, const double *cum) {
+    if (!ctx) return BB_ERR_ARG;
+    if (kmer_size < 1 || (kmer_size & 1) == 0 || n_keys <= 0 || !keys || !row_off || !scores || !cum)
+        return set_err(ctx, BB_ERR_ARG, "qscore model: bad arguments");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t bits = 6;
+    while ((1ull << bits) < 2ull * (uint64_t)n_keys) bits++;
+    const size_t hsize = (size_t)1 << bits;
+    std::vector<uint64_t> hk(hsize, 0);
+    std::vector<int32_t> hv(hsize, -1);
+    for (int32_t i = 0; i < n_keys; i++) {
+        if (keys[i] < 4) return set_err(ctx, BB_ERR_ARG, "qscore model: invalid packed key");
+        uint32_t h = (uint32_t)((keys[i] * 0x9E3779B97F4A7C15ull) >> (64 - bits));
+        while (hk[h] != 0 && hk[h] != keys[i]) h = (h + 1) & (uint32_t)(hsize - 1);
+        hk[h] = keys[i]; hv[h] = i;  // a repeated key keeps its last row, like the dict assignment in load_from_file
+    }
+    const int64_t ne = row_off[n_keys];
+    int rc;
+    if ((rc = upload(ctx, ctx->qm_hkeys, hk.data(), hsize))) return rc;
+    if ((rc = upload(ctx, ctx->qm_hvals, hv.data(), hsize))) return rc;
+    if ((rc = upload(ctx, ctx->qm_rowoff, row_off, (size_t)n_keys + 1))) return rc;
+    if ((rc = upload(ctx, ctx->qm_scores, scores, (size_t)ne))) return rc;
+    if ((rc = upload(ctx, ctx->qm_cum, cum, (size_t)ne))) return rc;
+    BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->qm.kmer_size = kmer_size; ctx->qm.hbits = bits;
+    ctx->qm.hkeys = ctx->qm_hkeys.as<uint64_t>(); ctx->qm.hvals = ctx->qm_hvals.as<int32_t>();
+    ctx->qm.row_off = ctx->qm_rowoff.as<int32_t>(); ctx->qm.scores = ctx->qm_scores.as<uint8_t>();
+    ctx->qm.cum = ctx->qm_cum.as<double>();
+    ctx->have_qm = true;
+    return BB_OK;
+}
+
+// Scratch shared by the warp-per-read kernels. hist is sized for the largest traceback edlib's 1 MiB rule
+// admits (ceil(n/64)*m < 52429 -> < 104858 32-row blocks); tbuf holds a joined 1000-slot window.
+static int ensure_scratch(bb_ctx *ctx, int hbuf_need, int lr_need) {
+    const int n_warps = ctx->n_warps;
+    const int hist_cap = 106496;
+    const int tbuf_stride = 1000 * 255 + 1024;
+    const int stack_cap = 64;
+    int hbuf_cap = std::max(hbuf_need + 64, tbuf_stride);
+    hbuf_cap = (hbuf_cap + 255) & ~255;
+    int lr_cap = std::max(lr_need + 64, 4096);
+    lr_cap = (lr_cap + 255) & ~255;
+    if (ctx->pool.hbuf_cap >= hbuf_cap) hbuf_cap = ctx->pool.hbuf_cap;
+    if (ctx->pool.lr_cap >= lr_cap) lr_cap = ctx->pool.lr_cap;
+    BB_CUDA(ctx, ctx->s_hist.ensure((size_t)n_warps * hist_cap * sizeof(uint2)));
+    BB_CUDA(ctx, ctx->s_tbuf.ensure((size_t)n_warps * tbuf_stride));
+    BB_CUDA(ctx, ctx->s_stack.ensure((size_t)n_warps * stack_cap * 5 * sizeof(int)));
+    BB_CUDA(ctx, ctx->s_hbuf.ensure((size_t)n_warps * hbuf_cap));
+    BB_CUDA(ctx, ctx->s_lr.ensure((size_t)n_warps * lr_cap * 2 * sizeof(int)));
+    BBScratchPool &p = ctx->pool;
+    p.hist = ctx->s_hist.as<uint2>(); p.hist_stride = hist_cap; p.hist_cap = hist_cap;
+    p.hbuf = ctx->s_hbuf.as<int8_t>(); p.hbuf_stride = hbuf_cap; p.hbuf_cap = hbuf_cap;
+    p.lr = ctx->s_lr.as<int>(); p.lr_stride = 2ll * lr_cap; p.lr_cap = lr_cap;
+    p.stack = ctx->s_stack.as<int>(); p.stack_cap = stack_cap;
+    p.tbuf = ctx->s_tbuf.as<uint8_t>(); p.tbuf_stride = tbuf_stride;
+    return BB_OK;
+}
+
+static BBBatchDev batch_dev(bb_ctx *ctx) {
+    BBBatchDev B{};
+    B.n_reads = ctx->n_reads;
+    B.read_index = ctx->d_read_index.as<unsigned long long>();
+    B.seg_off = ctx->d_seg_off.as<int>();
+    B.segs = ctx->d_segs.as<bb_segment>();
+    B.lit = ctx->d_lit.as<uint8_t>();
+    B.target = ctx->d_target.as<double>();
+    B.order = ctx->d_order.as<int>();
+    B.reads = ctx->d_reads.as<BBReadDev>();
+    B.frag = ctx->d_frag.as<uint8_t>();
+    B.state = ctx->d_state.as<uint32_t>();
+    B.seq = ctx->d_seq.as<uint8_t>();
+    B.ops = ctx->d_ops.as<uint8_t>();
+    B.dcnt = ctx->d_dcnt.as<uint16_t>();
+    B.qual = ctx->d_qual.as<uint8_t>();
+    B.out_seq = ctx->d_out_seq.as<uint8_t>();
+    B.out_qual = ctx->d_out_qual.as<uint8_t>();
+    return B;
+}
+
+extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_index, const int32_t *seg_off,
+                               const bb_segment *segs, const uint8_t *literal_pool, int64_t literal_len,
+                               const double *target_identity) {
+    if (!ctx) return BB_ERR_ARG;
+    if (n_reads <= 0 || !read_index || !seg_off || !segs || !target_identity || literal_len < 0)
+        return set_err(ctx, BB_ERR_ARG, "bb_batch_upload: bad arguments");
+    if (!ctx->have_em || !ctx->have_qm) return set_err(ctx, BB_ERR_STATE, "upload the error and qscore models first");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int k = ctx->em.k;
+    ctx->h_reads.assign((size_t)n_reads, BBReadDev{});
+    ctx->h_inlen.assign((size_t)n_reads, 0);
+    int64_t off = 0;
+    int max_len = 0;
+    for (int32_t r = 0; r < n_reads; r++) {
+        int64_t len = 0;
+        if (seg_off[r + 1] < seg_off[r]) return set_err(ctx, BB_ERR_ARG, "seg_off must be non-decreasing");
+        for (int32_t s = seg_off[r]; s < seg_off[r + 1]; s++) {
+            const bb_segment &sg = segs[s];
+            if (sg.len < 0 || sg.src < 0) return set_err(ctx, BB_ERR_ARG, "negative segment");
+            if (sg.kind == BB_SEG_LITERAL) { if (sg.src + sg.len > literal_len) return set_err(ctx, BB_ERR_ARG, "literal segment out of range"); }
+            else if (sg.kind == BB_SEG_REF_FWD || sg.kind == BB_SEG_REF_REV) { if (sg.src + sg.len > ctx->ref_len) return set_err(ctx, BB_ERR_ARG, "reference segment out of range"); }
+            else return set_err(ctx, BB_ERR_ARG, "unknown segment kind");
+            len += sg.len;
+        }
+        if (len + 2 * k > 0x3fffffff) return set_err(ctx, BB_ERR_ARG, "fragment too long");
+        ctx->h_inlen[(size_t)r] = (int32_t)len;
+        BBReadDev &rd = ctx->h_reads[(size_t)r];
+        rd.frag_off = off;
+        rd.frag_len = (int)(len + 2 * k);
+        off += (rd.frag_len + 15) & ~15;
+        max_len = std::max(max_len, rd.frag_len);
+    }
+    ctx->frag_total = off;
+    std::vector<int> order((size_t)n_reads);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int x, int y) { return ctx->h_reads[(size_t)x].frag_len > ctx->h_reads[(size_t)y].frag_len; });
+    ctx->n_reads = n_reads;
+    int rc;
+    if ((rc = upload(ctx, ctx->d_read_index, read_index, (size_t)n_reads))) return rc;
+    if ((rc = upload(ctx, ctx->d_seg_off, seg_off, (size_t)n_reads + 1))) return rc;
+    if ((rc = upload(ctx, ctx->d_segs, segs, (size_t)seg_off[n_reads]))) return rc;
+    if ((rc = upload(ctx, ctx->d_lit, literal_pool, (size_t)literal_len))) return rc;
+    if ((rc = upload(ctx, ctx->d_target, target_identity, (size_t)n_reads))) return rc;
+    if ((rc = upload(ctx, ctx->d_order, order.data(), (size_t)n_reads))) return rc;
+    if ((rc = upload(ctx, ctx->d_reads, ctx->h_reads.data(), (size_t)n_reads))) return rc;
+    BB_CUDA(ctx, ctx->d_frag.ensure((size_t)off + 16));
+    BB_CUDA(ctx, ctx->d_state.ensure(((size_t)off + 16) * sizeof(uint32_t)));
+    BB_CUDA(ctx, ctx->d_counter.ensure(16 * sizeof(int)));
+    if ((rc = ensure_scratch(ctx, max_len, 4096))) return rc;
+    BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->uploaded = true;
+    ctx->ran = false;
+    return BB_OK;
+}
+
+extern "C" int bb_batch_run(bb_ctx *ctx) {
+    if (!ctx) return BB_ERR_ARG;
+    if (!ctx->uploaded) return set_err(ctx, BB_ERR_STATE, "bb_batch_run: no batch uploaded");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->n_reads;
+    BBBatchDev B = batch_dev(ctx);
+    int *counters = ctx->d_counter.as<int>();
+    const int grid_warp = ctx->n_warps / BB_WARPS_PER_CTA;
+
+    // the per-read records start from the uploaded state on every run (bb_batch_run may be repeated)
+    BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, ctx->h_reads.data(), (size_t)n * sizeof(BBReadDev),
+                                 cudaMemcpyHostToDevice, st));
+    BB_CUDA(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(int), st));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    bb_k_build_fragments<<<n, 256, 0, st>>>(B, ctx->ref.as<uint8_t>(), ctx->em.k, ctx->seed);
+    ctx->launches++;
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    bb_k_error_loop<<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->seed, counters);
+    ctx->launches++;
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    // host scan of the joined lengths -> offsets of the per-read regions in seq / ops / dcnt / qual / out
+    std::vector<BBReadDev> reads((size_t)n);
+    BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(ctx, cudaStreamSynchronize(st));
+    int64_t seq_off = 0, out_off = 0;
+    int lr_need = 0, hbuf_need = 0;
+    for (int r = 0; r < n; r++) {
+        BBReadDev &rd = reads[(size_t)r];
+        rd.seq_off = seq_off;
+        rd.out_off = out_off;
+        int out_len = rd.seq_len - rd.start_trim - rd.end_trim;  // seq[start_trim:-end_trim]
+        if (out_len < 0) out_len = 0;
+        rd.out_len = out_len;
+        rd.lead_del = 0; rd.matches = 0; rd.dels = 0;
+        seq_off += (rd.seq_len + 15) & ~15;
+        out_off += out_len;
+        const int mx = std::max(rd.seq_len, rd.frag_len);
+        lr_need = std::max(lr_need, std::min(rd.seq_len, std::min(rd.upper, mx) + 2));
+        hbuf_need = std::max(hbuf_need, rd.frag_len);
+    }
+    ctx->seq_total = seq_off;
+    ctx->out_total = out_off;
+    BB_CUDA(ctx, ctx->d_seq.ensure((size_t)seq_off + 16));
+    BB_CUDA(ctx, ctx->d_ops.ensure((size_t)seq_off + 16));
+    BB_CUDA(ctx, ctx->d_dcnt.ensure(((size_t)seq_off + 16) * sizeof(uint16_t)));
+    BB_CUDA(ctx, ctx->d_qual.ensure((size_t)seq_off + 16));
+    BB_CUDA(ctx, ctx->d_out_seq.ensure((size_t)out_off + 16));
+    BB_CUDA(ctx, ctx->d_out_qual.ensure((size_t)out_off + 16));
+    int rc = ensure_scratch(ctx, hbuf_need, lr_need);
+    if (rc) return rc;
+    B = batch_dev(ctx);
+    BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, reads.data(), (size_t)n * sizeof(BBReadDev), cudaMemcpyHostToDevice, st));
+    BB_CUDA(ctx, cudaMemsetAsync(ctx->d_dcnt.p, 0, ((size_t)seq_off + 16) * sizeof(uint16_t), st));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    bb_k_join<<<n, 256, 0, st>>>(B, ctx->em);
+    ctx->launches++;
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+    bb_k_final_align<<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 1);
+    ctx->launches++;
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    bb_k_qscores<<<n, 256, 0, st>>>(B, ctx->qm, ctx->seed);
+    ctx->launches++;
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+    bb_k_compact<<<n, 256, 0, st>>>(B);
+    ctx->launches++;
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+    BB_CUDA(ctx, cudaGetLastError());
+    ctx->ran = true;
+    return BB_OK;
+}
+
+extern "C" int bb_synchronize(bb_ctx *ctx) {
+    if (!ctx) return BB_ERR_ARG;
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BB_OK;
+}
+
+extern "C" int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms) {
+    if (!ctx) return BB_ERR_ARG;
+    if (!ctx->ran) return set_err(ctx, BB_ERR_STATE, "no run to time");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    BB_CUDA(ctx, cudaEventSynchronize(ctx->ev[7]));
+    for (int i = 0; i < 7; i++) BB_CUDA(ctx, cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    BB_CUDA(ctx, cudaEventElapsedTime(&ctx->stage_ms[7], ctx->ev[0], ctx->ev[7]));
+    if (total_ms) *total_ms = ctx->stage_ms[7];
+    if (stage_ms) std::memcpy(stage_ms, ctx->stage_ms, sizeof(ctx->stage_ms));
+    return BB_OK;
+}
+
+extern "C" int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t *seq_out, uint8_t *qual_out,
+                                   int64_t out_cap, int64_t *out_total) {
+    if (!ctx) return BB_ERR_ARG;
+    if (!ctx->ran) return set_err(ctx, BB_ERR_STATE, "bb_fetch_last_batch: nothing to fetch");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (out_total) *out_total = ctx->out_total;
+    if (out_cap < ctx->out_total) return set_err(ctx, BB_ERR_CAPACITY, "output buffers too small");
+    const int n = ctx->n_reads;
+    std::vector<BBReadDev> reads((size_t)n);
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
+    if (ctx->out_total) {
+        if (!seq_out || !qual_out) return set_err(ctx, BB_ERR_ARG, "null output buffers");
+        BB_CUDA(ctx, cudaMemcpyAsync(seq_out, ctx->d_out_seq.p, (size_t)ctx->out_total, cudaMemcpyDeviceToHost, st));
+        BB_CUDA(ctx, cudaMemcpyAsync(qual_out, ctx->d_out_qual.p, (size_t)ctx->out_total, cudaMemcpyDeviceToHost, st));
+    }
+    BB_CUDA(ctx, cudaStreamSynchronize(st));
+    int bad = 0, bad_read = -1;
+    for (int r = 0; r < n; r++) {
+        const BBReadDev &rd = reads[(size_t)r];
+        if (results) {
+            bb_read_result &o = results[r];
+            o.out_off = rd.out_off; o.out_len = rd.out_len; o.frag_len = ctx->h_inlen[(size_t)r];
+            o.matches = rd.matches; o.columns = rd.seq_len + rd.dels; o.loop_count = rd.loop_count;
+            o.change_count = rd.change_count; o.n_alignments = rd.n_align; o.flags = rd.flags;
+        }
+        if (rd.flags && !bad) { bad = rd.flags; bad_read = r; }
+    }
+    if (bad) {
+        char msg[160];
+        std::snprintf(msg, sizeof(msg), "device invariant violated: read %d flags 0x%x", bad_read, bad);
+        return set_err(ctx, BB_ERR_INTERNAL, msg);
+    }
+    return BB_OK;
+}
+
+extern "C" int bb_sequence_batch(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_index, const int32_t *seg_off,
+                                 const bb_segment *segs, const uint8_t *literal_pool, int64_t literal_len,
+                                 const double *target_identity, bb_read_result *results, uint8_t *seq_out,
+                                 uint8_t *qual_out, int64_t out_cap, int64_t *out_total) {
+    int rc = bb_batch_upload(ctx, n_reads, read_index, seg_off, segs, literal_pool, literal_len, target_identity);
+    if (rc) return rc;
+    if ((rc = bb_batch_run(ctx))) return rc;
+    return bb_fetch_last_batch(ctx, results, seq_out, qual_out, out_cap, out_total);
+}
+
+// ---- single-pair entry points ------------------------------------------------------------------------
+static int align_pair_device(bb_ctx *ctx, const uint8_t *q, int n, const uint8_t *t, int m, DevBuf &dq, DevBuf &dt,
+                             DevBuf &dops, DevBuf &ddcnt, DevBuf &dout, int out5[5]) {
+    int rc;
+    if ((rc = upload(ctx, dq, q, (size_t)n))) return rc;
+    if ((rc = upload(ctx, dt, t, (size_t)m))) return rc;
+    BB_CUDA(ctx, dops.ensure((size_t)n + 16));
+    BB_CUDA(ctx, ddcnt.ensure(((size_t)n + 16) * sizeof(uint16_t)));
+    BB_CUDA(ctx, dout.ensure(8 * sizeof(int)));
+    if ((rc = ensure_scratch(ctx, std::max(n, m), std::max(n, m)))) return rc;
+    BB_CUDA(ctx, cudaMemsetAsync(ddcnt.p, 0, ((size_t)n + 16) * sizeof(uint16_t), ctx->stream));
+    BB_CUDA(ctx, cudaMemsetAsync(dout.p, 0, 8 * sizeof(int), ctx->stream));
+    bb_k_align_pair<<<1, 32, 0, ctx->stream>>>(dq.as<uint8_t>(), n, dt.as<uint8_t>(), m, std::max(n, m), ctx->pool,
+                                                dops.as<uint8_t>(), ddcnt.as<uint16_t>(), dout.as<int>());
+    ctx->launches++;
+    BB_CUDA(ctx, cudaMemcpyAsync(out5, dout.p, 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out5[4]) {
+        char msg[96];
+        std::snprintf(msg, sizeof(msg), "aligner invariant violated (code 0x%x)", out5[4]);
+        return set_err(ctx, BB_ERR_INTERNAL, msg);
+    }
+    return BB_OK;
+}
+
+extern "C" int bb_align_path(bb_ctx *ctx, const uint8_t *query, int32_t q_len, const uint8_t *target, int32_t t_len,
+                             uint8_t *ops_out, int64_t ops_cap, int64_t *n_ops, int32_t *distance) {
+    if (!ctx) return BB_ERR_ARG;
+    if (!query || !target || q_len <= 0 || t_len <= 0) return set_err(ctx, BB_ERR_ARG, "bb_align_path: empty sequence");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dq, dt, dops, ddcnt, dout;
+    int out5[5] = {0, 0, 0, 0, 0};
+    int rc = align_pair_device(ctx, query, q_len, target, t_len, dq, dt, dops, ddcnt, dout, out5);
+    std::vector<uint8_t> ops((size_t)q_len);
+    std::vector<uint16_t> dcnt((size_t)q_len);
+    if (rc == BB_OK) {
+        cudaMemcpy(ops.data(), dops.p, (size_t)q_len, cudaMemcpyDeviceToHost);
+        cudaMemcpy(dcnt.data(), ddcnt.p, (size_t)q_len * sizeof(uint16_t), cudaMemcpyDeviceToHost);
+    }
+    dq.release(); dt.release(); dops.release(); ddcnt.release(); dout.release();
+    if (rc) return rc;
+    const int64_t total = (int64_t)q_len + out5[1];
+    if (n_ops) *n_ops = total;
+    if (distance) *distance = out5[2];
+    if (total > ops_cap) return set_err(ctx, BB_ERR_CAPACITY, "ops buffer too small");
+    static const char sym[3] = {'=', 'X', 'I'};
+    int64_t w = 0;
+    for (int x = 0; x < out5[3]; x++) ops_out[w++] = 'D';
+    for (int i = 0; i < q_len; i++) {
+        ops_out[w++] = (uint8_t)sym[ops[(size_t)i] < 3 ? ops[(size_t)i] : 0];
+        if (dcnt[(size_t)i] == 0xffff) return set_err(ctx, BB_ERR_CAPACITY, "deletion run longer than 65534");
+        for (int x = 0; x < dcnt[(size_t)i]; x++) ops_out[w++] = 'D';
+    }
+    if (w != total) return set_err(ctx, BB_ERR_INTERNAL, "column count mismatch");
+    return BB_OK;
+}
+
+extern "C" int bb_get_qscores(bb_ctx *ctx, uint64_t read_index, const uint8_t *seq, int32_t seq_len,
+                              const uint8_t *frag, int32_t frag_len, uint8_t *qual_out, int32_t *matches,
+                              int32_t *columns) {
+    if (!ctx) return BB_ERR_ARG;
+    if (!seq || !frag || seq_len <= 0 || frag_len <= 0 || !qual_out) return set_err(ctx, BB_ERR_ARG, "bb_get_qscores: bad arguments");
+    if (!ctx->have_qm) return set_err(ctx, BB_ERR_STATE, "upload the qscore model first");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dq, dt, dops, ddcnt, dout, dqual;
+    int out5[5] = {0, 0, 0, 0, 0};
+    int rc = align_pair_device(ctx, seq, seq_len, frag, frag_len, dq, dt, dops, ddcnt, dout, out5);
+    if (rc == BB_OK) {
+        cudaError_t e = dqual.ensure((size_t)seq_len + 16);
+        if (e != cudaSuccess) rc = set_err(ctx, BB_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (rc == BB_OK) {
+        bb_k_qscores_pair<<<(seq_len + 255) / 256, 256, 0, ctx->stream>>>(dops.as<uint8_t>(), ddcnt.as<uint16_t>(), seq_len,
+                                                                            ctx->qm, ctx->seed, read_index, dqual.as<uint8_t>());
+        ctx->launches++;
+        cudaMemcpyAsync(qual_out, dqual.p, (size_t)seq_len, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = set_err(ctx, BB_ERR_CUDA, cudaGetErrorString(e));
+    }
+    dq.release(); dt.release(); dops.release(); ddcnt.release(); dout.release(); dqual.release();
+    if (rc) return rc;
+    if (matches) *matches = out5[0];
+    if (columns) *columns = seq_len + out5[1];
+    return BB_OK;
+}

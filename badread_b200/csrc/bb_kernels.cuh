@@ -1,0 +1,510 @@
+// bb_kernels.cuh — the per-read hot path as sm_100a kernels.
+//
+//   K1 bb_k_build_fragments   gather fragments from the HBM-resident reference / literal pool, draw the 2k pad
+//                             bases (simulate.py:260), reset slot states
+//   K2 bb_k_error_loop        simulate.sequence_fragment's while-loop (simulate.py:272-346): one warp per read,
+//                             32 loop iterations evaluated speculatively per step (one Philox stream per
+//                             iteration), changes committed in order, identity re-measured every 25 changes by
+//                             the warp aligner (bb_align.cuh)
+//   K3 bb_k_join              ''.join(new_fragment_bases) (simulate.py:351)
+//   K4 bb_k_final_align       edlib.align(seq, fragment) of get_qscores (qscore_model.py:37) -> per-base ops
+//   K5 bb_k_qscores           per-base CIGAR window -> QScoreModel.get_qscore (qscore_model.py:54-68,273-287)
+//   K6 bb_k_compact           seq[start_trim:-end_trim], qual likewise (simulate.py:355-356)
+#pragma once
+#include <cstdint>
+
+#include "../../include/badread_b200.h"
+#include "bb_align.cuh"
+#include "bb_rng.cuh"
+
+#define BB_SLOT_NONE 0xFFFFFFFFu
+#define BB_ALIGNMENT_INTERVAL 25  // settings.py:24
+#define BB_ALIGNMENT_SIZE 1000    // settings.py:25
+#define BB_WARPS_PER_CTA 4
+
+struct BBErrorModelDev {
+    int k, type;
+    const int32_t *kmer_to_row;
+    const int32_t *row_off;
+    const double *cum;
+    const uint8_t *flags;
+    const uint32_t *slots;
+    const uint8_t *pool;
+};
+
+struct BBQScoreModelDev {
+    int kmer_size;
+    const uint64_t *hkeys;  // open addressing, 0 = empty
+    const int32_t *hvals;
+    uint32_t hbits;
+    const int32_t *row_off;
+    const uint8_t *scores;
+    const double *cum;
+};
+
+struct BBReadDev {
+    long long frag_off;  // into frag / state
+    long long seq_off;   // into seq / ops / dcnt / qual
+    long long out_off;   // into out_seq / out_qual
+    int frag_len;        // padded (2k pad bases included)
+    int seq_len;         // untrimmed
+    int start_trim, end_trim;
+    int upper;           // upper bound on the edit distance seq <-> fragment (injected edits)
+    int loop_count, change_count, n_align;
+    int matches, dels, lead_del;
+    int out_len;
+    int flags;
+    int pad_;
+};
+
+struct BBBatchDev {
+    int n_reads;
+    const unsigned long long *read_index;
+    const int *seg_off;
+    const bb_segment *segs;
+    const uint8_t *lit;
+    const double *target;
+    const int *order;  // reads sorted by decreasing fragment length (work queue order)
+    BBReadDev *reads;
+    uint8_t *frag;
+    uint32_t *state;
+    uint8_t *seq;
+    uint8_t *ops;
+    uint16_t *dcnt;
+    uint8_t *qual;
+    uint8_t *out_seq, *out_qual;
+};
+
+struct BBScratchPool {
+    uint2 *hist; long long hist_stride; int hist_cap;
+    int8_t *hbuf; long long hbuf_stride; int hbuf_cap;
+    int *lr; long long lr_stride; int lr_cap;  // L at [0, lr_cap), R at [lr_cap, 2*lr_cap)
+    int *stack; int stack_cap;
+    uint8_t *tbuf; long long tbuf_stride;
+    __device__ BBScratch for_warp(int w) const {
+        BBScratch s;
+        s.hist = hist + (long long)w * hist_stride; s.hist_cap = hist_cap;
+        s.hbuf = hbuf + (long long)w * hbuf_stride; s.hbuf_cap = hbuf_cap;
+        s.L = lr + (long long)w * lr_stride; s.R = s.L + lr_cap; s.lr_cap = lr_cap;
+        s.stack = stack + (long long)w * stack_cap * 5; s.stack_cap = stack_cap;
+        return s;
+    }
+};
+
+__constant__ uint8_t bb_c_comp[256];  // misc.REV_COMP_DICT, unknown -> 'N' (misc.py:56-67)
+
+// ------------------------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(256) bb_k_build_fragments(BBBatchDev B, const uint8_t *__restrict__ ref, int k,
+                                                            unsigned long long seed) {
+    const int r = blockIdx.x;
+    if (r >= B.n_reads) return;
+    const BBReadDev rd = B.reads[r];
+    uint8_t *f = B.frag + rd.frag_off;
+    uint32_t *st = B.state + rd.frag_off;
+    const int flen = rd.frag_len;
+    if (threadIdx.x == 0) {
+        BBRng rng;
+        rng.init(seed, B.read_index[r]);
+        rng.stream(BB_PURPOSE_PAD, 0);
+        for (int j = 0; j < k; j++) f[j] = rng.random_base();
+        for (int j = 0; j < k; j++) f[flen - k + j] = rng.random_base();
+    }
+    int pos = k;
+    for (int s = B.seg_off[r]; s < B.seg_off[r + 1]; s++) {
+        const bb_segment sg = B.segs[s];
+        if (sg.kind == BB_SEG_REF_FWD) {
+            const uint8_t *src = ref + sg.src;
+            for (int x = threadIdx.x; x < sg.len; x += blockDim.x) f[pos + x] = __ldg(src + x);
+        } else if (sg.kind == BB_SEG_REF_REV) {
+            const uint8_t *src = ref + sg.src + sg.len - 1;
+            for (int x = threadIdx.x; x < sg.len; x += blockDim.x) f[pos + x] = bb_c_comp[__ldg(src - x)];
+        } else {
+            const uint8_t *src = B.lit + sg.src;
+            for (int x = threadIdx.x; x < sg.len; x += blockDim.x) f[pos + x] = __ldg(src + x);
+        }
+        pos += sg.len;
+    }
+    for (int x = threadIdx.x; x < flen; x += blockDim.x) st[x] = BB_SLOT_NONE;
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+__device__ __forceinline__ int bb_base_code(uint8_t c) {
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+}
+__device__ __forceinline__ uint32_t bb_slot_inline(int len, uint8_t c0, uint8_t c1) {
+    return (uint32_t)len | ((uint32_t)c0 << 8) | ((uint32_t)c1 << 16);
+}
+__device__ __forceinline__ uint8_t bb_slot_char(const BBErrorModelDev &em, uint32_t enc, int idx) {
+    const int len = enc & 0xff;
+    if (len <= 3) return (uint8_t)(enc >> (8 * (idx + 1)));
+    return em.pool[(enc >> 8) + idx];
+}
+
+// ''.join(new_fragment_bases[lo:lo+count]) into out (warp-cooperative). Returns the joined length; *upper gets
+// the number of edits that turn the original slice into the joined one (an upper bound on their edit distance).
+__device__ int bb_join_slots(const BBErrorModelDev &em, const uint8_t *frag, const uint32_t *state, int lo, int count,
+                             uint8_t *out, int *upper) {
+    const int lane = threadIdx.x & 31;
+    int total = 0, up = 0;
+    for (int base = 0; base < count; base += 32) {
+        const int x = base + lane;
+        uint32_t st = BB_SLOT_NONE;
+        int len = 0;
+        if (x < count) { st = state[lo + x]; len = st == BB_SLOT_NONE ? 1 : (int)(st & 0xff); }
+        int incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(BB_FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const int off = total + incl - len;
+        if (x < count) {
+            if (st == BB_SLOT_NONE) out[off] = frag[lo + x];
+            else {
+                for (int c = 0; c < len; c++) out[off + c] = bb_slot_char(em, st, c);
+                up += len < 1 ? 1 : len;
+            }
+        }
+        total += __shfl_sync(BB_FULL, incl, 31);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) up += __shfl_xor_sync(BB_FULL, up, d);
+    *upper = up;
+    __syncwarp();
+    return total;
+}
+
+// One speculative evaluation of simulate.py:294-296 for loop iteration n: position, k-mer, model draw.
+// kind 0: ''.join(new_kmer) == kmer (nothing to do); 1: table entry `payload`; 2: one random change where
+// slot `rpos` becomes the inline-encoded string `payload` (error_model.py:163-176).
+__device__ __forceinline__ void bb_eval_iteration(const BBErrorModelDev &em, const uint8_t *frag, int max_kmer_index,
+                                                  unsigned long long seed, unsigned long long read,
+                                                  unsigned int n, int &kind, int &pos_i, uint32_t &payload,
+                                                  int &rpos) {
+    BBRng rng;
+    rng.init(seed, read);
+    rng.stream(BB_PURPOSE_LOOP, n);
+    const int k = em.k;
+    const int i = (int)rng.randbelow((uint32_t)(max_kmer_index + 1));  // random.randint(0, max_kmer_index)
+    pos_i = i;
+    bool random_change = (em.type == 0);
+    if (!random_change) {
+        int idx = 0;
+        bool ok = true;
+        for (int j = 0; j < k; j++) {
+            const int c = bb_base_code(frag[i + j]);
+            if (c < 0) ok = false;
+            idx = idx * 4 + (c & 3);
+        }
+        const int row = ok ? em.kmer_to_row[idx] : -1;
+        if (row < 0) random_change = true;  // kmer not in self.alternatives (error_model.py:143-144)
+        else {
+            const int e0 = em.row_off[row], ne = em.row_off[row + 1] - e0;
+            const int e = e0 + bb_choices(rng, em.cum + e0, ne);
+            const uint8_t fl = em.flags[e];
+            if (fl & 2) random_change = true;  // alt is None (error_model.py:157-158)
+            else { kind = (fl & 1) ? 0 : 1; payload = (uint32_t)e; rpos = 0; return; }
+        }
+    }
+    // add_one_random_change
+    const uint32_t type = rng.randbelow(3);          // random.choice(['s','i','d'])
+    const int p = (int)rng.randbelow((uint32_t)k);   // random.randint(0, len(kmer)-1)
+    const uint8_t old = frag[i + p];
+    if (type == 0) payload = bb_slot_inline(1, rng.random_different_base(old), 0);
+    else if (type == 1) {
+        if (rng.random() < 0.5) { const uint8_t nb = rng.random_base(); payload = bb_slot_inline(2, old, nb); }
+        else { const uint8_t nb = rng.random_base(); payload = bb_slot_inline(2, nb, old); }
+    } else payload = bb_slot_inline(0, 0, 0);
+    kind = 2; rpos = p;
+}
+
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
+bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned long long seed, int *work_counter) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const BBScratch sc = pool.for_warp(warp);
+    uint8_t *tbuf = pool.tbuf + (long long)warp * pool.tbuf_stride;
+    const int k = em.k;
+    BBEmit no_emit = {nullptr, nullptr, nullptr};
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1);
+        w = __shfl_sync(BB_FULL, w, 0);
+        if (w >= B.n_reads) break;
+        const int r = B.order[w];
+        BBReadDev *rd = &B.reads[r];
+        const uint8_t *frag = B.frag + rd->frag_off;
+        uint32_t *state = B.state + rd->frag_off;
+        const int frag_len = rd->frag_len;
+        const unsigned long long read = B.read_index[r];
+        const double target = B.target[r];
+        const double fl = (double)frag_len;
+        const int max_kmer_index = frag_len - 1 - k;
+        const long long limit = 100ll * frag_len;  // loop_count > 100 * frag_len stops the loop (simulate.py:279)
+        double errors = 0.0;
+        int change_count = 0, n_align = 0, upper = 0, flags = 0;
+        long long loop_count = 0, n0 = 0;
+        const double est_needed = __dmul_rn(fl, __dsub_rn(1.0, target));
+        bool done = est_needed < 0.5;
+        if (!done && 1.0 <= target) { done = true; loop_count = 1; }
+        __syncwarp();
+        while (!done) {
+            const long long n = n0 + lane;
+            int kind = 0, pos_i = 0, rpos = 0;
+            uint32_t payload = 0;
+            if (n < limit) bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
+            __syncwarp();
+            uint32_t cmask = __ballot_sync(BB_FULL, kind != 0);
+            while (cmask && !done) {
+                const int L = __ffs(cmask) - 1;
+                cmask &= cmask - 1;
+                const int bi = __shfl_sync(BB_FULL, pos_i, L);
+                const int bkind = __shfl_sync(BB_FULL, kind, L);
+                const uint32_t bpay = __shfl_sync(BB_FULL, payload, L);
+                const int brpos = __shfl_sync(BB_FULL, rpos, L);
+                // estimated_identity of this iteration (simulate.py:290); errors are scaled by its 1.5th power
+                // computed as x*sqrt(x): two correctly rounded operations, identical on host and device
+                const double est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl));
+                const double scale = __dmul_rn(est_id, __dsqrt_rn(est_id));
+                uint32_t enc = 0;
+                bool app = false;
+                if (lane < k) {
+                    const uint8_t fb = frag[bi + lane];
+                    enc = bkind == 1 ? em.slots[(long long)bpay * k + lane]
+                                     : (lane == brpos ? bpay : bb_slot_inline(1, fb, 0));
+                    const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
+                    app = differs && state[bi + lane] == BB_SLOT_NONE;  // simulate.py:309
+                }
+                uint32_t amask = __ballot_sync(BB_FULL, app);
+                while (amask) {
+                    const int j = __ffs(amask) - 1;
+                    amask &= amask - 1;
+                    const uint32_t e = __shfl_sync(BB_FULL, enc, j);
+                    if (lane == j) state[bi + j] = e;
+                    __syncwarp();
+                    const int len = (int)(e & 0xff);
+                    change_count++;
+                    upper += len < 1 ? 1 : len;
+                    const int new_errors = len < 2 ? 1 : len - 1;
+                    errors = __dadd_rn(errors, __dmul_rn((double)new_errors, scale));  // simulate.py:321
+                    if (change_count % BB_ALIGNMENT_INTERVAL == 0) {  // simulate.py:325-346
+                        __syncwarp();
+                        int qpos = 0, qn = frag_len;
+                        if (frag_len > BB_ALIGNMENT_SIZE) {
+                            BBRng wr;
+                            wr.init(seed, read);
+                            wr.stream(BB_PURPOSE_WINDOW, (uint32_t)n_align);
+                            qpos = (int)wr.randbelow((uint32_t)(frag_len - BB_ALIGNMENT_SIZE + 1));
+                            qn = BB_ALIGNMENT_SIZE;
+                        }
+                        int uw = 0;
+                        const int tm = bb_join_slots(em, frag, state, qpos, qn, tbuf, &uw);
+                        BBAlnCounts cnt = {0, 0, 0, 0};
+                        bb_align<false>(frag + qpos, qn, tbuf, tm, uw, sc, no_emit, cnt);
+                        flags |= cnt.err;
+                        const int cols = qn + cnt.dels;
+                        const double actual = cols ? __ddiv_rn((double)cnt.matches, (double)cols) : 0.0;
+                        if (frag_len <= BB_ALIGNMENT_SIZE) {
+                            errors = __dmul_rn(__dsub_rn(1.0, actual), fl);
+                        } else {
+                            const double est_err = __dmul_rn(__dsub_rn(1.0, actual), fl);
+                            const double weight = __ddiv_rn((double)BB_ALIGNMENT_SIZE, fl);
+                            errors = __dadd_rn(__dmul_rn(est_err, weight), __dmul_rn(errors, __dsub_rn(1.0, weight)));
+                        }
+                        n_align++;
+                        __syncwarp();
+                    }
+                }
+                // the checks at the top of the next iteration (simulate.py:285-292) can only change after a commit
+                const long long nL = n0 + L;
+                if ((double)change_count > __dmul_rn(0.9, fl)) { done = true; loop_count = nL + 2; }
+                else {
+                    const double est = __dsub_rn(1.0, __ddiv_rn(errors, fl));
+                    if (est <= target) { done = true; loop_count = nL + 2; }
+                }
+                if (flags) { done = true; }
+            }
+            if (!done) {
+                n0 += 32;
+                if (n0 >= limit) { done = true; loop_count = limit + 1; }
+            }
+        }
+        __syncwarp();
+        // lengths of the joined read and of the two pad regions (simulate.py:348-351)
+        int total = 0, st_trim = 0, en_trim = 0;
+        for (int base = 0; base < frag_len; base += 32) {
+            const int x = base + lane;
+            int len = 0;
+            if (x < frag_len) { const uint32_t st = state[x]; len = st == BB_SLOT_NONE ? 1 : (int)(st & 0xff); }
+            total += len;
+            if (x < k) st_trim += len;
+            if (x < frag_len && x >= frag_len - k) en_trim += len;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            total += __shfl_xor_sync(BB_FULL, total, d);
+            st_trim += __shfl_xor_sync(BB_FULL, st_trim, d);
+            en_trim += __shfl_xor_sync(BB_FULL, en_trim, d);
+        }
+        if (lane == 0) {
+            rd->seq_len = total; rd->start_trim = st_trim; rd->end_trim = en_trim; rd->upper = upper;
+            rd->loop_count = (int)(loop_count > 0x7fffffff ? 0x7fffffff : loop_count);
+            rd->change_count = change_count; rd->n_align = n_align; rd->flags = flags;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+__global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev em) {
+    const int r = blockIdx.x;
+    if (r >= B.n_reads) return;
+    const BBReadDev rd = B.reads[r];
+    const uint8_t *frag = B.frag + rd.frag_off;
+    const uint32_t *state = B.state + rd.frag_off;
+    uint8_t *seq = B.seq + rd.seq_off;
+    __shared__ int warp_sum[8];
+    __shared__ int running;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < rd.frag_len; base += 256) {
+        const int x = base + threadIdx.x;
+        uint32_t st = BB_SLOT_NONE;
+        int len = 0;
+        if (x < rd.frag_len) { st = state[x]; len = st == BB_SLOT_NONE ? 1 : (int)(st & 0xff); }
+        int incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(BB_FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < wid; w++) woff += warp_sum[w];
+        const int off = running + woff + incl - len;
+        if (x < rd.frag_len) {
+            if (st == BB_SLOT_NONE) seq[off] = frag[x];
+            else for (int c = 0; c < len; c++) seq[off + c] = bb_slot_char(em, st, c);
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) running = off + len;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
+bb_k_final_align(BBBatchDev B, BBScratchPool pool, int *work_counter) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const BBScratch sc = pool.for_warp(warp);
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1);
+        w = __shfl_sync(BB_FULL, w, 0);
+        if (w >= B.n_reads) break;
+        const int r = B.order[w];
+        BBReadDev *rd = &B.reads[r];
+        BBEmit em;
+        em.ops = B.ops + rd->seq_off;
+        em.dcnt = B.dcnt + rd->seq_off;
+        em.lead_del = &rd->lead_del;
+        BBAlnCounts cnt = {0, 0, 0, 0};
+        // query = mutated read, target = original fragment (qscore_model.py:37)
+        bb_align<true>(B.seq + rd->seq_off, rd->seq_len, B.frag + rd->frag_off, rd->frag_len, rd->upper, sc, em, cnt);
+        __syncwarp();
+        if (lane == 0) { rd->matches = cnt.matches; rd->dels = cnt.dels; rd->flags |= cnt.err << 8; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+__device__ __forceinline__ int bb_qm_find(const BBQScoreModelDev &qm, unsigned long long key) {
+    const uint32_t mask = (1u << qm.hbits) - 1u;
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - qm.hbits));
+    for (;;) {
+        const unsigned long long kk = qm.hkeys[h];
+        if (kk == key) return qm.hvals[h];
+        if (kk == 0ull) return -1;
+        h = (h + 1) & mask;
+    }
+}
+
+// qscore for base i of a read of n bases given per-base ops and deletion counts (qscore_model.py:54-68 and
+// QScoreModel.get_qscore :273-287).  partial_cigar = ops[s] D^dcnt[s] ops[s+1] ... ops[e]; a CIGAR that is
+// not in the model loses its first and last symbol and then its outer D's, which is exactly the window
+// [s+1, e-1] of the same form.
+__device__ __forceinline__ uint8_t bb_qscore_base(const BBQScoreModelDev &qm, const uint8_t *ops, const uint16_t *dcnt,
+                                                  int n, int i, unsigned long long seed, unsigned long long read) {
+    int mm = (qm.kmer_size - 1) / 2;
+    if (mm > i) mm = i;
+    if (mm > n - 1 - i) mm = n - 1 - i;
+    int row = -1;
+    for (; mm >= 0 && row < 0; mm--) {
+        const int s = i - mm, e = i + mm;
+        unsigned long long key = 1ull;
+        int len = 0;
+        bool ok = true;
+        for (int x = s; x <= e && ok; x++) {
+            key = (key << 2) | ops[x];
+            len++;
+            if (x < e) {
+                const int d = dcnt[x];
+                if (len + d > 31) ok = false;
+                else { for (int c = 0; c < d; c++) key = (key << 2) | 3ull; len += d; }
+            }
+        }
+        if (ok && len <= 31) row = bb_qm_find(qm, key);
+    }
+    if (row < 0) return 0;  // cannot happen: '=', 'X', 'I' are asserted at model load (qscore_model.py:205-207)
+    const int e0 = qm.row_off[row], ne = qm.row_off[row + 1] - e0;
+    BBRng rng;
+    rng.init(seed, read);
+    rng.stream(BB_PURPOSE_QSCORE, (uint32_t)i);
+    const int pick = bb_choices(rng, qm.cum + e0, ne);
+    return (uint8_t)(qm.scores[e0 + pick] + 33);
+}
+
+__global__ void __launch_bounds__(256) bb_k_qscores(BBBatchDev B, BBQScoreModelDev qm, unsigned long long seed) {
+    const int r = blockIdx.x;
+    const BBReadDev rd = B.reads[r];
+    const int n = rd.seq_len;
+    const uint8_t *ops = B.ops + rd.seq_off;
+    const uint16_t *dcnt = B.dcnt + rd.seq_off;
+    uint8_t *qual = B.qual + rd.seq_off;
+    const unsigned long long read = B.read_index[r];
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        qual[i] = bb_qscore_base(qm, ops, dcnt, n, i, seed, read);
+}
+
+// ------------------------------------------------------------------------------------------------ K6
+__global__ void __launch_bounds__(256) bb_k_compact(BBBatchDev B) {
+    const int r = blockIdx.x;
+    const BBReadDev rd = B.reads[r];
+    const uint8_t *seq = B.seq + rd.seq_off + rd.start_trim;
+    const uint8_t *qual = B.qual + rd.seq_off + rd.start_trim;
+    uint8_t *os = B.out_seq + rd.out_off, *oq = B.out_qual + rd.out_off;
+    for (int i = threadIdx.x; i < rd.out_len; i += blockDim.x) {
+        os[i] = seq[i];
+        oq[i] = qual[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ single-pair entry points
+// edlib.align(query, target, task='path') for one pair (diagnostics / tests): ops + dcnt + lead_del + counts.
+__global__ void __launch_bounds__(32) bb_k_align_pair(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper,
+                                                      BBScratchPool pool, uint8_t *ops, uint16_t *dcnt, int *out4) {
+    const BBScratch sc = pool.for_warp(0);
+    BBEmit em = {ops, dcnt, &out4[3]};
+    BBAlnCounts cnt = {0, 0, 0, 0};
+    bb_align<true>(q, n, t, m, k_upper, sc, em, cnt);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) { out4[0] = cnt.matches; out4[1] = cnt.dels; out4[2] = cnt.dist; out4[4] = cnt.err; }
+}
+
+__global__ void __launch_bounds__(256) bb_k_qscores_pair(const uint8_t *ops, const uint16_t *dcnt, int n,
+                                                         BBQScoreModelDev qm, unsigned long long seed,
+                                                         unsigned long long read, uint8_t *qual) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        qual[i] = bb_qscore_base(qm, ops, dcnt, n, i, seed, read);
+}

@@ -1,0 +1,151 @@
+/*
+ * badread_b200.h — C ABI of libbadread_b200.so: the drop-in boundary for Badread's per-read
+ * error-injection hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (rrwick/Badread v0.4.2) is pure Python; its only native call on this path is
+ * `edlib.align` (third-party).  This ABI is what a ctypes binding inside the reference would bind to replace
+ *     simulate.sequence_fragment            badread/simulate.py:256-358
+ *     ErrorModel.add_errors_to_kmer         badread/error_model.py:135-176   (table sampling, on device)
+ *     qscore_model.get_qscores              badread/qscore_model.py:32-75
+ *     QScoreModel.get_qscore                badread/qscore_model.py:273-287
+ *     edlib.align(..., task='path')         call sites simulate.py:330,340; qscore_model.py:37; error_model.py:202
+ * Plain pointers and sizes only; the caller owns every host buffer, the library owns device memory behind an
+ * opaque bb_ctx.  All functions return 0 on success or a negative bb_status; bb_last_error() gives the text.
+ * The library never calls exit() and never falls back to a CPU implementation of the hot path.
+ */
+#ifndef BADREAD_B200_H
+#define BADREAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BB_API __attribute__((visibility("default")))
+#else
+#define BB_API
+#endif
+
+typedef struct bb_ctx bb_ctx;
+
+enum bb_status {
+    BB_OK = 0,
+    BB_ERR_CUDA = -1,      /* CUDA runtime error (no device, launch failure, out of memory) */
+    BB_ERR_ARG = -2,       /* invalid argument */
+    BB_ERR_STATE = -3,     /* models / reference not uploaded yet */
+    BB_ERR_CAPACITY = -4,  /* caller-provided output buffer too small (required size is reported) */
+    BB_ERR_INTERNAL = -5   /* device-side invariant violated (reported with a code in bb_last_error) */
+};
+
+/* Segment kinds of a fragment descriptor. A fragment (what simulate.build_fragment returns, simulate.py:91-115)
+ * is the concatenation of its segments: slices of the HBM-resident reference (either strand) and literal bytes
+ * (adapters, glitch inserts, junk / random reads). */
+enum bb_seg_kind {
+    BB_SEG_REF_FWD = 0, /* reference bytes [src, src+len) as stored */
+    BB_SEG_REF_REV = 1, /* reverse complement (misc.reverse_complement, misc.py:56-71) of reference [src, src+len) */
+    BB_SEG_LITERAL = 2  /* bytes [src, src+len) of the literal pool passed with the batch */
+};
+
+typedef struct bb_segment {
+    int64_t src;   /* offset into the uploaded reference or into the batch's literal pool */
+    int32_t len;
+    int32_t kind;  /* bb_seg_kind */
+} bb_segment;
+
+/* Per-read outputs besides the bases (header fields of simulate.py:73-75 come from these). */
+typedef struct bb_read_result {
+    int64_t out_off;      /* offset of this read's seq/qual in the output buffers */
+    int32_t out_len;      /* len(seq) after trimming; 0 => the reference skips the read (simulate.py:70) */
+    int32_t frag_len;     /* len(fragment) before padding ("error-free_length") */
+    int32_t matches;      /* '=' columns of the final alignment */
+    int32_t columns;      /* all columns; read identity = matches / columns (misc.py:228-240) */
+    int32_t loop_count;   /* iterations of the k-mer loop (simulate.py:278) */
+    int32_t change_count; /* applied slot changes (simulate.py:311) */
+    int32_t n_alignments; /* identity re-measurements (simulate.py:325-346) */
+    int32_t flags;        /* non-zero: device-side problem for this read (see bb_last_error) */
+} bb_read_result;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------- */
+/* Creates a context on CUDA device `device`. seed is `--seed` (simulate.py:34-36). Fails with BB_ERR_CUDA when
+ * there is no usable GPU: there is no CPU path. */
+BB_API int bb_create(bb_ctx **ctx, int device, uint64_t seed);
+BB_API int bb_destroy(bb_ctx *ctx);
+BB_API const char *bb_last_error(const bb_ctx *ctx); /* ctx may be NULL for creation errors */
+BB_API const char *bb_version(void);
+
+/* ---- one-time uploads ------------------------------------------------------------------------------- */
+/* Reference contigs concatenated (upper-case ASCII, misc.load_fasta misc.py:122-153). */
+BB_API int bb_upload_reference(bb_ctx *ctx, const uint8_t *bases, int64_t n_bases);
+
+/* Error model tables (flat form of ErrorModel.alternatives / .probabilities, error_model.py:86-133):
+ *  type 0 = 'random' (k = 1, no tables), 1 = 'model'.
+ *  kmer_to_row[4^k]: row of each ACGT k-mer or -1; row_off[n_rows+1] entry ranges; per entry: cum (the
+ *  list(accumulate(probs)) that random.choices builds), flags (bit0: ''.join(alt)==kmer, bit1: the
+ *  "random change" remainder entry appended at error_model.py:151-154), k slot strings encoded as
+ *  len | chars<<8 (len<=3) or len | pool_offset<<8. */
+BB_API int bb_upload_error_model(bb_ctx *ctx, int k, int type, const int32_t *kmer_to_row, int64_t n_index, int32_t n_rows,
+                          const int32_t *row_off, const double *cum, const uint8_t *flags, const uint32_t *slots,
+                          const uint8_t *pool, int64_t pool_len);
+
+/* Qscore model tables (flat form of QScoreModel.scores / .probabilities, qscore_model.py:178-271).
+ *  keys[n_keys]: CIGAR strings over {=,X,I,D} packed 2 bits per symbol under a leading 1 bit (<= 31 symbols);
+ *  row_off[n_keys+1]; scores / cum per entry. kmer_size as QScoreModel.kmer_size. */
+BB_API int bb_upload_qscore_model(bb_ctx *ctx, int kmer_size, int32_t n_keys, const uint64_t *keys, const int32_t *row_off,
+                           const uint8_t *scores, const double *cum);
+
+/* ---- the hot path ----------------------------------------------------------------------------------- */
+/* sequence_fragment for a batch of reads (simulate.py:256-358 for each).
+ *  read_index[n]: global read ordinal, keys the per-read Philox streams (output is independent of batching and
+ *  of the number of GPUs). seg_off[n+1] indexes segs. target_identity[n] as Identities.get_identity().
+ *  Outputs: results[n]; seq_out / qual_out receive the trimmed reads back to back (capacity out_cap bytes each);
+ *  *out_total = bytes written. If out_cap is too small: returns BB_ERR_CAPACITY with *out_total = required size
+ *  (device results are kept; call bb_fetch_last_batch with larger buffers). */
+BB_API int bb_sequence_batch(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_index, const int32_t *seg_off,
+                      const bb_segment *segs, const uint8_t *literal_pool, int64_t literal_len,
+                      const double *target_identity, bb_read_result *results, uint8_t *seq_out, uint8_t *qual_out,
+                      int64_t out_cap, int64_t *out_total);
+BB_API int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t *seq_out, uint8_t *qual_out, int64_t out_cap,
+                        int64_t *out_total);
+
+/* Split form used by bench.py to time the device work with inputs already resident in HBM:
+ * bb_batch_upload (H2D of descriptors) -> bb_batch_run (kernels only, asynchronous on the ctx stream;
+ * may be called repeatedly on the same uploaded batch) -> bb_fetch_last_batch (D2H). */
+BB_API int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_index, const int32_t *seg_off,
+                    const bb_segment *segs, const uint8_t *literal_pool, int64_t literal_len,
+                    const double *target_identity);
+BB_API int bb_batch_run(bb_ctx *ctx);
+BB_API int bb_synchronize(bb_ctx *ctx);
+/* CUDA-event time (ms) of the last bb_batch_run on the ctx stream, total and per stage
+ * (stage_ms[BB_N_STAGES], see bb_stage_name). Synchronizes. */
+#define BB_N_STAGES 8
+BB_API int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms);
+BB_API const char *bb_stage_name(int stage);
+/* Number of kernel launches issued by this context so far. */
+BB_API int64_t bb_launch_count(const bb_ctx *ctx);
+
+/* get_qscores(seq, frag, qscore_model) on its own (qscore_model.py:32-75) for one pair; qual_out has seq_len bytes. */
+BB_API int bb_get_qscores(bb_ctx *ctx, uint64_t read_index, const uint8_t *seq, int32_t seq_len, const uint8_t *frag,
+                   int32_t frag_len, uint8_t *qual_out, int32_t *matches, int32_t *columns);
+
+/* edlib.align(query, target, task='path') on the device for one pair: expanded CIGAR (one of "=XID" per column)
+ * into ops_out (capacity ops_cap); *n_ops = columns, *distance = edit distance. Diagnostic / test entry point
+ * for the aligner the kernels use. */
+BB_API int bb_align_path(bb_ctx *ctx, const uint8_t *query, int32_t q_len, const uint8_t *target, int32_t t_len,
+                  uint8_t *ops_out, int64_t ops_cap, int64_t *n_ops, int32_t *distance);
+
+/* ---- host-side helpers (no GPU needed) -------------------------------------------------------------- */
+/* error_model.align_kmers (error_model.py:179-229) for a batch of (kmer, alt) pairs: kmers is n_alts*k bytes,
+ * alts are concatenated with alt_off[n_alts+1]. Writes n_alts*k encoded slots, appends long strings to pool
+ * (capacity pool_cap, *pool_len updated) and flags bit0 = (''.join(slots) == kmer). */
+BB_API int bb_host_align_kmers(int k, int32_t n_alts, const uint8_t *kmers, const uint8_t *alts, const int32_t *alt_off,
+                        uint32_t *slots_out, uint8_t *flags_out, uint8_t *pool, int64_t pool_cap, int64_t *pool_len);
+/* edlib.align(query, target, task='path') on the host for SMALL inputs (full matrix; q_len*t_len <= 2^22). */
+BB_API int bb_host_align_path(const uint8_t *query, int32_t q_len, const uint8_t *target, int32_t t_len, uint8_t *ops_out,
+                       int64_t ops_cap, int64_t *n_ops, int32_t *distance);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BADREAD_B200_H */
