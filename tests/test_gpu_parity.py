@@ -1,0 +1,73 @@
+"""
+GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle in Philox mode on the same
+seeded inputs. Integer / byte / index work: the bar is bit-exact sequences, quality strings and alignment counts.
+"""
+import random
+
+import pytest
+
+from conftest import load_models, mutate, random_dna
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(em, qm):
+    from oracle import oracle as O
+    return O, O.Oracle(em, qm)
+
+
+def test_align_path_matches_oracle(engine):
+    from oracle import oracle as O
+    rnd = random.Random(11)
+    cases = []
+    for _ in range(60):
+        n = rnd.randint(1, 1500)
+        a = random_dna(rnd, n)
+        b = mutate(rnd, a, rnd.choice([0.0, 0.02, 0.1, 0.3])) if rnd.random() < 0.8 else random_dna(rnd, rnd.randint(1, 900), 'ACGTN')
+        cases.append((a, b))
+    # sizes beyond edlib's 1 MiB traceback estimate -> Hirschberg; multi-strip queries
+    for n, rate in ((2500, 0.05), (4000, 0.1), (6000, 0.02), (3000, 0.3)):
+        a = random_dna(rnd, n)
+        cases.append((a, mutate(rnd, a, rate)))
+        cases.append((mutate(rnd, a, rate), a))
+    cases.append((random_dna(rnd, 3000), random_dna(rnd, 700)))   # tall leaf: 3 strips, few columns
+    cases.append((random_dna(rnd, 40), random_dna(rnd, 30000)))   # wide leaf
+    for a, b in cases:
+        want_ops, want_d = O.align_path(a, b)
+        got_ops, got_d = engine.align_path(a, b)
+        assert got_d == want_d
+        assert got_ops == want_ops
+
+
+@pytest.mark.parametrize('error_name,qscore_name', [('random', 'ideal'), ('random', 'random'),
+                                                    ('nanopore2023', 'nanopore2023'),
+                                                    ('nanopore2020', 'nanopore2020'),
+                                                    ('pacbio2021', 'pacbio2021')])
+def test_sequence_batch_matches_oracle(engine, error_name, qscore_name):
+    from badread_b200.engine import FragmentBatch
+    em, qm = load_models(error_name, qscore_name)
+    O, orc = _oracle(em, qm)
+    engine.set_error_model(em)
+    engine.set_qscore_model(qm)
+    import zlib
+    rnd = random.Random(zlib.crc32((error_name + qscore_name).encode()))
+    lengths = [1, 2, 5, 30, 200, 985, 986, 987, 1000, 1400, 3000, 5000, 9000, 20000]
+    batch = FragmentBatch()
+    frags, idents = [], []
+    for i, n in enumerate(lengths * 2):
+        frag = random_dna(rnd, n, 'ACGT' if i % 5 else 'ACGTN')
+        ident = rnd.choice([1.0, 0.99, 0.95, 0.9, 0.8, 0.6]) if i >= len(lengths) else 0.93
+        frags.append(frag)
+        idents.append(ident)
+        batch.add_literal_read(1000 + i, frag, ident)
+    res, total = engine.sequence_batch(batch)
+    assert total == sum(res.records[i].out_len for i in range(len(frags)))
+    for i, (frag, ident) in enumerate(zip(frags, idents)):
+        s, q, identity, st = orc.sequence_fragment(frag, ident, engine.seed, read_index=1000 + i, with_stats=True)
+        gs, gq = res.read(i)
+        rec = res.records[i]
+        assert (rec.loop_count, rec.change_count, rec.n_alignments) == (st['loop_count'], st['change_count'], st['n_alignments']), (i, len(frag), ident)
+        assert gs == s, (i, len(frag), ident)
+        assert gq == q, (i, len(frag), ident)
+        assert (rec.matches, rec.columns) == (st['matches'], st['columns'])
+        assert rec.frag_len == len(frag)
