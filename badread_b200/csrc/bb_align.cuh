@@ -7,11 +7,17 @@
 //     diagonal, when its traceback state estimate 20*ceil(|q|/64)*|t| + 8*|t| is below 1 MiB;
 //   * otherwise Hirschberg on the target (split at |t|/2, smallest interior query row whose left+right scores
 //     equal the best score, then row -1, then row |q|-1) recursing with the same switch.
-// One warp aligns one pair.  Rows are query characters; lane l owns a 32-row word of the current 1024-row
-// strip and runs the Myers/Hyyrö bit-vector recurrence on column (step - l): a 32-lane wavefront whose
-// horizontal carries travel by __shfl_up.  Vertical (+1) and horizontal (+1) delta words of in-band blocks are
-// kept per column ("history") so the traceback needs two bits per cell; the traceback itself walks whole
-// diagonal runs per step with warp ballots.
+//
+// One warp aligns one pair.  The DP is the Myers/Hyyrö bit-vector recurrence restricted to the Ukkonen band
+// j - a <= i <= j + b.  Rows are cut into chunks of L 32-row words; chunk u belongs to lane slot (u mod K) of a
+// K-lane group and works on column (step - u): a wavefront that follows the diagonal, so a pass takes about
+// `ncols` steps whatever the band width (L grows with the band).  A lane retires a chunk when the band has
+// moved past it and picks up chunk u + K.  Horizontal carries (and the running score, for chunk hand-over)
+// travel to the next slot by one shuffle per step.  With K = 16 two independent problems (the forward and the
+// reverse pass of a Hirschberg node) share a warp.  Match masks come from a per-read bitmap built once with
+// ballots (bb_build_peq).  Vertical (+1) and horizontal (+1) delta words of in-band blocks are kept per column
+// for leaves ("history"), so the traceback needs two bits per cell; it consumes whole diagonal runs per step
+// with warp ballots.
 #pragma once
 #include <cstdint>
 
@@ -20,16 +26,19 @@
 #define BB_OP_EQ 0
 #define BB_OP_X 1
 #define BB_OP_I 2
+#define BB_MAX_SCORE 0x3fffff  // scores travel in 22 bits of the shuffle word
 
 struct BBScratch {
     uint2 *hist;     // (Pv, PhRaw) per (column, block - first_block(column))
     int hist_cap;    // entries
-    int8_t *hbuf;    // per-column horizontal delta leaving the bottom of the previous strip
+    int8_t *hbuf;    // strip fallback: per-column horizontal delta leaving the bottom of the previous strip
     int hbuf_cap;
     int *L, *R;      // Hirschberg column scores (forward / reverse), indexed by row - row_lo
     int lr_cap;
     int *stack;      // DFS stack, 5 ints per node
     int stack_cap;   // nodes
+    uint4 *peq;      // per-read match bitmap: word w holds rows [32(w-1), 32w) for (A, C, G, T)
+    int peq_cap;     // words
 };
 
 struct BBEmit {      // where the final alignment is written (nullptr members => counts only)
@@ -43,6 +52,16 @@ struct BBAlnCounts {
     int dels;        // 'D' columns (alignment columns = query length + dels)
     int dist;        // edit distance
     int err;         // non-zero: invariant violated
+};
+
+// One banded problem handed to bb_band_pass (all lanes of a group hold the same values).
+struct BBProb {
+    const uint8_t *q; int qs; int n;      // query rows: row r is q[r*qs]
+    const uint8_t *t; int ts; int ncols;  // target columns: column c is t[c*ts]
+    int a, b;                             // band: j - a <= i <= j + b
+    const uint4 *peq; int peq_bit0;       // bitmap + bit index of row 0 (rows ascend for qs > 0, descend for qs < 0)
+    uint2 *hist; int nb_alloc;
+    int *cols_out; int cols_lo;
 };
 
 __device__ __forceinline__ void bb_band(int n, int m, int k, int &a, int &b) {
@@ -66,13 +85,180 @@ __device__ __forceinline__ int bb_last_block(int j, int b, int n) {
     return hi >> 5;
 }
 
-// Banded NW over columns [0, ncols) of t (stride ts) against the n rows of q (stride qs).
-// HIST: store (Pv, PhRaw) of in-band blocks.  COLS: write D[row][ncols-1] for the in-band rows of the last
-// column to cols_out[row - cols_lo].  Returns D[n-1][ncols-1] when the last strip reaches the last column,
-// else BB_INF.  Values are exact for every cell on a path of cost <= the k the band was derived from and
-// upper bounds elsewhere.
+// Match bitmap of a whole read: peq[w] = ballots of (q[32(w-1)+lane] == A/C/G/T); word 0 and two trailing
+// words are zero so that any 32-bit window that touches the read can be cut out with one funnel shift.
+__device__ void bb_build_peq(const uint8_t *q, int n, uint4 *peq) {
+    const int lane = threadIdx.x & 31;
+    const int nw = (n + 31) >> 5;
+    if (lane == 0) peq[0] = make_uint4(0u, 0u, 0u, 0u);
+    for (int w = 0; w < nw + 2; w++) {
+        const int row = 32 * w + lane;
+        const uint8_t c = row < n ? q[row] : 0;
+        const uint32_t mA = __ballot_sync(BB_FULL, c == 'A'), mC = __ballot_sync(BB_FULL, c == 'C');
+        const uint32_t mG = __ballot_sync(BB_FULL, c == 'G'), mT = __ballot_sync(BB_FULL, c == 'T');
+        if (lane == 0) peq[w + 1] = make_uint4(mA, mC, mG, mT);
+    }
+    __syncwarp();
+}
+
+// The four match masks of the 32 rows [R, R+32) of a problem (rows >= n are cleared).
+__device__ __forceinline__ void bb_fetch_peq(const BBProb &P, int R, uint32_t &mA, uint32_t &mC, uint32_t &mG,
+                                             uint32_t &mT) {
+    mA = mC = mG = mT = 0u;
+    const int valid = P.n - R;
+    if (valid <= 0) return;
+    const int s = P.qs > 0 ? P.peq_bit0 + R : P.peq_bit0 - R - 31;
+    const int idx = s >> 5, sh = s & 31;
+    const uint4 lo = P.peq[idx], hi = P.peq[idx + 1];
+    mA = __funnelshift_r(lo.x, hi.x, sh); mC = __funnelshift_r(lo.y, hi.y, sh);
+    mG = __funnelshift_r(lo.z, hi.z, sh); mT = __funnelshift_r(lo.w, hi.w, sh);
+    if (P.qs < 0) { mA = __brev(mA); mC = __brev(mC); mG = __brev(mG); mT = __brev(mT); }
+    if (valid < 32) {
+        const uint32_t keep = (1u << valid) - 1u;
+        mA &= keep; mC &= keep; mG &= keep; mT &= keep;
+    }
+}
+
+// Banded NW of one or two problems (K = 32: one problem; K = 16: lanes 0-15 and 16-31 hold their own BBProb).
+// Requires (a + b) / (32 L) + 2 <= K.  HIST: store (Pv, PhRaw) of in-band blocks.  COLS: write D[row][ncols-1]
+// of the in-band rows of the last column to cols_out[row - cols_lo].  Returns D[n-1][ncols-1] of the lane's own
+// problem (BB_INF if the band does not contain that cell).  Values are exact for every cell on a path of cost
+// <= the k the band was derived from and upper bounds elsewhere.
+template <int L, bool HIST, bool COLS>
+__device__ int bb_band_pass(const BBProb &P, int K) {
+    const int lane = threadIdx.x & 31;
+    const int slot = lane & (K - 1);
+    const int prev = (lane & ~(K - 1)) | ((slot + K - 1) & (K - 1));
+    constexpr int CH = 32 * L;
+    const int n = P.n, ncols = P.ncols, a = P.a, b = P.b;
+    const int nblk = (n + 31) >> 5;
+    int ulast = -1;
+    if (ncols > 0 && n > 0) {
+        ulast = (ncols - 1 + b) / CH;
+        const int nchunks = (n + CH - 1) / CH;
+        if (ulast > nchunks - 1) ulast = nchunks - 1;
+    }
+    const int T = __reduce_max_sync(BB_FULL, ulast >= 0 ? ncols + ulast : 0);
+    const int cols_hi = min(n - 1, ncols - 1 + b);
+    uint32_t Pv[L], Mv[L], eA[L], eC[L], eG[L], eT[L];
+#pragma unroll
+    for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; eA[x] = eC[x] = eG[x] = eT[x] = 0u; }
+    int u = slot;
+    int cs = max(0, CH * u - b), ce = min(ncols - 1, CH * u + CH - 1 + a);
+    int score = 0, result = BB_INF;
+    uint32_t outpack = 0;
+    uint32_t tcn = 0;
+    if (u <= ulast && 0 - u >= cs && 0 - u <= ce) tcn = P.t[0];
+    for (int tau = 0; tau < T; tau++) {
+        const uint32_t in = __shfl_sync(BB_FULL, outpack, prev);
+        const int c = tau - u;
+        const bool active = (u <= ulast) && c >= cs && c <= ce;
+        if (active) {
+            const uint32_t tc = tcn;
+            int hin = 1;
+            if (u > 0 && c <= min(ncols - 1, CH * u - 1 + a)) hin = (int)((in >> 22) & 3u) - 1;
+            if (c == cs) {  // a chunk entering the band starts from the all-(+1) upper bound below chunk u-1
+                const int base = (u == 0) ? cs : (int)(in & BB_MAX_SCORE) - hin;
+                score = base + CH;
+#pragma unroll
+                for (int x = 0; x < L; x++) {
+                    Pv[x] = ~0u; Mv[x] = 0u;
+                    bb_fetch_peq(P, u * CH + 32 * x, eA[x], eC[x], eG[x], eT[x]);
+                }
+            }
+            const uint32_t code = (tc >> 1) & 3u;  // A->0, C->1, T->2, G->3
+            const bool acgt = ((0x47544341u >> (8 * code)) & 0xffu) == tc;
+            int h = hin;
+#pragma unroll
+            for (int x = 0; x < L; x++) {
+                uint32_t Eq = (code & 2u) ? ((code & 1u) ? eG[x] : eT[x]) : ((code & 1u) ? eC[x] : eA[x]);
+                if (!acgt) {  // non-ACGT target character: exact byte equality against every row of the word
+                    Eq = 0u;
+                    const int row0 = u * CH + 32 * x;
+                    for (int r = 0; r < 32; r++)
+                        if (row0 + r < n && P.q[(long long)(row0 + r) * P.qs] == tc) Eq |= 1u << r;
+                }
+                const uint32_t hin_neg = h < 0 ? 1u : 0u;
+                const uint32_t Xv = Eq | Mv[x];
+                Eq |= hin_neg;
+                const uint32_t Xh = (((Eq & Pv[x]) + Pv[x]) ^ Pv[x]) | Eq;
+                uint32_t Ph = Mv[x] | ~(Xh | Pv[x]);
+                uint32_t Mh = Pv[x] & Xh;
+                const int hout = (int)(Ph >> 31) - (int)(Mh >> 31);
+                const uint32_t ph_raw = Ph;
+                Ph = (Ph << 1) | (h > 0 ? 1u : 0u);
+                Mh = (Mh << 1) | hin_neg;
+                Pv[x] = Mh | ~(Xv | Ph);
+                Mv[x] = Ph & Xv;
+                h = hout;
+                if (HIST) {
+                    const int blk = u * L + x;
+                    const int rel = blk - bb_first_block(c, a, nblk);
+                    if (rel >= 0 && rel < P.nb_alloc && blk <= bb_last_block(c, b, n))
+                        P.hist[c * P.nb_alloc + rel] = make_uint2(Pv[x], ph_raw);
+                }
+            }
+            score += h;
+            outpack = ((uint32_t)(h + 1) << 22) | ((uint32_t)score & BB_MAX_SCORE);
+            if (c == ncols - 1) {
+                int run = score;
+#pragma unroll
+                for (int x = L - 1; x >= 0; x--) {
+                    const int row0 = u * CH + 32 * x;
+                    if (COLS) {
+                        int rr = run;
+                        for (int r = 31; r >= 0; r--) {
+                            const int row = row0 + r;
+                            if (row < n && row >= P.cols_lo && row <= cols_hi) P.cols_out[row - P.cols_lo] = rr;
+                            rr -= (int)((Pv[x] >> r) & 1u) - (int)((Mv[x] >> r) & 1u);
+                        }
+                    }
+                    if (row0 <= n - 1 && n - 1 < row0 + 32) {
+                        const int bit = (n - 1) - row0;
+                        const uint32_t up = bit == 31 ? 0u : (Pv[x] >> (bit + 1));
+                        const uint32_t um = bit == 31 ? 0u : (Mv[x] >> (bit + 1));
+                        result = run - __popc(up) + __popc(um);
+                    }
+                    run -= __popc(Pv[x]) - __popc(Mv[x]);
+                }
+            }
+            if (c == ce) {  // the band has moved past this chunk: take over chunk u + K
+                u += K;
+                cs = max(0, CH * u - b);
+                ce = min(ncols - 1, CH * u + CH - 1 + a);
+            }
+        }
+        const int cn = tau + 1 - u;
+        if (u <= ulast && cn >= cs && cn <= ce) tcn = P.t[(long long)cn * P.ts];
+    }
+    const int owner = (lane & ~(K - 1)) | ((n > 0 ? (n - 1) / CH : 0) & (K - 1));
+    result = __shfl_sync(BB_FULL, result, owner);
+    __syncwarp();
+    return result;
+}
+
+// Smallest L in {1,2,4,...,MAXL} with (a + b) / (32 L) + 2 <= K, or 0 if none.  MAXL bounds the variants a kernel
+// instantiates (and with them its register footprint).
+template <int MAXL>
+__device__ __forceinline__ int bb_pick_L(int a, int b, int K) {
+    for (int L = 1; L <= MAXL; L <<= 1)
+        if ((a + b) / (32 * L) + 2 <= K) return L;
+    return 0;
+}
+
+template <bool HIST, bool COLS, int MAXL>
+__device__ __forceinline__ int bb_band_dispatch(const BBProb &P, int K, int L) {
+    if (MAXL >= 16 && L == 16) return bb_band_pass<(MAXL >= 16 ? 16 : 1), HIST, COLS>(P, K);
+    if (MAXL >= 8 && L == 8) return bb_band_pass<(MAXL >= 8 ? 8 : 1), HIST, COLS>(P, K);
+    if (MAXL >= 4 && L == 4) return bb_band_pass<(MAXL >= 4 ? 4 : 1), HIST, COLS>(P, K);
+    if (MAXL >= 2 && L == 2) return bb_band_pass<(MAXL >= 2 ? 2 : 1), HIST, COLS>(P, K);
+    return bb_band_pass<1, HIST, COLS>(P, K);
+}
+
+// Fallback for bands wider than 32*16*30 rows: 1024-row strips, lane l owns one word of the strip and works on
+// column (step - l); carries between strips go through hbuf.  Same outputs as bb_band_pass.
 template <bool HIST, bool COLS>
-__device__ int bb_myers_pass(const uint8_t *q, int qs, int n, const uint8_t *t, int ts, int ncols, int a, int b,
+__device__ int bb_strip_pass(const uint8_t *q, int qs, int n, const uint8_t *t, int ts, int ncols, int a, int b,
                              uint2 *hist, int nb_alloc, int *cols_out, int cols_lo, int8_t *hbuf) {
     const int lane = threadIdx.x & 31;
     const int nblk = (n + 31) >> 5;
@@ -99,7 +285,7 @@ __device__ int bb_myers_pass(const uint8_t *q, int qs, int n, const uint8_t *t, 
             }
         }
         uint32_t Pv = ~0u, Mv = 0u;
-        int score = (jstart == 0 ? 1024 * s : bprev) + 32 * (lane + 1);  // D at this lane's bottom row, column jstart-1
+        int score = (jstart == 0 ? 1024 * s : bprev) + 32 * (lane + 1);
         int next_rec = BB_INF;
         uint32_t outpack = 0, prepack = 0;
         const int nsteps = (jend - jstart + 1) + 31;
@@ -126,7 +312,7 @@ __device__ int bb_myers_pass(const uint8_t *q, int qs, int n, const uint8_t *t, 
                 uint32_t Eq;
                 if (tc == 'A') Eq = pA; else if (tc == 'C') Eq = pC; else if (tc == 'G') Eq = pG;
                 else if (tc == 'T') Eq = pT;
-                else {  // non-ACGT target character: exact byte equality against the non-ACGT rows
+                else {
                     Eq = 0;
                     uint32_t rest = pO;
                     while (rest) {
@@ -180,7 +366,6 @@ __device__ int bb_myers_pass(const uint8_t *q, int qs, int n, const uint8_t *t, 
         bprev = __shfl_sync(BB_FULL, next_rec, 31);
         __syncwarp();
     }
-    // the lane that owns row n-1 holds the result
     const int owner = ((n - 1) & 1023) >> 5;
     result = __shfl_sync(BB_FULL, result, owner);
     return result;
@@ -261,18 +446,31 @@ __device__ void bb_traceback(const uint8_t *q, int n, const uint8_t *t, int m, i
 }
 
 // A leaf of edlib's recursion: forward pass with history, then traceback. k bounds the edit distance.
-template <bool EMIT>
+// q points at the leaf's first query character; qrel is that character's index in the emission arrays, qpeq its
+// index in the read whose match bitmap is sc.peq.
+template <bool EMIT, int MAXL>
 __device__ int bb_leaf(const uint8_t *q, int n, const uint8_t *t, int m, int k, const BBScratch &sc, BBEmit em,
-                       int qbase, BBAlnCounts &cnt) {
+                       int qrel, int qpeq, BBAlnCounts &cnt) {
     int a, b;
     bb_band(n, m, k, a, b);
     const int nblk = (n + 31) >> 5;
     int nb_alloc = ((a + b) >> 5) + 2;
     if (nb_alloc > nblk) nb_alloc = nblk;
-    if ((long long)nb_alloc * m > sc.hist_cap || m > sc.hbuf_cap) { cnt.err |= 2; return BB_INF; }
-    const int d = bb_myers_pass<true, false>(q, 1, n, t, 1, m, a, b, sc.hist, nb_alloc, nullptr, 0, sc.hbuf);
+    if ((long long)nb_alloc * m > sc.hist_cap) { cnt.err |= 2; return BB_INF; }
+    int d;
+    const int L = bb_pick_L<MAXL>(a, b, 32);
+    if (L > 0) {
+        BBProb P;
+        P.q = q; P.qs = 1; P.n = n; P.t = t; P.ts = 1; P.ncols = m; P.a = a; P.b = b;
+        P.peq = sc.peq; P.peq_bit0 = qpeq + 32;
+        P.hist = sc.hist; P.nb_alloc = nb_alloc; P.cols_out = nullptr; P.cols_lo = 0;
+        d = bb_band_dispatch<true, false, MAXL>(P, 32, L);
+    } else {
+        if (m > sc.hbuf_cap) { cnt.err |= 2; return BB_INF; }
+        d = bb_strip_pass<true, false>(q, 1, n, t, 1, m, a, b, sc.hist, nb_alloc, nullptr, 0, sc.hbuf);
+    }
     __syncwarp();
-    bb_traceback<EMIT>(q, n, t, m, a, b, sc.hist, nb_alloc, em, qbase, cnt);
+    bb_traceback<EMIT>(q, n, t, m, a, b, sc.hist, nb_alloc, em, qrel, cnt);
     __syncwarp();
     return d;
 }
@@ -290,11 +488,13 @@ __device__ __forceinline__ void bb_emit_all_deleted(int m, BBEmit em, int qbase,
     }
 }
 
-// edlib.align(q, t, task='path') for one pair by one warp. k_upper >= edit distance (the caller knows how many
-// edits it injected). Results accumulate into cnt; with EMIT the per-base ops / deletion counts are written.
-template <bool EMIT>
+// edlib.align(q, t, task='path') for one pair by one warp. q[0] is character `qabs` of the read whose match
+// bitmap is sc.peq (built with bb_build_peq). k_upper >= edit distance (the caller knows how many edits it
+// injected). Results accumulate into cnt; with EMIT the per-base ops / deletion counts are written at indices
+// relative to q[0].
+template <bool EMIT, int MAXL>
 __device__ void bb_align(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper, const BBScratch &sc,
-                         BBEmit em, BBAlnCounts &cnt) {
+                         BBEmit em, int qabs, BBAlnCounts &cnt) {
     const int lane = threadIdx.x & 31;
     {
         const int diff = n > m ? n - m : m - n;
@@ -302,14 +502,27 @@ __device__ void bb_align(const uint8_t *q, int n, const uint8_t *t, int m, int k
         const int mx = n > m ? n : m;
         if (k_upper > mx) k_upper = mx;
     }
+    if (n + m >= BB_MAX_SCORE) { cnt.err |= 128; return; }
     if (bb_uses_traceback(n, m)) {
-        cnt.dist = bb_leaf<EMIT>(q, n, t, m, k_upper, sc, em, 0, cnt);
+        cnt.dist = bb_leaf<EMIT, MAXL>(q, n, t, m, k_upper, sc, em, 0, qabs, cnt);
         return;
     }
-    if (m > sc.hbuf_cap) { cnt.err |= 4; return; }
     int a, b;
     bb_band(n, m, k_upper, a, b);
-    const int best_root = bb_myers_pass<false, false>(q, 1, n, t, 1, m, a, b, nullptr, 0, nullptr, 0, sc.hbuf);
+    int best_root;
+    {
+        const int L = bb_pick_L<MAXL>(a, b, 32);
+        if (L > 0) {
+            BBProb P;
+            P.q = q; P.qs = 1; P.n = n; P.t = t; P.ts = 1; P.ncols = m; P.a = a; P.b = b;
+            P.peq = sc.peq; P.peq_bit0 = qabs + 32;
+            P.hist = nullptr; P.nb_alloc = 0; P.cols_out = nullptr; P.cols_lo = 0;
+            best_root = bb_band_dispatch<false, false, MAXL>(P, 32, L);
+        } else {
+            if (m > sc.hbuf_cap) { cnt.err |= 4; return; }
+            best_root = bb_strip_pass<false, false>(q, 1, n, t, 1, m, a, b, nullptr, 0, nullptr, 0, sc.hbuf);
+        }
+    }
     cnt.dist = best_root;
     // depth-first Hirschberg (edlib.cpp obtainAlignmentHirschberg); left child is processed first so that
     // deletions in front of a leaf are credited to the query base that precedes them
@@ -329,7 +542,7 @@ __device__ void bb_align(const uint8_t *q, int n, const uint8_t *t, int m, int k
             continue;
         }
         if (bb_uses_traceback(nn, mm)) {
-            const int d = bb_leaf<EMIT>(q + q0, nn, t + t0, mm, best, sc, em, q0, cnt);
+            const int d = bb_leaf<EMIT, MAXL>(q + q0, nn, t + t0, mm, best, sc, em, q0, qabs + q0, cnt);
             if (d != best) cnt.err |= 8;
             if (cnt.err) return;
             continue;
@@ -339,9 +552,36 @@ __device__ void bb_align(const uint8_t *q, int n, const uint8_t *t, int m, int k
         const int loL = max(0, left_w - 1 - a), hiL = min(nn - 1, left_w - 1 + b);
         const int loR = max(0, right_w - 1 - a), hiR = min(nn - 1, right_w - 1 + b);
         if (hiL - loL + 1 > sc.lr_cap || hiR - loR + 1 > sc.lr_cap) { cnt.err |= 16; return; }
-        bb_myers_pass<false, true>(q + q0, 1, nn, t + t0, 1, left_w, a, b, nullptr, 0, sc.L, loL, sc.hbuf);
-        bb_myers_pass<false, true>(q + q0 + nn - 1, -1, nn, t + t0 + mm - 1, -1, right_w, a, b, nullptr, 0, sc.R,
-                                   loR, sc.hbuf);
+        {
+            auto make_prob = [&](bool rev) {
+                BBProb P;
+                P.n = nn; P.a = a; P.b = b; P.peq = sc.peq; P.hist = nullptr; P.nb_alloc = 0;
+                if (!rev) {
+                    P.q = q + q0; P.qs = 1; P.t = t + t0; P.ts = 1; P.ncols = left_w;
+                    P.peq_bit0 = qabs + q0 + 32; P.cols_out = sc.L; P.cols_lo = loL;
+                } else {
+                    P.q = q + q0 + nn - 1; P.qs = -1; P.t = t + t0 + mm - 1; P.ts = -1; P.ncols = right_w;
+                    P.peq_bit0 = qabs + q0 + nn - 1 + 32; P.cols_out = sc.R; P.cols_lo = loR;
+                }
+                return P;
+            };
+            const int L2 = bb_pick_L<MAXL>(a, b, 16);
+            if (L2 > 0) {  // forward and reverse pass side by side in two 16-lane groups
+                const BBProb PG = make_prob(lane >= 16);
+                bb_band_dispatch<false, true, MAXL>(PG, 16, L2);
+            } else {
+                const int L1 = bb_pick_L<MAXL>(a, b, 32);
+                if (L1 > 0) {
+                    bb_band_dispatch<false, true, MAXL>(make_prob(false), 32, L1);
+                    bb_band_dispatch<false, true, MAXL>(make_prob(true), 32, L1);
+                } else {
+                    if (mm > sc.hbuf_cap) { cnt.err |= 4; return; }
+                    bb_strip_pass<false, true>(q + q0, 1, nn, t + t0, 1, left_w, a, b, nullptr, 0, sc.L, loL, sc.hbuf);
+                    bb_strip_pass<false, true>(q + q0 + nn - 1, -1, nn, t + t0 + mm - 1, -1, right_w, a, b, nullptr, 0,
+                                               sc.R, loR, sc.hbuf);
+                }
+            }
+        }
         __syncwarp();
         // smallest interior row r in [0, nn-2] with L[r] + R[nn-2-r] == best
         int split = -2, ls = 0, rs = 0;

@@ -53,13 +53,14 @@ struct bb_ctx {
     std::vector<BBReadDev> h_reads;
     std::vector<int32_t> h_inlen;
     int64_t frag_total = 0, seq_total = 0, out_total = 0;
-    DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_reads;
+    DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_order_small, d_order_large, d_reads;
+    std::vector<int> h_order;
     DevBuf d_frag, d_state, d_seq, d_ops, d_dcnt, d_qual, d_out_seq, d_out_qual, d_counter;
 
     // scratch
     int n_warps = 0;
     BBScratchPool pool{};
-    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf;
+    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq;
 
     cudaEvent_t ev[BB_N_STAGES + 1] = {};
     float stage_ms[BB_N_STAGES] = {};
@@ -134,10 +135,10 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->ref, &ctx->em_k2r, &ctx->em_rowoff, &ctx->em_cum, &ctx->em_flags, &ctx->em_slots,
                       &ctx->em_pool, &ctx->qm_hkeys, &ctx->qm_hvals, &ctx->qm_rowoff, &ctx->qm_scores, &ctx->qm_cum,
-                      &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order,
+                      &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order, &ctx->d_order_small, &ctx->d_order_large,
                       &ctx->d_reads, &ctx->d_frag, &ctx->d_state, &ctx->d_seq, &ctx->d_ops, &ctx->d_dcnt,
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
-                      &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf};
+                      &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
@@ -226,7 +227,7 @@ extern "C" int bb_upload_qscore_model(bb_ctx *ctx, int kmer_size, int32_t n_keys
 
 // Scratch shared by the warp-per-read kernels. hist is sized for the largest traceback edlib's 1 MiB rule
 // admits (ceil(n/64)*m < 52429 -> < 104858 32-row blocks); tbuf holds a joined 1000-slot window.
-static int ensure_scratch(bb_ctx *ctx, int hbuf_need, int lr_need) {
+static int ensure_scratch(bb_ctx *ctx, int hbuf_need, int lr_need, int len_need) {
     const int n_warps = ctx->n_warps;
     const int hist_cap = 106496;
     const int tbuf_stride = 1000 * 255 + 1024;
@@ -235,6 +236,9 @@ static int ensure_scratch(bb_ctx *ctx, int hbuf_need, int lr_need) {
     hbuf_cap = (hbuf_cap + 255) & ~255;
     int lr_cap = std::max(lr_need + 64, 4096);
     lr_cap = (lr_cap + 255) & ~255;
+    int peq_cap = len_need / 32 + 16;
+    peq_cap = (peq_cap + 63) & ~63;
+    if (ctx->pool.peq_cap >= peq_cap) peq_cap = ctx->pool.peq_cap;
     if (ctx->pool.hbuf_cap >= hbuf_cap) hbuf_cap = ctx->pool.hbuf_cap;
     if (ctx->pool.lr_cap >= lr_cap) lr_cap = ctx->pool.lr_cap;
     BB_CUDA(ctx, ctx->s_hist.ensure((size_t)n_warps * hist_cap * sizeof(uint2)));
@@ -242,12 +246,14 @@ static int ensure_scratch(bb_ctx *ctx, int hbuf_need, int lr_need) {
     BB_CUDA(ctx, ctx->s_stack.ensure((size_t)n_warps * stack_cap * 5 * sizeof(int)));
     BB_CUDA(ctx, ctx->s_hbuf.ensure((size_t)n_warps * hbuf_cap));
     BB_CUDA(ctx, ctx->s_lr.ensure((size_t)n_warps * lr_cap * 2 * sizeof(int)));
+    BB_CUDA(ctx, ctx->s_peq.ensure((size_t)n_warps * peq_cap * sizeof(uint4)));
     BBScratchPool &p = ctx->pool;
     p.hist = ctx->s_hist.as<uint2>(); p.hist_stride = hist_cap; p.hist_cap = hist_cap;
     p.hbuf = ctx->s_hbuf.as<int8_t>(); p.hbuf_stride = hbuf_cap; p.hbuf_cap = hbuf_cap;
     p.lr = ctx->s_lr.as<int>(); p.lr_stride = 2ll * lr_cap; p.lr_cap = lr_cap;
     p.stack = ctx->s_stack.as<int>(); p.stack_cap = stack_cap;
     p.tbuf = ctx->s_tbuf.as<uint8_t>(); p.tbuf_stride = tbuf_stride;
+    p.peq = ctx->s_peq.as<uint4>(); p.peq_stride = peq_cap; p.peq_cap = peq_cap;
     return BB_OK;
 }
 
@@ -310,6 +316,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     std::stable_sort(order.begin(), order.end(),
                      [&](int x, int y) { return ctx->h_reads[(size_t)x].frag_len > ctx->h_reads[(size_t)y].frag_len; });
     ctx->n_reads = n_reads;
+    ctx->h_order = order;
     int rc;
     if ((rc = upload(ctx, ctx->d_read_index, read_index, (size_t)n_reads))) return rc;
     if ((rc = upload(ctx, ctx->d_seg_off, seg_off, (size_t)n_reads + 1))) return rc;
@@ -321,7 +328,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     BB_CUDA(ctx, ctx->d_frag.ensure((size_t)off + 16));
     BB_CUDA(ctx, ctx->d_state.ensure(((size_t)off + 16) * sizeof(uint32_t)));
     BB_CUDA(ctx, ctx->d_counter.ensure(16 * sizeof(int)));
-    if ((rc = ensure_scratch(ctx, max_len, 4096))) return rc;
+    if ((rc = ensure_scratch(ctx, max_len, 4096, max_len))) return rc;
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->uploaded = true;
     ctx->ran = false;
@@ -354,7 +361,8 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
     BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
     BB_CUDA(ctx, cudaStreamSynchronize(st));
     int64_t seq_off = 0, out_off = 0;
-    int lr_need = 0, hbuf_need = 0;
+    int rc0 = 0;
+    int lr_need = 0, hbuf_need = 0, len_need = 0;
     for (int r = 0; r < n; r++) {
         BBReadDev &rd = reads[(size_t)r];
         rd.seq_off = seq_off;
@@ -368,16 +376,26 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
         const int mx = std::max(rd.seq_len, rd.frag_len);
         lr_need = std::max(lr_need, std::min(rd.seq_len, std::min(rd.upper, mx) + 2));
         hbuf_need = std::max(hbuf_need, rd.frag_len);
+        len_need = std::max(len_need, mx);
     }
     ctx->seq_total = seq_off;
     ctx->out_total = out_off;
+    std::vector<int> small, large;  // work queues of the two final-alignment builds, longest fragments first
+    for (int r : ctx->h_order) {
+        const BBReadDev &rd = reads[(size_t)r];
+        const int bound = std::min(rd.upper, std::max(rd.seq_len, rd.frag_len));
+        (bound <= 1900 ? small : large).push_back(r);
+    }
+    const int grid_large = std::max(1, std::min(ctx->sm_count * 2, ((int)large.size() + BB_WARPS_PER_CTA - 1) / BB_WARPS_PER_CTA));
+    if ((rc0 = upload(ctx, ctx->d_order_small, small.data(), small.size()))) return rc0;
+    if ((rc0 = upload(ctx, ctx->d_order_large, large.data(), large.size()))) return rc0;
     BB_CUDA(ctx, ctx->d_seq.ensure((size_t)seq_off + 16));
     BB_CUDA(ctx, ctx->d_ops.ensure((size_t)seq_off + 16));
     BB_CUDA(ctx, ctx->d_dcnt.ensure(((size_t)seq_off + 16) * sizeof(uint16_t)));
     BB_CUDA(ctx, ctx->d_qual.ensure((size_t)seq_off + 16));
     BB_CUDA(ctx, ctx->d_out_seq.ensure((size_t)out_off + 16));
     BB_CUDA(ctx, ctx->d_out_qual.ensure((size_t)out_off + 16));
-    int rc = ensure_scratch(ctx, hbuf_need, lr_need);
+    int rc = ensure_scratch(ctx, hbuf_need, lr_need, len_need);
     if (rc) return rc;
     B = batch_dev(ctx);
     BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, reads.data(), (size_t)n * sizeof(BBReadDev), cudaMemcpyHostToDevice, st));
@@ -386,8 +404,17 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
     bb_k_join<<<n, 256, 0, st>>>(B, ctx->em);
     ctx->launches++;
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    bb_k_final_align<<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 1);
-    ctx->launches++;
+    // long / noisy reads (wide Ukkonen band) first with the MAXL = 16 build, the rest with the lean MAXL = 2 build
+    if (!large.empty()) {
+        bb_k_final_align<16><<<grid_large, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 1,
+                                                                         ctx->d_order_large.as<int>(), (int)large.size(), 0);
+        ctx->launches++;
+    }
+    if (!small.empty()) {
+        bb_k_final_align<2><<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 2,
+                                                                       ctx->d_order_small.as<int>(), (int)small.size(), 0);
+        ctx->launches++;
+    }
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
     bb_k_qscores<<<n, 256, 0, st>>>(B, ctx->qm, ctx->seed);
     ctx->launches++;
@@ -474,7 +501,7 @@ static int align_pair_device(bb_ctx *ctx, const uint8_t *q, int n, const uint8_t
     BB_CUDA(ctx, dops.ensure((size_t)n + 16));
     BB_CUDA(ctx, ddcnt.ensure(((size_t)n + 16) * sizeof(uint16_t)));
     BB_CUDA(ctx, dout.ensure(8 * sizeof(int)));
-    if ((rc = ensure_scratch(ctx, std::max(n, m), std::max(n, m)))) return rc;
+    if ((rc = ensure_scratch(ctx, std::max(n, m), std::max(n, m), std::max(n, m)))) return rc;
     BB_CUDA(ctx, cudaMemsetAsync(ddcnt.p, 0, ((size_t)n + 16) * sizeof(uint16_t), ctx->stream));
     BB_CUDA(ctx, cudaMemsetAsync(dout.p, 0, 8 * sizeof(int), ctx->stream));
     bb_k_align_pair<<<1, 32, 0, ctx->stream>>>(dq.as<uint8_t>(), n, dt.as<uint8_t>(), m, std::max(n, m), ctx->pool,

@@ -81,12 +81,14 @@ struct BBScratchPool {
     int *lr; long long lr_stride; int lr_cap;  // L at [0, lr_cap), R at [lr_cap, 2*lr_cap)
     int *stack; int stack_cap;
     uint8_t *tbuf; long long tbuf_stride;
+    uint4 *peq; long long peq_stride; int peq_cap;
     __device__ BBScratch for_warp(int w) const {
         BBScratch s;
         s.hist = hist + (long long)w * hist_stride; s.hist_cap = hist_cap;
         s.hbuf = hbuf + (long long)w * hbuf_stride; s.hbuf_cap = hbuf_cap;
         s.L = lr + (long long)w * lr_stride; s.R = s.L + lr_cap; s.lr_cap = lr_cap;
         s.stack = stack + (long long)w * stack_cap * 5; s.stack_cap = stack_cap;
+        s.peq = peq + (long long)w * peq_stride; s.peq_cap = peq_cap;
         return s;
     }
 };
@@ -218,7 +220,7 @@ __device__ __forceinline__ void bb_eval_iteration(const BBErrorModelDev &em, con
     kind = 2; rpos = p;
 }
 
-__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 4)
 bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned long long seed, int *work_counter) {
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -248,6 +250,11 @@ bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned l
         bool done = est_needed < 0.5;
         if (!done && 1.0 <= target) { done = true; loop_count = 1; }
         __syncwarp();
+        if (!done) {
+            // match bitmap of the original fragment: every window alignment of this read cuts its rows out of it
+            if (frag_len / 32 + 4 > sc.peq_cap) { flags |= 256; done = true; }
+            else bb_build_peq(frag, frag_len, sc.peq);
+        }
         while (!done) {
             const long long n = n0 + lane;
             int kind = 0, pos_i = 0, rpos = 0;
@@ -300,7 +307,7 @@ bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned l
                         int uw = 0;
                         const int tm = bb_join_slots(em, frag, state, qpos, qn, tbuf, &uw);
                         BBAlnCounts cnt = {0, 0, 0, 0};
-                        bb_align<false>(frag + qpos, qn, tbuf, tm, uw, sc, no_emit, cnt);
+                        bb_align<false, 1>(frag + qpos, qn, tbuf, tm, uw, sc, no_emit, qpos, cnt);
                         flags |= cnt.err;
                         const int cols = qn + cnt.dels;
                         const double actual = cols ? __ddiv_rn((double)cnt.matches, (double)cols) : 0.0;
@@ -394,17 +401,20 @@ __global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev e
 }
 
 // ------------------------------------------------------------------------------------------------ K4
-__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
-bb_k_final_align(BBBatchDev B, BBScratchPool pool, int *work_counter) {
+// MAXL bounds the band-pass variants (words per lane) the kernel instantiates: reads whose edit bound fits
+// 32*MAXL*30 rows go to the lean MAXL = 2 build, the few long / noisy ones to MAXL = 16 (more registers).
+template <int MAXL>
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (MAXL <= 2 ? 4 : 2))
+bb_k_final_align(BBBatchDev B, BBScratchPool pool, int *work_counter, const int *order, int n_items, int warp_base) {
     const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int warp = warp_base + blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
     const BBScratch sc = pool.for_warp(warp);
     for (;;) {
         int w = 0;
         if (lane == 0) w = atomicAdd(work_counter, 1);
         w = __shfl_sync(BB_FULL, w, 0);
-        if (w >= B.n_reads) break;
-        const int r = B.order[w];
+        if (w >= n_items) break;
+        const int r = order[w];
         BBReadDev *rd = &B.reads[r];
         BBEmit em;
         em.ops = B.ops + rd->seq_off;
@@ -412,7 +422,12 @@ bb_k_final_align(BBBatchDev B, BBScratchPool pool, int *work_counter) {
         em.lead_del = &rd->lead_del;
         BBAlnCounts cnt = {0, 0, 0, 0};
         // query = mutated read, target = original fragment (qscore_model.py:37)
-        bb_align<true>(B.seq + rd->seq_off, rd->seq_len, B.frag + rd->frag_off, rd->frag_len, rd->upper, sc, em, cnt);
+        if (rd->seq_len / 32 + 4 > sc.peq_cap) cnt.err |= 256;
+        else {
+            bb_build_peq(B.seq + rd->seq_off, rd->seq_len, sc.peq);
+            bb_align<true, MAXL>(B.seq + rd->seq_off, rd->seq_len, B.frag + rd->frag_off, rd->frag_len, rd->upper, sc,
+                                 em, 0, cnt);
+        }
         __syncwarp();
         if (lane == 0) { rd->matches = cnt.matches; rd->dels = cnt.dels; rd->flags |= cnt.err << 8; }
     }
@@ -497,7 +512,11 @@ __global__ void __launch_bounds__(32) bb_k_align_pair(const uint8_t *q, int n, c
     const BBScratch sc = pool.for_warp(0);
     BBEmit em = {ops, dcnt, &out4[3]};
     BBAlnCounts cnt = {0, 0, 0, 0};
-    bb_align<true>(q, n, t, m, k_upper, sc, em, cnt);
+    if (n / 32 + 4 > sc.peq_cap) cnt.err |= 256;
+    else {
+        bb_build_peq(q, n, sc.peq);
+        bb_align<true, 16>(q, n, t, m, k_upper, sc, em, 0, cnt);
+    }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) { out4[0] = cnt.matches; out4[1] = cnt.dels; out4[2] = cnt.dist; out4[4] = cnt.err; }
 }

@@ -1,0 +1,163 @@
+// cuda_emu.h — a single-threaded warp emulator (TEST INFRASTRUCTURE).
+// Runs the 32 lanes of one warp as cooperative fibers (ucontext); every warp collective (__shfl*_sync,
+// __ballot_sync, __syncwarp, __reduce_max_sync) is a rendezvous of all live lanes. This lets the device code in
+// badread_b200/csrc/*.cuh be compiled with g++ and checked against the CPU oracle in the CPU-only test tier,
+// before any GPU time is spent. Divergent code that calls a collective would deadlock here, exactly as it
+// would be undefined on the GPU.
+#pragma once
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+
+#define __device__
+#define __global__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(x)
+#define __constant__
+
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+struct EmuDim { unsigned x, y, z; };
+
+namespace emu {
+constexpr int W = 32;
+constexpr size_t STACK = 1 << 20;
+struct Warp {
+    ucontext_t main_ctx, fib[W];
+    char *stacks[W];
+    bool done[W];
+    int alive, cur, arrived;
+    uint64_t gen;
+    uint64_t xchg[W];
+    std::function<void()> body;
+};
+inline Warp &warp() { static Warp w; return w; }
+}  // namespace emu
+inline EmuDim threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {32, 1, 1}, gridDim = {1, 1, 1};
+
+namespace emu {
+inline int next_alive(int from) {
+    Warp &w = warp();
+    for (int k = 1; k <= W; k++) {
+        const int c = (from + k) % W;
+        if (!w.done[c]) return c;
+    }
+    return -1;
+}
+inline void yield() {
+    Warp &w = warp();
+    const int me = w.cur;
+    const int nxt = next_alive(me);
+    if (nxt < 0 || nxt == me) return;
+    w.cur = nxt;
+    swapcontext(&w.fib[me], &w.fib[nxt]);
+    threadIdx.x = (unsigned)w.cur;
+}
+inline void barrier() {
+    Warp &w = warp();
+    const uint64_t g = w.gen;
+    w.arrived++;
+    if (w.arrived >= w.alive) { w.arrived = 0; w.gen++; return; }
+    while (w.gen == g) yield();
+}
+inline void trampoline() {
+    Warp &w = warp();
+    threadIdx.x = (unsigned)w.cur;
+    w.body();
+    const int me = w.cur;
+    w.done[me] = true;
+    w.alive--;
+    if (w.alive > 0 && w.arrived >= w.alive) { w.arrived = 0; w.gen++; }
+    const int nxt = next_alive(me);
+    if (nxt < 0) { setcontext(&w.main_ctx); }
+    w.cur = nxt;
+    setcontext(&w.fib[nxt]);
+}
+inline void run_warp(std::function<void()> body) {
+    Warp &w = warp();
+    w.body = body;
+    w.alive = W; w.arrived = 0; w.gen = 0;
+    for (int i = 0; i < W; i++) {
+        w.done[i] = false;
+        if (!w.stacks[i]) w.stacks[i] = (char *)malloc(STACK);
+        getcontext(&w.fib[i]);
+        w.fib[i].uc_stack.ss_sp = w.stacks[i];
+        w.fib[i].uc_stack.ss_size = STACK;
+        w.fib[i].uc_link = nullptr;
+        makecontext(&w.fib[i], (void (*)())trampoline, 0);
+    }
+    w.cur = 0;
+    swapcontext(&w.main_ctx, &w.fib[0]);
+}
+template <typename T>
+inline T exchange(T v, int src) {
+    Warp &w = warp();
+    uint64_t bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    w.xchg[threadIdx.x] = bits;
+    barrier();
+    const uint64_t r = w.xchg[src & 31];
+    barrier();
+    T out;
+    std::memcpy(&out, &r, sizeof(T));
+    return out;
+}
+}  // namespace emu
+
+template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu::exchange(v, src); }
+template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+    const int me = (int)threadIdx.x;
+    const T r = emu::exchange(v, me - (int)d >= 0 ? me - (int)d : me);
+    return r;
+}
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::exchange(v, (int)threadIdx.x ^ m); }
+inline unsigned __ballot_sync(unsigned, bool p) {
+    emu::Warp &w = emu::warp();
+    w.xchg[threadIdx.x] = p ? 1 : 0;
+    emu::barrier();
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) if (!w.done[i] && w.xchg[i]) r |= 1u << i;
+    emu::barrier();
+    return r;
+}
+inline int __reduce_max_sync(unsigned, int v) {
+    emu::Warp &w = emu::warp();
+    w.xchg[threadIdx.x] = (uint64_t)(int64_t)v;
+    emu::barrier();
+    int r = INT32_MIN;
+    for (int i = 0; i < 32; i++) if (!w.done[i]) r = std::max(r, (int)(int64_t)w.xchg[i]);
+    emu::barrier();
+    return r;
+}
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier(); }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
+inline unsigned __brev(unsigned x) {
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    return __builtin_bswap32(x);
+}
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
+    const uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (unsigned)(v >> (sh & 31));
+}
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline double __dsqrt_rn(double a) { return __builtin_sqrt(a); }
+template <typename T> inline T __ldg(const T *p) { return *p; }
+inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }
+using std::max;
+using std::min;

@@ -1,0 +1,49 @@
+"""ctypes front end of the warp-emulated device aligner (tests/emu/emu_align.cpp). TEST INFRASTRUCTURE."""
+import ctypes
+import os
+import pathlib
+import subprocess
+
+import numpy as np
+
+HERE = pathlib.Path(os.path.dirname(os.path.realpath(__file__)))
+LIB = HERE / 'libemu_align.so'
+
+
+def build():
+    srcs = [HERE / 'emu_align.cpp', HERE / 'cuda_emu.h', HERE.parent.parent / 'badread_b200' / 'csrc' / 'bb_align.cuh']
+    if not LIB.is_file() or any(LIB.stat().st_mtime < s.stat().st_mtime for s in srcs):
+        subprocess.run(['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-o', str(LIB), str(srcs[0])], check=True)
+    return LIB
+
+
+_lib = None
+
+
+def align_path(query, target, k_upper=None, qabs_pad=0, maxl=16):
+    """Device bb_align under the emulator -> (expanded ops string, distance)."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(LIB))
+    q = query.encode('latin-1') if isinstance(query, str) else bytes(query)
+    t = target.encode('latin-1') if isinstance(target, str) else bytes(target)
+    n, m = len(q), len(t)
+    ops = np.zeros(n, dtype=np.uint8)
+    dcnt = np.zeros(n, dtype=np.uint16)
+    out5 = np.zeros(5, dtype=np.int32)
+    _lib.emu_align_path(q, n, t, m, max(n, m) if k_upper is None else k_upper, qabs_pad, maxl,
+                        ops.ctypes.data_as(ctypes.c_void_p), dcnt.ctypes.data_as(ctypes.c_void_p),
+                        out5.ctypes.data_as(ctypes.c_void_p))
+    if out5[4]:
+        raise RuntimeError(f'aligner error flags 0x{int(out5[4]):x}')
+    sym = '=XI'
+    parts = ['D' * int(out5[3])]
+    for i in range(n):
+        parts.append(sym[ops[i]])
+        if dcnt[i]:
+            parts.append('D' * int(dcnt[i]))
+    s = ''.join(parts)
+    assert len(s) == n + out5[1], (len(s), n, out5)
+    assert s.count('=') == out5[0]
+    return s, int(out5[2])
