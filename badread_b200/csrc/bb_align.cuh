@@ -69,6 +69,9 @@ __device__ __forceinline__ void bb_band(int n, int m, int k, int &a, int &b) {
     // every cell (i,j) it can visit satisfies j - a <= i <= j + b
     a = (k - (n - m)) / 2; if (a < 0) a = 0;
     b = (k + (n - m)) / 2; if (b < 0) b = 0;
+    // the wavefront hands a chunk's starting score over from the chunk above, which must still be inside the band
+    // at that column: that needs a + b >= 1 (a wider band is always valid)
+    if (a + b < 1) b = 1;
 }
 
 __device__ __forceinline__ bool bb_uses_traceback(int n, int m) {
@@ -543,7 +546,12 @@ __device__ void bb_align(const uint8_t *q, int n, const uint8_t *t, int m, int k
         }
         if (bb_uses_traceback(nn, mm)) {
             const int d = bb_leaf<EMIT, MAXL>(q + q0, nn, t + t0, mm, best, sc, em, q0, qabs + q0, cnt);
-            if (d != best) cnt.err |= 8;
+            if (d != best) {
+                cnt.err |= 8;
+#ifdef BB_EMU_DEBUG
+                if (lane == 0) printf("leaf mismatch: q0=%d nn=%d t0=%d mm=%d best=%d d=%d\n", q0, nn, t0, mm, best, d);
+#endif
+            }
             if (cnt.err) return;
             continue;
         }
@@ -605,6 +613,9 @@ __device__ void bb_align(const uint8_t *q, int n, const uint8_t *t, int m, int k
             const int v = sc.L[(nn - 1) - loL];
             if (v + right_w == best) { split = nn - 1; ls = v; rs = right_w; }
         }
+#ifdef BB_EMU_DEBUG
+        if (lane == 0) printf("node q0=%d nn=%d t0=%d mm=%d best=%d a=%d b=%d split=%d ls=%d rs=%d\n", q0, nn, t0, mm, best, a, b, split, ls, rs);
+#endif
         if (split == -2) { cnt.err |= 32; return; }
         if (sp + 2 > sc.stack_cap) { cnt.err |= 64; return; }
         __syncwarp();

@@ -740,6 +740,19 @@ static void get_qscores(const bo_qm *qm, bo_rng *rng, const uint8_t *seq, int64_
     free(pos2col); free(cg.ops);
 }
 
+/* Debug capture (tests only): when armed, bo_sequence_fragment leaves copies of the padded fragment and of the
+ * untrimmed read here so that a failing device alignment can be replayed in isolation. */
+static uint8_t *g_dbg_frag = NULL, *g_dbg_seq = NULL;
+static int64_t g_dbg_frag_len = 0, g_dbg_seq_len = 0;
+static int g_dbg_armed = 0;
+BO_EXPORT void bo_debug_arm(int on) { g_dbg_armed = on; }
+BO_EXPORT int64_t bo_debug_get(int which, uint8_t *out, int64_t cap) {
+    const uint8_t *p = which == 0 ? g_dbg_frag : g_dbg_seq;
+    int64_t n = which == 0 ? g_dbg_frag_len : g_dbg_seq_len;
+    if (out && n <= cap && n > 0) memcpy(out, p, (size_t)n);
+    return n;
+}
+
 #define ALIGNMENT_INTERVAL 25  /* settings.py:24 */
 #define ALIGNMENT_SIZE 1000    /* settings.py:25 */
 
@@ -828,6 +841,11 @@ BO_EXPORT int bo_sequence_fragment(const bo_em *em, const bo_qm *qm, bo_rng *rng
     }
     join_slots(em, fragment, state, 0, frag_len, &joined);
     int64_t seq_len = joined.n;
+    if (g_dbg_armed) {
+        free(g_dbg_frag); free(g_dbg_seq);
+        g_dbg_frag = (uint8_t *)dup_mem(fragment, (size_t)frag_len); g_dbg_frag_len = frag_len;
+        g_dbg_seq = (uint8_t *)dup_mem(joined.p, (size_t)seq_len); g_dbg_seq_len = seq_len;
+    }
     uint8_t *qual = (uint8_t *)malloc((size_t)(seq_len ? seq_len : 1));
     get_qscores(qm, rng, joined.p, seq_len, fragment, frag_len, qual, matches_out, cols_out);
 
