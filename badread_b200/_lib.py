@@ -14,7 +14,7 @@ LIB_PATH = _HERE / 'libbadread_b200.so'
 BB_OK = 0
 BB_ERR_CUDA, BB_ERR_ARG, BB_ERR_STATE, BB_ERR_CAPACITY, BB_ERR_INTERNAL = -1, -2, -3, -4, -5
 BB_SEG_REF_FWD, BB_SEG_REF_REV, BB_SEG_LITERAL = 0, 1, 2
-BB_N_STAGES = 8
+BB_N_STAGES = 9
 
 
 class Segment(ctypes.Structure):
@@ -24,7 +24,8 @@ class Segment(ctypes.Structure):
 class ReadResult(ctypes.Structure):
     _fields_ = [('out_off', ctypes.c_int64), ('out_len', ctypes.c_int32), ('frag_len', ctypes.c_int32),
                 ('matches', ctypes.c_int32), ('columns', ctypes.c_int32), ('loop_count', ctypes.c_int32),
-                ('change_count', ctypes.c_int32), ('n_alignments', ctypes.c_int32), ('flags', ctypes.c_int32)]
+                ('change_count', ctypes.c_int32), ('n_alignments', ctypes.c_int32), ('flags', ctypes.c_int32),
+                ('loop_kcycles', ctypes.c_int32), ('align_kcycles', ctypes.c_int32)]
 
 
 class LibraryMissing(RuntimeError):

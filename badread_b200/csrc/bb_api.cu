@@ -28,7 +28,7 @@ struct DevBuf {  // grow-only device allocation
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-const char *kStageNames[BB_N_STAGES] = {"build_fragments", "error_loop", "host_scan", "join",
+const char *kStageNames[BB_N_STAGES] = {"build_fragments", "error_loop", "host_scan", "join", "final_align_wide",
                                         "final_align", "qscores", "compact", "total"};
 
 }  // namespace
@@ -410,18 +410,19 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
                                                                          ctx->d_order_large.as<int>(), (int)large.size(), 0);
         ctx->launches++;
     }
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
     if (!small.empty()) {
         bb_k_final_align<2><<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 2,
                                                                        ctx->d_order_small.as<int>(), (int)small.size(), 0);
         ctx->launches++;
     }
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
     bb_k_qscores<<<n, 256, 0, st>>>(B, ctx->qm, ctx->seed);
     ctx->launches++;
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
     bb_k_compact<<<n, 256, 0, st>>>(B);
     ctx->launches++;
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
     BB_CUDA(ctx, cudaGetLastError());
     ctx->ran = true;
     return BB_OK;
@@ -438,10 +439,11 @@ extern "C" int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms) {
     if (!ctx) return BB_ERR_ARG;
     if (!ctx->ran) return set_err(ctx, BB_ERR_STATE, "no run to time");
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
-    BB_CUDA(ctx, cudaEventSynchronize(ctx->ev[7]));
-    for (int i = 0; i < 7; i++) BB_CUDA(ctx, cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]));
-    BB_CUDA(ctx, cudaEventElapsedTime(&ctx->stage_ms[7], ctx->ev[0], ctx->ev[7]));
-    if (total_ms) *total_ms = ctx->stage_ms[7];
+    BB_CUDA(ctx, cudaEventSynchronize(ctx->ev[BB_N_STAGES - 1]));
+    for (int i = 0; i < BB_N_STAGES - 1; i++)
+        BB_CUDA(ctx, cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    BB_CUDA(ctx, cudaEventElapsedTime(&ctx->stage_ms[BB_N_STAGES - 1], ctx->ev[0], ctx->ev[BB_N_STAGES - 1]));
+    if (total_ms) *total_ms = ctx->stage_ms[BB_N_STAGES - 1];
     if (stage_ms) std::memcpy(stage_ms, ctx->stage_ms, sizeof(ctx->stage_ms));
     return BB_OK;
 }
@@ -471,6 +473,7 @@ extern "C" int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t
             o.out_off = rd.out_off; o.out_len = rd.out_len; o.frag_len = ctx->h_inlen[(size_t)r];
             o.matches = rd.matches; o.columns = rd.seq_len + rd.dels; o.loop_count = rd.loop_count;
             o.change_count = rd.change_count; o.n_alignments = rd.n_align; o.flags = rd.flags;
+            o.loop_kcycles = rd.kc_loop; o.align_kcycles = rd.kc_align;
         }
         if (rd.flags && !bad) { bad = rd.flags; bad_read = r; }
     }

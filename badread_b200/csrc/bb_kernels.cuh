@@ -54,6 +54,7 @@ struct BBReadDev {
     int matches, dels, lead_del;
     int out_len;
     int flags;
+    int kc_loop, kc_align;  // kilo-cycles this read spent in the error loop / final alignment (diagnostics)
     int pad_;
 };
 
@@ -235,6 +236,7 @@ bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned l
         if (w >= B.n_reads) break;
         const int r = B.order[w];
         BBReadDev *rd = &B.reads[r];
+        const long long clk0 = clock64();
         const uint8_t *frag = B.frag + rd->frag_off;
         uint32_t *state = B.state + rd->frag_off;
         const int frag_len = rd->frag_len;
@@ -357,6 +359,7 @@ bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned l
             rd->seq_len = total; rd->start_trim = st_trim; rd->end_trim = en_trim; rd->upper = upper;
             rd->loop_count = (int)(loop_count > 0x7fffffff ? 0x7fffffff : loop_count);
             rd->change_count = change_count; rd->n_align = n_align; rd->flags = flags;
+            rd->kc_loop = (int)((clock64() - clk0) >> 10);
         }
     }
 }
@@ -416,6 +419,7 @@ bb_k_final_align(BBBatchDev B, BBScratchPool pool, int *work_counter, const int 
         if (w >= n_items) break;
         const int r = order[w];
         BBReadDev *rd = &B.reads[r];
+        const long long clk0 = clock64();
         BBEmit em;
         em.ops = B.ops + rd->seq_off;
         em.dcnt = B.dcnt + rd->seq_off;
@@ -429,7 +433,10 @@ bb_k_final_align(BBBatchDev B, BBScratchPool pool, int *work_counter, const int 
                                  em, 0, cnt);
         }
         __syncwarp();
-        if (lane == 0) { rd->matches = cnt.matches; rd->dels = cnt.dels; rd->flags |= cnt.err << 8; }
+        if (lane == 0) {
+            rd->matches = cnt.matches; rd->dels = cnt.dels; rd->flags |= cnt.err << 8;
+            rd->kc_align = (int)((clock64() - clk0) >> 10);
+        }
     }
 }
 

@@ -268,6 +268,7 @@ def main():
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = eng.launch_count() - launches0
+    recs = res.records if False else None
 
     # ---- end to end through bb_sequence_batch: host descriptors in, host seq/qual out, every step
     bases_e2e, e2e_elapsed = bases, float('nan')

@@ -65,6 +65,8 @@ typedef struct bb_read_result {
     int32_t change_count; /* applied slot changes (simulate.py:311) */
     int32_t n_alignments; /* identity re-measurements (simulate.py:325-346) */
     int32_t flags;        /* non-zero: device-side problem for this read (see bb_last_error) */
+    int32_t loop_kcycles; /* diagnostics: SM kilo-cycles this read spent in the error loop ... */
+    int32_t align_kcycles;/* ... and in the final alignment */
 } bb_read_result;
 
 /* ---- lifecycle -------------------------------------------------------------------------------------- */
@@ -119,7 +121,7 @@ BB_API int bb_batch_run(bb_ctx *ctx);
 BB_API int bb_synchronize(bb_ctx *ctx);
 /* CUDA-event time (ms) of the last bb_batch_run on the ctx stream, total and per stage
  * (stage_ms[BB_N_STAGES], see bb_stage_name). Synchronizes. */
-#define BB_N_STAGES 8
+#define BB_N_STAGES 9
 BB_API int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms);
 BB_API const char *bb_stage_name(int stage);
 /* Number of kernel launches issued by this context so far. */
