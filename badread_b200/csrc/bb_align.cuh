@@ -122,18 +122,41 @@ __device__ __forceinline__ void bb_fetch_peq(const BBProb &P, int R, uint32_t &m
     }
 }
 
+// S = A + B over L 32-bit words, least significant word first (one carry chain).
+template <int L>
+__device__ __forceinline__ void bb_add_words(const uint32_t (&A)[L], const uint32_t (&B)[L], uint32_t (&S)[L]) {
+#ifdef __CUDA_ARCH__
+    if (L == 1) { S[0] = A[0] + B[0]; return; }
+    asm("add.cc.u32 %0, %1, %2;" : "=r"(S[0]) : "r"(A[0]), "r"(B[0]));
+#pragma unroll
+    for (int x = 1; x < L - 1; x++) asm("addc.cc.u32 %0, %1, %2;" : "=r"(S[x]) : "r"(A[x]), "r"(B[x]));
+    asm("addc.u32 %0, %1, %2;" : "=r"(S[L - 1]) : "r"(A[L - 1]), "r"(B[L - 1]));
+#else
+    uint64_t carry = 0;
+    for (int x = 0; x < L; x++) {
+        const uint64_t v = (uint64_t)A[x] + B[x] + carry;
+        S[x] = (uint32_t)v;
+        carry = v >> 32;
+    }
+#endif
+}
+
 // Banded NW of one or two problems (K = 32: one problem; K = 16: lanes 0-15 and 16-31 hold their own BBProb).
-// Requires (a + b) / (32 L) + 2 <= K.  HIST: store (Pv, PhRaw) of in-band blocks.  COLS: write D[row][ncols-1]
-// of the in-band rows of the last column to cols_out[row - cols_lo].  Returns D[n-1][ncols-1] of the lane's own
-// problem (BB_INF if the band does not contain that cell).  Values are exact for every cell on a path of cost
-// <= the k the band was derived from and upper bounds elsewhere.
+// Requires 1 <= a + b and (a + b) / (32 L) + 2 <= K.  HIST: store (Pv, PhRaw) of in-band blocks.  COLS: write
+// D[row][ncols-1] of the in-band rows of the last column to cols_out[row - cols_lo].  Returns D[n-1][ncols-1] of
+// the lane's own problem (BB_INF if the band does not contain that cell).  Values are exact for every cell on a
+// path of cost <= the k the band was derived from and upper bounds elsewhere.
+// A chunk is handled as ONE 32L-bit Myers word: the only cross-word dependencies of a step are the carry chain
+// of the addition and the one-bit shifts, everything else is independent per word.
 template <int L, bool HIST, bool COLS>
 __device__ int bb_band_pass(const BBProb &P, int K) {
     const int lane = threadIdx.x & 31;
     const int slot = lane & (K - 1);
     const int prev = (lane & ~(K - 1)) | ((slot + K - 1) & (K - 1));
     constexpr int CH = 32 * L;
-    const int n = P.n, ncols = P.ncols, a = P.a, b = P.b;
+    const int n = P.n, ncols = P.ncols, a = P.a, b = P.b, ts = P.ts;
+    const int nb_alloc = P.nb_alloc;
+    uint2 *const hist = P.hist;
     const int nblk = (n + 31) >> 5;
     int ulast = -1;
     if (ncols > 0 && n > 0) {
@@ -148,10 +171,12 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
     for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; eA[x] = eC[x] = eG[x] = eT[x] = 0u; }
     int u = slot;
     int cs = max(0, CH * u - b), ce = min(ncols - 1, CH * u + CH - 1 + a);
+    int ce_up = min(ncols - 1, CH * u - 1 + a);  // last column of the chunk above
     int score = 0, result = BB_INF;
     uint32_t outpack = 0;
     uint32_t tcn = 0;
-    if (u <= ulast && 0 - u >= cs && 0 - u <= ce) tcn = P.t[0];
+    const uint8_t *tp = P.t - (long long)u * ts;  // tp + tau*ts is this lane's column at step tau
+    if (u <= ulast && 0 - u >= cs && 0 - u <= ce) tcn = *tp;
     for (int tau = 0; tau < T; tau++) {
         const uint32_t in = __shfl_sync(BB_FULL, outpack, prev);
         const int c = tau - u;
@@ -159,7 +184,7 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
         if (active) {
             const uint32_t tc = tcn;
             int hin = 1;
-            if (u > 0 && c <= min(ncols - 1, CH * u - 1 + a)) hin = (int)((in >> 22) & 3u) - 1;
+            if (u > 0 && c <= ce_up) hin = (int)((in >> 22) & 3u) - 1;
             if (c == cs) {  // a chunk entering the band starts from the all-(+1) upper bound below chunk u-1
                 const int base = (u == 0) ? cs : (int)(in & BB_MAX_SCORE) - hin;
                 score = base + CH;
@@ -171,38 +196,58 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
             }
             const uint32_t code = (tc >> 1) & 3u;  // A->0, C->1, T->2, G->3
             const bool acgt = ((0x47544341u >> (8 * code)) & 0xffu) == tc;
-            int h = hin;
+            uint32_t Eq[L], Xv[L], A[L], S[L];
 #pragma unroll
-            for (int x = 0; x < L; x++) {
-                uint32_t Eq = (code & 2u) ? ((code & 1u) ? eG[x] : eT[x]) : ((code & 1u) ? eC[x] : eA[x]);
-                if (!acgt) {  // non-ACGT target character: exact byte equality against every row of the word
-                    Eq = 0u;
+            for (int x = 0; x < L; x++)
+                Eq[x] = (code & 2u) ? ((code & 1u) ? eG[x] : eT[x]) : ((code & 1u) ? eC[x] : eA[x]);
+            if (!acgt) {  // non-ACGT target character: exact byte equality against every row of the chunk
+#pragma unroll
+                for (int x = 0; x < L; x++) {
+                    Eq[x] = 0u;
                     const int row0 = u * CH + 32 * x;
                     for (int r = 0; r < 32; r++)
-                        if (row0 + r < n && P.q[(long long)(row0 + r) * P.qs] == tc) Eq |= 1u << r;
-                }
-                const uint32_t hin_neg = h < 0 ? 1u : 0u;
-                const uint32_t Xv = Eq | Mv[x];
-                Eq |= hin_neg;
-                const uint32_t Xh = (((Eq & Pv[x]) + Pv[x]) ^ Pv[x]) | Eq;
-                uint32_t Ph = Mv[x] | ~(Xh | Pv[x]);
-                uint32_t Mh = Pv[x] & Xh;
-                const int hout = (int)(Ph >> 31) - (int)(Mh >> 31);
-                const uint32_t ph_raw = Ph;
-                Ph = (Ph << 1) | (h > 0 ? 1u : 0u);
-                Mh = (Mh << 1) | hin_neg;
-                Pv[x] = Mh | ~(Xv | Ph);
-                Mv[x] = Ph & Xv;
-                h = hout;
-                if (HIST) {
-                    const int blk = u * L + x;
-                    const int rel = blk - bb_first_block(c, a, nblk);
-                    if (rel >= 0 && rel < P.nb_alloc && blk <= bb_last_block(c, b, n))
-                        P.hist[c * P.nb_alloc + rel] = make_uint2(Pv[x], ph_raw);
+                        if (row0 + r < n && P.q[(long long)(row0 + r) * P.qs] == tc) Eq[x] |= 1u << r;
                 }
             }
-            score += h;
-            outpack = ((uint32_t)(h + 1) << 22) | ((uint32_t)score & BB_MAX_SCORE);
+            const uint32_t hin_neg = hin < 0 ? 1u : 0u;
+#pragma unroll
+            for (int x = 0; x < L; x++) Xv[x] = Eq[x] | Mv[x];
+            Eq[0] |= hin_neg;
+#pragma unroll
+            for (int x = 0; x < L; x++) A[x] = Eq[x] & Pv[x];
+            bb_add_words<L>(A, Pv, S);
+            uint32_t Ph[L], Mh[L];
+#pragma unroll
+            for (int x = 0; x < L; x++) {
+                const uint32_t Xh = (S[x] ^ Pv[x]) | Eq[x];
+                Ph[x] = Mv[x] | ~(Xh | Pv[x]);
+                Mh[x] = Pv[x] & Xh;
+            }
+            const int hout = (int)(Ph[L - 1] >> 31) - (int)(Mh[L - 1] >> 31);
+            if (HIST) {
+#pragma unroll
+                for (int x = 0; x < L; x++) S[x] = Ph[x];  // PhRaw of this column (S is free now)
+            }
+#pragma unroll
+            for (int x = L - 1; x >= 0; x--) {
+                const uint32_t ph_lo = x > 0 ? Ph[x - 1] : (hin > 0 ? 0x80000000u : 0u);
+                const uint32_t mh_lo = x > 0 ? Mh[x - 1] : (hin_neg << 31);
+                const uint32_t phs = __funnelshift_l(ph_lo, Ph[x], 1);
+                const uint32_t mhs = __funnelshift_l(mh_lo, Mh[x], 1);
+                Pv[x] = mhs | ~(Xv[x] | phs);
+                Mv[x] = phs & Xv[x];
+            }
+            if (HIST) {
+                const int bf = bb_first_block(c, a, nblk), bl = bb_last_block(c, b, n);
+#pragma unroll
+                for (int x = 0; x < L; x++) {
+                    const int blk = u * L + x;
+                    const int rel = blk - bf;
+                    if (rel >= 0 && rel < nb_alloc && blk <= bl) hist[c * nb_alloc + rel] = make_uint2(Pv[x], S[x]);
+                }
+            }
+            score += hout;
+            outpack = ((uint32_t)(hout + 1) << 22) | ((uint32_t)score & BB_MAX_SCORE);
             if (c == ncols - 1) {
                 int run = score;
 #pragma unroll
@@ -229,10 +274,12 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
                 u += K;
                 cs = max(0, CH * u - b);
                 ce = min(ncols - 1, CH * u + CH - 1 + a);
+                ce_up = min(ncols - 1, CH * u - 1 + a);
+                tp -= (long long)K * ts;
             }
         }
         const int cn = tau + 1 - u;
-        if (u <= ulast && cn >= cs && cn <= ce) tcn = P.t[(long long)cn * P.ts];
+        if (u <= ulast && cn >= cs && cn <= ce) tcn = tp[(long long)(tau + 1) * ts];
     }
     const int owner = (lane & ~(K - 1)) | ((n > 0 ? (n - 1) / CH : 0) & (K - 1));
     result = __shfl_sync(BB_FULL, result, owner);

@@ -151,6 +151,10 @@ inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
     const uint64_t v = ((uint64_t)hi << 32) | lo;
     return (unsigned)(v >> (sh & 31));
 }
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) {
+    const uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (unsigned)((v << (sh & 31)) >> 32);
+}
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
