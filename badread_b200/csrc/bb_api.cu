@@ -55,12 +55,15 @@ struct bb_ctx {
     int64_t frag_total = 0, seq_total = 0, out_total = 0;
     DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_order_small, d_order_large, d_reads;
     std::vector<int> h_order;
-    DevBuf d_frag, d_state, d_seq, d_ops, d_dcnt, d_qual, d_out_seq, d_out_qual, d_counter;
+    DevBuf d_frag, d_state, d_seq, d_ops, d_dcnt, d_qual, d_out_seq, d_out_qual, d_counter, d_fpeq, d_speq, d_fallback;
+    int64_t fpeq_total = 0;
 
     // scratch
     int n_warps = 0;
     BBScratchPool pool{};
-    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq;
+    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_lhist, s_ltbuf;
+    BBLanePool lane_pool{};
+    int n_lanes = 0;
 
     cudaEvent_t ev[BB_N_STAGES + 1] = {};
     float stage_ms[BB_N_STAGES] = {};
@@ -138,7 +141,8 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order, &ctx->d_order_small, &ctx->d_order_large,
                       &ctx->d_reads, &ctx->d_frag, &ctx->d_state, &ctx->d_seq, &ctx->d_ops, &ctx->d_dcnt,
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
-                      &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq};
+                      &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_lhist, &ctx->s_ltbuf,
+                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
@@ -275,6 +279,8 @@ static BBBatchDev batch_dev(bb_ctx *ctx) {
     B.qual = ctx->d_qual.as<uint8_t>();
     B.out_seq = ctx->d_out_seq.as<uint8_t>();
     B.out_qual = ctx->d_out_qual.as<uint8_t>();
+    B.fpeq = ctx->d_fpeq.as<uint4>();
+    B.speq = ctx->d_speq.as<uint4>();
     return B;
 }
 
@@ -289,7 +295,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     const int k = ctx->em.k;
     ctx->h_reads.assign((size_t)n_reads, BBReadDev{});
     ctx->h_inlen.assign((size_t)n_reads, 0);
-    int64_t off = 0;
+    int64_t off = 0, peq_off = 0;
     int max_len = 0;
     for (int32_t r = 0; r < n_reads; r++) {
         int64_t len = 0;
@@ -307,6 +313,8 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
         BBReadDev &rd = ctx->h_reads[(size_t)r];
         rd.frag_off = off;
         rd.frag_len = (int)(len + 2 * k);
+        rd.fpeq_off = peq_off;
+        peq_off += (rd.frag_len + 31) / 32 + 3;
         off += (rd.frag_len + 15) & ~15;
         max_len = std::max(max_len, rd.frag_len);
     }
@@ -328,7 +336,20 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     BB_CUDA(ctx, ctx->d_frag.ensure((size_t)off + 16));
     BB_CUDA(ctx, ctx->d_state.ensure(((size_t)off + 16) * sizeof(uint32_t)));
     BB_CUDA(ctx, ctx->d_counter.ensure(16 * sizeof(int)));
+    BB_CUDA(ctx, ctx->d_fpeq.ensure(((size_t)peq_off + 4) * sizeof(uint4)));
+    BB_CUDA(ctx, ctx->d_fallback.ensure(((size_t)n_reads + 4) * sizeof(int)));
+    ctx->fpeq_total = peq_off;
     if ((rc = ensure_scratch(ctx, max_len, 4096, max_len))) return rc;
+    {   // lane-per-read scratch: history of one window (<= 2048 columns x 8 words) and the joined window
+        const int n_lanes = std::min(((n_reads + 63) / 64) * 64, 32768);
+        const int max_cols = 2048, tbuf_cap = 4096;
+        BB_CUDA(ctx, ctx->s_lhist.ensure((size_t)n_lanes * max_cols * 8 * sizeof(uint2)));
+        BB_CUDA(ctx, ctx->s_ltbuf.ensure((size_t)n_lanes * tbuf_cap));
+        ctx->n_lanes = n_lanes;
+        ctx->lane_pool.hist = ctx->s_lhist.as<uint2>(); ctx->lane_pool.hist_stride = (long long)max_cols * 8;
+        ctx->lane_pool.tbuf = ctx->s_ltbuf.as<uint8_t>(); ctx->lane_pool.tbuf_cap = tbuf_cap;
+        ctx->lane_pool.max_cols = max_cols;
+    }
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->uploaded = true;
     ctx->ran = false;
@@ -353,20 +374,27 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
     bb_k_build_fragments<<<n, 256, 0, st>>>(B, ctx->ref.as<uint8_t>(), ctx->em.k, ctx->seed);
     ctx->launches++;
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    bb_k_error_loop<<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->seed, counters);
+    // one thread per read; reads whose windows exceed the lane-mode limits are redone by the warp kernel
+    bb_k_error_loop_lane<<<ctx->n_lanes / 64, 64, 0, st>>>(B, ctx->em, ctx->lane_pool, ctx->seed, counters,
+                                                          ctx->d_fallback.as<int>(), counters + 3);
+    ctx->launches++;
+    bb_k_error_loop<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->seed, counters + 4,
+                                                                      ctx->d_fallback.as<int>(), counters + 3, 1);
     ctx->launches++;
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     // host scan of the joined lengths -> offsets of the per-read regions in seq / ops / dcnt / qual / out
     std::vector<BBReadDev> reads((size_t)n);
     BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
     BB_CUDA(ctx, cudaStreamSynchronize(st));
-    int64_t seq_off = 0, out_off = 0;
+    int64_t seq_off = 0, out_off = 0, speq_off = 0;
     int rc0 = 0;
     int lr_need = 0, hbuf_need = 0, len_need = 0;
     for (int r = 0; r < n; r++) {
         BBReadDev &rd = reads[(size_t)r];
         rd.seq_off = seq_off;
         rd.out_off = out_off;
+        rd.speq_off = speq_off;
+        speq_off += (rd.seq_len + 31) / 32 + 3;
         int out_len = rd.seq_len - rd.start_trim - rd.end_trim;  // seq[start_trim:-end_trim]
         if (out_len < 0) out_len = 0;
         rd.out_len = out_len;
@@ -393,6 +421,7 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
     BB_CUDA(ctx, ctx->d_ops.ensure((size_t)seq_off + 16));
     BB_CUDA(ctx, ctx->d_dcnt.ensure(((size_t)seq_off + 16) * sizeof(uint16_t)));
     BB_CUDA(ctx, ctx->d_qual.ensure((size_t)seq_off + 16));
+    BB_CUDA(ctx, ctx->d_speq.ensure(((size_t)speq_off + 4) * sizeof(uint4)));
     BB_CUDA(ctx, ctx->d_out_seq.ensure((size_t)out_off + 16));
     BB_CUDA(ctx, ctx->d_out_qual.ensure((size_t)out_off + 16));
     int rc = ensure_scratch(ctx, hbuf_need, lr_need, len_need);

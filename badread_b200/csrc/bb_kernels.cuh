@@ -15,6 +15,7 @@
 
 #include "../../include/badread_b200.h"
 #include "bb_align.cuh"
+#include "bb_lane.cuh"
 #include "bb_rng.cuh"
 
 #define BB_SLOT_NONE 0xFFFFFFFFu
@@ -46,6 +47,8 @@ struct BBReadDev {
     long long frag_off;  // into frag / state
     long long seq_off;   // into seq / ops / dcnt / qual
     long long out_off;   // into out_seq / out_qual
+    long long fpeq_off;  // into fpeq (match bitmap of the padded fragment), uint4 units
+    long long speq_off;  // into speq (match bitmap of the untrimmed read)
     int frag_len;        // padded (2k pad bases included)
     int seq_len;         // untrimmed
     int start_trim, end_trim;
@@ -74,6 +77,7 @@ struct BBBatchDev {
     uint16_t *dcnt;
     uint8_t *qual;
     uint8_t *out_seq, *out_qual;
+    uint4 *fpeq, *speq;
 };
 
 struct BBScratchPool {
@@ -128,6 +132,18 @@ __global__ void __launch_bounds__(256) bb_k_build_fragments(BBBatchDev B, const 
         pos += sg.len;
     }
     for (int x = threadIdx.x; x < flen; x += blockDim.x) st[x] = BB_SLOT_NONE;
+    // match bitmap of the padded fragment (bb_build_peq layout), one ballot group per 32 bases
+    __syncthreads();
+    uint4 *pq = B.fpeq + rd.fpeq_off;
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) pq[0] = make_uint4(0u, 0u, 0u, 0u);
+    for (int w = threadIdx.x >> 5; w < ((flen + 31) >> 5) + 2; w += nwarps) {
+        const int row = 32 * w + lane;
+        const uint8_t c = row < flen ? f[row] : 0;
+        const uint32_t mA = __ballot_sync(BB_FULL, c == 'A'), mC = __ballot_sync(BB_FULL, c == 'C');
+        const uint32_t mG = __ballot_sync(BB_FULL, c == 'G'), mT = __ballot_sync(BB_FULL, c == 'T');
+        if (lane == 0) pq[w + 1] = make_uint4(mA, mC, mG, mT);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K2
@@ -222,19 +238,21 @@ __device__ __forceinline__ void bb_eval_iteration(const BBErrorModelDev &em, con
 }
 
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 4)
-bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned long long seed, int *work_counter) {
+bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned long long seed, int *work_counter,
+                const int *order, const int *n_items_ptr, int reinit) {
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
-    const BBScratch sc = pool.for_warp(warp);
+    BBScratch sc = pool.for_warp(warp);
     uint8_t *tbuf = pool.tbuf + (long long)warp * pool.tbuf_stride;
     const int k = em.k;
+    const int n_items = *n_items_ptr;
     BBEmit no_emit = {nullptr, nullptr, nullptr};
     for (;;) {
         int w = 0;
         if (lane == 0) w = atomicAdd(work_counter, 1);
         w = __shfl_sync(BB_FULL, w, 0);
-        if (w >= B.n_reads) break;
-        const int r = B.order[w];
+        if (w >= n_items) break;
+        const int r = order[w];
         BBReadDev *rd = &B.reads[r];
         const long long clk0 = clock64();
         const uint8_t *frag = B.frag + rd->frag_off;
@@ -252,10 +270,10 @@ bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned l
         bool done = est_needed < 0.5;
         if (!done && 1.0 <= target) { done = true; loop_count = 1; }
         __syncwarp();
-        if (!done) {
-            // match bitmap of the original fragment: every window alignment of this read cuts its rows out of it
-            if (frag_len / 32 + 4 > sc.peq_cap) { flags |= 256; done = true; }
-            else bb_build_peq(frag, frag_len, sc.peq);
+        sc.peq = B.fpeq + rd->fpeq_off;  // match bitmap of the padded fragment (built by bb_k_build_fragments)
+        if (reinit) {                    // a read handed over by the lane kernel starts again from pristine slots
+            for (int x = lane; x < frag_len; x += 32) state[x] = BB_SLOT_NONE;
+            __syncwarp();
         }
         while (!done) {
             const long long n = n0 + lane;
@@ -364,6 +382,138 @@ bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned l
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K2 (lane per read)
+struct BBLanePool {
+    uint2 *hist; long long hist_stride;  // entries per lane
+    uint8_t *tbuf; int tbuf_cap;         // joined window per lane
+    int max_cols;                        // hist_stride / 8: columns a lane can keep at 8 window words
+};
+
+// simulate.sequence_fragment's while-loop (simulate.py:272-346) for ONE read by ONE thread.  Returns false when a
+// window alignment exceeds the lane-mode limits (band wider than 8 window words, joined window longer than the
+// lane's buffers, or a window edlib would not trace back directly); the read is then redone by the warp kernel.
+__device__ bool bb_lane_process_read(const BBBatchDev &B, const BBErrorModelDev &em, int r, unsigned long long seed,
+                                     uint2 *hist, int max_cols, uint8_t *tbuf, int tbuf_cap) {
+    BBReadDev *rd = &B.reads[r];
+    const long long clk0 = clock64();
+    const uint8_t *frag = B.frag + rd->frag_off;
+    uint32_t *state = B.state + rd->frag_off;
+    const int frag_len = rd->frag_len;
+    const unsigned long long read = B.read_index[r];
+    const double target = B.target[r];
+    const double fl = (double)frag_len;
+    const int k = em.k;
+    const int max_kmer_index = frag_len - 1 - k;
+    const long long limit = 100ll * frag_len;
+    double errors = 0.0;
+    int change_count = 0, n_align = 0, upper = 0, flags = 0;
+    long long loop_count = 0;
+    const double est_needed = __dmul_rn(fl, __dsub_rn(1.0, target));
+    if (!(est_needed < 0.5)) {
+        const double cc_limit = __dmul_rn(0.9, fl);
+        double est_id = 1.0;
+        for (long long n = 0;; n++) {
+            // the checks at the top of every iteration (simulate.py:278-292)
+            if (n >= limit) { loop_count = limit + 1; break; }
+            if ((double)change_count > cc_limit) { loop_count = n + 1; break; }
+            if (est_id <= target) { loop_count = n + 1; break; }
+            int kind = 0, pos_i = 0, rpos = 0;
+            uint32_t payload = 0;
+            bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
+            if (kind == 0) continue;
+            const double scale = __dmul_rn(est_id, __dsqrt_rn(est_id));
+            for (int j = 0; j < k; j++) {
+                const uint8_t fb = frag[pos_i + j];
+                const uint32_t enc = kind == 1 ? em.slots[(long long)payload * k + j]
+                                               : (j == rpos ? payload : bb_slot_inline(1, fb, 0));
+                const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
+                if (!differs || state[pos_i + j] != BB_SLOT_NONE) continue;  // simulate.py:309
+                state[pos_i + j] = enc;
+                const int len = (int)(enc & 0xff);
+                change_count++;
+                upper += len < 1 ? 1 : len;
+                errors = __dadd_rn(errors, __dmul_rn((double)(len < 2 ? 1 : len - 1), scale));
+                if (change_count % BB_ALIGNMENT_INTERVAL != 0) continue;
+                // identity re-measurement (simulate.py:325-346)
+                int qpos = 0, qn = frag_len;
+                if (frag_len > BB_ALIGNMENT_SIZE) {
+                    BBRng wr;
+                    wr.init(seed, read);
+                    wr.stream(BB_PURPOSE_WINDOW, (uint32_t)n_align);
+                    qpos = (int)wr.randbelow((uint32_t)(frag_len - BB_ALIGNMENT_SIZE + 1));
+                    qn = BB_ALIGNMENT_SIZE;
+                }
+                int tm = 0, uw = 0;
+                for (int x = 0; x < qn; x++) {  // ''.join(new_fragment_bases[pos:pos2])
+                    const uint32_t st = state[qpos + x];
+                    if (st == BB_SLOT_NONE) { if (tm < tbuf_cap) tbuf[tm] = frag[qpos + x]; tm++; }
+                    else {
+                        const int sl = (int)(st & 0xff);
+                        for (int c = 0; c < sl; c++) { if (tm < tbuf_cap) tbuf[tm] = bb_slot_char(em, st, c); tm++; }
+                        uw += sl < 1 ? 1 : sl;
+                    }
+                }
+                {
+                    const int diff = qn > tm ? qn - tm : tm - qn;
+                    if (uw < diff) uw = diff;
+                    const int mx = qn > tm ? qn : tm;
+                    if (uw > mx) uw = mx;
+                }
+                BBLaneProb P;
+                bb_band(qn, tm, uw, P.a, P.b);
+                const int lw = bb_lane_words(P.a, P.b);
+                if (tm > tbuf_cap || tm > max_cols || lw > 8 || !bb_uses_traceback(qn, tm)) return false;
+                P.peq = B.fpeq + rd->fpeq_off; P.peq_bit0 = qpos + 32; P.q = frag + qpos; P.n = qn;
+                P.t = tbuf; P.m = tm; P.hist = hist;
+                int matches = 0, dels = 0, err = 0;
+                if (lw <= 4) { bb_lane_pass<4>(P); bb_lane_traceback<4>(P, matches, dels, err); }
+                else { bb_lane_pass<8>(P); bb_lane_traceback<8>(P, matches, dels, err); }
+                flags |= err;
+                const int cols = qn + dels;
+                const double actual = cols ? __ddiv_rn((double)matches, (double)cols) : 0.0;
+                if (frag_len <= BB_ALIGNMENT_SIZE) {
+                    errors = __dmul_rn(__dsub_rn(1.0, actual), fl);
+                } else {
+                    const double est_err = __dmul_rn(__dsub_rn(1.0, actual), fl);
+                    const double weight = __ddiv_rn((double)BB_ALIGNMENT_SIZE, fl);
+                    errors = __dadd_rn(__dmul_rn(est_err, weight), __dmul_rn(errors, __dsub_rn(1.0, weight)));
+                }
+                n_align++;
+            }
+            est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl));
+            if (flags) { loop_count = n + 1; break; }
+        }
+    }
+    int total = 0, st_trim = 0, en_trim = 0;
+    for (int x = 0; x < frag_len; x++) {
+        const uint32_t st = state[x];
+        const int len = st == BB_SLOT_NONE ? 1 : (int)(st & 0xff);
+        total += len;
+        if (x < k) st_trim += len;
+        if (x >= frag_len - k) en_trim += len;
+    }
+    rd->seq_len = total; rd->start_trim = st_trim; rd->end_trim = en_trim; rd->upper = upper;
+    rd->loop_count = (int)(loop_count > 0x7fffffff ? 0x7fffffff : loop_count);
+    rd->change_count = change_count; rd->n_align = n_align; rd->flags = flags;
+    rd->kc_loop = (int)((clock64() - clk0) >> 10);
+    return true;
+}
+
+__global__ void __launch_bounds__(64)
+bb_k_error_loop_lane(BBBatchDev B, BBErrorModelDev em, BBLanePool pool, unsigned long long seed, int *work_counter,
+                     int *fallback_list, int *fallback_count) {
+    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint2 *hist = pool.hist + gl * pool.hist_stride;
+    uint8_t *tbuf = pool.tbuf + gl * pool.tbuf_cap;
+    for (;;) {
+        const int w = atomicAdd(work_counter, 1);
+        if (w >= B.n_reads) break;
+        const int r = B.order[w];
+        if (!bb_lane_process_read(B, em, r, seed, hist, pool.max_cols, tbuf, pool.tbuf_cap))
+            fallback_list[atomicAdd(fallback_count, 1)] = r;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K3
 __global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev em) {
     const int r = blockIdx.x;
@@ -401,6 +551,16 @@ __global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev e
         if (threadIdx.x == 255) running = off + len;
         __syncthreads();
     }
+    uint4 *pq = B.speq + rd.speq_off;
+    const int nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) pq[0] = make_uint4(0u, 0u, 0u, 0u);
+    for (int w = wid; w < ((rd.seq_len + 31) >> 5) + 2; w += nwarps) {
+        const int row = 32 * w + lane;
+        const uint8_t c = row < rd.seq_len ? seq[row] : 0;
+        const uint32_t mA = __ballot_sync(BB_FULL, c == 'A'), mC = __ballot_sync(BB_FULL, c == 'C');
+        const uint32_t mG = __ballot_sync(BB_FULL, c == 'G'), mT = __ballot_sync(BB_FULL, c == 'T');
+        if (lane == 0) pq[w + 1] = make_uint4(mA, mC, mG, mT);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K4
@@ -411,7 +571,7 @@ __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (MAXL <= 2 ? 4 : 2))
 bb_k_final_align(BBBatchDev B, BBScratchPool pool, int *work_counter, const int *order, int n_items, int warp_base) {
     const int lane = threadIdx.x & 31;
     const int warp = warp_base + blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
-    const BBScratch sc = pool.for_warp(warp);
+    BBScratch sc = pool.for_warp(warp);
     for (;;) {
         int w = 0;
         if (lane == 0) w = atomicAdd(work_counter, 1);
@@ -420,18 +580,15 @@ bb_k_final_align(BBBatchDev B, BBScratchPool pool, int *work_counter, const int 
         const int r = order[w];
         BBReadDev *rd = &B.reads[r];
         const long long clk0 = clock64();
+        sc.peq = B.speq + rd->speq_off;  // match bitmap of the joined read (built by bb_k_join)
         BBEmit em;
         em.ops = B.ops + rd->seq_off;
         em.dcnt = B.dcnt + rd->seq_off;
         em.lead_del = &rd->lead_del;
         BBAlnCounts cnt = {0, 0, 0, 0};
         // query = mutated read, target = original fragment (qscore_model.py:37)
-        if (rd->seq_len / 32 + 4 > sc.peq_cap) cnt.err |= 256;
-        else {
-            bb_build_peq(B.seq + rd->seq_off, rd->seq_len, sc.peq);
-            bb_align<true, MAXL>(B.seq + rd->seq_off, rd->seq_len, B.frag + rd->frag_off, rd->frag_len, rd->upper, sc,
-                                 em, 0, cnt);
-        }
+        bb_align<true, MAXL>(B.seq + rd->seq_off, rd->seq_len, B.frag + rd->frag_off, rd->frag_len, rd->upper, sc, em,
+                             0, cnt);
         __syncwarp();
         if (lane == 0) {
             rd->matches = cnt.matches; rd->dels = cnt.dels; rd->flags |= cnt.err << 8;

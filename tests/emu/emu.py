@@ -11,7 +11,8 @@ LIB = HERE / 'libemu_align.so'
 
 
 def build():
-    srcs = [HERE / 'emu_align.cpp', HERE / 'cuda_emu.h', HERE.parent.parent / 'badread_b200' / 'csrc' / 'bb_align.cuh']
+    csrc = HERE.parent.parent / 'badread_b200' / 'csrc'
+    srcs = [HERE / 'emu_align.cpp', HERE / 'cuda_emu.h', csrc / 'bb_align.cuh', csrc / 'bb_lane.cuh']
     if not LIB.is_file() or any(LIB.stat().st_mtime < s.stat().st_mtime for s in srcs):
         subprocess.run(['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-o', str(LIB), str(srcs[0])], check=True)
     return LIB
@@ -47,3 +48,21 @@ def align_path(query, target, k_upper=None, qabs_pad=0, maxl=16):
     assert len(s) == n + out5[1], (len(s), n, out5)
     assert s.count('=') == out5[0]
     return s, int(out5[2])
+
+
+def lane_align(query, target, k_upper, qabs_pad=0, lw=4):
+    """Lane-mode pass + traceback under the emulator -> (matches, dels, distance) or None if the band needs more
+    than lw window words."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(LIB))
+    q = query.encode('latin-1') if isinstance(query, str) else bytes(query)
+    t = target.encode('latin-1') if isinstance(target, str) else bytes(target)
+    out4 = np.zeros(4, dtype=np.int32)
+    rc = _lib.emu_lane_align(q, len(q), t, len(t), k_upper, qabs_pad, lw, out4.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        return None
+    if out4[3]:
+        raise RuntimeError(f'lane aligner error flags 0x{int(out4[3]):x}')
+    return int(out4[0]), int(out4[1]), int(out4[2])
