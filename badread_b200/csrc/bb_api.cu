@@ -37,7 +37,8 @@ struct bb_ctx {
     int device = 0;
     int sm_count = 0;
     uint64_t seed = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int64_t launches = 0;
 
@@ -53,7 +54,8 @@ struct bb_ctx {
     std::vector<BBReadDev> h_reads;
     std::vector<int32_t> h_inlen;
     int64_t frag_total = 0, seq_total = 0, out_total = 0;
-    DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_order_small, d_order_large, d_reads;
+    DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_order_small, d_order_large, d_order_long, d_reads;
+    int n_lane_reads = 0, n_long_reads = 0;
     std::vector<int> h_order;
     DevBuf d_frag, d_state, d_seq, d_ops, d_dcnt, d_qual, d_out_seq, d_out_qual, d_counter, d_fpeq, d_speq, d_fallback;
     int64_t fpeq_total = 0;
@@ -118,6 +120,9 @@ extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     // misc.REV_COMP_DICT (misc.py:56-61); anything else complements to 'N' (misc.py:64-68)
     uint8_t comp[256];
     std::memset(comp, 'N', sizeof(comp));
@@ -138,7 +143,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->ref, &ctx->em_k2r, &ctx->em_rowoff, &ctx->em_cum, &ctx->em_flags, &ctx->em_slots,
                       &ctx->em_pool, &ctx->qm_hkeys, &ctx->qm_hvals, &ctx->qm_rowoff, &ctx->qm_scores, &ctx->qm_cum,
-                      &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order, &ctx->d_order_small, &ctx->d_order_large,
+                      &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order, &ctx->d_order_small, &ctx->d_order_large, &ctx->d_order_long,
                       &ctx->d_reads, &ctx->d_frag, &ctx->d_state, &ctx->d_seq, &ctx->d_ops, &ctx->d_dcnt,
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_lhist, &ctx->s_ltbuf,
@@ -146,6 +151,9 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
     return BB_OK;
 }
@@ -325,7 +333,16 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
                      [&](int x, int y) { return ctx->h_reads[(size_t)x].frag_len > ctx->h_reads[(size_t)y].frag_len; });
     ctx->n_reads = n_reads;
     ctx->h_order = order;
+    // error loop: one thread per read, except the longest reads (a single thread would be the makespan): they get
+    // a whole warp each, concurrently on a second stream
+    std::vector<int> lane_order, long_order;
+    for (int r : order) (ctx->h_reads[(size_t)r].frag_len > 50000 ? long_order : lane_order).push_back(r);
+    ctx->n_lane_reads = (int)lane_order.size();
+    ctx->n_long_reads = (int)long_order.size();
     int rc;
+    if ((rc = upload(ctx, ctx->d_order_long, long_order.data(), long_order.size()))) return rc;
+    order = lane_order;
+    order.resize((size_t)n_reads, 0);
     if ((rc = upload(ctx, ctx->d_read_index, read_index, (size_t)n_reads))) return rc;
     if ((rc = upload(ctx, ctx->d_seg_off, seg_off, (size_t)n_reads + 1))) return rc;
     if ((rc = upload(ctx, ctx->d_segs, segs, (size_t)seg_off[n_reads]))) return rc;
@@ -375,12 +392,29 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
     ctx->launches++;
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // one thread per read; reads whose windows exceed the lane-mode limits are redone by the warp kernel
-    bb_k_error_loop_lane<<<ctx->n_lanes / 64, 64, 0, st>>>(B, ctx->em, ctx->lane_pool, ctx->seed, counters,
-                                                          ctx->d_fallback.as<int>(), counters + 3);
-    ctx->launches++;
+    if (ctx->n_long_reads > 0) {  // the longest reads: one warp each, on the second stream
+        const int h_n_long = ctx->n_long_reads;
+        BB_CUDA(ctx, cudaMemcpyAsync(counters + 6, &h_n_long, sizeof(int), cudaMemcpyHostToDevice, st));
+        BB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        BB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        const int grid_long = std::min(ctx->sm_count * 2, (h_n_long + BB_WARPS_PER_CTA - 1) / BB_WARPS_PER_CTA);
+        // scratch of warps [n_warps/2, ...) so that it cannot collide with the fall-back launch below
+        bb_k_error_loop<<<grid_long, BB_WARPS_PER_CTA * 32, 0, ctx->stream2>>>(
+            B, ctx->em, ctx->pool, ctx->seed, counters + 5, ctx->d_order_long.as<int>(), counters + 6, 0, ctx->n_warps / 2);
+        ctx->launches++;
+        BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+    }
+    if (ctx->n_lane_reads > 0) {
+        const int lanes = std::min(ctx->n_lanes, ((ctx->n_lane_reads + 63) / 64) * 64);
+        bb_k_error_loop_lane<<<lanes / 64, 64, 0, st>>>(B, ctx->em, ctx->lane_pool, ctx->seed, counters, ctx->d_order.as<int>(),
+                                                        ctx->n_lane_reads, ctx->d_fallback.as<int>(), counters + 3);
+        ctx->launches++;
+    }
+    // reads whose windows exceeded the lane-mode limits are redone by the warp kernel
     bb_k_error_loop<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->seed, counters + 4,
-                                                                      ctx->d_fallback.as<int>(), counters + 3, 1);
+                                                                      ctx->d_fallback.as<int>(), counters + 3, 1, 0);
     ctx->launches++;
+    if (ctx->n_long_reads > 0) BB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     // host scan of the joined lengths -> offsets of the per-read regions in seq / ops / dcnt / qual / out
     std::vector<BBReadDev> reads((size_t)n);

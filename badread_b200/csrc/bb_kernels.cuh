@@ -239,9 +239,9 @@ __device__ __forceinline__ void bb_eval_iteration(const BBErrorModelDev &em, con
 
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 4)
 bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned long long seed, int *work_counter,
-                const int *order, const int *n_items_ptr, int reinit) {
+                const int *order, const int *n_items_ptr, int reinit, int warp_base) {
     const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int warp = warp_base + blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
     BBScratch sc = pool.for_warp(warp);
     uint8_t *tbuf = pool.tbuf + (long long)warp * pool.tbuf_stride;
     const int k = em.k;
@@ -389,80 +389,133 @@ struct BBLanePool {
     int max_cols;                        // hist_stride / 8: columns a lane can keep at 8 window words
 };
 
-// simulate.sequence_fragment's while-loop (simulate.py:272-346) for ONE read by ONE thread.  Returns false when a
-// window alignment exceeds the lane-mode limits (band wider than 8 window words, joined window longer than the
-// lane's buffers, or a window edlib would not trace back directly); the read is then redone by the warp kernel.
-__device__ bool bb_lane_process_read(const BBBatchDev &B, const BBErrorModelDev &em, int r, unsigned long long seed,
-                                     uint2 *hist, int max_cols, uint8_t *tbuf, int tbuf_cap) {
-    BBReadDev *rd = &B.reads[r];
-    const long long clk0 = clock64();
-    const uint8_t *frag = B.frag + rd->frag_off;
-    uint32_t *state = B.state + rd->frag_off;
-    const int frag_len = rd->frag_len;
-    const unsigned long long read = B.read_index[r];
-    const double target = B.target[r];
-    const double fl = (double)frag_len;
+// simulate.sequence_fragment's while-loop (simulate.py:272-346), one read per THREAD, written as a warp-synchronous
+// state machine so that the 32 lanes of a warp stay on the same instruction stream:
+//   phase A  every lane advances its own k-mer loop until it needs an identity re-measurement (every 25 applied
+//            changes) or runs out of reads;
+//   phase B  all lanes that need one join their window, run the lane aligner and fold the result into `errors`.
+// A read whose window exceeds the lane-mode limits (band wider than 8 window words, joined window longer than
+// the lane's buffers, or a window edlib would not trace back directly) is handed to the warp kernel.
+__global__ void __launch_bounds__(64)
+bb_k_error_loop_lane(BBBatchDev B, BBErrorModelDev em, BBLanePool pool, unsigned long long seed, int *work_counter,
+                     const int *order, int n_items, int *fallback_list, int *fallback_count) {
+    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint2 *const hist = pool.hist + gl * pool.hist_stride;
+    uint8_t *const tbuf = pool.tbuf + gl * pool.tbuf_cap;
     const int k = em.k;
-    const int max_kmer_index = frag_len - 1 - k;
-    const long long limit = 100ll * frag_len;
-    double errors = 0.0;
-    int change_count = 0, n_align = 0, upper = 0, flags = 0;
-    long long loop_count = 0;
-    const double est_needed = __dmul_rn(fl, __dsub_rn(1.0, target));
-    if (!(est_needed < 0.5)) {
-        const double cc_limit = __dmul_rn(0.9, fl);
-        double est_id = 1.0;
-        for (long long n = 0;; n++) {
-            // the checks at the top of every iteration (simulate.py:278-292)
-            if (n >= limit) { loop_count = limit + 1; break; }
-            if ((double)change_count > cc_limit) { loop_count = n + 1; break; }
-            if (est_id <= target) { loop_count = n + 1; break; }
-            int kind = 0, pos_i = 0, rpos = 0;
-            uint32_t payload = 0;
-            bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
-            if (kind == 0) continue;
-            const double scale = __dmul_rn(est_id, __dsqrt_rn(est_id));
-            for (int j = 0; j < k; j++) {
-                const uint8_t fb = frag[pos_i + j];
-                const uint32_t enc = kind == 1 ? em.slots[(long long)payload * k + j]
-                                               : (j == rpos ? payload : bb_slot_inline(1, fb, 0));
-                const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
-                if (!differs || state[pos_i + j] != BB_SLOT_NONE) continue;  // simulate.py:309
+    // per-read state
+    int r = -1;
+    BBReadDev *rd = nullptr;
+    const uint8_t *frag = nullptr;
+    uint32_t *state = nullptr;
+    int frag_len = 0, max_kmer_index = 0;
+    unsigned long long read = 0;
+    double target = 0.0, fl = 0.0, cc_limit = 0.0, errors = 0.0, est_id = 1.0, scale = 0.0;
+    long long limit = 0, n = 0, loop_count = 0, clk0 = 0;
+    int change_count = 0, n_align = 0, upper = 0, flags = 0, total = 0, st_trim = 0, en_trim = 0;
+    // per-iteration state (a changed k-mer is applied slot by slot; an alignment may interrupt it)
+    int jres = 0x7fffffff, pos_i = 0, kind = 0, rpos = 0;
+    uint32_t payload = 0;
+    bool have_read = false, idle = false, need_align = false;
+    for (;;) {
+        // ---------------------------------------------------------------- phase A
+        while (!idle && !need_align) {
+            if (!have_read) {
+                const int w = atomicAdd(work_counter, 1);
+                if (w >= n_items) { idle = true; break; }
+                r = order[w];
+                rd = &B.reads[r];
+                clk0 = clock64();
+                frag = B.frag + rd->frag_off;
+                state = B.state + rd->frag_off;
+                frag_len = rd->frag_len;
+                read = B.read_index[r];
+                target = B.target[r];
+                fl = (double)frag_len;
+                max_kmer_index = frag_len - 1 - k;
+                limit = 100ll * frag_len;
+                cc_limit = __dmul_rn(0.9, fl);
+                errors = 0.0; est_id = 1.0;
+                change_count = 0; n_align = 0; upper = 0; flags = 0;
+                total = frag_len; st_trim = k; en_trim = k;
+                n = 0; loop_count = 0; jres = 0x7fffffff;
+                have_read = true;
+                if (__dmul_rn(fl, __dsub_rn(1.0, target)) < 0.5) n = -1;  // estimated_errors_needed < 0.5: no loop
+            }
+            if (jres >= k) {
+                // top of an iteration (simulate.py:278-292), or the end of the read
+                bool finished = false;
+                if (n < 0) { finished = true; loop_count = 0; }
+                else if (n >= limit) { finished = true; loop_count = limit + 1; }
+                else if ((double)change_count > cc_limit || est_id <= target || flags) { finished = true; loop_count = n + 1; }
+                if (finished) {
+                    rd->seq_len = total; rd->start_trim = st_trim; rd->end_trim = en_trim; rd->upper = upper;
+                    rd->loop_count = (int)(loop_count > 0x7fffffff ? 0x7fffffff : loop_count);
+                    rd->change_count = change_count; rd->n_align = n_align; rd->flags = flags;
+                    rd->kc_loop = (int)((clock64() - clk0) >> 10);
+                    have_read = false;
+                    continue;
+                }
+                bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
+                n++;
+                if (kind == 0) continue;
+                scale = __dmul_rn(est_id, __dsqrt_rn(est_id));
+                jres = 0;
+            }
+            // apply slot jres of the changed k-mer (simulate.py:303-321)
+            const int j = jres++;
+            const uint8_t fb = frag[pos_i + j];
+            const uint32_t enc = kind == 1 ? em.slots[(long long)payload * k + j]
+                                           : (j == rpos ? payload : bb_slot_inline(1, fb, 0));
+            const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
+            if (differs && state[pos_i + j] == BB_SLOT_NONE) {
                 state[pos_i + j] = enc;
                 const int len = (int)(enc & 0xff);
                 change_count++;
                 upper += len < 1 ? 1 : len;
+                total += len - 1;
+                if (pos_i + j < k) st_trim += len - 1;
+                if (pos_i + j >= frag_len - k) en_trim += len - 1;
                 errors = __dadd_rn(errors, __dmul_rn((double)(len < 2 ? 1 : len - 1), scale));
-                if (change_count % BB_ALIGNMENT_INTERVAL != 0) continue;
-                // identity re-measurement (simulate.py:325-346)
-                int qpos = 0, qn = frag_len;
-                if (frag_len > BB_ALIGNMENT_SIZE) {
-                    BBRng wr;
-                    wr.init(seed, read);
-                    wr.stream(BB_PURPOSE_WINDOW, (uint32_t)n_align);
-                    qpos = (int)wr.randbelow((uint32_t)(frag_len - BB_ALIGNMENT_SIZE + 1));
-                    qn = BB_ALIGNMENT_SIZE;
+                if (change_count % BB_ALIGNMENT_INTERVAL == 0) need_align = true;
+            }
+            if (jres >= k && !need_align) { est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl)); jres = 0x7fffffff; }
+        }
+        __syncwarp();
+        if (__all_sync(BB_FULL, idle)) break;
+        // ---------------------------------------------------------------- phase B (simulate.py:325-346)
+        if (need_align) {
+            int qpos = 0, qn = frag_len;
+            if (frag_len > BB_ALIGNMENT_SIZE) {
+                BBRng wr;
+                wr.init(seed, read);
+                wr.stream(BB_PURPOSE_WINDOW, (uint32_t)n_align);
+                qpos = (int)wr.randbelow((uint32_t)(frag_len - BB_ALIGNMENT_SIZE + 1));
+                qn = BB_ALIGNMENT_SIZE;
+            }
+            int tm = 0, uw = 0;
+            for (int x = 0; x < qn; x++) {  // ''.join(new_fragment_bases[pos:pos2])
+                const uint32_t st = state[qpos + x];
+                if (st == BB_SLOT_NONE) { if (tm < pool.tbuf_cap) tbuf[tm] = frag[qpos + x]; tm++; }
+                else {
+                    const int sl = (int)(st & 0xff);
+                    for (int c = 0; c < sl; c++) { if (tm < pool.tbuf_cap) tbuf[tm] = bb_slot_char(em, st, c); tm++; }
+                    uw += sl < 1 ? 1 : sl;
                 }
-                int tm = 0, uw = 0;
-                for (int x = 0; x < qn; x++) {  // ''.join(new_fragment_bases[pos:pos2])
-                    const uint32_t st = state[qpos + x];
-                    if (st == BB_SLOT_NONE) { if (tm < tbuf_cap) tbuf[tm] = frag[qpos + x]; tm++; }
-                    else {
-                        const int sl = (int)(st & 0xff);
-                        for (int c = 0; c < sl; c++) { if (tm < tbuf_cap) tbuf[tm] = bb_slot_char(em, st, c); tm++; }
-                        uw += sl < 1 ? 1 : sl;
-                    }
-                }
-                {
-                    const int diff = qn > tm ? qn - tm : tm - qn;
-                    if (uw < diff) uw = diff;
-                    const int mx = qn > tm ? qn : tm;
-                    if (uw > mx) uw = mx;
-                }
-                BBLaneProb P;
-                bb_band(qn, tm, uw, P.a, P.b);
-                const int lw = bb_lane_words(P.a, P.b);
-                if (tm > tbuf_cap || tm > max_cols || lw > 8 || !bb_uses_traceback(qn, tm)) return false;
+            }
+            {
+                const int diff = qn > tm ? qn - tm : tm - qn;
+                if (uw < diff) uw = diff;
+                const int mx = qn > tm ? qn : tm;
+                if (uw > mx) uw = mx;
+            }
+            BBLaneProb P;
+            bb_band(qn, tm, uw, P.a, P.b);
+            const int lw = bb_lane_words(P.a, P.b);
+            if (tm > pool.tbuf_cap || tm > pool.max_cols || lw > 8 || !bb_uses_traceback(qn, tm)) {
+                fallback_list[atomicAdd(fallback_count, 1)] = r;  // the warp kernel redoes this read from scratch
+                have_read = false; need_align = false; jres = 0x7fffffff;
+            } else {
                 P.peq = B.fpeq + rd->fpeq_off; P.peq_bit0 = qpos + 32; P.q = frag + qpos; P.n = qn;
                 P.t = tbuf; P.m = tm; P.hist = hist;
                 int matches = 0, dels = 0, err = 0;
@@ -479,38 +532,11 @@ __device__ bool bb_lane_process_read(const BBBatchDev &B, const BBErrorModelDev 
                     errors = __dadd_rn(__dmul_rn(est_err, weight), __dmul_rn(errors, __dsub_rn(1.0, weight)));
                 }
                 n_align++;
+                need_align = false;
+                if (jres >= k) { est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl)); jres = 0x7fffffff; }
             }
-            est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl));
-            if (flags) { loop_count = n + 1; break; }
         }
-    }
-    int total = 0, st_trim = 0, en_trim = 0;
-    for (int x = 0; x < frag_len; x++) {
-        const uint32_t st = state[x];
-        const int len = st == BB_SLOT_NONE ? 1 : (int)(st & 0xff);
-        total += len;
-        if (x < k) st_trim += len;
-        if (x >= frag_len - k) en_trim += len;
-    }
-    rd->seq_len = total; rd->start_trim = st_trim; rd->end_trim = en_trim; rd->upper = upper;
-    rd->loop_count = (int)(loop_count > 0x7fffffff ? 0x7fffffff : loop_count);
-    rd->change_count = change_count; rd->n_align = n_align; rd->flags = flags;
-    rd->kc_loop = (int)((clock64() - clk0) >> 10);
-    return true;
-}
-
-__global__ void __launch_bounds__(64)
-bb_k_error_loop_lane(BBBatchDev B, BBErrorModelDev em, BBLanePool pool, unsigned long long seed, int *work_counter,
-                     int *fallback_list, int *fallback_count) {
-    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    uint2 *hist = pool.hist + gl * pool.hist_stride;
-    uint8_t *tbuf = pool.tbuf + gl * pool.tbuf_cap;
-    for (;;) {
-        const int w = atomicAdd(work_counter, 1);
-        if (w >= B.n_reads) break;
-        const int r = B.order[w];
-        if (!bb_lane_process_read(B, em, r, seed, hist, pool.max_cols, tbuf, pool.tbuf_cap))
-            fallback_list[atomicAdd(fallback_count, 1)] = r;
+        __syncwarp();
     }
 }
 
