@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -335,8 +336,11 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     ctx->h_order = order;
     // error loop: one thread per read, except the longest reads (a single thread would be the makespan): they get
     // a whole warp each, concurrently on a second stream
+    // (lane mode needs >= ~100k reads in flight to hide latency; below that every read gets a warp)
     std::vector<int> lane_order, long_order;
-    for (int r : order) (ctx->h_reads[(size_t)r].frag_len > 50000 ? long_order : lane_order).push_back(r);
+    bool lane_mode = n_reads >= 100000;
+    if (const char *e = std::getenv("BADREAD_B200_LANE_MODE")) lane_mode = (e[0] == '1');
+    for (int r : order) ((!lane_mode || ctx->h_reads[(size_t)r].frag_len > 50000) ? long_order : lane_order).push_back(r);
     ctx->n_lane_reads = (int)lane_order.size();
     ctx->n_long_reads = (int)long_order.size();
     int rc;
@@ -397,10 +401,12 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
         BB_CUDA(ctx, cudaMemcpyAsync(counters + 6, &h_n_long, sizeof(int), cudaMemcpyHostToDevice, st));
         BB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         BB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-        const int grid_long = std::min(ctx->sm_count * 2, (h_n_long + BB_WARPS_PER_CTA - 1) / BB_WARPS_PER_CTA);
+        const int grid_long = std::min(ctx->n_lane_reads > 0 ? ctx->sm_count * 2 : ctx->sm_count * 4,
+                                       (h_n_long + BB_WARPS_PER_CTA - 1) / BB_WARPS_PER_CTA);
         // scratch of warps [n_warps/2, ...) so that it cannot collide with the fall-back launch below
         bb_k_error_loop<<<grid_long, BB_WARPS_PER_CTA * 32, 0, ctx->stream2>>>(
-            B, ctx->em, ctx->pool, ctx->seed, counters + 5, ctx->d_order_long.as<int>(), counters + 6, 0, ctx->n_warps / 2);
+            B, ctx->em, ctx->pool, ctx->seed, counters + 5, ctx->d_order_long.as<int>(), counters + 6, 0,
+            ctx->n_lane_reads > 0 ? ctx->n_warps / 2 : 0);
         ctx->launches++;
         BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
     }
@@ -410,10 +416,11 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
                                                         ctx->n_lane_reads, ctx->d_fallback.as<int>(), counters + 3);
         ctx->launches++;
     }
-    // reads whose windows exceeded the lane-mode limits are redone by the warp kernel
-    bb_k_error_loop<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->seed, counters + 4,
-                                                                      ctx->d_fallback.as<int>(), counters + 3, 1, 0);
-    ctx->launches++;
+    if (ctx->n_lane_reads > 0) {  // reads whose windows exceeded the lane-mode limits are redone by the warp kernel
+        bb_k_error_loop<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->seed, counters + 4,
+                                                                          ctx->d_fallback.as<int>(), counters + 3, 1, 0);
+        ctx->launches++;
+    }
     if (ctx->n_long_reads > 0) BB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     // host scan of the joined lengths -> offsets of the per-read regions in seq / ops / dcnt / qual / out
