@@ -43,7 +43,8 @@ struct BBScratch {
 
 struct BBEmit {      // where the final alignment is written (nullptr members => counts only)
     uint8_t *ops;    // per query base: BB_OP_EQ / BB_OP_X / BB_OP_I
-    uint16_t *dcnt;  // per query base: 'D' columns between this base and the next (saturating)
+    unsigned int *dcnt;  // per query base: 'D' columns between this base and the next (updated atomically: leaves of
+                         // one read may run concurrently and share the base at their boundary)
     int *lead_del;   // 'D' columns before the first query base
 };
 
@@ -463,10 +464,7 @@ __device__ void bb_traceback(const uint8_t *q, int n, const uint8_t *t, int m, i
                 if (EMIT && lane == 0) em.ops[qbase + i] = BB_OP_I;
                 i--;
             } else if ((lmask >> r) & 1u) {
-                if (EMIT && lane == 0) {
-                    const uint16_t v = em.dcnt[qbase + i];
-                    if (v != 0xffff) em.dcnt[qbase + i] = v + 1;
-                }
+                if (EMIT && lane == 0) atomicAdd(&em.dcnt[qbase + i], 1u);
                 dels++;
                 j--;
             } else {
@@ -482,12 +480,8 @@ __device__ void bb_traceback(const uint8_t *q, int n, const uint8_t *t, int m, i
         if (j >= 0) {  // row boundary reached: the remaining target characters are deletions before q[0]
             dels += j + 1;
             if (EMIT && lane == 0) {
-                if (qbase > 0) {
-                    const uint32_t v = (uint32_t)em.dcnt[qbase - 1] + (uint32_t)(j + 1);
-                    em.dcnt[qbase - 1] = v > 0xffffu ? 0xffff : (uint16_t)v;
-                } else {
-                    *em.lead_del += j + 1;
-                }
+                if (qbase > 0) atomicAdd(&em.dcnt[qbase - 1], (unsigned int)(j + 1));
+                else atomicAdd(em.lead_del, j + 1);
             }
         }
     }
@@ -529,13 +523,88 @@ __device__ __forceinline__ void bb_emit_all_deleted(int m, BBEmit em, int qbase,
     // empty query: edlib.cpp obtainAlignment emits |t| deletions
     cnt.dels += m;
     if (emit && (threadIdx.x & 31) == 0) {
-        if (qbase > 0) {
-            const uint32_t v = (uint32_t)em.dcnt[qbase - 1] + (uint32_t)m;
-            em.dcnt[qbase - 1] = v > 0xffffu ? 0xffff : (uint16_t)v;
+        if (qbase > 0) atomicAdd(&em.dcnt[qbase - 1], (unsigned int)m);
+        else atomicAdd(em.lead_del, m);
+    }
+}
+
+// One Hirschberg node by one warp (edlib.cpp obtainAlignmentHirschberg): forward pass over the left half of the
+// target, reverse pass over the right half, split row by edlib's rule.  q / t point at the read's first query /
+// target character, the node is q[q0, q0+nn) x t[t0, t0+mm); band (a, b) must admit every optimal path.
+// best < 0 on entry (root): the minimum of forward + reverse scores over the split column is the edit distance and
+// is returned in best.  Returns 0 or an error code.
+template <int MAXL>
+__device__ int bb_node_warp(const uint8_t *q, const uint8_t *t, int q0, int nn, int t0, int mm, int a, int b,
+                            const BBScratch &sc, int &best, int &split, int &ls, int &rs, int qabs = 0) {
+    const int lane = threadIdx.x & 31;
+    const int left_w = mm / 2, right_w = mm - left_w;
+    const int loL = max(0, left_w - 1 - a), hiL = min(nn - 1, left_w - 1 + b);
+    const int loR = max(0, right_w - 1 - a), hiR = min(nn - 1, right_w - 1 + b);
+    if (hiL - loL + 1 > sc.lr_cap || hiR - loR + 1 > sc.lr_cap) return 16;
+    {
+        auto make_prob = [&](bool rev) {
+            BBProb P;
+            P.n = nn; P.a = a; P.b = b; P.peq = sc.peq; P.hist = nullptr; P.nb_alloc = 0;
+            if (!rev) {
+                P.q = q + q0; P.qs = 1; P.t = t + t0; P.ts = 1; P.ncols = left_w;
+                P.peq_bit0 = qabs + q0 + 32; P.cols_out = sc.L; P.cols_lo = loL;
+            } else {
+                P.q = q + q0 + nn - 1; P.qs = -1; P.t = t + t0 + mm - 1; P.ts = -1; P.ncols = right_w;
+                P.peq_bit0 = qabs + q0 + nn - 1 + 32; P.cols_out = sc.R; P.cols_lo = loR;
+            }
+            return P;
+        };
+        const int L2 = bb_pick_L<MAXL>(a, b, 16);
+        if (L2 > 0) {  // forward and reverse pass side by side in two 16-lane groups
+            const BBProb PG = make_prob(lane >= 16);
+            bb_band_dispatch<false, true, MAXL>(PG, 16, L2);
         } else {
-            *em.lead_del += m;
+            const int L1 = bb_pick_L<MAXL>(a, b, 32);
+            if (L1 > 0) {
+                bb_band_dispatch<false, true, MAXL>(make_prob(false), 32, L1);
+                bb_band_dispatch<false, true, MAXL>(make_prob(true), 32, L1);
+            } else {
+                if (mm > sc.hbuf_cap) return 4;
+                bb_strip_pass<false, true>(q + q0, 1, nn, t + t0, 1, left_w, a, b, nullptr, 0, sc.L, loL, sc.hbuf);
+                bb_strip_pass<false, true>(q + q0 + nn - 1, -1, nn, t + t0 + mm - 1, -1, right_w, a, b, nullptr, 0,
+                                           sc.R, loR, sc.hbuf);
+            }
         }
     }
+    __syncwarp();
+    int rlo = max(loL, nn - 2 - hiR); if (rlo < 0) rlo = 0;
+    int rhi = min(hiL, nn - 2 - loR); if (rhi > nn - 2) rhi = nn - 2;
+    const bool have_top = nn - 1 >= loR && nn - 1 <= hiR;  // empty query prefix on the left
+    const bool have_bot = nn - 1 >= loL && nn - 1 <= hiL;  // empty query suffix on the right
+    if (best < 0) {  // root: every optimal path crosses the split column, so the minimum sum is the distance
+        int mn = BB_INF;
+        for (int r = rlo + lane; r <= rhi; r += 32) mn = min(mn, sc.L[r - loL] + sc.R[(nn - 2 - r) - loR]);
+        if (have_top) mn = min(mn, left_w + sc.R[(nn - 1) - loR]);
+        if (have_bot) mn = min(mn, sc.L[(nn - 1) - loL] + right_w);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(BB_FULL, mn, d));
+        best = mn;
+    }
+    // smallest interior row r in [0, nn-2] with L[r] + R[nn-2-r] == best
+    split = -2; ls = 0; rs = 0;
+    for (int base = rlo; base <= rhi; base += 32) {
+        const int r = base + lane;
+        bool hit = false;
+        if (r <= rhi) hit = (sc.L[r - loL] + sc.R[(nn - 2 - r) - loR] == best);
+        const uint32_t hm = __ballot_sync(BB_FULL, hit);
+        if (hm) { split = base + __ffs(hm) - 1; break; }
+    }
+    if (split >= 0) { ls = sc.L[split - loL]; rs = sc.R[(nn - 2 - split) - loR]; }
+    if (split == -2 && have_top) {
+        const int v = sc.R[(nn - 1) - loR];
+        if (left_w + v == best) { split = -1; ls = left_w; rs = v; }
+    }
+    if (split == -2 && have_bot) {
+        const int v = sc.L[(nn - 1) - loL];
+        if (v + right_w == best) { split = nn - 1; ls = v; rs = right_w; }
+    }
+    __syncwarp();
+    return split == -2 ? 32 : 0;
 }
 
 // edlib.align(q, t, task='path') for one pair by one warp. q[0] is character `qabs` of the read whose match
@@ -602,68 +671,12 @@ __device__ void bb_align(const uint8_t *q, int n, const uint8_t *t, int m, int k
             if (cnt.err) return;
             continue;
         }
-        const int left_w = mm / 2, right_w = mm - left_w;
         bb_band(nn, mm, best, a, b);
-        const int loL = max(0, left_w - 1 - a), hiL = min(nn - 1, left_w - 1 + b);
-        const int loR = max(0, right_w - 1 - a), hiR = min(nn - 1, right_w - 1 + b);
-        if (hiL - loL + 1 > sc.lr_cap || hiR - loR + 1 > sc.lr_cap) { cnt.err |= 16; return; }
-        {
-            auto make_prob = [&](bool rev) {
-                BBProb P;
-                P.n = nn; P.a = a; P.b = b; P.peq = sc.peq; P.hist = nullptr; P.nb_alloc = 0;
-                if (!rev) {
-                    P.q = q + q0; P.qs = 1; P.t = t + t0; P.ts = 1; P.ncols = left_w;
-                    P.peq_bit0 = qabs + q0 + 32; P.cols_out = sc.L; P.cols_lo = loL;
-                } else {
-                    P.q = q + q0 + nn - 1; P.qs = -1; P.t = t + t0 + mm - 1; P.ts = -1; P.ncols = right_w;
-                    P.peq_bit0 = qabs + q0 + nn - 1 + 32; P.cols_out = sc.R; P.cols_lo = loR;
-                }
-                return P;
-            };
-            const int L2 = bb_pick_L<MAXL>(a, b, 16);
-            if (L2 > 0) {  // forward and reverse pass side by side in two 16-lane groups
-                const BBProb PG = make_prob(lane >= 16);
-                bb_band_dispatch<false, true, MAXL>(PG, 16, L2);
-            } else {
-                const int L1 = bb_pick_L<MAXL>(a, b, 32);
-                if (L1 > 0) {
-                    bb_band_dispatch<false, true, MAXL>(make_prob(false), 32, L1);
-                    bb_band_dispatch<false, true, MAXL>(make_prob(true), 32, L1);
-                } else {
-                    if (mm > sc.hbuf_cap) { cnt.err |= 4; return; }
-                    bb_strip_pass<false, true>(q + q0, 1, nn, t + t0, 1, left_w, a, b, nullptr, 0, sc.L, loL, sc.hbuf);
-                    bb_strip_pass<false, true>(q + q0 + nn - 1, -1, nn, t + t0 + mm - 1, -1, right_w, a, b, nullptr, 0,
-                                               sc.R, loR, sc.hbuf);
-                }
-            }
-        }
-        __syncwarp();
-        // smallest interior row r in [0, nn-2] with L[r] + R[nn-2-r] == best
-        int split = -2, ls = 0, rs = 0;
-        {
-            int rlo = max(loL, nn - 2 - hiR); if (rlo < 0) rlo = 0;
-            int rhi = min(hiL, nn - 2 - loR); if (rhi > nn - 2) rhi = nn - 2;
-            for (int base = rlo; base <= rhi; base += 32) {
-                const int r = base + lane;
-                bool hit = false;
-                if (r <= rhi) hit = (sc.L[r - loL] + sc.R[(nn - 2 - r) - loR] == best);
-                const uint32_t hm = __ballot_sync(BB_FULL, hit);
-                if (hm) { split = base + __ffs(hm) - 1; break; }
-            }
-            if (split >= 0) { ls = sc.L[split - loL]; rs = sc.R[(nn - 2 - split) - loR]; }
-        }
-        if (split == -2 && nn - 1 >= loR && nn - 1 <= hiR) {  // empty query prefix on the left
-            const int v = sc.R[(nn - 1) - loR];
-            if (left_w + v == best) { split = -1; ls = left_w; rs = v; }
-        }
-        if (split == -2 && nn - 1 >= loL && nn - 1 <= hiL) {  // empty query suffix on the right
-            const int v = sc.L[(nn - 1) - loL];
-            if (v + right_w == best) { split = nn - 1; ls = v; rs = right_w; }
-        }
-#ifdef BB_EMU_DEBUG
-        if (lane == 0) printf("node q0=%d nn=%d t0=%d mm=%d best=%d a=%d b=%d split=%d ls=%d rs=%d\n", q0, nn, t0, mm, best, a, b, split, ls, rs);
-#endif
-        if (split == -2) { cnt.err |= 32; return; }
+        const int left_w = mm / 2;
+        int split = 0, ls = 0, rs = 0, node_best = best;
+        const int nerr = bb_node_warp<MAXL>(q, t, q0, nn, t0, mm, a, b, sc, node_best, split, ls, rs, qabs);
+        if (nerr) { cnt.err |= nerr; return; }
+        const int right_w = mm - left_w;
         if (sp + 2 > sc.stack_cap) { cnt.err |= 64; return; }
         __syncwarp();
         if (lane == 0) {

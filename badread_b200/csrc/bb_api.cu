@@ -64,7 +64,9 @@ struct bb_ctx {
     // scratch
     int n_warps = 0;
     BBScratchPool pool{};
-    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_lhist, s_ltbuf;
+    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_lhist, s_ltbuf, s_leafhist;
+    DevBuf q_node[3][2], q_leaf[2], q_count;
+    bool use_tasks = true;
     BBLanePool lane_pool{};
     int n_lanes = 0;
 
@@ -134,6 +136,7 @@ extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     // persistent warps: 4 CTAs of 4 warps per SM for the warp-per-read kernels
     ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
+    if (const char *e = std::getenv("BADREAD_B200_ALIGN_TASKS")) ctx->use_tasks = (e[0] != '0');
     *out = ctx;
     return BB_OK;
 }
@@ -148,7 +151,9 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_reads, &ctx->d_frag, &ctx->d_state, &ctx->d_seq, &ctx->d_ops, &ctx->d_dcnt,
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_lhist, &ctx->s_ltbuf,
-                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback};
+                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->q_leaf[0], &ctx->q_leaf[1],
+                      &ctx->q_count, &ctx->q_node[0][0], &ctx->q_node[0][1], &ctx->q_node[1][0], &ctx->q_node[1][1],
+                      &ctx->q_node[2][0], &ctx->q_node[2][1]};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
@@ -284,7 +289,7 @@ static BBBatchDev batch_dev(bb_ctx *ctx) {
     B.state = ctx->d_state.as<uint32_t>();
     B.seq = ctx->d_seq.as<uint8_t>();
     B.ops = ctx->d_ops.as<uint8_t>();
-    B.dcnt = ctx->d_dcnt.as<uint16_t>();
+    B.dcnt = ctx->d_dcnt.as<unsigned int>();
     B.qual = ctx->d_qual.as<uint8_t>();
     B.out_seq = ctx->d_out_seq.as<uint8_t>();
     B.out_qual = ctx->d_out_qual.as<uint8_t>();
@@ -377,6 +382,56 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     return BB_OK;
 }
 
+// Final alignment as level-synchronous tasks (bb_tasks.cuh): roots are classified here, every level of all
+// reads' Hirschberg trees is three launches (wide-warp, lean-warp, lane nodes), leaves run at the end.
+static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<BBReadDev> &reads) {
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->n_reads;
+    const int cap_node = (int)std::min<int64_t>(ctx->seq_total / 256 + 4ll * n + 1024, 0x7ffffff0);
+    const int cap_leaf = cap_node;
+    for (int c = 0; c < 3; c++)
+        for (int p = 0; p < 2; p++) BB_CUDA(ctx, ctx->q_node[c][p].ensure((size_t)cap_node * sizeof(BBNode)));
+    for (int w = 0; w < 2; w++) BB_CUDA(ctx, ctx->q_leaf[w].ensure((size_t)cap_leaf * sizeof(BBNode)));
+    BB_CUDA(ctx, ctx->q_count.ensure(512 * sizeof(int)));
+    const int lane_ctas = ctx->sm_count * 4;  // 64-thread CTAs of the lane kernels
+    BB_CUDA(ctx, ctx->s_leafhist.ensure((size_t)lane_ctas * 64 * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
+    BBQueues Q;
+    for (int c = 0; c < 3; c++)
+        for (int p = 0; p < 2; p++) Q.node[c][p] = ctx->q_node[c][p].as<BBNode>();
+    Q.leaf[0] = ctx->q_leaf[0].as<BBNode>(); Q.leaf[1] = ctx->q_leaf[1].as<BBNode>();
+    int *cnt = ctx->q_count.as<int>();
+    Q.count = cnt; Q.overflow = cnt + 8; Q.cap_node = cap_node; Q.cap_leaf = cap_leaf;
+    BB_CUDA(ctx, cudaMemsetAsync(cnt, 0, 512 * sizeof(int), st));
+    bb_k_push_roots<<<(n + 255) / 256, 256, 0, st>>>(B, Q);
+    ctx->launches++;
+    int *cursor = cnt + 16;
+    const int grid_wide = ctx->sm_count * 2, grid_lean = ctx->sm_count * 3;
+    const int max_levels = 40;  // the target halves at every level: 2^40 columns is beyond any read
+    for (int level = 0; level < max_levels; level++) {
+        const int p = level & 1;
+        // the queues of the next level start empty
+        for (int c = 0; c < 3; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt + c * 2 + (p ^ 1), 0, sizeof(int), st));
+        bb_k_node_warp<16><<<grid_wide, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, BBQ_NODE_WIDE, p, cursor++);
+        bb_k_node_warp<4><<<grid_lean, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, BBQ_NODE_LEAN, p, cursor++);
+        bb_k_node_lane<<<lane_ctas, 64, 0, st>>>(B, Q, p, cursor++);
+        ctx->launches += 3;
+        if (level >= 3 && (level & 3) == 3) {  // every few levels: stop as soon as the queues are empty
+            int h[6];
+            BB_CUDA(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
+            BB_CUDA(ctx, cudaStreamSynchronize(st));
+            if (h[0 + (p ^ 1)] + h[2 + (p ^ 1)] + h[4 + (p ^ 1)] == 0) break;
+        }
+    }
+    bb_k_leaf_warp<<<grid_wide, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, cursor++);
+    bb_k_leaf_lane<<<lane_ctas, 64, 0, st>>>(B, Q, ctx->s_leafhist.as<uint2>(), cursor++);
+    ctx->launches += 2;
+    int h_over = 0;
+    BB_CUDA(ctx, cudaMemcpyAsync(&h_over, Q.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_over) return set_err(ctx, BB_ERR_INTERNAL, "alignment task queue overflow");
+    return BB_OK;
+}
+
 extern "C" int bb_batch_run(bb_ctx *ctx) {
     if (!ctx) return BB_ERR_ARG;
     if (!ctx->uploaded) return set_err(ctx, BB_ERR_STATE, "bb_batch_run: no batch uploaded");
@@ -460,7 +515,7 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
     if ((rc0 = upload(ctx, ctx->d_order_large, large.data(), large.size()))) return rc0;
     BB_CUDA(ctx, ctx->d_seq.ensure((size_t)seq_off + 16));
     BB_CUDA(ctx, ctx->d_ops.ensure((size_t)seq_off + 16));
-    BB_CUDA(ctx, ctx->d_dcnt.ensure(((size_t)seq_off + 16) * sizeof(uint16_t)));
+    BB_CUDA(ctx, ctx->d_dcnt.ensure(((size_t)seq_off + 16) * sizeof(unsigned int)));
     BB_CUDA(ctx, ctx->d_qual.ensure((size_t)seq_off + 16));
     BB_CUDA(ctx, ctx->d_speq.ensure(((size_t)speq_off + 4) * sizeof(uint4)));
     BB_CUDA(ctx, ctx->d_out_seq.ensure((size_t)out_off + 16));
@@ -469,22 +524,28 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
     if (rc) return rc;
     B = batch_dev(ctx);
     BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, reads.data(), (size_t)n * sizeof(BBReadDev), cudaMemcpyHostToDevice, st));
-    BB_CUDA(ctx, cudaMemsetAsync(ctx->d_dcnt.p, 0, ((size_t)seq_off + 16) * sizeof(uint16_t), st));
+    BB_CUDA(ctx, cudaMemsetAsync(ctx->d_dcnt.p, 0, ((size_t)seq_off + 16) * sizeof(unsigned int), st));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     bb_k_join<<<n, 256, 0, st>>>(B, ctx->em);
     ctx->launches++;
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    // long / noisy reads (wide Ukkonen band) first with the MAXL = 16 build, the rest with the lean MAXL = 2 build
-    if (!large.empty()) {
-        bb_k_final_align<16><<<grid_large, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 1,
-                                                                         ctx->d_order_large.as<int>(), (int)large.size(), 0);
-        ctx->launches++;
-    }
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-    if (!small.empty()) {
-        bb_k_final_align<2><<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 2,
-                                                                       ctx->d_order_small.as<int>(), (int)small.size(), 0);
-        ctx->launches++;
+    if (ctx->use_tasks) {
+        int rc2 = run_align_tasks(ctx, B, reads);
+        if (rc2) return rc2;
+        BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    } else {
+        // depth-first variant: one warp walks the whole Hirschberg tree of a read (kept for comparison / testing)
+        if (!large.empty()) {
+            bb_k_final_align<16><<<grid_large, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 1,
+                                                                             ctx->d_order_large.as<int>(), (int)large.size(), 0);
+            ctx->launches++;
+        }
+        BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+        if (!small.empty()) {
+            bb_k_final_align<2><<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 2,
+                                                                           ctx->d_order_small.as<int>(), (int)small.size(), 0);
+            ctx->launches++;
+        }
     }
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
     bb_k_qscores<<<n, 256, 0, st>>>(B, ctx->qm, ctx->seed);
@@ -572,13 +633,13 @@ static int align_pair_device(bb_ctx *ctx, const uint8_t *q, int n, const uint8_t
     if ((rc = upload(ctx, dq, q, (size_t)n))) return rc;
     if ((rc = upload(ctx, dt, t, (size_t)m))) return rc;
     BB_CUDA(ctx, dops.ensure((size_t)n + 16));
-    BB_CUDA(ctx, ddcnt.ensure(((size_t)n + 16) * sizeof(uint16_t)));
+    BB_CUDA(ctx, ddcnt.ensure(((size_t)n + 16) * sizeof(unsigned int)));
     BB_CUDA(ctx, dout.ensure(8 * sizeof(int)));
     if ((rc = ensure_scratch(ctx, std::max(n, m), std::max(n, m), std::max(n, m)))) return rc;
-    BB_CUDA(ctx, cudaMemsetAsync(ddcnt.p, 0, ((size_t)n + 16) * sizeof(uint16_t), ctx->stream));
+    BB_CUDA(ctx, cudaMemsetAsync(ddcnt.p, 0, ((size_t)n + 16) * sizeof(unsigned int), ctx->stream));
     BB_CUDA(ctx, cudaMemsetAsync(dout.p, 0, 8 * sizeof(int), ctx->stream));
     bb_k_align_pair<<<1, 32, 0, ctx->stream>>>(dq.as<uint8_t>(), n, dt.as<uint8_t>(), m, std::max(n, m), ctx->pool,
-                                                dops.as<uint8_t>(), ddcnt.as<uint16_t>(), dout.as<int>());
+                                                dops.as<uint8_t>(), ddcnt.as<unsigned int>(), dout.as<int>());
     ctx->launches++;
     BB_CUDA(ctx, cudaMemcpyAsync(out5, dout.p, 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -599,10 +660,10 @@ extern "C" int bb_align_path(bb_ctx *ctx, const uint8_t *query, int32_t q_len, c
     int out5[5] = {0, 0, 0, 0, 0};
     int rc = align_pair_device(ctx, query, q_len, target, t_len, dq, dt, dops, ddcnt, dout, out5);
     std::vector<uint8_t> ops((size_t)q_len);
-    std::vector<uint16_t> dcnt((size_t)q_len);
+    std::vector<unsigned int> dcnt((size_t)q_len);
     if (rc == BB_OK) {
         cudaMemcpy(ops.data(), dops.p, (size_t)q_len, cudaMemcpyDeviceToHost);
-        cudaMemcpy(dcnt.data(), ddcnt.p, (size_t)q_len * sizeof(uint16_t), cudaMemcpyDeviceToHost);
+        cudaMemcpy(dcnt.data(), ddcnt.p, (size_t)q_len * sizeof(unsigned int), cudaMemcpyDeviceToHost);
     }
     dq.release(); dt.release(); dops.release(); ddcnt.release(); dout.release();
     if (rc) return rc;
@@ -615,8 +676,7 @@ extern "C" int bb_align_path(bb_ctx *ctx, const uint8_t *query, int32_t q_len, c
     for (int x = 0; x < out5[3]; x++) ops_out[w++] = 'D';
     for (int i = 0; i < q_len; i++) {
         ops_out[w++] = (uint8_t)sym[ops[(size_t)i] < 3 ? ops[(size_t)i] : 0];
-        if (dcnt[(size_t)i] == 0xffff) return set_err(ctx, BB_ERR_CAPACITY, "deletion run longer than 65534");
-        for (int x = 0; x < dcnt[(size_t)i]; x++) ops_out[w++] = 'D';
+        for (unsigned int x = 0; x < dcnt[(size_t)i]; x++) ops_out[w++] = 'D';
     }
     if (w != total) return set_err(ctx, BB_ERR_INTERNAL, "column count mismatch");
     return BB_OK;
@@ -637,7 +697,7 @@ extern "C" int bb_get_qscores(bb_ctx *ctx, uint64_t read_index, const uint8_t *s
         if (e != cudaSuccess) rc = set_err(ctx, BB_ERR_CUDA, cudaGetErrorString(e));
     }
     if (rc == BB_OK) {
-        bb_k_qscores_pair<<<(seq_len + 255) / 256, 256, 0, ctx->stream>>>(dops.as<uint8_t>(), ddcnt.as<uint16_t>(), seq_len,
+        bb_k_qscores_pair<<<(seq_len + 255) / 256, 256, 0, ctx->stream>>>(dops.as<uint8_t>(), ddcnt.as<unsigned int>(), seq_len,
                                                                             ctx->qm, ctx->seed, read_index, dqual.as<uint8_t>());
         ctx->launches++;
         cudaMemcpyAsync(qual_out, dqual.p, (size_t)seq_len, cudaMemcpyDeviceToHost, ctx->stream);

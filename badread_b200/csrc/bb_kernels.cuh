@@ -74,7 +74,7 @@ struct BBBatchDev {
     uint32_t *state;
     uint8_t *seq;
     uint8_t *ops;
-    uint16_t *dcnt;
+    unsigned int *dcnt;
     uint8_t *qual;
     uint8_t *out_seq, *out_qual;
     uint4 *fpeq, *speq;
@@ -639,7 +639,7 @@ __device__ __forceinline__ int bb_qm_find(const BBQScoreModelDev &qm, unsigned l
 // QScoreModel.get_qscore :273-287).  partial_cigar = ops[s] D^dcnt[s] ops[s+1] ... ops[e]; a CIGAR that is
 // not in the model loses its first and last symbol and then its outer D's, which is exactly the window
 // [s+1, e-1] of the same form.
-__device__ __forceinline__ uint8_t bb_qscore_base(const BBQScoreModelDev &qm, const uint8_t *ops, const uint16_t *dcnt,
+__device__ __forceinline__ uint8_t bb_qscore_base(const BBQScoreModelDev &qm, const uint8_t *ops, const unsigned int *dcnt,
                                                   int n, int i, unsigned long long seed, unsigned long long read) {
     int mm = (qm.kmer_size - 1) / 2;
     if (mm > i) mm = i;
@@ -654,9 +654,9 @@ __device__ __forceinline__ uint8_t bb_qscore_base(const BBQScoreModelDev &qm, co
             key = (key << 2) | ops[x];
             len++;
             if (x < e) {
-                const int d = dcnt[x];
-                if (len + d > 31) ok = false;
-                else { for (int c = 0; c < d; c++) key = (key << 2) | 3ull; len += d; }
+                const unsigned int d = dcnt[x];
+                if (d > 31u || len + (int)d > 31) ok = false;
+                else { for (unsigned int c = 0; c < d; c++) key = (key << 2) | 3ull; len += (int)d; }
             }
         }
         if (ok && len <= 31) row = bb_qm_find(qm, key);
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(256) bb_k_qscores(BBBatchDev B, BBQScoreModelD
     const BBReadDev rd = B.reads[r];
     const int n = rd.seq_len;
     const uint8_t *ops = B.ops + rd.seq_off;
-    const uint16_t *dcnt = B.dcnt + rd.seq_off;
+    const unsigned int *dcnt = B.dcnt + rd.seq_off;
     uint8_t *qual = B.qual + rd.seq_off;
     const unsigned long long read = B.read_index[r];
     for (int i = threadIdx.x; i < n; i += blockDim.x)
@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(256) bb_k_compact(BBBatchDev B) {
 // ------------------------------------------------------------------------------------------------ single-pair entry points
 // edlib.align(query, target, task='path') for one pair (diagnostics / tests): ops + dcnt + lead_del + counts.
 __global__ void __launch_bounds__(32) bb_k_align_pair(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper,
-                                                      BBScratchPool pool, uint8_t *ops, uint16_t *dcnt, int *out4) {
+                                                      BBScratchPool pool, uint8_t *ops, unsigned int *dcnt, int *out4) {
     const BBScratch sc = pool.for_warp(0);
     BBEmit em = {ops, dcnt, &out4[3]};
     BBAlnCounts cnt = {0, 0, 0, 0};
@@ -711,9 +711,11 @@ __global__ void __launch_bounds__(32) bb_k_align_pair(const uint8_t *q, int n, c
     if ((threadIdx.x & 31) == 0) { out4[0] = cnt.matches; out4[1] = cnt.dels; out4[2] = cnt.dist; out4[4] = cnt.err; }
 }
 
-__global__ void __launch_bounds__(256) bb_k_qscores_pair(const uint8_t *ops, const uint16_t *dcnt, int n,
+__global__ void __launch_bounds__(256) bb_k_qscores_pair(const uint8_t *ops, const unsigned int *dcnt, int n,
                                                          BBQScoreModelDev qm, unsigned long long seed,
                                                          unsigned long long read, uint8_t *qual) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         qual[i] = bb_qscore_base(qm, ops, dcnt, n, i, seed, read);
 }
+
+#include "bb_tasks.cuh"

@@ -1,0 +1,438 @@
+// bb_tasks.cuh — the final alignment (edlib.align(seq, fragment), qscore_model.py:37) as level-synchronous tasks.
+//
+// edlib's recursion (Hirschberg split on the target until its traceback estimate drops below 1 MiB, then a leaf
+// traceback) is a tree whose nodes are independent once their parent has chosen the split row.  Instead of one
+// warp walking the tree of one read depth-first, every level of all reads' trees is processed by a few kernel
+// launches:
+//   node kernels   forward pass over the left half + reverse pass over the right half of the node, split row by
+//                  edlib's rule, children appended to the next level's queues (or to the leaf queues)
+//   leaf kernels   forward pass with history + traceback, emitting the per-base ops / deletion counts
+// Tasks are routed by band width: narrow bands go to LANE kernels (one task per thread, persistent lanes that all
+// execute the same column step; 32 tasks per warp), wide bands to WARP kernels (the wavefront of bb_align.cuh).
+// The root needs no separate distance pass: with the band derived from the injected-edit bound, the minimum of
+// forward + reverse scores over the split column IS the edit distance.
+#pragma once
+#include <cstdint>
+
+#include "bb_align.cuh"
+#include "bb_lane.cuh"
+
+#define BB_NODE_LW 16        // window words of the lane node kernel (bands up to 32*14 rows)
+#define BB_LEAF_LW 8         // window words of the lane leaf kernel
+#define BB_LEAF_LANE_COLS 2048
+#define BB_WARP_LEAN_BAND 1792  // a + b the MAXL = 4 warp build can pair (448 * 4)
+
+enum { BBQ_NODE_LANE = 0, BBQ_NODE_LEAN = 1, BBQ_NODE_WIDE = 2, BBQ_LEAF_LANE = 3, BBQ_LEAF_WARP = 4, BBQ_N = 5 };
+
+struct BBNode { int r, q0, nn, t0, mm, best; };  // best < 0: root (band from the read's edit bound)
+
+struct BBQueues {
+    BBNode *node[3][2];  // [class][level parity]
+    BBNode *leaf[2];     // lane, warp
+    int *count;          // node counts: [class*2 + parity]; leaf counts: [6 + which]
+    int *overflow;
+    int cap_node, cap_leaf;
+};
+
+struct BBAlignOut {      // where a read's alignment goes
+    uint8_t *ops;
+    unsigned int *dcnt;
+    BBReadDev *rd;
+};
+
+__device__ __forceinline__ void bb_add_dels(const BBAlignOut &o, int qidx_after, int count) {
+    // `count` deletion columns that follow query base qidx_after (-1: before the first base)
+    if (count <= 0) return;
+    if (qidx_after >= 0) atomicAdd(&o.dcnt[qidx_after], (unsigned int)count);
+    else atomicAdd(&o.rd->lead_del, count);
+}
+
+// Band a task will be processed with (the root uses the injected-edit bound of its read).
+__device__ __forceinline__ void bb_task_band(const BBNode &nd, int upper, int &a, int &b) {
+    int k = nd.best >= 0 ? nd.best : upper;
+    const int diff = nd.nn > nd.mm ? nd.nn - nd.mm : nd.mm - nd.nn;
+    if (k < diff) k = diff;
+    const int mx = nd.nn > nd.mm ? nd.nn : nd.mm;
+    if (k > mx) k = mx;
+    bb_band(nd.nn, nd.mm, k, a, b);
+}
+
+// Queue a child (or finish it on the spot when one side is empty, edlib.cpp obtainAlignment).
+__device__ void bb_push_task(const BBQueues &Q, int next_parity, const BBAlignOut &o, const BBNode &nd, int upper) {
+    if (nd.nn == 0) {
+        atomicAdd(&o.rd->dels, nd.mm);
+        bb_add_dels(o, nd.q0 - 1, nd.mm);
+        return;
+    }
+    if (nd.mm == 0) {
+        for (int x = 0; x < nd.nn; x++) o.ops[nd.q0 + x] = BB_OP_I;
+        return;
+    }
+    int a, b;
+    bb_task_band(nd, upper, a, b);
+    const int lw = bb_lane_words(a, b);
+    if (bb_uses_traceback(nd.nn, nd.mm)) {
+        const int which = (lw <= BB_LEAF_LW && nd.mm <= BB_LEAF_LANE_COLS) ? 0 : 1;
+        const int idx = atomicAdd(&Q.count[6 + which], 1);
+        if (idx >= Q.cap_leaf) { atomicExch(Q.overflow, 1); return; }
+        Q.leaf[which][idx] = nd;
+    } else {
+        const int cls = lw <= BB_NODE_LW ? BBQ_NODE_LANE : (a + b <= BB_WARP_LEAN_BAND ? BBQ_NODE_LEAN : BBQ_NODE_WIDE);
+        const int idx = atomicAdd(&Q.count[cls * 2 + next_parity], 1);
+        if (idx >= Q.cap_node) { atomicExch(Q.overflow, 1); return; }
+        Q.node[cls][next_parity][idx] = nd;
+    }
+}
+
+// edlib.cpp obtainAlignmentHirschberg's choice of the split row from the two column-score arrays
+// (L[r - loL] = D(q[0..r], t[0..left_w)), R[x - loR] = D(rq[0..x], rt[0..right_w))), sequential version.
+// best < 0 (root): the minimum over all splits is the edit distance.  Returns false if no split matches.
+__device__ bool bb_choose_split_seq(const int *L, int loL, int hiL, const int *R, int loR, int hiR, int nn, int left_w,
+                                    int right_w, int &best, int &split, int &ls, int &rs) {
+    int rlo = max(loL, nn - 2 - hiR); if (rlo < 0) rlo = 0;
+    int rhi = min(hiL, nn - 2 - loR); if (rhi > nn - 2) rhi = nn - 2;
+    const bool have_top = nn - 1 >= loR && nn - 1 <= hiR;  // empty query prefix on the left
+    const bool have_bot = nn - 1 >= loL && nn - 1 <= hiL;  // empty query suffix on the right
+    if (best < 0) {
+        int mn = BB_INF;
+        for (int r = rlo; r <= rhi; r++) mn = min(mn, L[r - loL] + R[(nn - 2 - r) - loR]);
+        if (have_top) mn = min(mn, left_w + R[(nn - 1) - loR]);
+        if (have_bot) mn = min(mn, L[(nn - 1) - loL] + right_w);
+        best = mn;
+    }
+    for (int r = rlo; r <= rhi; r++) {
+        const int lv = L[r - loL], rv = R[(nn - 2 - r) - loR];
+        if (lv + rv == best) { split = r; ls = lv; rs = rv; return true; }
+    }
+    if (have_top) {
+        const int v = R[(nn - 1) - loR];
+        if (left_w + v == best) { split = -1; ls = left_w; rs = v; return true; }
+    }
+    if (have_bot) {
+        const int v = L[(nn - 1) - loL];
+        if (v + right_w == best) { split = nn - 1; ls = v; rs = right_w; return true; }
+    }
+    return false;
+}
+
+// Roots of all reads of the batch (same routing rule as every other task).
+__global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues Q) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.n_reads) return;
+    BBReadDev *rd = &B.reads[r];
+    BBAlignOut o;
+    o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
+    const BBNode nd = {r, 0, rd->seq_len, 0, rd->frag_len, -1};
+    bb_push_task(Q, 0, o, nd, rd->upper);
+}
+
+// ---------------------------------------------------------------------------------------------- lane column step
+// State of one banded pass owned by one thread (window of LW words following the band).
+template <int LW>
+struct BBLanePass {
+    uint32_t Pv[LW], Mv[LW], eA[LW], eC[LW], eG[LW], eT[LW];
+    int wt, score, c;
+};
+
+template <int LW>
+__device__ __forceinline__ void bb_lane_begin(BBLanePass<LW> &S, const BBProb &P) {
+#pragma unroll
+    for (int x = 0; x < LW; x++) {
+        S.Pv[x] = ~0u; S.Mv[x] = 0u;
+        bb_fetch_peq(P, 32 * x, S.eA[x], S.eC[x], S.eG[x], S.eT[x]);
+    }
+    S.wt = 0; S.score = 32 * LW; S.c = 0;
+}
+
+// One column of the pass. hist (optional): LW entries for this column.
+template <int LW, bool HIST>
+__device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P, uint2 *hist) {
+    const int c = S.c;
+    if (c - P.a >= 32 * (S.wt + 1)) {  // slide the window down one word
+#pragma unroll
+        for (int x = 0; x + 1 < LW; x++) {
+            S.Pv[x] = S.Pv[x + 1]; S.Mv[x] = S.Mv[x + 1];
+            S.eA[x] = S.eA[x + 1]; S.eC[x] = S.eC[x + 1]; S.eG[x] = S.eG[x + 1]; S.eT[x] = S.eT[x + 1];
+        }
+        S.wt++;
+        S.Pv[LW - 1] = ~0u; S.Mv[LW - 1] = 0u;
+        bb_fetch_peq(P, 32 * (S.wt + LW - 1), S.eA[LW - 1], S.eC[LW - 1], S.eG[LW - 1], S.eT[LW - 1]);
+        S.score += 32;
+    }
+    const uint32_t tc = P.t[(long long)c * P.ts];
+    const uint32_t code = (tc >> 1) & 3u;  // A->0, C->1, T->2, G->3
+    const bool acgt = ((0x47544341u >> (8 * code)) & 0xffu) == tc;
+    uint32_t Eq[LW], Xv[LW], A[LW], Sm[LW], Ph[LW], Mh[LW];
+#pragma unroll
+    for (int x = 0; x < LW; x++)
+        Eq[x] = (code & 2u) ? ((code & 1u) ? S.eG[x] : S.eT[x]) : ((code & 1u) ? S.eC[x] : S.eA[x]);
+    if (!acgt) {
+#pragma unroll
+        for (int x = 0; x < LW; x++) {
+            Eq[x] = 0u;
+            const int row0 = (S.wt + x) * 32;
+            for (int r = 0; r < 32; r++)
+                if (row0 + r < P.n && P.q[(long long)(row0 + r) * P.qs] == tc) Eq[x] |= 1u << r;
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < LW; x++) { Xv[x] = Eq[x] | S.Mv[x]; A[x] = Eq[x] & S.Pv[x]; }
+    bb_add_words<LW>(A, S.Pv, Sm);
+#pragma unroll
+    for (int x = 0; x < LW; x++) {
+        const uint32_t Xh = (Sm[x] ^ S.Pv[x]) | Eq[x];
+        Ph[x] = S.Mv[x] | ~(Xh | S.Pv[x]);
+        Mh[x] = S.Pv[x] & Xh;
+    }
+    S.score += (int)(Ph[LW - 1] >> 31) - (int)(Mh[LW - 1] >> 31);
+#pragma unroll
+    for (int x = LW - 1; x >= 0; x--) {
+        const uint32_t phs = __funnelshift_l(x > 0 ? Ph[x - 1] : 0x80000000u, Ph[x], 1);
+        const uint32_t mhs = __funnelshift_l(x > 0 ? Mh[x - 1] : 0u, Mh[x], 1);
+        const uint32_t raw = Ph[x];
+        S.Pv[x] = mhs | ~(Xv[x] | phs);
+        S.Mv[x] = phs & Xv[x];
+        if (HIST) hist[x] = make_uint2(S.Pv[x], raw);
+    }
+    S.c = c + 1;
+}
+
+// D[row][last column] of the window rows in [lo, hi] -> out[row - lo]; returns D[n-1][last] if inside the window.
+template <int LW>
+__device__ int bb_lane_column_scores(const BBLanePass<LW> &S, int n, int lo, int hi, int *out) {
+    int result = BB_INF;
+    int run = S.score;
+#pragma unroll
+    for (int x = LW - 1; x >= 0; x--) {
+        const int row0 = (S.wt + x) * 32;
+        int rr = run;
+        for (int r = 31; r >= 0; r--) {
+            const int row = row0 + r;
+            if (row < n) {
+                if (out && row >= lo && row <= hi) out[row - lo] = rr;
+                if (row == n - 1) result = rr;
+            }
+            rr -= (int)((S.Pv[x] >> r) & 1u) - (int)((S.Mv[x] >> r) & 1u);
+        }
+        run -= __popc(S.Pv[x]) - __popc(S.Mv[x]);
+    }
+    return result;
+}
+
+// ---------------------------------------------------------------------------------------------- lane node kernel
+__global__ void __launch_bounds__(64)
+bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
+    constexpr int LW = BB_NODE_LW;
+    const BBNode *list = Q.node[BBQ_NODE_LANE][parity];
+    const int count = min(Q.count[BBQ_NODE_LANE * 2 + parity], Q.cap_node);
+    BBLanePass<LW> S;
+    BBProb P;
+    BBNode nd;
+    int Lc[32 * LW], Rc[32 * LW];
+    int loL = 0, hiL = 0, loR = 0, hiR = 0, left_w = 0, right_w = 0, ncols = 0, upper = 0;
+    int phase = 0;  // 0: fetch, 1: forward pass, 2: reverse pass, 3: done
+    BBAlignOut o;
+    for (;;) {
+        if (phase == 0) {
+            const int w = atomicAdd(cursor, 1);
+            if (w >= count) phase = 3;
+            else {
+                nd = list[w];
+                BBReadDev *rd = &B.reads[nd.r];
+                o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
+                upper = rd->upper;
+                bb_task_band(nd, upper, P.a, P.b);
+                left_w = nd.mm / 2; right_w = nd.mm - left_w;
+                loL = max(0, left_w - 1 - P.a); hiL = min(nd.nn - 1, left_w - 1 + P.b);
+                loR = max(0, right_w - 1 - P.a); hiR = min(nd.nn - 1, right_w - 1 + P.b);
+                P.n = nd.nn; P.peq = B.speq + rd->speq_off;
+                P.q = B.seq + rd->seq_off + nd.q0; P.qs = 1; P.peq_bit0 = nd.q0 + 32;
+                P.t = B.frag + rd->frag_off + nd.t0; P.ts = 1;
+                ncols = left_w;
+                bb_lane_begin<LW>(S, P);
+                phase = 1;
+            }
+        }
+        if (__all_sync(BB_FULL, phase == 3)) break;
+        // the hot loop: every lane advances its current pass by one column per iteration
+        for (int it = 0; it < 128; it++) {
+            if (phase == 1 || phase == 2) {
+                bb_lane_step<LW, false>(S, P, nullptr);
+                if (S.c >= ncols) {
+                    if (phase == 1) {
+                        bb_lane_column_scores<LW>(S, nd.nn, loL, hiL, Lc);
+                        const BBReadDev *rd = o.rd;
+                        P.q = B.seq + rd->seq_off + nd.q0 + nd.nn - 1; P.qs = -1; P.peq_bit0 = nd.q0 + nd.nn - 1 + 32;
+                        P.t = B.frag + rd->frag_off + nd.t0 + nd.mm - 1; P.ts = -1;
+                        ncols = right_w;
+                        bb_lane_begin<LW>(S, P);
+                        phase = 2;
+                    } else {
+                        bb_lane_column_scores<LW>(S, nd.nn, loR, hiR, Rc);
+                        int best = nd.best, split = 0, ls = 0, rs = 0;
+                        if (!bb_choose_split_seq(Lc, loL, hiL, Rc, loR, hiR, nd.nn, left_w, right_w, best, split, ls, rs)) {
+                            atomicOr(&o.rd->flags, 32 << 8);
+                        } else {
+                            BBNode c0 = {nd.r, nd.q0, split + 1, nd.t0, left_w, ls};
+                            BBNode c1 = {nd.r, nd.q0 + split + 1, nd.nn - split - 1, nd.t0 + left_w, right_w, rs};
+                            bb_push_task(Q, parity ^ 1, o, c0, upper);
+                            bb_push_task(Q, parity ^ 1, o, c1, upper);
+                        }
+                        phase = 0;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- lane leaf kernel
+__global__ void __launch_bounds__(64)
+bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
+    constexpr int LW = BB_LEAF_LW;
+    const BBNode *list = Q.leaf[0];
+    const int count = min(Q.count[6], Q.cap_leaf);
+    uint2 *const hist = hist_pool + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * (long long)(BB_LEAF_LANE_COLS * LW);
+    BBLanePass<LW> S;
+    BBProb P;
+    BBNode nd;
+    BBAlignOut o;
+    const uint8_t *qp = nullptr, *tp = nullptr;
+    int phase = 0;  // 0: fetch, 1: forward pass, 2: traceback, 3: done
+    int ti = 0, tj = 0, matches = 0, dels = 0;
+    for (;;) {
+        if (phase == 0) {
+            const int w = atomicAdd(cursor, 1);
+            if (w >= count) phase = 3;
+            else {
+                nd = list[w];
+                BBReadDev *rd = &B.reads[nd.r];
+                o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
+                bb_task_band(nd, rd->upper, P.a, P.b);
+                P.n = nd.nn; P.peq = B.speq + rd->speq_off;
+                qp = B.seq + rd->seq_off + nd.q0; tp = B.frag + rd->frag_off + nd.t0;
+                P.q = qp; P.qs = 1; P.peq_bit0 = nd.q0 + 32; P.t = tp; P.ts = 1;
+                bb_lane_begin<LW>(S, P);
+                phase = 1;
+            }
+        }
+        if (__all_sync(BB_FULL, phase == 3)) break;
+        for (int it = 0; it < 128; it++) {  // forward columns with history
+            if (phase == 1) {
+                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
+                if (S.c >= nd.mm) {
+                    const int d = bb_lane_column_scores<LW>(S, nd.nn, 0, -1, nullptr);
+                    if (nd.best >= 0 && d != nd.best) atomicOr(&o.rd->flags, 8 << 8);
+                    ti = nd.nn - 1; tj = nd.mm - 1; matches = 0; dels = 0;
+                    phase = 2;
+                }
+            }
+        }
+        for (int it = 0; it < 256; it++) {  // traceback moves (edlib's rule: 'I' > 'D' > diagonal)
+            if (phase == 2) {
+                if (ti >= 0 && tj >= 0) {
+                    int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
+                    const int x = (ti >> 5) - wt;
+                    if (x < 0 || x >= LW) { atomicOr(&o.rd->flags, 1 << 8); ti = -1; tj = -1; }
+                    else {
+                        const uint2 e = hist[(long long)tj * LW + x];
+                        const int bit = ti & 31;
+                        if ((e.x >> bit) & 1u) { o.ops[nd.q0 + ti] = BB_OP_I; ti--; }
+                        else if ((e.y >> bit) & 1u) { bb_add_dels(o, nd.q0 + ti, 1); dels++; tj--; }
+                        else {
+                            const bool eq = qp[ti] == tp[tj];
+                            o.ops[nd.q0 + ti] = eq ? BB_OP_EQ : BB_OP_X;
+                            matches += eq ? 1 : 0;
+                            ti--; tj--;
+                        }
+                    }
+                } else {
+                    for (int x = 0; x <= ti; x++) o.ops[nd.q0 + x] = BB_OP_I;  // column boundary: insertions remain
+                    if (tj >= 0) { bb_add_dels(o, nd.q0 - 1, tj + 1); dels += tj + 1; }  // row boundary: deletions
+                    atomicAdd(&o.rd->matches, matches);
+                    atomicAdd(&o.rd->dels, dels);
+                    phase = 0;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- warp kernels
+// One Hirschberg node per warp with the wavefront passes of bb_align.cuh (MAXL bounds the instantiated variants).
+template <int MAXL>
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (MAXL <= 4 ? 3 : 2))
+bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity, int *cursor) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
+    BBScratch sc = pool.for_warp(warp);
+    const BBNode *list = Q.node[cls][parity];
+    const int count = min(Q.count[cls * 2 + parity], Q.cap_node);
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(cursor, 1);
+        w = __shfl_sync(BB_FULL, w, 0);
+        if (w >= count) break;
+        const BBNode nd = list[w];
+        BBReadDev *rd = &B.reads[nd.r];
+        BBAlignOut o;
+        o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
+        sc.peq = B.speq + rd->speq_off;
+        const uint8_t *q = B.seq + rd->seq_off, *t = B.frag + rd->frag_off;
+        int a, b;
+        bb_task_band(nd, rd->upper, a, b);
+        int best = nd.best, split = 0, ls = 0, rs = 0;
+        const int err = bb_node_warp<MAXL>(q, t, nd.q0, nd.nn, nd.t0, nd.mm, a, b, sc, best, split, ls, rs);
+        __syncwarp();
+        if (lane == 0) {
+            if (err) atomicOr(&rd->flags, err << 8);
+            else {
+                const int left_w = nd.mm / 2;
+                BBNode c0 = {nd.r, nd.q0, split + 1, nd.t0, left_w, ls};
+                BBNode c1 = {nd.r, nd.q0 + split + 1, nd.nn - split - 1, nd.t0 + left_w, nd.mm - left_w, rs};
+                bb_push_task(Q, parity ^ 1, o, c0, rd->upper);
+                bb_push_task(Q, parity ^ 1, o, c1, rd->upper);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// One leaf per warp (bands or lengths beyond the lane kernel's limits).
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 2)
+bb_k_leaf_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int *cursor) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
+    BBScratch sc = pool.for_warp(warp);
+    const BBNode *list = Q.leaf[1];
+    const int count = min(Q.count[7], Q.cap_leaf);
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(cursor, 1);
+        w = __shfl_sync(BB_FULL, w, 0);
+        if (w >= count) break;
+        const BBNode nd = list[w];
+        BBReadDev *rd = &B.reads[nd.r];
+        sc.peq = B.speq + rd->speq_off;
+        BBEmit em;
+        em.ops = B.ops + rd->seq_off; em.dcnt = B.dcnt + rd->seq_off; em.lead_del = &rd->lead_del;
+        BBAlnCounts cnt = {0, 0, 0, 0};
+        int k = nd.best >= 0 ? nd.best : rd->upper;
+        {
+            const int diff = nd.nn > nd.mm ? nd.nn - nd.mm : nd.mm - nd.nn;
+            if (k < diff) k = diff;
+            const int mx = nd.nn > nd.mm ? nd.nn : nd.mm;
+            if (k > mx) k = mx;
+        }
+        const int d = bb_leaf<true, 16>(B.seq + rd->seq_off + nd.q0, nd.nn, B.frag + rd->frag_off + nd.t0, nd.mm, k, sc, em,
+                                        nd.q0, nd.q0, cnt);
+        if (nd.best >= 0 && d != nd.best) cnt.err |= 8;
+        __syncwarp();
+        if (lane == 0) {
+            atomicAdd(&rd->matches, cnt.matches);
+            atomicAdd(&rd->dels, cnt.dels);
+            if (cnt.err) atomicOr(&rd->flags, cnt.err << 8);
+        }
+        __syncwarp();
+    }
+}

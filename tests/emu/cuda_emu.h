@@ -18,7 +18,8 @@
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
+#define __shared__ static
 #define __constant__
 
 struct uint2 { uint32_t x, y; };
@@ -163,5 +164,28 @@ inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __dsqrt_rn(double a) { return __builtin_sqrt(a); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+inline int atomicOr(int *p, int v) { const int o = *p; *p = o | v; return o; }
+inline int atomicExch(int *p, int v) { const int o = *p; *p = v; return o; }
+inline long long clock64() { return 0; }
+inline void __syncthreads() { emu::barrier(); }
+inline bool __all_sync(unsigned, bool p) {
+    emu::Warp &w = emu::warp();
+    w.xchg[threadIdx.x] = p ? 1 : 0;
+    emu::barrier();
+    bool r = true;
+    for (int i = 0; i < 32; i++) if (!w.done[i] && !w.xchg[i]) r = false;
+    emu::barrier();
+    return r;
+}
+inline bool __any_sync(unsigned, bool p) {
+    emu::Warp &w = emu::warp();
+    w.xchg[threadIdx.x] = p ? 1 : 0;
+    emu::barrier();
+    bool r = false;
+    for (int i = 0; i < 32; i++) if (!w.done[i] && w.xchg[i]) r = true;
+    emu::barrier();
+    return r;
+}
 using std::max;
 using std::min;

@@ -12,7 +12,7 @@ LIB = HERE / 'libemu_align.so'
 
 def build():
     csrc = HERE.parent.parent / 'badread_b200' / 'csrc'
-    srcs = [HERE / 'emu_align.cpp', HERE / 'cuda_emu.h', csrc / 'bb_align.cuh', csrc / 'bb_lane.cuh']
+    srcs = [HERE / 'emu_align.cpp', HERE / 'cuda_emu.h'] + sorted(csrc.glob('*.cuh'))
     if not LIB.is_file() or any(LIB.stat().st_mtime < s.stat().st_mtime for s in srcs):
         subprocess.run(['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-o', str(LIB), str(srcs[0])], check=True)
     return LIB
@@ -31,7 +31,7 @@ def align_path(query, target, k_upper=None, qabs_pad=0, maxl=16):
     t = target.encode('latin-1') if isinstance(target, str) else bytes(target)
     n, m = len(q), len(t)
     ops = np.zeros(n, dtype=np.uint8)
-    dcnt = np.zeros(n, dtype=np.uint16)
+    dcnt = np.zeros(n, dtype=np.uint32)
     out5 = np.zeros(5, dtype=np.int32)
     _lib.emu_align_path(q, n, t, m, max(n, m) if k_upper is None else k_upper, qabs_pad, maxl,
                         ops.ctypes.data_as(ctypes.c_void_p), dcnt.ctypes.data_as(ctypes.c_void_p),
@@ -66,3 +66,31 @@ def lane_align(query, target, k_upper, qabs_pad=0, lw=4):
     if out4[3]:
         raise RuntimeError(f'lane aligner error flags 0x{int(out4[3]):x}')
     return int(out4[0]), int(out4[1]), int(out4[2])
+
+
+def tasks_align(seq, frag, upper):
+    """The level-synchronous alignment task pipeline under the emulator -> expanded ops string."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(LIB))
+    q = seq.encode('latin-1') if isinstance(seq, str) else bytes(seq)
+    t = frag.encode('latin-1') if isinstance(frag, str) else bytes(frag)
+    n, m = len(q), len(t)
+    ops = np.zeros(n, dtype=np.uint8)
+    dcnt = np.zeros(n, dtype=np.uint32)
+    out5 = np.zeros(5, dtype=np.int32)
+    _lib.emu_tasks_align(q, n, t, m, upper, ops.ctypes.data_as(ctypes.c_void_p), dcnt.ctypes.data_as(ctypes.c_void_p),
+                         out5.ctypes.data_as(ctypes.c_void_p))
+    if out5[4] or out5[2]:
+        raise RuntimeError(f'task pipeline error flags 0x{int(out5[4]):x} overflow {int(out5[2])}')
+    sym = '=XI'
+    parts = ['D' * int(out5[3])]
+    for i in range(n):
+        parts.append(sym[ops[i]])
+        if dcnt[i]:
+            parts.append('D' * int(dcnt[i]))
+    s = ''.join(parts)
+    assert len(s) == n + out5[1], (len(s), n, out5)
+    assert s.count('=') == out5[0], (s.count('='), out5)
+    return s

@@ -4,11 +4,11 @@
 
 #include <vector>
 
-#include "../../badread_b200/csrc/bb_align.cuh"
+#include "../../badread_b200/csrc/bb_kernels.cuh"
 
 extern "C" __attribute__((visibility("default")))
 int emu_align_path(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper, int qabs_pad, int maxl, uint8_t *ops,
-                   uint16_t *dcnt, int *out5) {
+                   unsigned int *dcnt, int *out5) {
     // qabs_pad > 0: the query is embedded at offset qabs_pad of a longer "read" (exercises the bitmap offsets)
     std::vector<uint8_t> read((size_t)qabs_pad + n + 64, 'C');
     std::memcpy(read.data() + qabs_pad, q, (size_t)n);
@@ -25,7 +25,7 @@ int emu_align_path(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper
     sc.peq = peq.data(); sc.peq_cap = (int)peq.size();
     int lead = 0;
     BBAlnCounts result = {0, 0, 0, 0};
-    std::memset(dcnt, 0, (size_t)n * sizeof(uint16_t));
+    std::memset(dcnt, 0, (size_t)n * sizeof(unsigned int));
     emu::run_warp([&]() {
         bb_build_peq(read.data(), read_len, sc.peq);
         BBEmit em = {ops, dcnt, &lead};
@@ -40,7 +40,6 @@ int emu_align_path(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper
     return 0;
 }
 
-#include "../../badread_b200/csrc/bb_lane.cuh"
 
 // Lane-mode aligner (one problem per thread): every emulated lane solves the same problem, lane 0 reports.
 extern "C" __attribute__((visibility("default")))
@@ -72,5 +71,63 @@ int emu_lane_align(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper
         res[0] = mt; res[1] = dl; res[2] = d; res[3] = err;
     });
     for (int i = 0; i < 4; i++) out4[i] = res[i];
+    return 0;
+}
+
+
+// The level-synchronous task pipeline (bb_tasks.cuh) for one read, every kernel as one emulated warp.
+extern "C" __attribute__((visibility("default")))
+int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int upper, uint8_t *ops, unsigned int *dcnt,
+                    int *out5) {
+    std::vector<uint8_t> sq(seq, seq + n), fr(frag, frag + m);
+    sq.resize((size_t)n + 64, 0); fr.resize((size_t)m + 64, 0);
+    std::vector<uint4> speq((size_t)n / 32 + 8);
+    BBReadDev rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.seq_len = n; rd.frag_len = m; rd.upper = upper;
+    BBBatchDev B;
+    std::memset(&B, 0, sizeof(B));
+    unsigned long long ridx = 0;
+    B.n_reads = 1; B.read_index = &ridx; B.reads = &rd; B.frag = fr.data(); B.seq = sq.data(); B.ops = ops; B.dcnt = dcnt;
+    B.speq = speq.data();
+    std::memset(dcnt, 0, (size_t)n * sizeof(unsigned int));
+    const int cap = 8192;
+    std::vector<BBNode> qn[3][2], ql[2];
+    std::vector<int> cnt(512, 0);
+    BBQueues Q;
+    for (int c = 0; c < 3; c++) for (int p = 0; p < 2; p++) { qn[c][p].resize(cap); Q.node[c][p] = qn[c][p].data(); }
+    for (int w = 0; w < 2; w++) { ql[w].resize(cap); Q.leaf[w] = ql[w].data(); }
+    Q.count = cnt.data(); Q.overflow = cnt.data() + 8; Q.cap_node = cap; Q.cap_leaf = cap;
+    // scratch for the warp kernels (warp 0 only) and the lane leaf kernel
+    const int big = std::max(n, m) + 64;
+    std::vector<uint2> hist(106496), lhist((size_t)32 * BB_LEAF_LANE_COLS * BB_LEAF_LW);
+    std::vector<int8_t> hbuf((size_t)big);
+    std::vector<int> LR(2 * (size_t)big), stack(5 * 64);
+    std::vector<uint8_t> tbuf(16);
+    BBScratchPool pool;
+    std::memset(&pool, 0, sizeof(pool));
+    pool.hist = hist.data(); pool.hist_stride = 0; pool.hist_cap = (int)hist.size();
+    pool.hbuf = hbuf.data(); pool.hbuf_stride = 0; pool.hbuf_cap = big;
+    pool.lr = LR.data(); pool.lr_stride = 0; pool.lr_cap = big;
+    pool.stack = stack.data(); pool.stack_cap = 64;
+    pool.tbuf = tbuf.data(); pool.tbuf_stride = 0;
+    pool.peq = speq.data(); pool.peq_stride = 0; pool.peq_cap = (int)speq.size();
+    blockDim.x = 32;
+    emu::run_warp([&]() { bb_build_peq(sq.data(), n, speq.data()); });
+    emu::run_warp([&]() { bb_k_push_roots(B, Q); });
+    int *cursor = cnt.data() + 16;
+    for (int level = 0; level < 40; level++) {
+        const int p = level & 1;
+        for (int c = 0; c < 3; c++) cnt[c * 2 + (p ^ 1)] = 0;
+        int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++;
+        emu::run_warp([&]() { bb_k_node_warp<16>(B, Q, pool, BBQ_NODE_WIDE, p, c0); });
+        emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, BBQ_NODE_LEAN, p, c1); });
+        emu::run_warp([&]() { bb_k_node_lane(B, Q, p, c2); });
+        if (cnt[0 + (p ^ 1)] + cnt[2 + (p ^ 1)] + cnt[4 + (p ^ 1)] == 0) break;
+    }
+    int *c3 = cursor++, *c4 = cursor++;
+    emu::run_warp([&]() { bb_k_leaf_warp(B, Q, pool, c3); });
+    emu::run_warp([&]() { bb_k_leaf_lane(B, Q, lhist.data(), c4); });
+    out5[0] = rd.matches; out5[1] = rd.dels; out5[2] = cnt[8]; out5[3] = rd.lead_del; out5[4] = rd.flags;
     return 0;
 }
