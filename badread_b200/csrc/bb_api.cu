@@ -411,7 +411,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
         const int p = level & 1;
         // the queues of the next level start empty
         for (int c = 0; c < 3; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt + c * 2 + (p ^ 1), 0, sizeof(int), st));
-        bb_k_node_warp<16><<<grid_wide, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, BBQ_NODE_WIDE, p, cursor++);
+        bb_k_node_cta<<<ctx->sm_count, BB_CTA_THREADS, 0, st>>>(B, Q, ctx->pool, p, cursor++);
         bb_k_node_warp<4><<<grid_lean, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, BBQ_NODE_LEAN, p, cursor++);
         bb_k_node_lane<<<lane_ctas, 64, 0, st>>>(B, Q, p, cursor++);
         ctx->launches += 3;

@@ -29,32 +29,35 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 struct EmuDim { unsigned x, y, z; };
 
 namespace emu {
-constexpr int W = 32;
+constexpr int MAXT = 512;
 constexpr size_t STACK = 1 << 20;
-struct Warp {
-    ucontext_t main_ctx, fib[W];
-    char *stacks[W];
-    bool done[W];
-    int alive, cur, arrived;
-    uint64_t gen;
-    uint64_t xchg[W];
+struct Block {
+    ucontext_t main_ctx, fib[MAXT];
+    char *stacks[MAXT];
+    bool done[MAXT];
+    int nthreads, cur, alive;
+    int w_alive[MAXT / 32], w_arrived[MAXT / 32];
+    uint64_t w_gen[MAXT / 32];
+    int b_arrived;
+    uint64_t b_gen;
+    uint64_t xchg[MAXT];
     std::function<void()> body;
 };
-inline Warp &warp() { static Warp w; return w; }
+inline Block &blk() { static Block b; return b; }
 }  // namespace emu
 inline EmuDim threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {32, 1, 1}, gridDim = {1, 1, 1};
 
 namespace emu {
 inline int next_alive(int from) {
-    Warp &w = warp();
-    for (int k = 1; k <= W; k++) {
-        const int c = (from + k) % W;
+    Block &w = blk();
+    for (int k = 1; k <= w.nthreads; k++) {
+        const int c = (from + k) % w.nthreads;
         if (!w.done[c]) return c;
     }
     return -1;
 }
 inline void yield() {
-    Warp &w = warp();
+    Block &w = blk();
     const int me = w.cur;
     const int nxt = next_alive(me);
     if (nxt < 0 || nxt == me) return;
@@ -62,32 +65,46 @@ inline void yield() {
     swapcontext(&w.fib[me], &w.fib[nxt]);
     threadIdx.x = (unsigned)w.cur;
 }
-inline void barrier() {
-    Warp &w = warp();
-    const uint64_t g = w.gen;
-    w.arrived++;
-    if (w.arrived >= w.alive) { w.arrived = 0; w.gen++; return; }
-    while (w.gen == g) yield();
+inline void barrier() {  // warp-level rendezvous of the live lanes of the caller's warp
+    Block &w = blk();
+    const int wi = (int)threadIdx.x >> 5;
+    const uint64_t g = w.w_gen[wi];
+    w.w_arrived[wi]++;
+    if (w.w_arrived[wi] >= w.w_alive[wi]) { w.w_arrived[wi] = 0; w.w_gen[wi]++; return; }
+    while (w.w_gen[wi] == g) yield();
+}
+inline void block_barrier() {
+    Block &w = blk();
+    const uint64_t g = w.b_gen;
+    w.b_arrived++;
+    if (w.b_arrived >= w.alive) { w.b_arrived = 0; w.b_gen++; return; }
+    while (w.b_gen == g) yield();
 }
 inline void trampoline() {
-    Warp &w = warp();
+    Block &w = blk();
     threadIdx.x = (unsigned)w.cur;
     w.body();
     const int me = w.cur;
+    const int wi = me >> 5;
     w.done[me] = true;
     w.alive--;
-    if (w.alive > 0 && w.arrived >= w.alive) { w.arrived = 0; w.gen++; }
+    w.w_alive[wi]--;
+    if (w.w_alive[wi] > 0 && w.w_arrived[wi] >= w.w_alive[wi]) { w.w_arrived[wi] = 0; w.w_gen[wi]++; }
+    if (w.alive > 0 && w.b_arrived >= w.alive) { w.b_arrived = 0; w.b_gen++; }
     const int nxt = next_alive(me);
     if (nxt < 0) { setcontext(&w.main_ctx); }
     w.cur = nxt;
     setcontext(&w.fib[nxt]);
 }
-inline void run_warp(std::function<void()> body) {
-    Warp &w = warp();
+inline void run_block(int nthreads, std::function<void()> body) {
+    Block &w = blk();
     w.body = body;
-    w.alive = W; w.arrived = 0; w.gen = 0;
-    for (int i = 0; i < W; i++) {
+    w.nthreads = nthreads; w.alive = nthreads; w.b_arrived = 0; w.b_gen = 0;
+    blockDim.x = (unsigned)nthreads;
+    for (int i = 0; i < MAXT / 32; i++) { w.w_alive[i] = 0; w.w_arrived[i] = 0; w.w_gen[i] = 0; }
+    for (int i = 0; i < nthreads; i++) {
         w.done[i] = false;
+        w.w_alive[i >> 5]++;
         if (!w.stacks[i]) w.stacks[i] = (char *)malloc(STACK);
         getcontext(&w.fib[i]);
         w.fib[i].uc_stack.ss_sp = w.stacks[i];
@@ -98,43 +115,47 @@ inline void run_warp(std::function<void()> body) {
     w.cur = 0;
     swapcontext(&w.main_ctx, &w.fib[0]);
 }
+inline void run_warp(std::function<void()> body) { run_block(32, body); }
 template <typename T>
 inline T exchange(T v, int src) {
-    Warp &w = warp();
+    Block &w = blk();
     uint64_t bits = 0;
     std::memcpy(&bits, &v, sizeof(T));
     w.xchg[threadIdx.x] = bits;
     barrier();
-    const uint64_t r = w.xchg[src & 31];
+    const uint64_t r = w.xchg[((int)threadIdx.x & ~31) | (src & 31)];
     barrier();
     T out;
     std::memcpy(&out, &r, sizeof(T));
     return out;
 }
+inline int lane_id() { return (int)threadIdx.x & 31; }
+inline int warp_base() { return (int)threadIdx.x & ~31; }
 }  // namespace emu
 
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu::exchange(v, src); }
 template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
-    const int me = (int)threadIdx.x;
-    const T r = emu::exchange(v, me - (int)d >= 0 ? me - (int)d : me);
-    return r;
+    const int me = emu::lane_id();
+    return emu::exchange(v, me - (int)d >= 0 ? me - (int)d : me);
 }
-template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::exchange(v, (int)threadIdx.x ^ m); }
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::exchange(v, emu::lane_id() ^ m); }
 inline unsigned __ballot_sync(unsigned, bool p) {
-    emu::Warp &w = emu::warp();
+    emu::Block &w = emu::blk();
+    const int b0 = emu::warp_base();
     w.xchg[threadIdx.x] = p ? 1 : 0;
     emu::barrier();
     unsigned r = 0;
-    for (int i = 0; i < 32; i++) if (!w.done[i] && w.xchg[i]) r |= 1u << i;
+    for (int i = 0; i < 32; i++) if (b0 + i < w.nthreads && !w.done[b0 + i] && w.xchg[b0 + i]) r |= 1u << i;
     emu::barrier();
     return r;
 }
 inline int __reduce_max_sync(unsigned, int v) {
-    emu::Warp &w = emu::warp();
+    emu::Block &w = emu::blk();
+    const int b0 = emu::warp_base();
     w.xchg[threadIdx.x] = (uint64_t)(int64_t)v;
     emu::barrier();
     int r = INT32_MIN;
-    for (int i = 0; i < 32; i++) if (!w.done[i]) r = std::max(r, (int)(int64_t)w.xchg[i]);
+    for (int i = 0; i < 32; i++) if (b0 + i < w.nthreads && !w.done[b0 + i]) r = std::max(r, (int)(int64_t)w.xchg[b0 + i]);
     emu::barrier();
     return r;
 }
@@ -168,24 +189,9 @@ inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p =
 inline int atomicOr(int *p, int v) { const int o = *p; *p = o | v; return o; }
 inline int atomicExch(int *p, int v) { const int o = *p; *p = v; return o; }
 inline long long clock64() { return 0; }
-inline void __syncthreads() { emu::barrier(); }
-inline bool __all_sync(unsigned, bool p) {
-    emu::Warp &w = emu::warp();
-    w.xchg[threadIdx.x] = p ? 1 : 0;
-    emu::barrier();
-    bool r = true;
-    for (int i = 0; i < 32; i++) if (!w.done[i] && !w.xchg[i]) r = false;
-    emu::barrier();
-    return r;
-}
-inline bool __any_sync(unsigned, bool p) {
-    emu::Warp &w = emu::warp();
-    w.xchg[threadIdx.x] = p ? 1 : 0;
-    emu::barrier();
-    bool r = false;
-    for (int i = 0; i < 32; i++) if (!w.done[i] && w.xchg[i]) r = true;
-    emu::barrier();
-    return r;
-}
+inline void __syncthreads() { emu::block_barrier(); }
+inline void __threadfence_block() {}
+inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, !p) == 0u; }
+inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0u; }
 using std::max;
 using std::min;

@@ -112,7 +112,6 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     pool.stack = stack.data(); pool.stack_cap = 64;
     pool.tbuf = tbuf.data(); pool.tbuf_stride = 0;
     pool.peq = speq.data(); pool.peq_stride = 0; pool.peq_cap = (int)speq.size();
-    blockDim.x = 32;
     emu::run_warp([&]() { bb_build_peq(sq.data(), n, speq.data()); });
     emu::run_warp([&]() { bb_k_push_roots(B, Q); });
     int *cursor = cnt.data() + 16;
@@ -120,7 +119,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
         const int p = level & 1;
         for (int c = 0; c < 3; c++) cnt[c * 2 + (p ^ 1)] = 0;
         int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++;
-        emu::run_warp([&]() { bb_k_node_warp<16>(B, Q, pool, BBQ_NODE_WIDE, p, c0); });
+        emu::run_block(BB_CTA_THREADS, [&]() { bb_k_node_cta(B, Q, pool, p, c0); });
         emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, BBQ_NODE_LEAN, p, c1); });
         emu::run_warp([&]() { bb_k_node_lane(B, Q, p, c2); });
         if (cnt[0 + (p ^ 1)] + cnt[2 + (p ^ 1)] + cnt[4 + (p ^ 1)] == 0) break;
