@@ -27,6 +27,8 @@
 #define BB_OP_X 1
 #define BB_OP_I 2
 #define BB_MAX_SCORE 0x3fffff  // scores travel in 22 bits of the shuffle word
+#define BB_PEQ_PAD 34          // zero words in front of and behind a read's match bitmap (covers 32-word chunks)
+#define BB_PEQ_BIT0 (32 * BB_PEQ_PAD)  // bit index of the read's first base
 
 struct BBScratch {
     uint2 *hist;     // (Pv, PhRaw) per (column, block - first_block(column))
@@ -37,7 +39,7 @@ struct BBScratch {
     int lr_cap;
     int *stack;      // DFS stack, 5 ints per node
     int stack_cap;   // nodes
-    uint4 *peq;      // per-read match bitmap: word w holds rows [32(w-1), 32w) for (A, C, G, T)
+    uint4 *peq;      // per-read match bitmap: word BB_PEQ_PAD + w holds rows [32w, 32w+32) for (A, C, G, T)
     int peq_cap;     // words
 };
 
@@ -60,7 +62,8 @@ struct BBProb {
     const uint8_t *q; int qs; int n;      // query rows: row r is q[r*qs]
     const uint8_t *t; int ts; int ncols;  // target columns: column c is t[c*ts]
     int a, b;                             // band: j - a <= i <= j + b
-    const uint4 *peq; int peq_bit0;       // bitmap + bit index of row 0 (rows ascend for qs > 0, descend for qs < 0)
+    const uint4 *peq; int peq_bit0;       // bitmap + bit index of row 0 (BB_PEQ_BIT0 + index of that base in the
+                                          // read; rows ascend for qs > 0, descend for qs < 0)
     uint2 *hist; int nb_alloc;
     int *cols_out; int cols_lo;
 };
@@ -89,18 +92,24 @@ __device__ __forceinline__ int bb_last_block(int j, int b, int n) {
     return hi >> 5;
 }
 
-// Match bitmap of a whole read: peq[w] = ballots of (q[32(w-1)+lane] == A/C/G/T); word 0 and two trailing
-// words are zero so that any 32-bit window that touches the read can be cut out with one funnel shift.
+// Match bitmap of a whole read: peq[BB_PEQ_PAD + w] = ballots of (q[32w + lane] == A/C/G/T); BB_PEQ_PAD zero words
+// in front and behind, so that any window of up to 32 words that touches the read can be cut out with funnel
+// shifts without bounds checks.  Size: bb_peq_words(n).
+__host__ __device__ __forceinline__ int bb_peq_words(int n) { return ((n + 31) >> 5) + 2 * BB_PEQ_PAD; }
+
 __device__ void bb_build_peq(const uint8_t *q, int n, uint4 *peq) {
     const int lane = threadIdx.x & 31;
     const int nw = (n + 31) >> 5;
-    if (lane == 0) peq[0] = make_uint4(0u, 0u, 0u, 0u);
-    for (int w = 0; w < nw + 2; w++) {
+    for (int w = lane; w < BB_PEQ_PAD; w += 32) {
+        peq[w] = make_uint4(0u, 0u, 0u, 0u);
+        peq[BB_PEQ_PAD + nw + w] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int w = 0; w < nw; w++) {
         const int row = 32 * w + lane;
         const uint8_t c = row < n ? q[row] : 0;
         const uint32_t mA = __ballot_sync(BB_FULL, c == 'A'), mC = __ballot_sync(BB_FULL, c == 'C');
         const uint32_t mG = __ballot_sync(BB_FULL, c == 'G'), mT = __ballot_sync(BB_FULL, c == 'T');
-        if (lane == 0) peq[w + 1] = make_uint4(mA, mC, mG, mT);
+        if (lane == 0) peq[BB_PEQ_PAD + w] = make_uint4(mA, mC, mG, mT);
     }
     __syncwarp();
 }
@@ -167,9 +176,14 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
     }
     const int T = __reduce_max_sync(BB_FULL, ulast >= 0 ? ncols + ulast : 0);
     const int cols_hi = min(n - 1, ncols - 1 + b);
-    uint32_t Pv[L], Mv[L], eA[L], eC[L], eG[L], eT[L];
+    // Only the vertical deltas live in registers; the match words of the current target base are streamed from
+    // the (L1-resident) bitmap every step: L + 1 loads and L funnel shifts.
+    uint32_t Pv[L], Mv[L];
 #pragma unroll
-    for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; eA[x] = eC[x] = eG[x] = eT[x] = 0u; }
+    for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; }
+    const uint32_t *const ewords = reinterpret_cast<const uint32_t *>(P.peq);
+    const bool fwd = P.qs > 0;
+    int eidx = 0, esh = 0, evalid = 0;  // bitmap word / shift of the chunk's first word; rows of the chunk below n
     int u = slot;
     int cs = max(0, CH * u - b), ce = min(ncols - 1, CH * u + CH - 1 + a);
     int ce_up = min(ncols - 1, CH * u - 1 + a);  // last column of the chunk above
@@ -190,17 +204,36 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
                 const int base = (u == 0) ? cs : (int)(in & BB_MAX_SCORE) - hin;
                 score = base + CH;
 #pragma unroll
-                for (int x = 0; x < L; x++) {
-                    Pv[x] = ~0u; Mv[x] = 0u;
-                    bb_fetch_peq(P, u * CH + 32 * x, eA[x], eC[x], eG[x], eT[x]);
-                }
+                for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; }
+                const int s0 = fwd ? P.peq_bit0 + u * CH : P.peq_bit0 - u * CH - 31;
+                eidx = s0 >> 5; esh = s0 & 31;
+                evalid = n - u * CH;
             }
             const uint32_t code = (tc >> 1) & 3u;  // A->0, C->1, T->2, G->3
             const bool acgt = ((0x47544341u >> (8 * code)) & 0xffu) == tc;
             uint32_t Eq[L], Xv[L], A[L], S[L];
+            {
+                const uint32_t *ep = ewords + (code ^ (code >> 1));  // uint4 component: A, C, G, T
+                uint32_t wv[L + 1];
+                if (fwd) {
 #pragma unroll
-            for (int x = 0; x < L; x++)
-                Eq[x] = (code & 2u) ? ((code & 1u) ? eG[x] : eT[x]) : ((code & 1u) ? eC[x] : eA[x]);
+                    for (int x = 0; x <= L; x++) wv[x] = ep[(eidx + x) * 4];
+#pragma unroll
+                    for (int x = 0; x < L; x++) Eq[x] = __funnelshift_r(wv[x], wv[x + 1], esh);
+                } else {
+#pragma unroll
+                    for (int x = 0; x <= L; x++) wv[x] = ep[(eidx + 1 - x) * 4];
+#pragma unroll
+                    for (int x = 0; x < L; x++) Eq[x] = __brev(__funnelshift_r(wv[x + 1], wv[x], esh));
+                }
+                if (evalid < CH) {  // the chunk reaches past the node's last row: those rows match nothing
+#pragma unroll
+                    for (int x = 0; x < L; x++) {
+                        const int v = evalid - 32 * x;
+                        Eq[x] = v >= 32 ? Eq[x] : (v <= 0 ? 0u : (Eq[x] & ((1u << v) - 1u)));
+                    }
+                }
+            }
             if (!acgt) {  // non-ACGT target character: exact byte equality against every row of the chunk
 #pragma unroll
                 for (int x = 0; x < L; x++) {
@@ -299,6 +332,7 @@ __device__ __forceinline__ int bb_pick_L(int a, int b, int K) {
 
 template <bool HIST, bool COLS, int MAXL>
 __device__ __forceinline__ int bb_band_dispatch(const BBProb &P, int K, int L) {
+    if (MAXL >= 32 && L == 32) return bb_band_pass<(MAXL >= 32 ? 32 : 1), HIST, COLS>(P, K);
     if (MAXL >= 16 && L == 16) return bb_band_pass<(MAXL >= 16 ? 16 : 1), HIST, COLS>(P, K);
     if (MAXL >= 8 && L == 8) return bb_band_pass<(MAXL >= 8 ? 8 : 1), HIST, COLS>(P, K);
     if (MAXL >= 4 && L == 4) return bb_band_pass<(MAXL >= 4 ? 4 : 1), HIST, COLS>(P, K);
@@ -306,7 +340,7 @@ __device__ __forceinline__ int bb_band_dispatch(const BBProb &P, int K, int L) {
     return bb_band_pass<1, HIST, COLS>(P, K);
 }
 
-// Fallback for bands wider than 32*16*30 rows: 1024-row strips, lane l owns one word of the strip and works on
+// Fallback for bands wider than 32*32*30 rows: 1024-row strips, lane l owns one word of the strip and works on
 // column (step - l); carries between strips go through hbuf.  Same outputs as bb_band_pass.
 template <bool HIST, bool COLS>
 __device__ int bb_strip_pass(const uint8_t *q, int qs, int n, const uint8_t *t, int ts, int ncols, int a, int b,
@@ -506,7 +540,7 @@ __device__ int bb_leaf(const uint8_t *q, int n, const uint8_t *t, int m, int k, 
     if (L > 0) {
         BBProb P;
         P.q = q; P.qs = 1; P.n = n; P.t = t; P.ts = 1; P.ncols = m; P.a = a; P.b = b;
-        P.peq = sc.peq; P.peq_bit0 = qpeq + 32;
+        P.peq = sc.peq; P.peq_bit0 = qpeq + BB_PEQ_BIT0;
         P.hist = sc.hist; P.nb_alloc = nb_alloc; P.cols_out = nullptr; P.cols_lo = 0;
         d = bb_band_dispatch<true, false, MAXL>(P, 32, L);
     } else {
@@ -547,10 +581,10 @@ __device__ int bb_node_warp(const uint8_t *q, const uint8_t *t, int q0, int nn, 
             P.n = nn; P.a = a; P.b = b; P.peq = sc.peq; P.hist = nullptr; P.nb_alloc = 0;
             if (!rev) {
                 P.q = q + q0; P.qs = 1; P.t = t + t0; P.ts = 1; P.ncols = left_w;
-                P.peq_bit0 = qabs + q0 + 32; P.cols_out = sc.L; P.cols_lo = loL;
+                P.peq_bit0 = qabs + q0 + BB_PEQ_BIT0; P.cols_out = sc.L; P.cols_lo = loL;
             } else {
                 P.q = q + q0 + nn - 1; P.qs = -1; P.t = t + t0 + mm - 1; P.ts = -1; P.ncols = right_w;
-                P.peq_bit0 = qabs + q0 + nn - 1 + 32; P.cols_out = sc.R; P.cols_lo = loR;
+                P.peq_bit0 = qabs + q0 + nn - 1 + BB_PEQ_BIT0; P.cols_out = sc.R; P.cols_lo = loR;
             }
             return P;
         };
@@ -634,7 +668,7 @@ __device__ void bb_align(const uint8_t *q, int n, const uint8_t *t, int m, int k
         if (L > 0) {
             BBProb P;
             P.q = q; P.qs = 1; P.n = n; P.t = t; P.ts = 1; P.ncols = m; P.a = a; P.b = b;
-            P.peq = sc.peq; P.peq_bit0 = qabs + 32;
+            P.peq = sc.peq; P.peq_bit0 = qabs + BB_PEQ_BIT0;
             P.hist = nullptr; P.nb_alloc = 0; P.cols_out = nullptr; P.cols_lo = 0;
             best_root = bb_band_dispatch<false, false, MAXL>(P, 32, L);
         } else {

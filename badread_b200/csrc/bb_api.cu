@@ -254,7 +254,7 @@ static int ensure_scratch(bb_ctx *ctx, int hbuf_need, int lr_need, int len_need)
     hbuf_cap = (hbuf_cap + 255) & ~255;
     int lr_cap = std::max(lr_need + 64, 4096);
     lr_cap = (lr_cap + 255) & ~255;
-    int peq_cap = len_need / 32 + 16;
+    int peq_cap = bb_peq_words(len_need) + 8;
     peq_cap = (peq_cap + 63) & ~63;
     if (ctx->pool.peq_cap >= peq_cap) peq_cap = ctx->pool.peq_cap;
     if (ctx->pool.hbuf_cap >= hbuf_cap) hbuf_cap = ctx->pool.hbuf_cap;
@@ -328,7 +328,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
         rd.frag_off = off;
         rd.frag_len = (int)(len + 2 * k);
         rd.fpeq_off = peq_off;
-        peq_off += (rd.frag_len + 31) / 32 + 3;
+        peq_off += bb_peq_words(rd.frag_len);
         off += (rd.frag_len + 15) & ~15;
         max_len = std::max(max_len, rd.frag_len);
     }
@@ -411,7 +411,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
         const int p = level & 1;
         // the queues of the next level start empty
         for (int c = 0; c < 3; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt + c * 2 + (p ^ 1), 0, sizeof(int), st));
-        bb_k_node_cta<<<ctx->sm_count, BB_CTA_THREADS, 0, st>>>(B, Q, ctx->pool, p, cursor++);
+        bb_k_node_warp<32><<<grid_wide, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, BBQ_NODE_WIDE, p, cursor++);
         bb_k_node_warp<4><<<grid_lean, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, BBQ_NODE_LEAN, p, cursor++);
         bb_k_node_lane<<<lane_ctas, 64, 0, st>>>(B, Q, p, cursor++);
         ctx->launches += 3;
@@ -490,7 +490,7 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
         rd.seq_off = seq_off;
         rd.out_off = out_off;
         rd.speq_off = speq_off;
-        speq_off += (rd.seq_len + 31) / 32 + 3;
+        speq_off += bb_peq_words(rd.seq_len);
         int out_len = rd.seq_len - rd.start_trim - rd.end_trim;  // seq[start_trim:-end_trim]
         if (out_len < 0) out_len = 0;
         rd.out_len = out_len;

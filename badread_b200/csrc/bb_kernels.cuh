@@ -136,13 +136,17 @@ __global__ void __launch_bounds__(256) bb_k_build_fragments(BBBatchDev B, const 
     __syncthreads();
     uint4 *pq = B.fpeq + rd.fpeq_off;
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    if (threadIdx.x == 0) pq[0] = make_uint4(0u, 0u, 0u, 0u);
-    for (int w = threadIdx.x >> 5; w < ((flen + 31) >> 5) + 2; w += nwarps) {
+    const int fw = (flen + 31) >> 5;
+    for (int w = threadIdx.x; w < BB_PEQ_PAD; w += blockDim.x) {
+        pq[w] = make_uint4(0u, 0u, 0u, 0u);
+        pq[BB_PEQ_PAD + fw + w] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int w = threadIdx.x >> 5; w < fw; w += nwarps) {
         const int row = 32 * w + lane;
         const uint8_t c = row < flen ? f[row] : 0;
         const uint32_t mA = __ballot_sync(BB_FULL, c == 'A'), mC = __ballot_sync(BB_FULL, c == 'C');
         const uint32_t mG = __ballot_sync(BB_FULL, c == 'G'), mT = __ballot_sync(BB_FULL, c == 'T');
-        if (lane == 0) pq[w + 1] = make_uint4(mA, mC, mG, mT);
+        if (lane == 0) pq[BB_PEQ_PAD + w] = make_uint4(mA, mC, mG, mT);
     }
 }
 
@@ -516,7 +520,7 @@ bb_k_error_loop_lane(BBBatchDev B, BBErrorModelDev em, BBLanePool pool, unsigned
                 fallback_list[atomicAdd(fallback_count, 1)] = r;  // the warp kernel redoes this read from scratch
                 have_read = false; need_align = false; jres = 0x7fffffff;
             } else {
-                P.peq = B.fpeq + rd->fpeq_off; P.peq_bit0 = qpos + 32; P.q = frag + qpos; P.n = qn;
+                P.peq = B.fpeq + rd->fpeq_off; P.peq_bit0 = qpos + BB_PEQ_BIT0; P.q = frag + qpos; P.n = qn;
                 P.t = tbuf; P.m = tm; P.hist = hist;
                 int matches = 0, dels = 0, err = 0;
                 if (lw <= 4) { bb_lane_pass<4>(P); bb_lane_traceback<4>(P, matches, dels, err); }
@@ -579,13 +583,17 @@ __global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev e
     }
     uint4 *pq = B.speq + rd.speq_off;
     const int nwarps = blockDim.x >> 5;
-    if (threadIdx.x == 0) pq[0] = make_uint4(0u, 0u, 0u, 0u);
-    for (int w = wid; w < ((rd.seq_len + 31) >> 5) + 2; w += nwarps) {
+    const int sw = (rd.seq_len + 31) >> 5;
+    for (int w = threadIdx.x; w < BB_PEQ_PAD; w += blockDim.x) {
+        pq[w] = make_uint4(0u, 0u, 0u, 0u);
+        pq[BB_PEQ_PAD + sw + w] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int w = wid; w < sw; w += nwarps) {
         const int row = 32 * w + lane;
         const uint8_t c = row < rd.seq_len ? seq[row] : 0;
         const uint32_t mA = __ballot_sync(BB_FULL, c == 'A'), mC = __ballot_sync(BB_FULL, c == 'C');
         const uint32_t mG = __ballot_sync(BB_FULL, c == 'G'), mT = __ballot_sync(BB_FULL, c == 'T');
-        if (lane == 0) pq[w + 1] = make_uint4(mA, mC, mG, mT);
+        if (lane == 0) pq[BB_PEQ_PAD + w] = make_uint4(mA, mC, mG, mT);
     }
 }
 
@@ -702,7 +710,7 @@ __global__ void __launch_bounds__(32) bb_k_align_pair(const uint8_t *q, int n, c
     const BBScratch sc = pool.for_warp(0);
     BBEmit em = {ops, dcnt, &out4[3]};
     BBAlnCounts cnt = {0, 0, 0, 0};
-    if (n / 32 + 4 > sc.peq_cap) cnt.err |= 256;
+    if (bb_peq_words(n) > sc.peq_cap) cnt.err |= 256;
     else {
         bb_build_peq(q, n, sc.peq);
         bb_align<true, 16>(q, n, t, m, k_upper, sc, em, 0, cnt);

@@ -246,7 +246,7 @@ bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
                 loL = max(0, left_w - 1 - P.a); hiL = min(nd.nn - 1, left_w - 1 + P.b);
                 loR = max(0, right_w - 1 - P.a); hiR = min(nd.nn - 1, right_w - 1 + P.b);
                 P.n = nd.nn; P.peq = B.speq + rd->speq_off;
-                P.q = B.seq + rd->seq_off + nd.q0; P.qs = 1; P.peq_bit0 = nd.q0 + 32;
+                P.q = B.seq + rd->seq_off + nd.q0; P.qs = 1; P.peq_bit0 = nd.q0 + BB_PEQ_BIT0;
                 P.t = B.frag + rd->frag_off + nd.t0; P.ts = 1;
                 ncols = left_w;
                 bb_lane_begin<LW>(S, P);
@@ -262,7 +262,7 @@ bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
                     if (phase == 1) {
                         bb_lane_column_scores<LW>(S, nd.nn, loL, hiL, Lc);
                         const BBReadDev *rd = o.rd;
-                        P.q = B.seq + rd->seq_off + nd.q0 + nd.nn - 1; P.qs = -1; P.peq_bit0 = nd.q0 + nd.nn - 1 + 32;
+                        P.q = B.seq + rd->seq_off + nd.q0 + nd.nn - 1; P.qs = -1; P.peq_bit0 = nd.q0 + nd.nn - 1 + BB_PEQ_BIT0;
                         P.t = B.frag + rd->frag_off + nd.t0 + nd.mm - 1; P.ts = -1;
                         ncols = right_w;
                         bb_lane_begin<LW>(S, P);
@@ -311,7 +311,7 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
                 bb_task_band(nd, rd->upper, P.a, P.b);
                 P.n = nd.nn; P.peq = B.speq + rd->speq_off;
                 qp = B.seq + rd->seq_off + nd.q0; tp = B.frag + rd->frag_off + nd.t0;
-                P.q = qp; P.qs = 1; P.peq_bit0 = nd.q0 + 32; P.t = tp; P.ts = 1;
+                P.q = qp; P.qs = 1; P.peq_bit0 = nd.q0 + BB_PEQ_BIT0; P.t = tp; P.ts = 1;
                 bb_lane_begin<LW>(S, P);
                 phase = 1;
             }
@@ -361,7 +361,7 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
 // ---------------------------------------------------------------------------------------------- warp kernels
 // One Hirschberg node per warp with the wavefront passes of bb_align.cuh (MAXL bounds the instantiated variants).
 template <int MAXL>
-__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (MAXL <= 4 ? 3 : 2))
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (MAXL <= 4 ? 3 : 1))
 bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity, int *cursor) {
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -395,231 +395,6 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity
             }
         }
         __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- CTA node kernel
-// Wide-band nodes (long or noisy reads): one CTA of 512 threads per node.  Threads 0-255 run the forward pass,
-// threads 256-511 the reverse pass, each as a 256-lane instance of the diagonal wavefront of bb_band_pass (chunk u
-// belongs to slot u mod 256 and works on column step - u).  Inside a warp the horizontal carry travels by shuffle;
-// between warps it goes through a double-buffered shared-memory mailbox, one __syncthreads per step.
-#define BB_CTA_K 256
-#define BB_CTA_THREADS 512
-
-template <int L>
-__device__ void bb_band_pass_cta(const BBProb &P, int slot, int T, uint32_t (*mbox)[BB_CTA_THREADS / 32]) {
-    constexpr int K = BB_CTA_K;
-    constexpr int CH = 32 * L;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int half_base = (warp >> 3) << 3;                      // first warp of this thread's half
-    const int prev_warp = half_base + ((warp - half_base + 7) & 7);  // the warp holding slot - 1 of lane 0
-    const int n = P.n, ncols = P.ncols, a = P.a, b = P.b, ts = P.ts;
-    int ulast = -1;
-    if (ncols > 0 && n > 0) {
-        ulast = (ncols - 1 + b) / CH;
-        const int nchunks = (n + CH - 1) / CH;
-        if (ulast > nchunks - 1) ulast = nchunks - 1;
-    }
-    const int cols_hi = min(n - 1, ncols - 1 + b);
-    uint32_t Pv[L], Mv[L], eA[L], eC[L], eG[L], eT[L];
-#pragma unroll
-    for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; eA[x] = eC[x] = eG[x] = eT[x] = 0u; }
-    int u = slot;
-    int cs = max(0, CH * u - b), ce = min(ncols - 1, CH * u + CH - 1 + a);
-    int ce_up = min(ncols - 1, CH * u - 1 + a);
-    int score = 0;
-    uint32_t outpack = 0, tcn = 0;
-    const uint8_t *tp = P.t - (long long)u * ts;
-    if (u <= ulast && 0 - u >= cs && 0 - u <= ce) tcn = *tp;
-    if (lane == 31) mbox[1][warp] = 0u;
-    __syncthreads();
-    for (int tau = 0; tau < T; tau++) {
-        const uint32_t up = __shfl_up_sync(BB_FULL, outpack, 1);
-        const uint32_t in = lane == 0 ? mbox[(tau & 1) ^ 1][prev_warp] : up;
-        const int c = tau - u;
-        const bool active = (u <= ulast) && c >= cs && c <= ce;
-        if (active) {
-            const uint32_t tc = tcn;
-            int hin = 1;
-            if (u > 0 && c <= ce_up) hin = (int)((in >> 22) & 3u) - 1;
-            if (c == cs) {
-                const int base = (u == 0) ? cs : (int)(in & BB_MAX_SCORE) - hin;
-                score = base + CH;
-#pragma unroll
-                for (int x = 0; x < L; x++) {
-                    Pv[x] = ~0u; Mv[x] = 0u;
-                    bb_fetch_peq(P, u * CH + 32 * x, eA[x], eC[x], eG[x], eT[x]);
-                }
-            }
-            const uint32_t code = (tc >> 1) & 3u;
-            const bool acgt = ((0x47544341u >> (8 * code)) & 0xffu) == tc;
-            uint32_t Eq[L], Xv[L], A[L], S[L], Ph[L], Mh[L];
-#pragma unroll
-            for (int x = 0; x < L; x++)
-                Eq[x] = (code & 2u) ? ((code & 1u) ? eG[x] : eT[x]) : ((code & 1u) ? eC[x] : eA[x]);
-            if (!acgt) {
-#pragma unroll
-                for (int x = 0; x < L; x++) {
-                    Eq[x] = 0u;
-                    const int row0 = u * CH + 32 * x;
-                    for (int r = 0; r < 32; r++)
-                        if (row0 + r < n && P.q[(long long)(row0 + r) * P.qs] == tc) Eq[x] |= 1u << r;
-                }
-            }
-            const uint32_t hin_neg = hin < 0 ? 1u : 0u;
-#pragma unroll
-            for (int x = 0; x < L; x++) Xv[x] = Eq[x] | Mv[x];
-            Eq[0] |= hin_neg;
-#pragma unroll
-            for (int x = 0; x < L; x++) A[x] = Eq[x] & Pv[x];
-            bb_add_words<L>(A, Pv, S);
-#pragma unroll
-            for (int x = 0; x < L; x++) {
-                const uint32_t Xh = (S[x] ^ Pv[x]) | Eq[x];
-                Ph[x] = Mv[x] | ~(Xh | Pv[x]);
-                Mh[x] = Pv[x] & Xh;
-            }
-            const int hout = (int)(Ph[L - 1] >> 31) - (int)(Mh[L - 1] >> 31);
-#pragma unroll
-            for (int x = L - 1; x >= 0; x--) {
-                const uint32_t ph_lo = x > 0 ? Ph[x - 1] : (hin > 0 ? 0x80000000u : 0u);
-                const uint32_t mh_lo = x > 0 ? Mh[x - 1] : (hin_neg << 31);
-                const uint32_t phs = __funnelshift_l(ph_lo, Ph[x], 1);
-                const uint32_t mhs = __funnelshift_l(mh_lo, Mh[x], 1);
-                Pv[x] = mhs | ~(Xv[x] | phs);
-                Mv[x] = phs & Xv[x];
-            }
-            score += hout;
-            outpack = ((uint32_t)(hout + 1) << 22) | ((uint32_t)score & BB_MAX_SCORE);
-            if (c == ncols - 1) {
-                int run = score;
-#pragma unroll
-                for (int x = L - 1; x >= 0; x--) {
-                    const int row0 = u * CH + 32 * x;
-                    int rr = run;
-                    for (int r = 31; r >= 0; r--) {
-                        const int row = row0 + r;
-                        if (row < n && row >= P.cols_lo && row <= cols_hi) P.cols_out[row - P.cols_lo] = rr;
-                        rr -= (int)((Pv[x] >> r) & 1u) - (int)((Mv[x] >> r) & 1u);
-                    }
-                    run -= __popc(Pv[x]) - __popc(Mv[x]);
-                }
-            }
-            if (c == ce) {
-                u += K;
-                cs = max(0, CH * u - b);
-                ce = min(ncols - 1, CH * u + CH - 1 + a);
-                ce_up = min(ncols - 1, CH * u - 1 + a);
-                tp -= (long long)K * ts;
-            }
-        }
-        const int cn = tau + 1 - u;
-        if (u <= ulast && cn >= cs && cn <= ce) tcn = tp[(long long)(tau + 1) * ts];
-        if (lane == 31) mbox[tau & 1][warp] = outpack;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(BB_CTA_THREADS, 1)
-bb_k_node_cta(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor) {
-    __shared__ uint32_t mbox[2][BB_CTA_THREADS / 32];
-    __shared__ int s_task;
-    const int lane = threadIdx.x & 31;
-    BBScratch sc = pool.for_warp(blockIdx.x);
-    const BBNode *list = Q.node[BBQ_NODE_WIDE][parity];
-    const int count = min(Q.count[BBQ_NODE_WIDE * 2 + parity], Q.cap_node);
-    for (;;) {
-        if (threadIdx.x == 0) s_task = atomicAdd(cursor, 1);
-        __syncthreads();
-        const int w = s_task;
-        __syncthreads();
-        if (w >= count) break;
-        const BBNode nd = list[w];
-        BBReadDev *rd = &B.reads[nd.r];
-        sc.peq = B.speq + rd->speq_off;
-        const uint8_t *q = B.seq + rd->seq_off, *t = B.frag + rd->frag_off;
-        int a, b;
-        bb_task_band(nd, rd->upper, a, b);
-        const int left_w = nd.mm / 2, right_w = nd.mm - left_w;
-        const int loL = max(0, left_w - 1 - a), hiL = min(nd.nn - 1, left_w - 1 + b);
-        const int loR = max(0, right_w - 1 - a), hiR = min(nd.nn - 1, right_w - 1 + b);
-        int L = 0;
-        if ((a + b) / 32 + 2 <= BB_CTA_K) L = 1;
-        else if ((a + b) / 64 + 2 <= BB_CTA_K) L = 2;
-        int err = 0, best = nd.best, split = 0, ls = 0, rs = 0;
-        if (hiL - loL + 1 > sc.lr_cap || hiR - loR + 1 > sc.lr_cap) err = 16;
-        else if (L > 0) {
-            const bool rev = threadIdx.x >= BB_CTA_K;
-            BBProb P;
-            P.n = nd.nn; P.a = a; P.b = b; P.peq = sc.peq; P.hist = nullptr; P.nb_alloc = 0;
-            if (!rev) {
-                P.q = q + nd.q0; P.qs = 1; P.t = t + nd.t0; P.ts = 1; P.ncols = left_w;
-                P.peq_bit0 = nd.q0 + 32; P.cols_out = sc.L; P.cols_lo = loL;
-            } else {
-                P.q = q + nd.q0 + nd.nn - 1; P.qs = -1; P.t = t + nd.t0 + nd.mm - 1; P.ts = -1; P.ncols = right_w;
-                P.peq_bit0 = nd.q0 + nd.nn - 1 + 32; P.cols_out = sc.R; P.cols_lo = loR;
-            }
-            // both halves run the same number of steps: the longer of the two passes
-            const int CH = 32 * L;
-            const int nchunks = (nd.nn + CH - 1) / CH;
-            const int T = max(left_w + min((left_w - 1 + b) / CH, nchunks - 1), right_w + min((right_w - 1 + b) / CH, nchunks - 1));
-            if (L == 1) bb_band_pass_cta<1>(P, threadIdx.x & (BB_CTA_K - 1), T, mbox);
-            else bb_band_pass_cta<2>(P, threadIdx.x & (BB_CTA_K - 1), T, mbox);
-            __threadfence_block();
-            __syncthreads();
-        }
-        if (threadIdx.x < 32 && !err) {
-            if (L > 0) {
-                // split row by edlib's rule (same search as bb_node_warp) on the column scores just written
-                int rlo = max(loL, nd.nn - 2 - hiR); if (rlo < 0) rlo = 0;
-                int rhi = min(hiL, nd.nn - 2 - loR); if (rhi > nd.nn - 2) rhi = nd.nn - 2;
-                const bool have_top = nd.nn - 1 >= loR && nd.nn - 1 <= hiR;
-                const bool have_bot = nd.nn - 1 >= loL && nd.nn - 1 <= hiL;
-                if (best < 0) {
-                    int mn = BB_INF;
-                    for (int r = rlo + lane; r <= rhi; r += 32) mn = min(mn, sc.L[r - loL] + sc.R[(nd.nn - 2 - r) - loR]);
-                    if (have_top) mn = min(mn, left_w + sc.R[(nd.nn - 1) - loR]);
-                    if (have_bot) mn = min(mn, sc.L[(nd.nn - 1) - loL] + right_w);
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(BB_FULL, mn, d));
-                    best = mn;
-                }
-                split = -2;
-                for (int base = rlo; base <= rhi; base += 32) {
-                    const int r = base + lane;
-                    bool hit = false;
-                    if (r <= rhi) hit = (sc.L[r - loL] + sc.R[(nd.nn - 2 - r) - loR] == best);
-                    const uint32_t hm = __ballot_sync(BB_FULL, hit);
-                    if (hm) { split = base + __ffs(hm) - 1; break; }
-                }
-                if (split >= 0) { ls = sc.L[split - loL]; rs = sc.R[(nd.nn - 2 - split) - loR]; }
-                if (split == -2 && have_top) {
-                    const int v = sc.R[(nd.nn - 1) - loR];
-                    if (left_w + v == best) { split = -1; ls = left_w; rs = v; }
-                }
-                if (split == -2 && have_bot) {
-                    const int v = sc.L[(nd.nn - 1) - loL];
-                    if (v + right_w == best) { split = nd.nn - 1; ls = v; rs = right_w; }
-                }
-                if (split == -2) err = 32;
-            } else {
-                // band beyond 256 lanes x 2 words: the single-warp wavefront (with its strip fall-back) handles it
-                err = bb_node_warp<16>(q, t, nd.q0, nd.nn, nd.t0, nd.mm, a, b, sc, best, split, ls, rs);
-            }
-        }
-        if (threadIdx.x == 0) {
-            BBAlignOut o;
-            o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
-            if (err) atomicOr(&rd->flags, err << 8);
-            else {
-                BBNode c0 = {nd.r, nd.q0, split + 1, nd.t0, left_w, ls};
-                BBNode c1 = {nd.r, nd.q0 + split + 1, nd.nn - split - 1, nd.t0 + left_w, right_w, rs};
-                bb_push_task(Q, parity ^ 1, o, c0, rd->upper);
-                bb_push_task(Q, parity ^ 1, o, c1, rd->upper);
-            }
-        }
-        __syncthreads();
     }
 }
 

@@ -16,7 +16,7 @@ int emu_align_path(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper
     std::vector<uint2> hist(106496);
     std::vector<int8_t> hbuf((size_t)std::max(n, m) + 64);
     std::vector<int> LR(2 * ((size_t)std::max(n, m) + 64)), stack(5 * 64);
-    std::vector<uint4> peq((size_t)read_len / 32 + 8);
+    std::vector<uint4> peq((size_t)bb_peq_words(read_len) + 8);
     BBScratch sc;
     sc.hist = hist.data(); sc.hist_cap = (int)hist.size();
     sc.hbuf = hbuf.data(); sc.hbuf_cap = (int)hbuf.size();
@@ -47,7 +47,7 @@ int emu_lane_align(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper
     std::vector<uint8_t> read((size_t)qabs_pad + n + 64, 'G');
     std::memcpy(read.data() + qabs_pad, q, (size_t)n);
     const int read_len = qabs_pad + n + 9;
-    std::vector<uint4> peq((size_t)read_len / 32 + 8);
+    std::vector<uint4> peq((size_t)bb_peq_words(read_len) + 8);
     int a, b;
     {
         const int diff = n > m ? n - m : m - n;
@@ -63,7 +63,7 @@ int emu_lane_align(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper
         bb_build_peq(read.data(), read_len, peq.data());
         if (threadIdx.x != 0) return;
         BBLaneProb P;
-        P.peq = peq.data(); P.peq_bit0 = qabs_pad + 32; P.q = read.data() + qabs_pad; P.n = n; P.t = t; P.m = m;
+        P.peq = peq.data(); P.peq_bit0 = qabs_pad + BB_PEQ_BIT0; P.q = read.data() + qabs_pad; P.n = n; P.t = t; P.m = m;
         P.a = a; P.b = b; P.hist = hist.data();
         int d, mt = 0, dl = 0, err = 0;
         if (lw == 4) { d = bb_lane_pass<4>(P); bb_lane_traceback<4>(P, mt, dl, err); }
@@ -81,7 +81,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
                     int *out5) {
     std::vector<uint8_t> sq(seq, seq + n), fr(frag, frag + m);
     sq.resize((size_t)n + 64, 0); fr.resize((size_t)m + 64, 0);
-    std::vector<uint4> speq((size_t)n / 32 + 8);
+    std::vector<uint4> speq((size_t)bb_peq_words(n) + 8);
     BBReadDev rd;
     std::memset(&rd, 0, sizeof(rd));
     rd.seq_len = n; rd.frag_len = m; rd.upper = upper;
@@ -119,7 +119,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
         const int p = level & 1;
         for (int c = 0; c < 3; c++) cnt[c * 2 + (p ^ 1)] = 0;
         int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++;
-        emu::run_block(BB_CTA_THREADS, [&]() { bb_k_node_cta(B, Q, pool, p, c0); });
+        emu::run_warp([&]() { bb_k_node_warp<32>(B, Q, pool, BBQ_NODE_WIDE, p, c0); });
         emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, BBQ_NODE_LEAN, p, c1); });
         emu::run_warp([&]() { bb_k_node_lane(B, Q, p, c2); });
         if (cnt[0 + (p ^ 1)] + cnt[2 + (p ^ 1)] + cnt[4 + (p ^ 1)] == 0) break;
