@@ -176,11 +176,16 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
     }
     const int T = __reduce_max_sync(BB_FULL, ulast >= 0 ? ncols + ulast : 0);
     const int cols_hi = min(n - 1, ncols - 1 + b);
-    // Only the vertical deltas live in registers; the match words of the current target base are streamed from
-    // the (L1-resident) bitmap every step: L + 1 loads and L funnel shifts.
-    uint32_t Pv[L], Mv[L];
+    // Vertical deltas live in registers.  Match words: for L <= 4 the four per-letter masks of the chunk are held in
+    // registers as well; wider chunks stream the words of the current target base from the (L1-resident) bitmap
+    // every step (L + 1 loads and L funnel shifts) so that the register footprint stays at 2L.
+    constexpr bool STREAM = (L >= 8);
+    constexpr int LR = STREAM ? 1 : L;
+    uint32_t Pv[L], Mv[L], eA[LR], eC[LR], eG[LR], eT[LR];
 #pragma unroll
     for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; }
+#pragma unroll
+    for (int x = 0; x < LR; x++) { eA[x] = eC[x] = eG[x] = eT[x] = 0u; }
     const uint32_t *const ewords = reinterpret_cast<const uint32_t *>(P.peq);
     const bool fwd = P.qs > 0;
     int eidx = 0, esh = 0, evalid = 0;  // bitmap word / shift of the chunk's first word; rows of the chunk below n
@@ -205,14 +210,19 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
                 score = base + CH;
 #pragma unroll
                 for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; }
-                const int s0 = fwd ? P.peq_bit0 + u * CH : P.peq_bit0 - u * CH - 31;
-                eidx = s0 >> 5; esh = s0 & 31;
-                evalid = n - u * CH;
+                if (STREAM) {
+                    const int s0 = fwd ? P.peq_bit0 + u * CH : P.peq_bit0 - u * CH - 31;
+                    eidx = s0 >> 5; esh = s0 & 31;
+                    evalid = n - u * CH;
+                } else {
+#pragma unroll
+                    for (int x = 0; x < LR; x++) bb_fetch_peq(P, u * CH + 32 * x, eA[x], eC[x], eG[x], eT[x]);
+                }
             }
             const uint32_t code = (tc >> 1) & 3u;  // A->0, C->1, T->2, G->3
             const bool acgt = ((0x47544341u >> (8 * code)) & 0xffu) == tc;
             uint32_t Eq[L], Xv[L], A[L], S[L];
-            {
+            if (STREAM) {
                 const uint32_t *ep = ewords + (code ^ (code >> 1));  // uint4 component: A, C, G, T
                 uint32_t wv[L + 1];
                 if (fwd) {
@@ -232,6 +242,12 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
                         const int v = evalid - 32 * x;
                         Eq[x] = v >= 32 ? Eq[x] : (v <= 0 ? 0u : (Eq[x] & ((1u << v) - 1u)));
                     }
+                }
+            } else {
+#pragma unroll
+                for (int x = 0; x < L; x++) {
+                    const int y = x < LR ? x : 0;
+                    Eq[x] = (code & 2u) ? ((code & 1u) ? eG[y] : eT[y]) : ((code & 1u) ? eC[y] : eA[y]);
                 }
             }
             if (!acgt) {  // non-ACGT target character: exact byte equality against every row of the chunk

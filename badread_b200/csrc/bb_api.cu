@@ -65,7 +65,7 @@ struct bb_ctx {
     int n_warps = 0;
     BBScratchPool pool{};
     DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_lhist, s_ltbuf, s_leafhist;
-    DevBuf q_node[3][2], q_leaf[2], q_count;
+    DevBuf q_node[BBQ_NODE_CLASSES][2], q_leaf[2], q_count;
     bool use_tasks = true;
     BBLanePool lane_pool{};
     int n_lanes = 0;
@@ -153,7 +153,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_lhist, &ctx->s_ltbuf,
                       &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->q_leaf[0], &ctx->q_leaf[1],
                       &ctx->q_count, &ctx->q_node[0][0], &ctx->q_node[0][1], &ctx->q_node[1][0], &ctx->q_node[1][1],
-                      &ctx->q_node[2][0], &ctx->q_node[2][1]};
+                      &ctx->q_node[2][0], &ctx->q_node[2][1], &ctx->q_node[3][0], &ctx->q_node[3][1]};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
@@ -385,45 +385,60 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
 // Final alignment as level-synchronous tasks (bb_tasks.cuh): roots are classified here, every level of all
 // reads' Hirschberg trees is three launches (wide-warp, lean-warp, lane nodes), leaves run at the end.
 static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<BBReadDev> &reads) {
-    cudaStream_t st = ctx->stream;
+    (void)reads;
+    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
     const int n = ctx->n_reads;
     const int cap_node = (int)std::min<int64_t>(ctx->seq_total / 256 + 4ll * n + 1024, 0x7ffffff0);
     const int cap_leaf = cap_node;
-    for (int c = 0; c < 3; c++)
+    for (int c = 0; c < BBQ_NODE_CLASSES; c++)
         for (int p = 0; p < 2; p++) BB_CUDA(ctx, ctx->q_node[c][p].ensure((size_t)cap_node * sizeof(BBNode)));
     for (int w = 0; w < 2; w++) BB_CUDA(ctx, ctx->q_leaf[w].ensure((size_t)cap_leaf * sizeof(BBNode)));
     BB_CUDA(ctx, ctx->q_count.ensure(512 * sizeof(int)));
     const int lane_ctas = ctx->sm_count * 4;  // 64-thread CTAs of the lane kernels
     BB_CUDA(ctx, ctx->s_leafhist.ensure((size_t)lane_ctas * 64 * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
     BBQueues Q;
-    for (int c = 0; c < 3; c++)
+    for (int c = 0; c < BBQ_NODE_CLASSES; c++)
         for (int p = 0; p < 2; p++) Q.node[c][p] = ctx->q_node[c][p].as<BBNode>();
     Q.leaf[0] = ctx->q_leaf[0].as<BBNode>(); Q.leaf[1] = ctx->q_leaf[1].as<BBNode>();
     int *cnt = ctx->q_count.as<int>();
-    Q.count = cnt; Q.overflow = cnt + 8; Q.cap_node = cap_node; Q.cap_leaf = cap_leaf;
+    Q.count = cnt; Q.overflow = cnt + BBQ_OVERFLOW; Q.cap_node = cap_node; Q.cap_leaf = cap_leaf;
     BB_CUDA(ctx, cudaMemsetAsync(cnt, 0, 512 * sizeof(int), st));
     bb_k_push_roots<<<(n + 255) / 256, 256, 0, st>>>(B, Q);
     ctx->launches++;
     int *cursor = cnt + 16;
-    const int grid_wide = ctx->sm_count * 2, grid_lean = ctx->sm_count * 3;
+    // the wide-band warp kernel (one CTA per SM, 255 registers) runs on the second stream next to the lean and lane
+    // kernels of the same level; its warps use the upper half of the scratch pool
+    const int grid_wide = ctx->sm_count, grid_lean = ctx->sm_count * 2;
+    const int wide_base = ctx->n_warps / 2;
     const int max_levels = 40;  // the target halves at every level: 2^40 columns is beyond any read
     for (int level = 0; level < max_levels; level++) {
         const int p = level & 1;
         // the queues of the next level start empty
-        for (int c = 0; c < 3; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt + c * 2 + (p ^ 1), 0, sizeof(int), st));
-        bb_k_node_warp<32><<<grid_wide, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, BBQ_NODE_WIDE, p, cursor++);
-        bb_k_node_warp<4><<<grid_lean, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, BBQ_NODE_LEAN, p, cursor++);
-        bb_k_node_lane<<<lane_ctas, 64, 0, st>>>(B, Q, p, cursor++);
-        ctx->launches += 3;
+        for (int c = 0; c < BBQ_NODE_CLASSES; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt + c * 2 + (p ^ 1), 0, sizeof(int), st));
+        BB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        BB_CUDA(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
+        bb_k_node_warp<32><<<grid_wide, BB_WARPS_PER_CTA * 32, 0, st2>>>(B, Q, ctx->pool, BBQ_NODE_WIDE, p, cursor++, wide_base);
+        BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, st2));
+        bb_k_node_warp<4><<<grid_lean, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, BBQ_NODE_LEAN, p, cursor++, 0);
+        bb_k_node_lane<BB_NODE_LW><<<lane_ctas, 64, 0, st>>>(B, Q, p, cursor++);
+        bb_k_node_lane<BB_NODE_LW_SMALL><<<lane_ctas, 64, 0, st>>>(B, Q, p, cursor++);
+        BB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        ctx->launches += 4;
         if (level >= 3 && (level & 3) == 3) {  // every few levels: stop as soon as the queues are empty
-            int h[6];
+            int h[2 * BBQ_NODE_CLASSES];
             BB_CUDA(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
             BB_CUDA(ctx, cudaStreamSynchronize(st));
-            if (h[0 + (p ^ 1)] + h[2 + (p ^ 1)] + h[4 + (p ^ 1)] == 0) break;
+            int pending = 0;
+            for (int c = 0; c < BBQ_NODE_CLASSES; c++) pending += h[c * 2 + (p ^ 1)];
+            if (pending == 0) break;
         }
     }
-    bb_k_leaf_warp<<<grid_wide, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, cursor++);
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    BB_CUDA(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
+    bb_k_leaf_warp<<<grid_wide, BB_WARPS_PER_CTA * 32, 0, st2>>>(B, Q, ctx->pool, cursor++, wide_base);
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, st2));
     bb_k_leaf_lane<<<lane_ctas, 64, 0, st>>>(B, Q, ctx->s_leafhist.as<uint2>(), cursor++);
+    BB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     ctx->launches += 2;
     int h_over = 0;
     BB_CUDA(ctx, cudaMemcpyAsync(&h_over, Q.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -17,19 +17,22 @@
 #include "bb_align.cuh"
 #include "bb_lane.cuh"
 
-#define BB_NODE_LW 16        // window words of the lane node kernel (bands up to 32*14 rows)
+#define BB_NODE_LW 16        // window words of the wider lane node kernel (bands up to 32*14 rows)
+#define BB_NODE_LW_SMALL 8   // window words of the narrow lane node kernel
 #define BB_LEAF_LW 8         // window words of the lane leaf kernel
 #define BB_LEAF_LANE_COLS 2048
 #define BB_WARP_LEAN_BAND 1792  // a + b the MAXL = 4 warp build can pair (448 * 4)
 
-enum { BBQ_NODE_LANE = 0, BBQ_NODE_LEAN = 1, BBQ_NODE_WIDE = 2, BBQ_LEAF_LANE = 3, BBQ_LEAF_WARP = 4, BBQ_N = 5 };
+enum { BBQ_NODE_LANE8 = 0, BBQ_NODE_LANE16 = 1, BBQ_NODE_LEAN = 2, BBQ_NODE_WIDE = 3, BBQ_NODE_CLASSES = 4 };
+#define BBQ_LEAF_COUNT 8   // Q.count index of the leaf counters (lane, warp)
+#define BBQ_OVERFLOW 10
 
 struct BBNode { int r, q0, nn, t0, mm, best; };  // best < 0: root (band from the read's edit bound)
 
 struct BBQueues {
-    BBNode *node[3][2];  // [class][level parity]
+    BBNode *node[BBQ_NODE_CLASSES][2];  // [class][level parity]
     BBNode *leaf[2];     // lane, warp
-    int *count;          // node counts: [class*2 + parity]; leaf counts: [6 + which]
+    int *count;          // node counts: [class*2 + parity]; leaf counts: [BBQ_LEAF_COUNT + which]
     int *overflow;
     int cap_node, cap_leaf;
 };
@@ -73,11 +76,13 @@ __device__ void bb_push_task(const BBQueues &Q, int next_parity, const BBAlignOu
     const int lw = bb_lane_words(a, b);
     if (bb_uses_traceback(nd.nn, nd.mm)) {
         const int which = (lw <= BB_LEAF_LW && nd.mm <= BB_LEAF_LANE_COLS) ? 0 : 1;
-        const int idx = atomicAdd(&Q.count[6 + which], 1);
+        const int idx = atomicAdd(&Q.count[BBQ_LEAF_COUNT + which], 1);
         if (idx >= Q.cap_leaf) { atomicExch(Q.overflow, 1); return; }
         Q.leaf[which][idx] = nd;
     } else {
-        const int cls = lw <= BB_NODE_LW ? BBQ_NODE_LANE : (a + b <= BB_WARP_LEAN_BAND ? BBQ_NODE_LEAN : BBQ_NODE_WIDE);
+        const int cls = lw <= BB_NODE_LW_SMALL ? BBQ_NODE_LANE8
+                        : lw <= BB_NODE_LW ? BBQ_NODE_LANE16
+                                           : (a + b <= BB_WARP_LEAN_BAND ? BBQ_NODE_LEAN : BBQ_NODE_WIDE);
         const int idx = atomicAdd(&Q.count[cls * 2 + next_parity], 1);
         if (idx >= Q.cap_node) { atomicExch(Q.overflow, 1); return; }
         Q.node[cls][next_parity][idx] = nd;
@@ -220,11 +225,12 @@ __device__ int bb_lane_column_scores(const BBLanePass<LW> &S, int n, int lo, int
 }
 
 // ---------------------------------------------------------------------------------------------- lane node kernel
+template <int LW>
 __global__ void __launch_bounds__(64)
 bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
-    constexpr int LW = BB_NODE_LW;
-    const BBNode *list = Q.node[BBQ_NODE_LANE][parity];
-    const int count = min(Q.count[BBQ_NODE_LANE * 2 + parity], Q.cap_node);
+    constexpr int CLS = LW <= BB_NODE_LW_SMALL ? BBQ_NODE_LANE8 : BBQ_NODE_LANE16;
+    const BBNode *list = Q.node[CLS][parity];
+    const int count = min(Q.count[CLS * 2 + parity], Q.cap_node);
     BBLanePass<LW> S;
     BBProb P;
     BBNode nd;
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(64)
 bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
     constexpr int LW = BB_LEAF_LW;
     const BBNode *list = Q.leaf[0];
-    const int count = min(Q.count[6], Q.cap_leaf);
+    const int count = min(Q.count[BBQ_LEAF_COUNT], Q.cap_leaf);
     uint2 *const hist = hist_pool + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * (long long)(BB_LEAF_LANE_COLS * LW);
     BBLanePass<LW> S;
     BBProb P;
@@ -362,9 +368,9 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
 // One Hirschberg node per warp with the wavefront passes of bb_align.cuh (MAXL bounds the instantiated variants).
 template <int MAXL>
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (MAXL <= 4 ? 3 : 1))
-bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity, int *cursor) {
+bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity, int *cursor, int warp_base) {
     const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int warp = warp_base + blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
     BBScratch sc = pool.for_warp(warp);
     const BBNode *list = Q.node[cls][parity];
     const int count = min(Q.count[cls * 2 + parity], Q.cap_node);
@@ -400,12 +406,12 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity
 
 // One leaf per warp (bands or lengths beyond the lane kernel's limits).
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 2)
-bb_k_leaf_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int *cursor) {
+bb_k_leaf_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int *cursor, int warp_base) {
     const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int warp = warp_base + blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
     BBScratch sc = pool.for_warp(warp);
     const BBNode *list = Q.leaf[1];
-    const int count = min(Q.count[7], Q.cap_leaf);
+    const int count = min(Q.count[BBQ_LEAF_COUNT + 1], Q.cap_leaf);
     for (;;) {
         int w = 0;
         if (lane == 0) w = atomicAdd(cursor, 1);

@@ -92,12 +92,12 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     B.speq = speq.data();
     std::memset(dcnt, 0, (size_t)n * sizeof(unsigned int));
     const int cap = 8192;
-    std::vector<BBNode> qn[3][2], ql[2];
+    std::vector<BBNode> qn[BBQ_NODE_CLASSES][2], ql[2];
     std::vector<int> cnt(512, 0);
     BBQueues Q;
-    for (int c = 0; c < 3; c++) for (int p = 0; p < 2; p++) { qn[c][p].resize(cap); Q.node[c][p] = qn[c][p].data(); }
+    for (int c = 0; c < BBQ_NODE_CLASSES; c++) for (int p = 0; p < 2; p++) { qn[c][p].resize(cap); Q.node[c][p] = qn[c][p].data(); }
     for (int w = 0; w < 2; w++) { ql[w].resize(cap); Q.leaf[w] = ql[w].data(); }
-    Q.count = cnt.data(); Q.overflow = cnt.data() + 8; Q.cap_node = cap; Q.cap_leaf = cap;
+    Q.count = cnt.data(); Q.overflow = cnt.data() + BBQ_OVERFLOW; Q.cap_node = cap; Q.cap_leaf = cap;
     // scratch for the warp kernels (warp 0 only) and the lane leaf kernel
     const int big = std::max(n, m) + 64;
     std::vector<uint2> hist(106496), lhist((size_t)32 * BB_LEAF_LANE_COLS * BB_LEAF_LW);
@@ -117,16 +117,19 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     int *cursor = cnt.data() + 16;
     for (int level = 0; level < 40; level++) {
         const int p = level & 1;
-        for (int c = 0; c < 3; c++) cnt[c * 2 + (p ^ 1)] = 0;
-        int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++;
-        emu::run_warp([&]() { bb_k_node_warp<32>(B, Q, pool, BBQ_NODE_WIDE, p, c0); });
-        emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, BBQ_NODE_LEAN, p, c1); });
-        emu::run_warp([&]() { bb_k_node_lane(B, Q, p, c2); });
-        if (cnt[0 + (p ^ 1)] + cnt[2 + (p ^ 1)] + cnt[4 + (p ^ 1)] == 0) break;
+        for (int c = 0; c < BBQ_NODE_CLASSES; c++) cnt[c * 2 + (p ^ 1)] = 0;
+        int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++, *c2b = cursor++;
+        emu::run_warp([&]() { bb_k_node_warp<32>(B, Q, pool, BBQ_NODE_WIDE, p, c0, 0); });
+        emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, BBQ_NODE_LEAN, p, c1, 0); });
+        emu::run_warp([&]() { bb_k_node_lane<BB_NODE_LW>(B, Q, p, c2); });
+        emu::run_warp([&]() { bb_k_node_lane<BB_NODE_LW_SMALL>(B, Q, p, c2b); });
+        int pending = 0;
+        for (int c = 0; c < BBQ_NODE_CLASSES; c++) pending += cnt[c * 2 + (p ^ 1)];
+        if (pending == 0) break;
     }
     int *c3 = cursor++, *c4 = cursor++;
-    emu::run_warp([&]() { bb_k_leaf_warp(B, Q, pool, c3); });
+    emu::run_warp([&]() { bb_k_leaf_warp(B, Q, pool, c3, 0); });
     emu::run_warp([&]() { bb_k_leaf_lane(B, Q, lhist.data(), c4); });
-    out5[0] = rd.matches; out5[1] = rd.dels; out5[2] = cnt[8]; out5[3] = rd.lead_del; out5[4] = rd.flags;
+    out5[0] = rd.matches; out5[1] = rd.dels; out5[2] = cnt[BBQ_OVERFLOW]; out5[3] = rd.lead_del; out5[4] = rd.flags;
     return 0;
 }
