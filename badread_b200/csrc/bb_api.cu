@@ -64,11 +64,12 @@ struct bb_ctx {
     // scratch
     int n_warps = 0;
     BBScratchPool pool{};
-    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_lhist, s_ltbuf, s_leafhist;
+    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist;
+    DevBuf d_ctime, d_chlog, d_wres, d_wtasks, d_wfallback, d_active;
+    bool use_spec_loop = true;
     DevBuf q_node[BBQ_NODE_CLASSES][2], q_leaf[2], q_count;
     bool use_tasks = true;
-    BBLanePool lane_pool{};
-    int n_lanes = 0;
+
 
     cudaEvent_t ev[BB_N_STAGES + 1] = {};
     float stage_ms[BB_N_STAGES] = {};
@@ -137,6 +138,7 @@ extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
     // persistent warps: 4 CTAs of 4 warps per SM for the warp-per-read kernels
     ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
     if (const char *e = std::getenv("BADREAD_B200_ALIGN_TASKS")) ctx->use_tasks = (e[0] != '0');
+    if (const char *e = std::getenv("BADREAD_B200_SPEC_LOOP")) ctx->use_spec_loop = (e[0] != '0');
     *out = ctx;
     return BB_OK;
 }
@@ -150,7 +152,8 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order, &ctx->d_order_small, &ctx->d_order_large, &ctx->d_order_long,
                       &ctx->d_reads, &ctx->d_frag, &ctx->d_state, &ctx->d_seq, &ctx->d_ops, &ctx->d_dcnt,
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
-                      &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_lhist, &ctx->s_ltbuf,
+                      &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
+                      &ctx->d_wtasks, &ctx->d_wfallback, &ctx->d_active,
                       &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->q_leaf[0], &ctx->q_leaf[1],
                       &ctx->q_count, &ctx->q_node[0][0], &ctx->q_node[0][1], &ctx->q_node[1][0], &ctx->q_node[1][1],
                       &ctx->q_node[2][0], &ctx->q_node[2][1], &ctx->q_node[3][0], &ctx->q_node[3][1]};
@@ -295,6 +298,9 @@ static BBBatchDev batch_dev(bb_ctx *ctx) {
     B.out_qual = ctx->d_out_qual.as<uint8_t>();
     B.fpeq = ctx->d_fpeq.as<uint4>();
     B.speq = ctx->d_speq.as<uint4>();
+    B.ctime = ctx->d_ctime.as<unsigned int>();
+    B.chlog = ctx->d_chlog.as<uint2>();
+    B.wres = ctx->d_wres.as<int2>();
     return B;
 }
 
@@ -309,7 +315,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     const int k = ctx->em.k;
     ctx->h_reads.assign((size_t)n_reads, BBReadDev{});
     ctx->h_inlen.assign((size_t)n_reads, 0);
-    int64_t off = 0, peq_off = 0;
+    int64_t off = 0, peq_off = 0, log_off = 0, wres_off = 0;
     int max_len = 0;
     for (int32_t r = 0; r < n_reads; r++) {
         int64_t len = 0;
@@ -329,6 +335,14 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
         rd.frag_len = (int)(len + 2 * k);
         rd.fpeq_off = peq_off;
         peq_off += bb_peq_words(rd.frag_len);
+        {   // speculative loop bookkeeping: the loop cannot apply more than 0.9*len + k changes (simulate.py:285)
+            const int cap = (int)(0.9 * (double)rd.frag_len) + k + 2;
+            rd.log_off = log_off; rd.wres_off = wres_off;
+            log_off += cap; wres_off += cap / BB_ALIGNMENT_INTERVAL + 1;
+            const double need = (double)rd.frag_len * (1.0 - target_identity[r]);
+            rd.horizon = (int)std::min<double>((double)cap, std::max(0.0, 1.25 * need) + 48.0);
+            rd.n_logged = 0; rd.n_resume = 0; rd.a_done = 0; rd.status = BB_READ_PENDING; rd.stop_reason = 0;
+        }
         off += (rd.frag_len + 15) & ~15;
         max_len = std::max(max_len, rd.frag_len);
     }
@@ -339,19 +353,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
                      [&](int x, int y) { return ctx->h_reads[(size_t)x].frag_len > ctx->h_reads[(size_t)y].frag_len; });
     ctx->n_reads = n_reads;
     ctx->h_order = order;
-    // error loop: one thread per read, except the longest reads (a single thread would be the makespan): they get
-    // a whole warp each, concurrently on a second stream
-    // (lane mode needs >= ~100k reads in flight to hide latency; below that every read gets a warp)
-    std::vector<int> lane_order, long_order;
-    bool lane_mode = n_reads >= 100000;
-    if (const char *e = std::getenv("BADREAD_B200_LANE_MODE")) lane_mode = (e[0] == '1');
-    for (int r : order) ((!lane_mode || ctx->h_reads[(size_t)r].frag_len > 50000) ? long_order : lane_order).push_back(r);
-    ctx->n_lane_reads = (int)lane_order.size();
-    ctx->n_long_reads = (int)long_order.size();
     int rc;
-    if ((rc = upload(ctx, ctx->d_order_long, long_order.data(), long_order.size()))) return rc;
-    order = lane_order;
-    order.resize((size_t)n_reads, 0);
     if ((rc = upload(ctx, ctx->d_read_index, read_index, (size_t)n_reads))) return rc;
     if ((rc = upload(ctx, ctx->d_seg_off, seg_off, (size_t)n_reads + 1))) return rc;
     if ((rc = upload(ctx, ctx->d_segs, segs, (size_t)seg_off[n_reads]))) return rc;
@@ -366,19 +368,67 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     BB_CUDA(ctx, ctx->d_fallback.ensure(((size_t)n_reads + 4) * sizeof(int)));
     ctx->fpeq_total = peq_off;
     if ((rc = ensure_scratch(ctx, max_len, 4096, max_len))) return rc;
-    {   // lane-per-read scratch: history of one window (<= 2048 columns x 8 words) and the joined window
-        const int n_lanes = std::min(((n_reads + 63) / 64) * 64, 32768);
-        const int max_cols = 2048, tbuf_cap = 4096;
-        BB_CUDA(ctx, ctx->s_lhist.ensure((size_t)n_lanes * max_cols * 8 * sizeof(uint2)));
-        BB_CUDA(ctx, ctx->s_ltbuf.ensure((size_t)n_lanes * tbuf_cap));
-        ctx->n_lanes = n_lanes;
-        ctx->lane_pool.hist = ctx->s_lhist.as<uint2>(); ctx->lane_pool.hist_stride = (long long)max_cols * 8;
-        ctx->lane_pool.tbuf = ctx->s_ltbuf.as<uint8_t>(); ctx->lane_pool.tbuf_cap = tbuf_cap;
-        ctx->lane_pool.max_cols = max_cols;
+    BB_CUDA(ctx, ctx->d_ctime.ensure(((size_t)off + 16) * sizeof(unsigned int)));
+    BB_CUDA(ctx, ctx->d_chlog.ensure(((size_t)log_off + 16) * sizeof(uint2)));
+    BB_CUDA(ctx, ctx->d_wres.ensure(((size_t)wres_off + 16) * sizeof(int2)));
+    BB_CUDA(ctx, ctx->d_wtasks.ensure(((size_t)wres_off + 16) * sizeof(BBWinTask)));
+    BB_CUDA(ctx, ctx->d_wfallback.ensure(((size_t)wres_off + 16) * sizeof(BBWinTask)));
+    BB_CUDA(ctx, ctx->d_active.ensure(((size_t)n_reads + 16) * sizeof(int)));
+    {   // lane pools shared by the window aligner and the leaf aligner: history of 2048 columns x 8 words per thread
+        const size_t lanes = (size_t)ctx->sm_count * 4 * 64;
+        BB_CUDA(ctx, ctx->s_leafhist.ensure(lanes * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
+        BB_CUDA(ctx, ctx->s_ltbuf.ensure(lanes * BB_WIN_MAX_COLS));
     }
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->uploaded = true;
     ctx->ran = false;
+    return BB_OK;
+}
+
+// The error loop decoupled from its identity re-measurements (bb_loop.cuh): mutate ahead -> all window alignments
+// as independent lane tasks -> scalar replay; reads whose horizon was too short go round again.
+static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev> &reads) {
+    cudaStream_t st = ctx->stream;
+    const int n = ctx->n_reads;
+    int *cnt = ctx->d_counter.as<int>();
+    std::vector<int> active = ctx->h_order;  // longest fragments first
+    const int grid_warp = ctx->n_warps / BB_WARPS_PER_CTA;
+    const int lane_ctas = ctx->sm_count * 4;
+    std::vector<BBWinTask> tasks;
+    for (int round = 0; !active.empty(); round++) {
+        if (round >= 12) return set_err(ctx, BB_ERR_INTERNAL, "error loop did not converge");
+        const int n_active = (int)active.size();
+        BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, active.data(), (size_t)n_active * sizeof(int), cudaMemcpyHostToDevice, st));
+        BB_CUDA(ctx, cudaMemsetAsync(cnt + 8, 0, 8 * sizeof(int), st));
+        bb_k_mutate<<<std::min(grid_warp, (n_active + BB_WARPS_PER_CTA - 1) / BB_WARPS_PER_CTA), BB_WARPS_PER_CTA * 32, 0, st>>>(
+            B, ctx->em, ctx->seed, cnt + 8, ctx->d_active.as<int>(), n_active);
+        ctx->launches++;
+        BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
+        BB_CUDA(ctx, cudaStreamSynchronize(st));
+        tasks.clear();
+        for (int r : active) {
+            const BBReadDev &rd = reads[(size_t)r];
+            for (int a = rd.a_done + 1; a <= rd.n_logged / BB_ALIGNMENT_INTERVAL; a++) tasks.push_back(BBWinTask{r, a});
+        }
+        const int n_tasks = (int)tasks.size();
+        if (n_tasks > 0) {
+            BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_wtasks.p, tasks.data(), (size_t)n_tasks * sizeof(BBWinTask), cudaMemcpyHostToDevice, st));
+            bb_k_window_lane<<<std::min(lane_ctas, (n_tasks + 63) / 64), 64, 0, st>>>(
+                B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), n_tasks, ctx->seed, ctx->s_leafhist.as<uint2>(),
+                ctx->s_ltbuf.as<uint8_t>(), cnt + 9, ctx->d_wfallback.as<BBWinTask>(), cnt + 10);
+            bb_k_window_warp<<<ctx->sm_count * 2, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->d_wfallback.as<BBWinTask>(),
+                                                                                 cnt + 10, ctx->seed, cnt + 11);
+            ctx->launches += 2;
+        }
+        bb_k_replay<<<(n_active + 127) / 128, 128, 0, st>>>(B, ctx->d_active.as<int>(), n_active, ctx->em.k);
+        ctx->launches++;
+        BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
+        BB_CUDA(ctx, cudaStreamSynchronize(st));
+        std::vector<int> next;
+        for (int r : active)
+            if (reads[(size_t)r].status != BB_READ_DONE) next.push_back(r);
+        active.swap(next);
+    }
     return BB_OK;
 }
 
@@ -466,35 +516,20 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
     ctx->launches++;
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // one thread per read; reads whose windows exceed the lane-mode limits are redone by the warp kernel
-    if (ctx->n_long_reads > 0) {  // the longest reads: one warp each, on the second stream
-        const int h_n_long = ctx->n_long_reads;
-        BB_CUDA(ctx, cudaMemcpyAsync(counters + 6, &h_n_long, sizeof(int), cudaMemcpyHostToDevice, st));
-        BB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-        BB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-        const int grid_long = std::min(ctx->n_lane_reads > 0 ? ctx->sm_count * 2 : ctx->sm_count * 4,
-                                       (h_n_long + BB_WARPS_PER_CTA - 1) / BB_WARPS_PER_CTA);
-        // scratch of warps [n_warps/2, ...) so that it cannot collide with the fall-back launch below
-        bb_k_error_loop<<<grid_long, BB_WARPS_PER_CTA * 32, 0, ctx->stream2>>>(
-            B, ctx->em, ctx->pool, ctx->seed, counters + 5, ctx->d_order_long.as<int>(), counters + 6, 0,
-            ctx->n_lane_reads > 0 ? ctx->n_warps / 2 : 0);
-        ctx->launches++;
-        BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
-    }
-    if (ctx->n_lane_reads > 0) {
-        const int lanes = std::min(ctx->n_lanes, ((ctx->n_lane_reads + 63) / 64) * 64);
-        bb_k_error_loop_lane<<<lanes / 64, 64, 0, st>>>(B, ctx->em, ctx->lane_pool, ctx->seed, counters, ctx->d_order.as<int>(),
-                                                        ctx->n_lane_reads, ctx->d_fallback.as<int>(), counters + 3);
+    std::vector<BBReadDev> reads((size_t)n);
+    if (ctx->use_spec_loop) {
+        int rcl = run_spec_loop(ctx, B, reads);
+        if (rcl) return rcl;
+    } else {
+        // sequential variant: one warp per read interleaves the k-mer loop with its window alignments
+        const int h_n = n;
+        BB_CUDA(ctx, cudaMemcpyAsync(counters + 6, &h_n, sizeof(int), cudaMemcpyHostToDevice, st));
+        bb_k_error_loop<<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->seed, counters + 5,
+                                                                     ctx->d_order.as<int>(), counters + 6, 0, 0);
         ctx->launches++;
     }
-    if (ctx->n_lane_reads > 0) {  // reads whose windows exceeded the lane-mode limits are redone by the warp kernel
-        bb_k_error_loop<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->seed, counters + 4,
-                                                                          ctx->d_fallback.as<int>(), counters + 3, 1, 0);
-        ctx->launches++;
-    }
-    if (ctx->n_long_reads > 0) BB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     // host scan of the joined lengths -> offsets of the per-read regions in seq / ops / dcnt / qual / out
-    std::vector<BBReadDev> reads((size_t)n);
     BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
     BB_CUDA(ctx, cudaStreamSynchronize(st));
     int64_t seq_off = 0, out_off = 0, speq_off = 0;

@@ -58,7 +58,15 @@ struct BBReadDev {
     int out_len;
     int flags;
     int kc_loop, kc_align;  // kilo-cycles this read spent in the error loop / final alignment (diagnostics)
-    int pad_;
+    // speculative error loop (bb_loop.cuh)
+    long long log_off;   // into chlog (change log), entries
+    long long wres_off;  // into wres (window alignment results), entries
+    int horizon;         // changes the mutate kernel may log before pausing
+    int n_logged;        // changes logged so far
+    int n_resume;        // next loop iteration to evaluate
+    int stop_reason;     // why the mutate kernel stopped (BB_STOP_*)
+    int a_done;          // window alignments already computed
+    int status;          // BB_READ_*
 };
 
 struct BBBatchDev {
@@ -78,6 +86,9 @@ struct BBBatchDev {
     uint8_t *qual;
     uint8_t *out_seq, *out_qual;
     uint4 *fpeq, *speq;
+    unsigned int *ctime;   // per slot: ordinal of the change that rewrote it (0 = pristine)
+    uint2 *chlog;          // per read: (iteration, position) of every applied change, in order
+    int2 *wres;            // per read: (matches, columns) of every window alignment
 };
 
 struct BBScratchPool {
@@ -131,7 +142,8 @@ __global__ void __launch_bounds__(256) bb_k_build_fragments(BBBatchDev B, const 
         }
         pos += sg.len;
     }
-    for (int x = threadIdx.x; x < flen; x += blockDim.x) st[x] = BB_SLOT_NONE;
+    unsigned int *ct = B.ctime + rd.frag_off;
+    for (int x = threadIdx.x; x < flen; x += blockDim.x) { st[x] = BB_SLOT_NONE; ct[x] = 0u; }
     // match bitmap of the padded fragment (bb_build_peq layout), one ballot group per 32 bases
     __syncthreads();
     uint4 *pq = B.fpeq + rd.fpeq_off;
@@ -386,164 +398,6 @@ bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned l
     }
 }
 
-// ------------------------------------------------------------------------------------------------ K2 (lane per read)
-struct BBLanePool {
-    uint2 *hist; long long hist_stride;  // entries per lane
-    uint8_t *tbuf; int tbuf_cap;         // joined window per lane
-    int max_cols;                        // hist_stride / 8: columns a lane can keep at 8 window words
-};
-
-// simulate.sequence_fragment's while-loop (simulate.py:272-346), one read per THREAD, written as a warp-synchronous
-// state machine so that the 32 lanes of a warp stay on the same instruction stream:
-//   phase A  every lane advances its own k-mer loop until it needs an identity re-measurement (every 25 applied
-//            changes) or runs out of reads;
-//   phase B  all lanes that need one join their window, run the lane aligner and fold the result into `errors`.
-// A read whose window exceeds the lane-mode limits (band wider than 8 window words, joined window longer than
-// the lane's buffers, or a window edlib would not trace back directly) is handed to the warp kernel.
-__global__ void __launch_bounds__(64)
-bb_k_error_loop_lane(BBBatchDev B, BBErrorModelDev em, BBLanePool pool, unsigned long long seed, int *work_counter,
-                     const int *order, int n_items, int *fallback_list, int *fallback_count) {
-    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    uint2 *const hist = pool.hist + gl * pool.hist_stride;
-    uint8_t *const tbuf = pool.tbuf + gl * pool.tbuf_cap;
-    const int k = em.k;
-    // per-read state
-    int r = -1;
-    BBReadDev *rd = nullptr;
-    const uint8_t *frag = nullptr;
-    uint32_t *state = nullptr;
-    int frag_len = 0, max_kmer_index = 0;
-    unsigned long long read = 0;
-    double target = 0.0, fl = 0.0, cc_limit = 0.0, errors = 0.0, est_id = 1.0, scale = 0.0;
-    long long limit = 0, n = 0, loop_count = 0, clk0 = 0;
-    int change_count = 0, n_align = 0, upper = 0, flags = 0, total = 0, st_trim = 0, en_trim = 0;
-    // per-iteration state (a changed k-mer is applied slot by slot; an alignment may interrupt it)
-    int jres = 0x7fffffff, pos_i = 0, kind = 0, rpos = 0;
-    uint32_t payload = 0;
-    bool have_read = false, idle = false, need_align = false;
-    for (;;) {
-        // ---------------------------------------------------------------- phase A
-        while (!idle && !need_align) {
-            if (!have_read) {
-                const int w = atomicAdd(work_counter, 1);
-                if (w >= n_items) { idle = true; break; }
-                r = order[w];
-                rd = &B.reads[r];
-                clk0 = clock64();
-                frag = B.frag + rd->frag_off;
-                state = B.state + rd->frag_off;
-                frag_len = rd->frag_len;
-                read = B.read_index[r];
-                target = B.target[r];
-                fl = (double)frag_len;
-                max_kmer_index = frag_len - 1 - k;
-                limit = 100ll * frag_len;
-                cc_limit = __dmul_rn(0.9, fl);
-                errors = 0.0; est_id = 1.0;
-                change_count = 0; n_align = 0; upper = 0; flags = 0;
-                total = frag_len; st_trim = k; en_trim = k;
-                n = 0; loop_count = 0; jres = 0x7fffffff;
-                have_read = true;
-                if (__dmul_rn(fl, __dsub_rn(1.0, target)) < 0.5) n = -1;  // estimated_errors_needed < 0.5: no loop
-            }
-            if (jres >= k) {
-                // top of an iteration (simulate.py:278-292), or the end of the read
-                bool finished = false;
-                if (n < 0) { finished = true; loop_count = 0; }
-                else if (n >= limit) { finished = true; loop_count = limit + 1; }
-                else if ((double)change_count > cc_limit || est_id <= target || flags) { finished = true; loop_count = n + 1; }
-                if (finished) {
-                    rd->seq_len = total; rd->start_trim = st_trim; rd->end_trim = en_trim; rd->upper = upper;
-                    rd->loop_count = (int)(loop_count > 0x7fffffff ? 0x7fffffff : loop_count);
-                    rd->change_count = change_count; rd->n_align = n_align; rd->flags = flags;
-                    rd->kc_loop = (int)((clock64() - clk0) >> 10);
-                    have_read = false;
-                    continue;
-                }
-                bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
-                n++;
-                if (kind == 0) continue;
-                scale = __dmul_rn(est_id, __dsqrt_rn(est_id));
-                jres = 0;
-            }
-            // apply slot jres of the changed k-mer (simulate.py:303-321)
-            const int j = jres++;
-            const uint8_t fb = frag[pos_i + j];
-            const uint32_t enc = kind == 1 ? em.slots[(long long)payload * k + j]
-                                           : (j == rpos ? payload : bb_slot_inline(1, fb, 0));
-            const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
-            if (differs && state[pos_i + j] == BB_SLOT_NONE) {
-                state[pos_i + j] = enc;
-                const int len = (int)(enc & 0xff);
-                change_count++;
-                upper += len < 1 ? 1 : len;
-                total += len - 1;
-                if (pos_i + j < k) st_trim += len - 1;
-                if (pos_i + j >= frag_len - k) en_trim += len - 1;
-                errors = __dadd_rn(errors, __dmul_rn((double)(len < 2 ? 1 : len - 1), scale));
-                if (change_count % BB_ALIGNMENT_INTERVAL == 0) need_align = true;
-            }
-            if (jres >= k && !need_align) { est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl)); jres = 0x7fffffff; }
-        }
-        __syncwarp();
-        if (__all_sync(BB_FULL, idle)) break;
-        // ---------------------------------------------------------------- phase B (simulate.py:325-346)
-        if (need_align) {
-            int qpos = 0, qn = frag_len;
-            if (frag_len > BB_ALIGNMENT_SIZE) {
-                BBRng wr;
-                wr.init(seed, read);
-                wr.stream(BB_PURPOSE_WINDOW, (uint32_t)n_align);
-                qpos = (int)wr.randbelow((uint32_t)(frag_len - BB_ALIGNMENT_SIZE + 1));
-                qn = BB_ALIGNMENT_SIZE;
-            }
-            int tm = 0, uw = 0;
-            for (int x = 0; x < qn; x++) {  // ''.join(new_fragment_bases[pos:pos2])
-                const uint32_t st = state[qpos + x];
-                if (st == BB_SLOT_NONE) { if (tm < pool.tbuf_cap) tbuf[tm] = frag[qpos + x]; tm++; }
-                else {
-                    const int sl = (int)(st & 0xff);
-                    for (int c = 0; c < sl; c++) { if (tm < pool.tbuf_cap) tbuf[tm] = bb_slot_char(em, st, c); tm++; }
-                    uw += sl < 1 ? 1 : sl;
-                }
-            }
-            {
-                const int diff = qn > tm ? qn - tm : tm - qn;
-                if (uw < diff) uw = diff;
-                const int mx = qn > tm ? qn : tm;
-                if (uw > mx) uw = mx;
-            }
-            BBLaneProb P;
-            bb_band(qn, tm, uw, P.a, P.b);
-            const int lw = bb_lane_words(P.a, P.b);
-            if (tm > pool.tbuf_cap || tm > pool.max_cols || lw > 8 || !bb_uses_traceback(qn, tm)) {
-                fallback_list[atomicAdd(fallback_count, 1)] = r;  // the warp kernel redoes this read from scratch
-                have_read = false; need_align = false; jres = 0x7fffffff;
-            } else {
-                P.peq = B.fpeq + rd->fpeq_off; P.peq_bit0 = qpos + BB_PEQ_BIT0; P.q = frag + qpos; P.n = qn;
-                P.t = tbuf; P.m = tm; P.hist = hist;
-                int matches = 0, dels = 0, err = 0;
-                if (lw <= 4) { bb_lane_pass<4>(P); bb_lane_traceback<4>(P, matches, dels, err); }
-                else { bb_lane_pass<8>(P); bb_lane_traceback<8>(P, matches, dels, err); }
-                flags |= err;
-                const int cols = qn + dels;
-                const double actual = cols ? __ddiv_rn((double)matches, (double)cols) : 0.0;
-                if (frag_len <= BB_ALIGNMENT_SIZE) {
-                    errors = __dmul_rn(__dsub_rn(1.0, actual), fl);
-                } else {
-                    const double est_err = __dmul_rn(__dsub_rn(1.0, actual), fl);
-                    const double weight = __ddiv_rn((double)BB_ALIGNMENT_SIZE, fl);
-                    errors = __dadd_rn(__dmul_rn(est_err, weight), __dmul_rn(errors, __dsub_rn(1.0, weight)));
-                }
-                n_align++;
-                need_align = false;
-                if (jres >= k) { est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl)); jres = 0x7fffffff; }
-            }
-        }
-        __syncwarp();
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ K3
 __global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev em) {
     const int r = blockIdx.x;
@@ -727,3 +581,4 @@ __global__ void __launch_bounds__(256) bb_k_qscores_pair(const uint8_t *ops, con
 }
 
 #include "bb_tasks.cuh"
+#include "bb_loop.cuh"

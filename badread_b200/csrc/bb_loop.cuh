@@ -1,0 +1,355 @@
+// bb_loop.cuh — simulate.sequence_fragment's error loop (simulate.py:272-346) decoupled from its identity
+// re-measurements.
+//
+// Which slot mutates, and into what, never depends on the running error estimate `errors`: the position and the
+// alternative come from the iteration's own random stream, and whether a slot takes the change depends only on
+// the slots changed before.  `errors` (and with it every window alignment) decides one thing only: at the top of
+// which iteration the loop stops.  So the loop is split into three kernels that can each use the whole GPU:
+//   bb_k_mutate        one warp per read runs the k-mer loop AHEAD without any alignment, logging every applied
+//                      change (iteration, position) and stamping the slot with the change's ordinal; it stops at
+//                      the loop's own guards (simulate.py:278-286) or when a generous horizon of changes is reached.
+//   bb_k_window_lane   every identity re-measurement of every read is an independent task: "the window as it was
+//                      after 25*a changes" is rebuilt from the ordinals; one task per THREAD (bb_lane.cuh), so
+//                      several hundred thousand alignments are in flight at once.  Windows beyond the lane limits
+//                      go to bb_k_window_warp.
+//   bb_k_replay        one thread per read replays the scalar recurrence of `errors` over the change log with the
+//                      alignment results, finds the iteration at whose top the reference loop breaks, and rolls
+//                      back the changes logged past it.  A read whose horizon was too short is resumed.
+// The result is identical to running the loop sequentially (the oracle does exactly that).
+#pragma once
+#include <cstdint>
+
+#include "bb_lane.cuh"
+
+enum { BB_STOP_HORIZON = 0, BB_STOP_LIMIT = 1, BB_STOP_COUNT = 2, BB_STOP_NOLOOP = 3 };
+enum { BB_READ_PENDING = 0, BB_READ_DONE = 1 };
+
+#define BB_WIN_LW 8          // window words of the lane window aligner (bands up to 32*6 rows)
+#define BB_WIN_MAX_COLS 2048 // joined window length a lane can keep
+
+struct BBWinTask { int r, a; };  // read, alignment ordinal (1-based: after 25*a changes)
+
+// ------------------------------------------------------------------------------------------------ mutate
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
+bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter, const int *order,
+            int n_items) {
+    const int lane = threadIdx.x & 31;
+    const int k = em.k;
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1);
+        w = __shfl_sync(BB_FULL, w, 0);
+        if (w >= n_items) break;
+        const int r = order[w];
+        BBReadDev *rd = &B.reads[r];
+        const long long clk0 = clock64();
+        const uint8_t *frag = B.frag + rd->frag_off;
+        uint32_t *state = B.state + rd->frag_off;
+        unsigned int *ctime = B.ctime + rd->frag_off;
+        uint2 *chlog = B.chlog + rd->log_off;
+        const int frag_len = rd->frag_len;
+        const unsigned long long read = B.read_index[r];
+        const double target = B.target[r];
+        const double fl = (double)frag_len;
+        const int max_kmer_index = frag_len - 1 - k;
+        const long long limit = 100ll * frag_len;  // loop_count > 100 * frag_len stops the loop (simulate.py:279)
+        const double cc_limit = __dmul_rn(0.9, fl);
+        const int horizon = rd->horizon;
+        int change_count = rd->n_logged;
+        long long n0 = rd->n_resume;
+        int stop = -1;
+        if (__dmul_rn(fl, __dsub_rn(1.0, target)) < 0.5) stop = BB_STOP_NOLOOP;  // simulate.py:274
+        else if ((double)change_count > cc_limit) stop = BB_STOP_COUNT;
+        while (stop < 0) {
+            if (n0 >= limit) { stop = BB_STOP_LIMIT; break; }
+            const long long n = n0 + lane;
+            int kind = 0, pos_i = 0, rpos = 0;
+            uint32_t payload = 0;
+            if (n < limit) bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
+            __syncwarp();
+            uint32_t cmask = __ballot_sync(BB_FULL, kind != 0);
+            long long next_n0 = n0 + 32;
+            while (cmask) {
+                const int L = __ffs(cmask) - 1;
+                cmask &= cmask - 1;
+                if (change_count >= horizon) { stop = BB_STOP_HORIZON; next_n0 = n0 + L; break; }  // pause at an iteration top
+                const int bi = __shfl_sync(BB_FULL, pos_i, L);
+                const int bkind = __shfl_sync(BB_FULL, kind, L);
+                const uint32_t bpay = __shfl_sync(BB_FULL, payload, L);
+                const int brpos = __shfl_sync(BB_FULL, rpos, L);
+                uint32_t enc = 0;
+                bool app = false;
+                if (lane < k) {
+                    const uint8_t fb = frag[bi + lane];
+                    enc = bkind == 1 ? em.slots[(long long)bpay * k + lane]
+                                     : (lane == brpos ? bpay : bb_slot_inline(1, fb, 0));
+                    const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
+                    app = differs && state[bi + lane] == BB_SLOT_NONE;  // simulate.py:309
+                }
+                const uint32_t amask = __ballot_sync(BB_FULL, app);
+                if (app) {  // slots of one k-mer are distinct positions: apply them together, ordinals in slot order
+                    const int ord = change_count + __popc(amask & ((1u << lane) - 1u)) + 1;
+                    state[bi + lane] = enc;
+                    ctime[bi + lane] = (unsigned int)ord;
+                    chlog[ord - 1] = make_uint2((unsigned int)(n0 + L), (unsigned int)(bi + lane));
+                }
+                change_count += __popc(amask);
+                __syncwarp();
+                // the guard at the top of the next iteration (simulate.py:285) can only change after a commit
+                if ((double)change_count > cc_limit) { stop = BB_STOP_COUNT; next_n0 = n0 + L + 1; break; }
+            }
+            n0 = next_n0;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            rd->n_logged = change_count;
+            rd->n_resume = (int)(n0 > 0x7fffffff ? 0x7fffffff : n0);
+            rd->stop_reason = stop;
+            rd->kc_loop += (int)((clock64() - clk0) >> 10);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ window alignments
+// The window of identity re-measurement `a` of a read (simulate.py:325-346): position and length.
+__device__ __forceinline__ void bb_window_of(int frag_len, unsigned long long seed, unsigned long long read, int a,
+                                             int &qpos, int &qn) {
+    qpos = 0; qn = frag_len;
+    if (frag_len > BB_ALIGNMENT_SIZE) {
+        BBRng wr;
+        wr.init(seed, read);
+        wr.stream(BB_PURPOSE_WINDOW, (uint32_t)(a - 1));
+        qpos = (int)wr.randbelow((uint32_t)(frag_len - BB_ALIGNMENT_SIZE + 1));
+        qn = BB_ALIGNMENT_SIZE;
+    }
+}
+
+// One window alignment per thread; persistent lanes, all on the same step of the same phase.
+__global__ void __launch_bounds__(64)
+bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, int n_tasks, unsigned long long seed,
+                 uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback, int *fallback_count) {
+    constexpr int LW = BB_WIN_LW;
+    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint2 *const hist = hist_pool + gl * (long long)(BB_WIN_MAX_COLS * LW);
+    uint8_t *const tbuf = tbuf_pool + gl * (long long)BB_WIN_MAX_COLS;
+    BBLanePass<LW> S;
+    BBProb P;
+    BBWinTask tk = {0, 0};
+    const uint8_t *frag = nullptr;
+    const uint32_t *state = nullptr;
+    const unsigned int *ctime = nullptr;
+    int phase = 0;  // 0: fetch, 1: join, 2: forward pass, 3: traceback, 4: done
+    int qpos = 0, qn = 0, jx = 0, tm = 0, uw = 0, ti = 0, tj = 0, matches = 0, dels = 0;
+    unsigned int tmax = 0;
+    for (;;) {
+        if (phase == 0) {
+            const int w = atomicAdd(cursor, 1);
+            if (w >= n_tasks) phase = 4;
+            else {
+                tk = tasks[w];
+                const BBReadDev *rd = &B.reads[tk.r];
+                frag = B.frag + rd->frag_off; state = B.state + rd->frag_off; ctime = B.ctime + rd->frag_off;
+                bb_window_of(rd->frag_len, seed, B.read_index[tk.r], tk.a, qpos, qn);
+                tmax = (unsigned int)(BB_ALIGNMENT_INTERVAL * tk.a);
+                jx = 0; tm = 0; uw = 0;
+                phase = 1;
+            }
+        }
+        if (__all_sync(BB_FULL, phase == 4)) break;
+        for (int it = 0; it < 256; it++) {  // ''.join(new_fragment_bases[pos:pos2]) as it was after 25*a changes
+            if (phase == 1) {
+                const unsigned int ct = ctime[qpos + jx];
+                if (ct == 0u || ct > tmax) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = frag[qpos + jx]; tm++; }
+                else {
+                    const uint32_t st = state[qpos + jx];
+                    const int sl = (int)(st & 0xff);
+                    for (int c = 0; c < sl; c++) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = bb_slot_char(em, st, c); tm++; }
+                    uw += sl < 1 ? 1 : sl;
+                }
+                if (++jx >= qn) {
+                    const int diff = qn > tm ? qn - tm : tm - qn;
+                    if (uw < diff) uw = diff;
+                    const int mx = qn > tm ? qn : tm;
+                    if (uw > mx) uw = mx;
+                    bb_band(qn, tm, uw, P.a, P.b);
+                    if (tm > BB_WIN_MAX_COLS || bb_lane_words(P.a, P.b) > LW || !bb_uses_traceback(qn, tm)) {
+                        fallback[atomicAdd(fallback_count, 1)] = tk;  // the warp kernel handles this window
+                        phase = 0;
+                    } else {
+                        const BBReadDev *rd = &B.reads[tk.r];
+                        P.n = qn; P.peq = B.fpeq + rd->fpeq_off; P.q = frag + qpos; P.qs = 1;
+                        P.peq_bit0 = qpos + BB_PEQ_BIT0; P.t = tbuf; P.ts = 1;
+                        bb_lane_begin<LW>(S, P);
+                        phase = 2;
+                    }
+                }
+            }
+        }
+        for (int it = 0; it < 128; it++) {  // forward columns with history
+            if (phase == 2) {
+                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
+                if (S.c >= tm) { ti = qn - 1; tj = tm - 1; matches = 0; dels = 0; phase = 3; }
+            }
+        }
+        for (int it = 0; it < 256; it++) {  // traceback (edlib's rule), counting '=' and 'D' columns
+            if (phase == 3) {
+                if (ti >= 0 && tj >= 0) {
+                    int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
+                    const int x = (ti >> 5) - wt;
+                    if (x < 0 || x >= LW) { atomicOr(&B.reads[tk.r].flags, 1); ti = -1; tj = -1; }
+                    else {
+                        const uint2 e = hist[(long long)tj * LW + x];
+                        const int bit = ti & 31;
+                        if ((e.x >> bit) & 1u) ti--;
+                        else if ((e.y >> bit) & 1u) { dels++; tj--; }
+                        else { matches += (frag[qpos + ti] == tbuf[tj]) ? 1 : 0; ti--; tj--; }
+                    }
+                } else {
+                    if (tj >= 0) dels += tj + 1;
+                    B.wres[B.reads[tk.r].wres_off + tk.a - 1] = make_int2(matches, qn + dels);
+                    phase = 0;
+                }
+            }
+        }
+    }
+}
+
+// Windows beyond the lane limits: one warp each, with the general aligner.
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 4)
+bb_k_window_warp(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, const BBWinTask *tasks, const int *n_tasks_ptr,
+                 unsigned long long seed, int *cursor) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
+    BBScratch sc = pool.for_warp(warp);
+    uint8_t *tbuf = pool.tbuf + (long long)warp * pool.tbuf_stride;
+    const int n_tasks = *n_tasks_ptr;
+    BBEmit no_emit = {nullptr, nullptr, nullptr};
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(cursor, 1);
+        w = __shfl_sync(BB_FULL, w, 0);
+        if (w >= n_tasks) break;
+        const BBWinTask tk = tasks[w];
+        BBReadDev *rd = &B.reads[tk.r];
+        const uint8_t *frag = B.frag + rd->frag_off;
+        const uint32_t *state = B.state + rd->frag_off;
+        const unsigned int *ctime = B.ctime + rd->frag_off;
+        int qpos, qn;
+        bb_window_of(rd->frag_len, seed, B.read_index[tk.r], tk.a, qpos, qn);
+        const unsigned int tmax = (unsigned int)(BB_ALIGNMENT_INTERVAL * tk.a);
+        // warp-cooperative join of the snapshot
+        int total = 0, up = 0;
+        for (int base = 0; base < qn; base += 32) {
+            const int x = base + lane;
+            uint32_t st = BB_SLOT_NONE;
+            int len = 0;
+            if (x < qn) {
+                const unsigned int ct = ctime[qpos + x];
+                if (ct != 0u && ct <= tmax) st = state[qpos + x];
+                len = st == BB_SLOT_NONE ? 1 : (int)(st & 0xff);
+            }
+            int incl = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(BB_FULL, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const int off = total + incl - len;
+            if (x < qn) {
+                if (st == BB_SLOT_NONE) tbuf[off] = frag[qpos + x];
+                else {
+                    for (int c = 0; c < len; c++) tbuf[off + c] = bb_slot_char(em, st, c);
+                    up += len < 1 ? 1 : len;
+                }
+            }
+            total += __shfl_sync(BB_FULL, incl, 31);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) up += __shfl_xor_sync(BB_FULL, up, d);
+        __syncwarp();
+        sc.peq = B.fpeq + rd->fpeq_off;
+        BBAlnCounts cnt = {0, 0, 0, 0};
+        bb_align<false, 1>(frag + qpos, qn, tbuf, total, up, sc, no_emit, qpos, cnt);
+        __syncwarp();
+        if (lane == 0) {
+            if (cnt.err) atomicOr(&rd->flags, cnt.err);
+            B.wres[rd->wres_off + tk.a - 1] = make_int2(cnt.matches, qn + cnt.dels);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ replay
+// One thread per read: the scalar recurrence of simulate.py:290-346 over the change log.
+__global__ void __launch_bounds__(128)
+bb_k_replay(BBBatchDev B, const int *order, int n_items, int k) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_items) return;
+    const int r = order[w];
+    BBReadDev *rd = &B.reads[r];
+    if (rd->status == BB_READ_DONE) return;
+    uint32_t *state = B.state + rd->frag_off;
+    const uint2 *chlog = B.chlog + rd->log_off;
+    const int2 *wres = B.wres + rd->wres_off;
+    const int frag_len = rd->frag_len;
+    const double target = B.target[r];
+    const double fl = (double)frag_len;
+    const double cc_limit = __dmul_rn(0.9, fl);
+    const long long limit = 100ll * frag_len;
+    const int n_logged = rd->n_logged;
+    double errors = 0.0, est_id = 1.0;
+    int total = frag_len, st_trim = k, en_trim = k, upper = 0;
+    long long loop_count = -1;
+    int kstop = n_logged;  // changes that survive
+    bool stopped = false;
+    if (rd->stop_reason == BB_STOP_NOLOOP) { stopped = true; loop_count = 0; kstop = 0; }
+    else if (1.0 <= target) { stopped = true; loop_count = 1; kstop = 0; }  // first check of the first iteration
+    int c = 0;
+    while (!stopped && c < n_logged) {
+        // all changes of one iteration (est_id is the value from the top of that iteration, simulate.py:290,321)
+        const unsigned int n = chlog[c].x;
+        const double scale = __dmul_rn(est_id, __dsqrt_rn(est_id));
+        while (c < n_logged && chlog[c].x == n) {
+            const int pos = (int)chlog[c].y;
+            const int len = (int)(state[pos] & 0xff);
+            c++;
+            upper += len < 1 ? 1 : len;
+            total += len - 1;
+            if (pos < k) st_trim += len - 1;
+            if (pos >= frag_len - k) en_trim += len - 1;
+            errors = __dadd_rn(errors, __dmul_rn((double)(len < 2 ? 1 : len - 1), scale));
+            if (c % BB_ALIGNMENT_INTERVAL == 0) {  // simulate.py:325-346
+                const int2 res = wres[c / BB_ALIGNMENT_INTERVAL - 1];
+                const double actual = res.y ? __ddiv_rn((double)res.x, (double)res.y) : 0.0;
+                if (frag_len <= BB_ALIGNMENT_SIZE) {
+                    errors = __dmul_rn(__dsub_rn(1.0, actual), fl);
+                } else {
+                    const double est_err = __dmul_rn(__dsub_rn(1.0, actual), fl);
+                    const double weight = __ddiv_rn((double)BB_ALIGNMENT_SIZE, fl);
+                    errors = __dadd_rn(__dmul_rn(est_err, weight), __dmul_rn(errors, __dsub_rn(1.0, weight)));
+                }
+            }
+        }
+        // the checks at the top of iteration n + 1 (simulate.py:278-292)
+        est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl));
+        if ((long long)n + 1 >= limit) { stopped = true; loop_count = limit + 1; kstop = c; }
+        else if ((double)c > cc_limit || est_id <= target) { stopped = true; loop_count = (long long)n + 2; kstop = c; }
+    }
+    if (!stopped) {
+        if (rd->stop_reason == BB_STOP_LIMIT) { stopped = true; loop_count = limit + 1; kstop = n_logged; }
+        else if (rd->stop_reason == BB_STOP_COUNT) { stopped = true; loop_count = (long long)rd->n_resume + 1; kstop = n_logged; }
+    }
+    if (!stopped) {  // the horizon was too short: log more changes and come back
+        rd->horizon = n_logged + max(64, n_logged / 2);
+        rd->a_done = n_logged / BB_ALIGNMENT_INTERVAL;
+        return;
+    }
+    for (int x = kstop; x < n_logged; x++) {  // changes logged past the stop never happened
+        const int pos = (int)chlog[x].y;
+        state[pos] = BB_SLOT_NONE;
+    }
+    rd->seq_len = total; rd->start_trim = st_trim; rd->end_trim = en_trim; rd->upper = upper;
+    rd->loop_count = (int)(loop_count > 0x7fffffff ? 0x7fffffff : loop_count);
+    rd->change_count = kstop; rd->n_align = kstop / BB_ALIGNMENT_INTERVAL;
+    rd->status = BB_READ_DONE;
+}
