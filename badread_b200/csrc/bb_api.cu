@@ -328,7 +328,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
             else return set_err(ctx, BB_ERR_ARG, "unknown segment kind");
             len += sg.len;
         }
-        if (len + 2 * k > 0x3fffffff) return set_err(ctx, BB_ERR_ARG, "fragment too long");
+        if (len + 2 * k >= (1 << 24)) return set_err(ctx, BB_ERR_ARG, "fragment too long (16 Mb limit)");
         ctx->h_inlen[(size_t)r] = (int32_t)len;
         BBReadDev &rd = ctx->h_reads[(size_t)r];
         rd.frag_off = off;
@@ -372,7 +372,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     BB_CUDA(ctx, ctx->d_chlog.ensure(((size_t)log_off + 16) * sizeof(uint2)));
     BB_CUDA(ctx, ctx->d_wres.ensure(((size_t)wres_off + 16) * sizeof(int2)));
     BB_CUDA(ctx, ctx->d_wtasks.ensure(((size_t)wres_off + 16) * sizeof(BBWinTask)));
-    BB_CUDA(ctx, ctx->d_wfallback.ensure(((size_t)wres_off + 16) * sizeof(BBWinTask)));
+    BB_CUDA(ctx, ctx->d_wfallback.ensure((2 * (size_t)wres_off + 16) * sizeof(BBWinTask)));
     BB_CUDA(ctx, ctx->d_active.ensure(((size_t)n_reads + 16) * sizeof(int)));
     {   // lane pools shared by the window aligner and the leaf aligner: history of 2048 columns x 8 words per thread
         const size_t lanes = (size_t)ctx->sm_count * 4 * 64;
@@ -413,12 +413,17 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
         const int n_tasks = (int)tasks.size();
         if (n_tasks > 0) {
             BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_wtasks.p, tasks.data(), (size_t)n_tasks * sizeof(BBWinTask), cudaMemcpyHostToDevice, st));
-            bb_k_window_lane<<<std::min(lane_ctas, (n_tasks + 63) / 64), 64, 0, st>>>(
-                B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), n_tasks, ctx->seed, ctx->s_leafhist.as<uint2>(),
-                ctx->s_ltbuf.as<uint8_t>(), cnt + 9, ctx->d_wfallback.as<BBWinTask>(), cnt + 10);
-            bb_k_window_warp<<<ctx->sm_count * 2, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->d_wfallback.as<BBWinTask>(),
-                                                                                 cnt + 10, ctx->seed, cnt + 11);
-            ctx->launches += 2;
+            BB_CUDA(ctx, cudaMemcpyAsync(cnt + 12, &n_tasks, sizeof(int), cudaMemcpyHostToDevice, st));
+            // 4-word windows first (bands up to 64 rows: almost every window); what does not fit falls through to
+            // the 8-word build and from there to the warp kernel
+            BBWinTask *fb1 = ctx->d_wfallback.as<BBWinTask>(), *fb2 = fb1 + n_tasks;
+            const int lane_grid = std::min(lane_ctas, (n_tasks + 63) / 64);
+            bb_k_window_lane<4><<<lane_grid, 64, 0, st>>>(B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
+                                                          ctx->s_leafhist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), cnt + 9, fb1, cnt + 10);
+            bb_k_window_lane<BB_WIN_LW><<<lane_grid, 64, 0, st>>>(B, ctx->em, fb1, cnt + 10, ctx->seed, ctx->s_leafhist.as<uint2>(),
+                                                                  ctx->s_ltbuf.as<uint8_t>(), cnt + 13, fb2, cnt + 14);
+            bb_k_window_warp<<<ctx->sm_count * 2, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, fb2, cnt + 14, ctx->seed, cnt + 11);
+            ctx->launches += 3;
         }
         bb_k_replay<<<(n_active + 127) / 128, 128, 0, st>>>(B, ctx->d_active.as<int>(), n_active, ctx->em.k);
         ctx->launches++;
@@ -453,7 +458,8 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
     int *cnt = ctx->q_count.as<int>();
     Q.count = cnt; Q.overflow = cnt + BBQ_OVERFLOW; Q.cap_node = cap_node; Q.cap_leaf = cap_leaf;
     BB_CUDA(ctx, cudaMemsetAsync(cnt, 0, 512 * sizeof(int), st));
-    bb_k_push_roots<<<(n + 255) / 256, 256, 0, st>>>(B, Q);
+    BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, ctx->h_order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    bb_k_push_roots<<<(n + 255) / 256, 256, 0, st>>>(B, Q, ctx->d_active.as<int>());
     ctx->launches++;
     int *cursor = cnt + 16;
     // the wide-band warp kernel (one CTA per SM, 255 registers) runs on the second stream next to the lean and lane

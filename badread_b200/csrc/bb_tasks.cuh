@@ -121,9 +121,10 @@ __device__ bool bb_choose_split_seq(const int *L, int loL, int hiL, const int *R
 }
 
 // Roots of all reads of the batch (same routing rule as every other task).
-__global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues Q) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= B.n_reads) return;
+__global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues Q, const int *order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.n_reads) return;
+    const int r = order[i];  // longest fragments first, so the biggest nodes start early
     BBReadDev *rd = &B.reads[r];
     BBAlignOut o;
     o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;

@@ -113,7 +113,8 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     pool.tbuf = tbuf.data(); pool.tbuf_stride = 0;
     pool.peq = speq.data(); pool.peq_stride = 0; pool.peq_cap = (int)speq.size();
     emu::run_warp([&]() { bb_build_peq(sq.data(), n, speq.data()); });
-    emu::run_warp([&]() { bb_k_push_roots(B, Q); });
+    int order0 = 0;
+    emu::run_warp([&]() { bb_k_push_roots(B, Q, &order0); });
     int *cursor = cnt.data() + 16;
     for (int level = 0; level < 40; level++) {
         const int p = level & 1;
