@@ -578,6 +578,46 @@ __device__ __forceinline__ void bb_emit_all_deleted(int m, BBEmit em, int qbase,
     }
 }
 
+// edlib.cpp obtainAlignmentHirschberg's choice of the split row from the column scores in sc.L / sc.R, by one
+// warp.  best < 0 (root): every optimal path crosses the split column, so the minimum sum is the edit distance.
+__device__ int bb_split_warp(const BBScratch &sc, int loL, int hiL, int loR, int hiR, int nn, int left_w, int right_w,
+                             int &best, int &split, int &ls, int &rs) {
+    const int lane = threadIdx.x & 31;
+    int rlo = max(loL, nn - 2 - hiR); if (rlo < 0) rlo = 0;
+    int rhi = min(hiL, nn - 2 - loR); if (rhi > nn - 2) rhi = nn - 2;
+    const bool have_top = nn - 1 >= loR && nn - 1 <= hiR;  // empty query prefix on the left
+    const bool have_bot = nn - 1 >= loL && nn - 1 <= hiL;  // empty query suffix on the right
+    if (best < 0) {  // root: every optimal path crosses the split column, so the minimum sum is the distance
+        int mn = BB_INF;
+        for (int r = rlo + lane; r <= rhi; r += 32) mn = min(mn, sc.L[r - loL] + sc.R[(nn - 2 - r) - loR]);
+        if (have_top) mn = min(mn, left_w + sc.R[(nn - 1) - loR]);
+        if (have_bot) mn = min(mn, sc.L[(nn - 1) - loL] + right_w);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(BB_FULL, mn, d));
+        best = mn;
+    }
+    // smallest interior row r in [0, nn-2] with L[r] + R[nn-2-r] == best
+    split = -2; ls = 0; rs = 0;
+    for (int base = rlo; base <= rhi; base += 32) {
+        const int r = base + lane;
+        bool hit = false;
+        if (r <= rhi) hit = (sc.L[r - loL] + sc.R[(nn - 2 - r) - loR] == best);
+        const uint32_t hm = __ballot_sync(BB_FULL, hit);
+        if (hm) { split = base + __ffs(hm) - 1; break; }
+    }
+    if (split >= 0) { ls = sc.L[split - loL]; rs = sc.R[(nn - 2 - split) - loR]; }
+    if (split == -2 && have_top) {
+        const int v = sc.R[(nn - 1) - loR];
+        if (left_w + v == best) { split = -1; ls = left_w; rs = v; }
+    }
+    if (split == -2 && have_bot) {
+        const int v = sc.L[(nn - 1) - loL];
+        if (v + right_w == best) { split = nn - 1; ls = v; rs = right_w; }
+    }
+    __syncwarp();
+    return split == -2 ? 32 : 0;
+}
+
 // One Hirschberg node by one warp (edlib.cpp obtainAlignmentHirschberg): forward pass over the left half of the
 // target, reverse pass over the right half, split row by edlib's rule.  q / t point at the read's first query /
 // target character, the node is q[q0, q0+nn) x t[t0, t0+mm); band (a, b) must admit every optimal path.
@@ -622,39 +662,7 @@ __device__ int bb_node_warp(const uint8_t *q, const uint8_t *t, int q0, int nn, 
         }
     }
     __syncwarp();
-    int rlo = max(loL, nn - 2 - hiR); if (rlo < 0) rlo = 0;
-    int rhi = min(hiL, nn - 2 - loR); if (rhi > nn - 2) rhi = nn - 2;
-    const bool have_top = nn - 1 >= loR && nn - 1 <= hiR;  // empty query prefix on the left
-    const bool have_bot = nn - 1 >= loL && nn - 1 <= hiL;  // empty query suffix on the right
-    if (best < 0) {  // root: every optimal path crosses the split column, so the minimum sum is the distance
-        int mn = BB_INF;
-        for (int r = rlo + lane; r <= rhi; r += 32) mn = min(mn, sc.L[r - loL] + sc.R[(nn - 2 - r) - loR]);
-        if (have_top) mn = min(mn, left_w + sc.R[(nn - 1) - loR]);
-        if (have_bot) mn = min(mn, sc.L[(nn - 1) - loL] + right_w);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(BB_FULL, mn, d));
-        best = mn;
-    }
-    // smallest interior row r in [0, nn-2] with L[r] + R[nn-2-r] == best
-    split = -2; ls = 0; rs = 0;
-    for (int base = rlo; base <= rhi; base += 32) {
-        const int r = base + lane;
-        bool hit = false;
-        if (r <= rhi) hit = (sc.L[r - loL] + sc.R[(nn - 2 - r) - loR] == best);
-        const uint32_t hm = __ballot_sync(BB_FULL, hit);
-        if (hm) { split = base + __ffs(hm) - 1; break; }
-    }
-    if (split >= 0) { ls = sc.L[split - loL]; rs = sc.R[(nn - 2 - split) - loR]; }
-    if (split == -2 && have_top) {
-        const int v = sc.R[(nn - 1) - loR];
-        if (left_w + v == best) { split = -1; ls = left_w; rs = v; }
-    }
-    if (split == -2 && have_bot) {
-        const int v = sc.L[(nn - 1) - loL];
-        if (v + right_w == best) { split = nn - 1; ls = v; rs = right_w; }
-    }
-    __syncwarp();
-    return split == -2 ? 32 : 0;
+    return bb_split_warp(sc, loL, hiL, loR, hiR, nn, left_w, right_w, best, split, ls, rs);
 }
 
 // edlib.align(q, t, task='path') for one pair by one warp. q[0] is character `qabs` of the read whose match

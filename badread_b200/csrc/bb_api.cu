@@ -67,7 +67,7 @@ struct bb_ctx {
     DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist;
     DevBuf d_ctime, d_chlog, d_wres, d_wtasks, d_wfallback, d_active;
     bool use_spec_loop = true;
-    DevBuf q_node[BBQ_NODE_CLASSES][2], q_leaf[2], q_count;
+    struct QueueBufs { DevBuf node[BBQ_NODE_CLASSES][2], leaf[2], count; } qbuf[2];  // [0] normal, [1] wide-root reads
     bool use_tasks = true;
 
 
@@ -154,9 +154,11 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
                       &ctx->d_wtasks, &ctx->d_wfallback, &ctx->d_active,
-                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->q_leaf[0], &ctx->q_leaf[1],
-                      &ctx->q_count, &ctx->q_node[0][0], &ctx->q_node[0][1], &ctx->q_node[1][0], &ctx->q_node[1][1],
-                      &ctx->q_node[2][0], &ctx->q_node[2][1], &ctx->q_node[3][0], &ctx->q_node[3][1]};
+                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist};
+    for (auto &qb : ctx->qbuf) {
+        for (auto &cl : qb.node) for (auto &d : cl) d.release();
+        qb.leaf[0].release(); qb.leaf[1].release(); qb.count.release();
+    }
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
@@ -376,7 +378,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     BB_CUDA(ctx, ctx->d_active.ensure(((size_t)n_reads + 16) * sizeof(int)));
     {   // lane pools shared by the window aligner and the leaf aligner: history of 2048 columns x 8 words per thread
         const size_t lanes = (size_t)ctx->sm_count * 4 * 64;
-        BB_CUDA(ctx, ctx->s_leafhist.ensure(lanes * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
+        BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * lanes * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
         BB_CUDA(ctx, ctx->s_ltbuf.ensure(lanes * BB_WIN_MAX_COLS));
     }
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -441,65 +443,78 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
 // reads' Hirschberg trees is three launches (wide-warp, lean-warp, lane nodes), leaves run at the end.
 static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<BBReadDev> &reads) {
     (void)reads;
-    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+    cudaStream_t stream[2] = {ctx->stream, ctx->stream2};
     const int n = ctx->n_reads;
     const int cap_node = (int)std::min<int64_t>(ctx->seq_total / 256 + 4ll * n + 1024, 0x7ffffff0);
     const int cap_leaf = cap_node;
-    for (int c = 0; c < BBQ_NODE_CLASSES; c++)
-        for (int p = 0; p < 2; p++) BB_CUDA(ctx, ctx->q_node[c][p].ensure((size_t)cap_node * sizeof(BBNode)));
-    for (int w = 0; w < 2; w++) BB_CUDA(ctx, ctx->q_leaf[w].ensure((size_t)cap_leaf * sizeof(BBNode)));
-    BB_CUDA(ctx, ctx->q_count.ensure(512 * sizeof(int)));
     const int lane_ctas = ctx->sm_count * 4;  // 64-thread CTAs of the lane kernels
-    BB_CUDA(ctx, ctx->s_leafhist.ensure((size_t)lane_ctas * 64 * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
-    BBQueues Q;
-    for (int c = 0; c < BBQ_NODE_CLASSES; c++)
-        for (int p = 0; p < 2; p++) Q.node[c][p] = ctx->q_node[c][p].as<BBNode>();
-    Q.leaf[0] = ctx->q_leaf[0].as<BBNode>(); Q.leaf[1] = ctx->q_leaf[1].as<BBNode>();
-    int *cnt = ctx->q_count.as<int>();
-    Q.count = cnt; Q.overflow = cnt + BBQ_OVERFLOW; Q.cap_node = cap_node; Q.cap_leaf = cap_leaf;
-    BB_CUDA(ctx, cudaMemsetAsync(cnt, 0, 512 * sizeof(int), st));
-    BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, ctx->h_order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
-    bb_k_push_roots<<<(n + 255) / 256, 256, 0, st>>>(B, Q, ctx->d_active.as<int>());
+    const size_t hist_per_pipe = (size_t)lane_ctas * 64 * BB_LEAF_LANE_COLS * BB_LEAF_LW;
+    BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * hist_per_pipe * sizeof(uint2)));
+    BBQueues Q[2];
+    int *cnt[2];
+    for (int s = 0; s < 2; s++) {
+        auto &qb = ctx->qbuf[s];
+        for (int c = 0; c < BBQ_NODE_CLASSES; c++)
+            for (int p = 0; p < 2; p++) {
+                BB_CUDA(ctx, qb.node[c][p].ensure((size_t)cap_node * sizeof(BBNode)));
+                Q[s].node[c][p] = qb.node[c][p].as<BBNode>();
+            }
+        for (int w = 0; w < 2; w++) {
+            BB_CUDA(ctx, qb.leaf[w].ensure((size_t)cap_leaf * sizeof(BBNode)));
+            Q[s].leaf[w] = qb.leaf[w].as<BBNode>();
+        }
+        BB_CUDA(ctx, qb.count.ensure(512 * sizeof(int)));
+        cnt[s] = qb.count.as<int>();
+        Q[s].count = cnt[s]; Q[s].overflow = cnt[s] + BBQ_OVERFLOW; Q[s].cap_node = cap_node; Q[s].cap_leaf = cap_leaf;
+        BB_CUDA(ctx, cudaMemsetAsync(cnt[s], 0, 512 * sizeof(int), stream[0]));
+    }
+    BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, ctx->h_order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream[0]));
+    bb_k_push_roots<<<(n + 255) / 256, 256, 0, stream[0]>>>(B, Q[0], Q[1], ctx->d_active.as<int>());
     ctx->launches++;
-    int *cursor = cnt + 16;
-    // the wide-band warp kernel (one CTA per SM, 255 registers) runs on the second stream next to the lean and lane
-    // kernels of the same level; its warps use the upper half of the scratch pool
-    const int grid_wide = ctx->sm_count, grid_lean = ctx->sm_count * 2;
-    const int wide_base = ctx->n_warps / 2;
+    // pipeline 0 (stream 0): every read whose root band fits the lean / lane kernels; pipeline 1 (stream 1): reads
+    // with a wide root (long or noisy reads).  The two never wait for each other's levels.
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, stream[0]));
+    BB_CUDA(ctx, cudaStreamWaitEvent(stream[1], ctx->ev_fork, 0));
+    int *cursor[2] = {cnt[0] + 16, cnt[1] + 16};
+    const int warp_base[2] = {0, ctx->n_warps / 2};
+    const int grid_lean[2] = {ctx->sm_count * 2, ctx->sm_count};
     const int max_levels = 40;  // the target halves at every level: 2^40 columns is beyond any read
     for (int level = 0; level < max_levels; level++) {
         const int p = level & 1;
-        // the queues of the next level start empty
-        for (int c = 0; c < BBQ_NODE_CLASSES; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt + c * 2 + (p ^ 1), 0, sizeof(int), st));
-        BB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-        BB_CUDA(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
-        bb_k_node_warp<32><<<grid_wide, BB_WARPS_PER_CTA * 32, 0, st2>>>(B, Q, ctx->pool, BBQ_NODE_WIDE, p, cursor++, wide_base);
-        BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, st2));
-        bb_k_node_warp<4><<<grid_lean, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, ctx->pool, BBQ_NODE_LEAN, p, cursor++, 0);
-        bb_k_node_lane<BB_NODE_LW><<<lane_ctas, 64, 0, st>>>(B, Q, p, cursor++);
-        bb_k_node_lane<BB_NODE_LW_SMALL><<<lane_ctas, 64, 0, st>>>(B, Q, p, cursor++);
-        BB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-        ctx->launches += 4;
-        if (level >= 3 && (level & 3) == 3) {  // every few levels: stop as soon as the queues are empty
-            int h[2 * BBQ_NODE_CLASSES];
-            BB_CUDA(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
-            BB_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int s = 0; s < 2; s++) {
+            cudaStream_t st = stream[s];
+            for (int c = 0; c < BBQ_NODE_CLASSES; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt[s] + c * 2 + (p ^ 1), 0, sizeof(int), st));
+            if (s == 1) {
+                bb_k_node_pair<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
+                ctx->launches++;
+            }
+            bb_k_node_warp<4><<<grid_lean[s], BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, BBQ_NODE_LEAN, p, cursor[s]++, warp_base[s]);
+            bb_k_node_lane<BB_NODE_LW><<<lane_ctas, 64, 0, st>>>(B, Q[s], p, cursor[s]++);
+            bb_k_node_lane<BB_NODE_LW_SMALL><<<lane_ctas, 64, 0, st>>>(B, Q[s], p, cursor[s]++);
+            ctx->launches += 3;
+        }
+        if (level >= 3 && (level & 3) == 3) {  // every few levels: stop as soon as all queues are empty
+            int h[2][2 * BBQ_NODE_CLASSES];
+            for (int s = 0; s < 2; s++) BB_CUDA(ctx, cudaMemcpyAsync(h[s], cnt[s], sizeof(h[s]), cudaMemcpyDeviceToHost, stream[s]));
+            for (int s = 0; s < 2; s++) BB_CUDA(ctx, cudaStreamSynchronize(stream[s]));
             int pending = 0;
-            for (int c = 0; c < BBQ_NODE_CLASSES; c++) pending += h[c * 2 + (p ^ 1)];
+            for (int s = 0; s < 2; s++)
+                for (int c = 0; c < BBQ_NODE_CLASSES; c++) pending += h[s][c * 2 + (p ^ 1)];
             if (pending == 0) break;
         }
     }
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-    BB_CUDA(ctx, cudaStreamWaitEvent(st2, ctx->ev_fork, 0));
-    bb_k_leaf_warp<<<grid_wide, BB_WARPS_PER_CTA * 32, 0, st2>>>(B, Q, ctx->pool, cursor++, wide_base);
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, st2));
-    bb_k_leaf_lane<<<lane_ctas, 64, 0, st>>>(B, Q, ctx->s_leafhist.as<uint2>(), cursor++);
-    BB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    ctx->launches += 2;
-    int h_over = 0;
-    BB_CUDA(ctx, cudaMemcpyAsync(&h_over, Q.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
-    BB_CUDA(ctx, cudaStreamSynchronize(st));
-    if (h_over) return set_err(ctx, BB_ERR_INTERNAL, "alignment task queue overflow");
+    for (int s = 0; s < 2; s++) {
+        cudaStream_t st = stream[s];
+        bb_k_leaf_warp<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, cursor[s]++, warp_base[s]);
+        bb_k_leaf_lane<<<lane_ctas, 64, 0, st>>>(B, Q[s], ctx->s_leafhist.as<uint2>() + s * hist_per_pipe, cursor[s]++);
+        ctx->launches += 2;
+    }
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, stream[1]));
+    BB_CUDA(ctx, cudaStreamWaitEvent(stream[0], ctx->ev_join, 0));
+    int h_over[2] = {0, 0};
+    for (int s = 0; s < 2; s++) BB_CUDA(ctx, cudaMemcpyAsync(&h_over[s], Q[s].overflow, sizeof(int), cudaMemcpyDeviceToHost, stream[0]));
+    BB_CUDA(ctx, cudaStreamSynchronize(stream[0]));
+    if (h_over[0] || h_over[1]) return set_err(ctx, BB_ERR_INTERNAL, "alignment task queue overflow");
     return BB_OK;
 }
 

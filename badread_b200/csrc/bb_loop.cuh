@@ -62,52 +62,42 @@ bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work
         else if ((double)change_count > cc_limit) stop = BB_STOP_COUNT;
         while (stop < 0) {
             if (n0 >= limit) { stop = BB_STOP_LIMIT; break; }
-            // 4 x 32 iterations are evaluated per step: the four evaluations of a lane are independent chains of
-            // loads (fragment, k-mer row, thresholds), which hides most of their latency
-            int kind[4], pos_i[4], rpos[4];
-            uint32_t payload[4];
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                kind[g] = 0; pos_i[g] = 0; rpos[g] = 0; payload[g] = 0;
-                const long long n = n0 + 32 * g + lane;
-                if (n < limit) bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind[g], pos_i[g], payload[g], rpos[g]);
-            }
+            const long long n = n0 + lane;
+            int kind = 0, pos_i = 0, rpos = 0;
+            uint32_t payload = 0;
+            if (n < limit) bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
             __syncwarp();
-            long long next_n0 = n0 + 128;
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                if (stop >= 0) break;
-                uint32_t cmask = __ballot_sync(BB_FULL, kind[g] != 0);
-                while (cmask) {
-                    const int L = __ffs(cmask) - 1;
-                    cmask &= cmask - 1;
-                    const long long nL = n0 + 32 * g + L;
-                    if (change_count >= horizon) { stop = BB_STOP_HORIZON; next_n0 = nL; break; }  // pause at an iteration top
-                    const int bi = __shfl_sync(BB_FULL, pos_i[g], L);
-                    const int bkind = __shfl_sync(BB_FULL, kind[g], L);
-                    const uint32_t bpay = __shfl_sync(BB_FULL, payload[g], L);
-                    const int brpos = __shfl_sync(BB_FULL, rpos[g], L);
-                    uint32_t enc = 0;
-                    bool app = false;
-                    if (lane < k) {
-                        const uint8_t fb = frag[bi + lane];
-                        enc = bkind == 1 ? em.slots[(long long)bpay * k + lane]
-                                         : (lane == brpos ? bpay : bb_slot_inline(1, fb, 0));
-                        const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
-                        app = differs && state[bi + lane] == BB_SLOT_NONE;  // simulate.py:309
-                    }
-                    const uint32_t amask = __ballot_sync(BB_FULL, app);
-                    if (app) {  // slots of one k-mer are distinct positions: apply them together, ordinals in slot order
-                        const int ord = change_count + __popc(amask & ((1u << lane) - 1u)) + 1;
-                        state[bi + lane] = enc;
-                        ctime[bi + lane] = (unsigned int)ord;
-                        chlog[ord - 1] = make_uint2((unsigned int)nL, (unsigned int)(bi + lane) | ((enc & 0xffu) << 24));
-                    }
-                    change_count += __popc(amask);
-                    __syncwarp();
-                    // the guard at the top of the next iteration (simulate.py:285) can only change after a commit
-                    if ((double)change_count > cc_limit) { stop = BB_STOP_COUNT; next_n0 = nL + 1; break; }
+            uint32_t cmask = __ballot_sync(BB_FULL, kind != 0);
+            long long next_n0 = n0 + 32;
+            while (cmask) {
+                const int L = __ffs(cmask) - 1;
+                cmask &= cmask - 1;
+                const long long nL = n0 + L;
+                if (change_count >= horizon) { stop = BB_STOP_HORIZON; next_n0 = nL; break; }  // pause at an iteration top
+                const int bi = __shfl_sync(BB_FULL, pos_i, L);
+                const int bkind = __shfl_sync(BB_FULL, kind, L);
+                const uint32_t bpay = __shfl_sync(BB_FULL, payload, L);
+                const int brpos = __shfl_sync(BB_FULL, rpos, L);
+                uint32_t enc = 0;
+                bool app = false;
+                if (lane < k) {
+                    const uint8_t fb = frag[bi + lane];
+                    enc = bkind == 1 ? em.slots[(long long)bpay * k + lane]
+                                     : (lane == brpos ? bpay : bb_slot_inline(1, fb, 0));
+                    const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
+                    app = differs && state[bi + lane] == BB_SLOT_NONE;  // simulate.py:309
                 }
+                const uint32_t amask = __ballot_sync(BB_FULL, app);
+                if (app) {  // slots of one k-mer are distinct positions: apply them together, ordinals in slot order
+                    const int ord = change_count + __popc(amask & ((1u << lane) - 1u)) + 1;
+                    state[bi + lane] = enc;
+                    ctime[bi + lane] = (unsigned int)ord;
+                    chlog[ord - 1] = make_uint2((unsigned int)nL, (unsigned int)(bi + lane) | ((enc & 0xffu) << 24));
+                }
+                change_count += __popc(amask);
+                __syncwarp();
+                // the guard at the top of the next iteration (simulate.py:285) can only change after a commit
+                if ((double)change_count > cc_limit) { stop = BB_STOP_COUNT; next_n0 = nL + 1; break; }
             }
             n0 = next_n0;
         }

@@ -121,7 +121,9 @@ __device__ bool bb_choose_split_seq(const int *L, int loL, int hiL, const int *R
 }
 
 // Roots of all reads of the batch (same routing rule as every other task).
-__global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues Q, const int *order) {
+// Reads whose root has a wide band form their own pipeline (QW): its levels are not held up by, and do not hold
+// up, the levels of all other reads (QN).
+__global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues QN, BBQueues QW, const int *order) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B.n_reads) return;
     const int r = order[i];  // longest fragments first, so the biggest nodes start early
@@ -129,7 +131,10 @@ __global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues Q,
     BBAlignOut o;
     o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
     const BBNode nd = {r, 0, rd->seq_len, 0, rd->frag_len, -1};
-    bb_push_task(Q, 0, o, nd, rd->upper);
+    int a, b;
+    bb_task_band(nd, rd->upper, a, b);
+    const bool wide = !bb_uses_traceback(nd.nn, nd.mm) && bb_lane_words(a, b) > BB_NODE_LW && a + b > BB_WARP_LEAN_BAND;
+    bb_push_task(wide ? QW : QN, 0, o, nd, rd->upper);
 }
 
 // ---------------------------------------------------------------------------------------------- lane column step
@@ -402,6 +407,83 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity
             }
         }
         __syncwarp();
+    }
+}
+
+// Rendezvous of the two warps of a pair (named barrier `id`, 64 threads).
+__device__ __forceinline__ void bb_pair_sync(int id) {
+#ifdef BB_EMULATOR
+    emu::named_barrier(id, 64);
+#else
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+#endif
+}
+
+// Wide-band nodes: a PAIR of warps per node.  The even warp runs the forward pass over the left half of the target,
+// the odd warp the reverse pass over the right half, each as a full 32-lane wavefront (half the words per lane of
+// the paired single-warp variant, so the steps are half as long); the even warp then picks the split.
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 1)
+bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
+    __shared__ int s_task[BB_WARPS_PER_CTA / 2];
+    const int lane = threadIdx.x & 31;
+    const int wi = threadIdx.x >> 5;
+    const int pair = wi >> 1;
+    const bool rev = (wi & 1) != 0;
+    // both warps of a pair use the even warp's scratch (L and R live there)
+    BBScratch sc = pool.for_warp(warp_base + blockIdx.x * BB_WARPS_PER_CTA + (wi & ~1));
+    const BBNode *list = Q.node[BBQ_NODE_WIDE][parity];
+    const int count = min(Q.count[BBQ_NODE_WIDE * 2 + parity], Q.cap_node);
+    for (;;) {
+        if (!rev && lane == 0) s_task[pair] = atomicAdd(cursor, 1);
+        bb_pair_sync(pair + 1);
+        const int w = s_task[pair];
+        bb_pair_sync(pair + 1);
+        if (w >= count) break;
+        const BBNode nd = list[w];
+        BBReadDev *rd = &B.reads[nd.r];
+        sc.peq = B.speq + rd->speq_off;
+        const uint8_t *q = B.seq + rd->seq_off, *t = B.frag + rd->frag_off;
+        int a, b;
+        bb_task_band(nd, rd->upper, a, b);
+        const int left_w = nd.mm / 2, right_w = nd.mm - left_w;
+        const int loL = max(0, left_w - 1 - a), hiL = min(nd.nn - 1, left_w - 1 + b);
+        const int loR = max(0, right_w - 1 - a), hiR = min(nd.nn - 1, right_w - 1 + b);
+        const int L = bb_pick_L<32>(a, b, 32);
+        int err = 0;
+        if (hiL - loL + 1 > sc.lr_cap || hiR - loR + 1 > sc.lr_cap) err = 16;
+        else if (L > 0) {
+            BBProb P;
+            P.n = nd.nn; P.a = a; P.b = b; P.peq = sc.peq; P.hist = nullptr; P.nb_alloc = 0;
+            if (!rev) {
+                P.q = q + nd.q0; P.qs = 1; P.t = t + nd.t0; P.ts = 1; P.ncols = left_w;
+                P.peq_bit0 = nd.q0 + BB_PEQ_BIT0; P.cols_out = sc.L; P.cols_lo = loL;
+            } else {
+                P.q = q + nd.q0 + nd.nn - 1; P.qs = -1; P.t = t + nd.t0 + nd.mm - 1; P.ts = -1; P.ncols = right_w;
+                P.peq_bit0 = nd.q0 + nd.nn - 1 + BB_PEQ_BIT0; P.cols_out = sc.R; P.cols_lo = loR;
+            }
+            bb_band_dispatch<false, true, 32>(P, 32, L);
+        }
+        __threadfence_block();
+        bb_pair_sync(pair + 1);
+        if (!rev) {
+            int best = nd.best, split = 0, ls = 0, rs = 0;
+            if (!err) {
+                if (L > 0) err = bb_split_warp(sc, loL, hiL, loR, hiR, nd.nn, left_w, right_w, best, split, ls, rs);
+                else err = bb_node_warp<1>(q, t, nd.q0, nd.nn, nd.t0, nd.mm, a, b, sc, best, split, ls, rs);  // strips
+            }
+            if (lane == 0) {
+                BBAlignOut o;
+                o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
+                if (err) atomicOr(&rd->flags, err << 8);
+                else {
+                    BBNode c0 = {nd.r, nd.q0, split + 1, nd.t0, left_w, ls};
+                    BBNode c1 = {nd.r, nd.q0 + split + 1, nd.nn - split - 1, nd.t0 + left_w, right_w, rs};
+                    bb_push_task(Q, parity ^ 1, o, c0, rd->upper);
+                    bb_push_task(Q, parity ^ 1, o, c1, rd->upper);
+                }
+            }
+            __syncwarp();
+        }
     }
 }
 

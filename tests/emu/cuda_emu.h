@@ -22,7 +22,10 @@
 #define __shared__ static
 #define __constant__
 
+#define BB_EMULATOR 1
 struct uint2 { uint32_t x, y; };
+struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
@@ -116,6 +119,15 @@ inline void run_block(int nthreads, std::function<void()> body) {
     swapcontext(&w.main_ctx, &w.fib[0]);
 }
 inline void run_warp(std::function<void()> body) { run_block(32, body); }
+// bar.sync id, count: rendezvous of `count` threads on barrier `id` (ids 1..15)
+inline void named_barrier(int id, int count) {
+    static int arrived[16];
+    static uint64_t gen[16];
+    const uint64_t g = gen[id];
+    arrived[id]++;
+    if (arrived[id] >= count) { arrived[id] = 0; gen[id]++; return; }
+    while (gen[id] == g) yield();
+}
 template <typename T>
 inline T exchange(T v, int src) {
     Block &w = blk();

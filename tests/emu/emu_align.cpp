@@ -100,27 +100,28 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     Q.count = cnt.data(); Q.overflow = cnt.data() + BBQ_OVERFLOW; Q.cap_node = cap; Q.cap_leaf = cap;
     // scratch for the warp kernels (warp 0 only) and the lane leaf kernel
     const int big = std::max(n, m) + 64;
-    std::vector<uint2> hist(106496), lhist((size_t)32 * BB_LEAF_LANE_COLS * BB_LEAF_LW);
-    std::vector<int8_t> hbuf((size_t)big);
-    std::vector<int> LR(2 * (size_t)big), stack(5 * 64);
+    const int NW = BB_WARPS_PER_CTA;  // scratch for every warp of one emulated CTA
+    std::vector<uint2> hist((size_t)NW * 106496), lhist((size_t)32 * BB_LEAF_LANE_COLS * BB_LEAF_LW);
+    std::vector<int8_t> hbuf((size_t)NW * big);
+    std::vector<int> LR((size_t)NW * 2 * big), stack((size_t)NW * 5 * 64);
     std::vector<uint8_t> tbuf(16);
     BBScratchPool pool;
     std::memset(&pool, 0, sizeof(pool));
-    pool.hist = hist.data(); pool.hist_stride = 0; pool.hist_cap = (int)hist.size();
-    pool.hbuf = hbuf.data(); pool.hbuf_stride = 0; pool.hbuf_cap = big;
-    pool.lr = LR.data(); pool.lr_stride = 0; pool.lr_cap = big;
+    pool.hist = hist.data(); pool.hist_stride = 106496; pool.hist_cap = 106496;
+    pool.hbuf = hbuf.data(); pool.hbuf_stride = big; pool.hbuf_cap = big;
+    pool.lr = LR.data(); pool.lr_stride = 2 * (long long)big; pool.lr_cap = big;
     pool.stack = stack.data(); pool.stack_cap = 64;
     pool.tbuf = tbuf.data(); pool.tbuf_stride = 0;
     pool.peq = speq.data(); pool.peq_stride = 0; pool.peq_cap = (int)speq.size();
     emu::run_warp([&]() { bb_build_peq(sq.data(), n, speq.data()); });
     int order0 = 0;
-    emu::run_warp([&]() { bb_k_push_roots(B, Q, &order0); });
+    emu::run_warp([&]() { bb_k_push_roots(B, Q, Q, &order0); });
     int *cursor = cnt.data() + 16;
     for (int level = 0; level < 40; level++) {
         const int p = level & 1;
         for (int c = 0; c < BBQ_NODE_CLASSES; c++) cnt[c * 2 + (p ^ 1)] = 0;
         int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++, *c2b = cursor++;
-        emu::run_warp([&]() { bb_k_node_warp<32>(B, Q, pool, BBQ_NODE_WIDE, p, c0, 0); });
+        emu::run_block(BB_WARPS_PER_CTA * 32, [&]() { bb_k_node_pair(B, Q, pool, p, c0, 0); });
         emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, BBQ_NODE_LEAN, p, c1, 0); });
         emu::run_warp([&]() { bb_k_node_lane<BB_NODE_LW>(B, Q, p, c2); });
         emu::run_warp([&]() { bb_k_node_lane<BB_NODE_LW_SMALL>(B, Q, p, c2b); });
