@@ -402,7 +402,7 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
         const int n_active = (int)active.size();
         BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, active.data(), (size_t)n_active * sizeof(int), cudaMemcpyHostToDevice, st));
         BB_CUDA(ctx, cudaMemsetAsync(cnt + 8, 0, 8 * sizeof(int), st));
-        bb_k_mutate<<<std::min(grid_warp, (n_active + BB_WARPS_PER_CTA - 1) / BB_WARPS_PER_CTA), BB_WARPS_PER_CTA * 32, 0, st>>>(
+        bb_k_mutate<<<std::min(ctx->sm_count * 8, n_active), BB_WARPS_PER_CTA * 32, 0, st>>>(
             B, ctx->em, ctx->seed, cnt + 8, ctx->d_active.as<int>(), n_active);
         ctx->launches++;
         BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
@@ -420,7 +420,8 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
             // the 8-word build and from there to the warp kernel
             BBWinTask *fb1 = ctx->d_wfallback.as<BBWinTask>(), *fb2 = fb1 + n_tasks;
             const int lane_grid = std::min(lane_ctas, (n_tasks + 63) / 64);
-            bb_k_window_lane<4><<<lane_grid, 64, 0, st>>>(B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
+            const int lane_grid4 = std::min(2 * lane_ctas, (n_tasks + 63) / 64);  // half the history per thread
+            bb_k_window_lane<4><<<lane_grid4, 64, 0, st>>>(B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
                                                           ctx->s_leafhist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), cnt + 9, fb1, cnt + 10);
             bb_k_window_lane<BB_WIN_LW><<<lane_grid, 64, 0, st>>>(B, ctx->em, fb1, cnt + 10, ctx->seed, ctx->s_leafhist.as<uint2>(),
                                                                   ctx->s_ltbuf.as<uint8_t>(), cnt + 13, fb2, cnt + 14);
@@ -490,7 +491,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
             }
             bb_k_node_warp<4><<<grid_lean[s], BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, BBQ_NODE_LEAN, p, cursor[s]++, warp_base[s]);
             bb_k_node_lane<BB_NODE_LW><<<lane_ctas, 64, 0, st>>>(B, Q[s], p, cursor[s]++);
-            bb_k_node_lane<BB_NODE_LW_SMALL><<<lane_ctas, 64, 0, st>>>(B, Q[s], p, cursor[s]++);
+            bb_k_node_lane<BB_NODE_LW_SMALL><<<ctx->sm_count * 6, 64, 0, st>>>(B, Q[s], p, cursor[s]++);
             ctx->launches += 3;
         }
         if (level >= 3 && (level & 3) == 3) {  // every few levels: stop as soon as all queues are empty

@@ -30,15 +30,25 @@ enum { BB_READ_PENDING = 0, BB_READ_DONE = 1 };
 struct BBWinTask { int r, a; };  // read, alignment ordinal (1-based: after 25*a changes)
 
 // ------------------------------------------------------------------------------------------------ mutate
+// One CTA (4 warps) per read: every step the 128 threads evaluate 128 consecutive loop iterations (position, k-mer,
+// model draw: chains of dependent loads, independent across iterations), then warp 0 commits the iterations that
+// change something, in order.
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
 bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter, const int *order,
             int n_items) {
+    constexpr int NT = BB_WARPS_PER_CTA * 32;
+    __shared__ int s_kind[NT], s_pos[NT], s_rpos[NT];
+    __shared__ uint32_t s_pay[NT];
+    __shared__ int s_w, s_stop, s_cc;
+    __shared__ long long s_n0;
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int k = em.k;
     for (;;) {
-        int w = 0;
-        if (lane == 0) w = atomicAdd(work_counter, 1);
-        w = __shfl_sync(BB_FULL, w, 0);
+        if (threadIdx.x == 0) s_w = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int w = s_w;
+        __syncthreads();
         if (w >= n_items) break;
         const int r = order[w];
         BBReadDev *rd = &B.reads[r];
@@ -55,59 +65,74 @@ bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work
         const long long limit = 100ll * frag_len;  // loop_count > 100 * frag_len stops the loop (simulate.py:279)
         const double cc_limit = __dmul_rn(0.9, fl);
         const int horizon = rd->horizon;
-        int change_count = rd->n_logged;
-        long long n0 = rd->n_resume;
-        int stop = -1;
-        if (__dmul_rn(fl, __dsub_rn(1.0, target)) < 0.5) stop = BB_STOP_NOLOOP;  // simulate.py:274
-        else if ((double)change_count > cc_limit) stop = BB_STOP_COUNT;
-        while (stop < 0) {
-            if (n0 >= limit) { stop = BB_STOP_LIMIT; break; }
-            const long long n = n0 + lane;
-            int kind = 0, pos_i = 0, rpos = 0;
-            uint32_t payload = 0;
-            if (n < limit) bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
-            __syncwarp();
-            uint32_t cmask = __ballot_sync(BB_FULL, kind != 0);
-            long long next_n0 = n0 + 32;
-            while (cmask) {
-                const int L = __ffs(cmask) - 1;
-                cmask &= cmask - 1;
-                const long long nL = n0 + L;
-                if (change_count >= horizon) { stop = BB_STOP_HORIZON; next_n0 = nL; break; }  // pause at an iteration top
-                const int bi = __shfl_sync(BB_FULL, pos_i, L);
-                const int bkind = __shfl_sync(BB_FULL, kind, L);
-                const uint32_t bpay = __shfl_sync(BB_FULL, payload, L);
-                const int brpos = __shfl_sync(BB_FULL, rpos, L);
-                uint32_t enc = 0;
-                bool app = false;
-                if (lane < k) {
-                    const uint8_t fb = frag[bi + lane];
-                    enc = bkind == 1 ? em.slots[(long long)bpay * k + lane]
-                                     : (lane == brpos ? bpay : bb_slot_inline(1, fb, 0));
-                    const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
-                    app = differs && state[bi + lane] == BB_SLOT_NONE;  // simulate.py:309
-                }
-                const uint32_t amask = __ballot_sync(BB_FULL, app);
-                if (app) {  // slots of one k-mer are distinct positions: apply them together, ordinals in slot order
-                    const int ord = change_count + __popc(amask & ((1u << lane) - 1u)) + 1;
-                    state[bi + lane] = enc;
-                    ctime[bi + lane] = (unsigned int)ord;
-                    chlog[ord - 1] = make_uint2((unsigned int)nL, (unsigned int)(bi + lane) | ((enc & 0xffu) << 24));
-                }
-                change_count += __popc(amask);
-                __syncwarp();
-                // the guard at the top of the next iteration (simulate.py:285) can only change after a commit
-                if ((double)change_count > cc_limit) { stop = BB_STOP_COUNT; next_n0 = nL + 1; break; }
-            }
-            n0 = next_n0;
+        if (threadIdx.x == 0) {
+            int stop = -1;
+            if (__dmul_rn(fl, __dsub_rn(1.0, target)) < 0.5) stop = BB_STOP_NOLOOP;  // simulate.py:274
+            else if ((double)rd->n_logged > cc_limit) stop = BB_STOP_COUNT;
+            s_stop = stop; s_cc = rd->n_logged; s_n0 = rd->n_resume;
         }
-        __syncwarp();
-        if (lane == 0) {
-            rd->n_logged = change_count;
-            rd->n_resume = (int)(n0 > 0x7fffffff ? 0x7fffffff : n0);
-            rd->stop_reason = stop;
+        __syncthreads();
+        while (s_stop < 0) {
+            const long long n0 = s_n0;
+            if (n0 >= limit) {
+                __syncthreads();
+                if (threadIdx.x == 0) s_stop = BB_STOP_LIMIT;
+                __syncthreads();
+                break;
+            }
+            {
+                const long long n = n0 + threadIdx.x;
+                int kind = 0, pos_i = 0, rpos = 0;
+                uint32_t payload = 0;
+                if (n < limit) bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
+                s_kind[threadIdx.x] = kind; s_pos[threadIdx.x] = pos_i; s_rpos[threadIdx.x] = rpos; s_pay[threadIdx.x] = payload;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int change_count = s_cc, stop = -1;
+                long long next_n0 = n0 + NT;
+                for (int g = 0; g < BB_WARPS_PER_CTA && stop < 0; g++) {
+                    uint32_t cmask = __ballot_sync(BB_FULL, s_kind[32 * g + lane] != 0);
+                    while (cmask) {
+                        const int L = 32 * g + __ffs(cmask) - 1;
+                        cmask &= cmask - 1;
+                        const long long nL = n0 + L;
+                        if (change_count >= horizon) { stop = BB_STOP_HORIZON; next_n0 = nL; break; }  // pause at an iteration top
+                        const int bi = s_pos[L], bkind = s_kind[L], brpos = s_rpos[L];
+                        const uint32_t bpay = s_pay[L];
+                        uint32_t enc = 0;
+                        bool app = false;
+                        if (lane < k) {
+                            const uint8_t fb = frag[bi + lane];
+                            enc = bkind == 1 ? em.slots[(long long)bpay * k + lane]
+                                             : (lane == brpos ? bpay : bb_slot_inline(1, fb, 0));
+                            const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
+                            app = differs && state[bi + lane] == BB_SLOT_NONE;  // simulate.py:309
+                        }
+                        const uint32_t amask = __ballot_sync(BB_FULL, app);
+                        if (app) {  // slots of one k-mer are distinct positions: applied together, ordinals in slot order
+                            const int ord = change_count + __popc(amask & ((1u << lane) - 1u)) + 1;
+                            state[bi + lane] = enc;
+                            ctime[bi + lane] = (unsigned int)ord;
+                            chlog[ord - 1] = make_uint2((unsigned int)nL, (unsigned int)(bi + lane) | ((enc & 0xffu) << 24));
+                        }
+                        change_count += __popc(amask);
+                        __syncwarp();
+                        // the guard at the top of the next iteration (simulate.py:285) can only change after a commit
+                        if ((double)change_count > cc_limit) { stop = BB_STOP_COUNT; next_n0 = nL + 1; break; }
+                    }
+                }
+                if (lane == 0) { s_cc = change_count; s_stop = stop; s_n0 = next_n0; }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            rd->n_logged = s_cc;
+            rd->n_resume = (int)(s_n0 > 0x7fffffff ? 0x7fffffff : s_n0);
+            rd->stop_reason = s_stop;
             rd->kc_loop += (int)((clock64() - clk0) >> 10);
         }
+        __syncthreads();
     }
 }
 
@@ -127,12 +152,12 @@ __device__ __forceinline__ void bb_window_of(int frag_len, unsigned long long se
 
 // One window alignment per thread; persistent lanes, all on the same step of the same phase.
 template <int LW>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, (LW <= 4 ? 8 : 4))
 bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks_ptr, unsigned long long seed,
                  uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback, int *fallback_count) {
     const int n_tasks = *n_tasks_ptr;
     const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    uint2 *const hist = hist_pool + gl * (long long)(BB_WIN_MAX_COLS * BB_WIN_LW);
+    uint2 *const hist = hist_pool + gl * (long long)(BB_WIN_MAX_COLS * LW);
     uint8_t *const tbuf = tbuf_pool + gl * (long long)BB_WIN_MAX_COLS;
     BBLanePass<LW> S;
     BBProb P;

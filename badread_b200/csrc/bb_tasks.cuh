@@ -232,7 +232,7 @@ __device__ int bb_lane_column_scores(const BBLanePass<LW> &S, int n, int lo, int
 
 // ---------------------------------------------------------------------------------------------- lane node kernel
 template <int LW>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, (LW <= 8 ? 6 : 4))
 bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
     constexpr int CLS = LW <= BB_NODE_LW_SMALL ? BBQ_NODE_LANE8 : BBQ_NODE_LANE16;
     const BBNode *list = Q.node[CLS][parity];
