@@ -379,7 +379,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     {   // lane pools shared by the window aligner and the leaf aligner: history of 2048 columns x 8 words per thread
         const size_t lanes = (size_t)ctx->sm_count * 4 * 64;
         BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * lanes * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
-        BB_CUDA(ctx, ctx->s_ltbuf.ensure(lanes * BB_WIN_MAX_COLS));
+        BB_CUDA(ctx, ctx->s_ltbuf.ensure(2 * lanes * BB_WIN_MAX_COLS));  // the 4-word window kernel runs 2x the lanes
     }
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->uploaded = true;
