@@ -29,8 +29,8 @@ struct DevBuf {  // grow-only device allocation
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-const char *kStageNames[BB_N_STAGES] = {"build_fragments", "error_loop", "host_scan", "join", "final_align_wide",
-                                        "final_align", "qscores", "compact", "total"};
+const char *kStageNames[BB_N_STAGES] = {"build_fragments", "error_loop", "host_scan", "join", "final_align",
+                                        "final_align_dfs_lean", "qscores", "compact", "total"};
 
 }  // namespace
 
