@@ -154,11 +154,13 @@ __device__ __forceinline__ void bb_window_of(int frag_len, unsigned long long se
 template <int LW>
 __global__ void __launch_bounds__(64, (LW <= 4 ? 8 : 4))
 bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks_ptr, unsigned long long seed,
-                 uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback, int *fallback_count) {
+                 uint2 *hist_pool, uint8_t *tbuf_pool, uint16_t *wtab_pool, int *cursor, BBWinTask *fallback,
+                 int *fallback_count) {
     const int n_tasks = *n_tasks_ptr;
     const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     uint2 *const hist = hist_pool + gl * (long long)(BB_WIN_MAX_COLS * LW);
     uint8_t *const tbuf = tbuf_pool + gl * (long long)BB_WIN_MAX_COLS;
+    uint16_t *const wtab = wtab_pool + gl * (long long)BB_WIN_MAX_COLS;
     BBLanePass<LW> S;
     BBProb P;
     BBWinTask tk = {0, 0};
@@ -214,15 +216,14 @@ bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const
         }
         for (int it = 0; it < 128; it++) {  // forward columns with history
             if (phase == 2) {
-                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
+                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW, wtab, (it & 31) == 0);
                 if (S.c >= tm) { ti = qn - 1; tj = tm - 1; matches = 0; dels = 0; phase = 3; }
             }
         }
         for (int it = 0; it < 256; it++) {  // traceback (edlib's rule), counting '=' and 'D' columns
             if (phase == 3) {
                 if (ti >= 0 && tj >= 0) {
-                    int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
-                    const int x = (ti >> 5) - wt;
+                    const int x = (ti >> 5) - (int)wtab[tj];
                     if (x < 0 || x >= LW) { atomicOr(&B.reads[tk.r].flags, 1); ti = -1; tj = -1; }
                     else {
                         const uint2 e = hist[(long long)tj * LW + x];

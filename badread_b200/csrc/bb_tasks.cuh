@@ -155,11 +155,14 @@ __device__ __forceinline__ void bb_lane_begin(BBLanePass<LW> &S, const BBProb &P
     S.wt = 0; S.score = 32 * LW; S.c = 0;
 }
 
-// One column of the pass. hist (optional): LW entries for this column.
+// One column of the pass. hist / wtab (optional): LW history entries and the window top for this column.
+// may_shift must be warp-uniform: sliding the window (register moves + a bitmap fetch) is a rare path per lane,
+// and taking it only at common points keeps it from being executed, mostly masked off, on every step.
 template <int LW, bool HIST>
-__device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P, uint2 *hist) {
+__device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P, uint2 *hist, uint16_t *wtab,
+                                             bool may_shift) {
     const int c = S.c;
-    if (c - P.a >= 32 * (S.wt + 1)) {  // slide the window down one word
+    if (may_shift && c - P.a >= 32 * (S.wt + 1)) {  // slide the window down one word
 #pragma unroll
         for (int x = 0; x + 1 < LW; x++) {
             S.Pv[x] = S.Pv[x + 1]; S.Mv[x] = S.Mv[x + 1];
@@ -205,6 +208,7 @@ __device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P,
         S.Mv[x] = phs & Xv[x];
         if (HIST) hist[x] = make_uint2(S.Pv[x], raw);
     }
+    if (HIST) wtab[c] = (uint16_t)S.wt;
     S.c = c + 1;
 }
 
@@ -269,7 +273,7 @@ bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
         // the hot loop: every lane advances its current pass by one column per iteration
         for (int it = 0; it < 128; it++) {
             if (phase == 1 || phase == 2) {
-                bb_lane_step<LW, false>(S, P, nullptr);
+                bb_lane_step<LW, false>(S, P, nullptr, nullptr, (it & 31) == 0);
                 if (S.c >= ncols) {
                     if (phase == 1) {
                         bb_lane_column_scores<LW>(S, nd.nn, loL, hiL, Lc);
@@ -300,11 +304,13 @@ bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
 
 // ---------------------------------------------------------------------------------------------- lane leaf kernel
 __global__ void __launch_bounds__(64)
-bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
+bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, uint16_t *wtab_pool, int *cursor) {
     constexpr int LW = BB_LEAF_LW;
     const BBNode *list = Q.leaf[0];
     const int count = min(Q.count[BBQ_LEAF_COUNT], Q.cap_leaf);
-    uint2 *const hist = hist_pool + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * (long long)(BB_LEAF_LANE_COLS * LW);
+    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint2 *const hist = hist_pool + gl * (long long)(BB_LEAF_LANE_COLS * LW);
+    uint16_t *const wtab = wtab_pool + gl * (long long)BB_LEAF_LANE_COLS;
     BBLanePass<LW> S;
     BBProb P;
     BBNode nd;
@@ -331,7 +337,7 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
         if (__all_sync(BB_FULL, phase == 3)) break;
         for (int it = 0; it < 128; it++) {  // forward columns with history
             if (phase == 1) {
-                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
+                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW, wtab, (it & 31) == 0);
                 if (S.c >= nd.mm) {
                     const int d = bb_lane_column_scores<LW>(S, nd.nn, 0, -1, nullptr);
                     if (nd.best >= 0 && d != nd.best) atomicOr(&o.rd->flags, 8 << 8);
@@ -343,8 +349,7 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
         for (int it = 0; it < 256; it++) {  // traceback moves (edlib's rule: 'I' > 'D' > diagonal)
             if (phase == 2) {
                 if (ti >= 0 && tj >= 0) {
-                    int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
-                    const int x = (ti >> 5) - wt;
+                    const int x = (ti >> 5) - (int)wtab[tj];
                     if (x < 0 || x >= LW) { atomicOr(&o.rd->flags, 1 << 8); ti = -1; tj = -1; }
                     else {
                         const uint2 e = hist[(long long)tj * LW + x];
