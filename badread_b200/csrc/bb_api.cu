@@ -417,12 +417,12 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
         if (n_tasks > 0) {
             BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_wtasks.p, tasks.data(), (size_t)n_tasks * sizeof(BBWinTask), cudaMemcpyHostToDevice, st));
             BB_CUDA(ctx, cudaMemcpyAsync(cnt + 12, &n_tasks, sizeof(int), cudaMemcpyHostToDevice, st));
-            // 4-word windows first (bands up to 64 rows: almost every window); what does not fit falls through to
+            // 5-word windows first (bands up to 95 rows: almost every window); what does not fit falls through to
             // the 8-word build and from there to the warp kernel
             BBWinTask *fb1 = ctx->d_wfallback.as<BBWinTask>(), *fb2 = fb1 + n_tasks;
             const int lane_grid = std::min(lane_ctas, (n_tasks + 63) / 64);
             const int lane_grid4 = std::min(2 * lane_ctas, (n_tasks + 63) / 64);  // half the history per thread
-            bb_k_window_lane<4><<<lane_grid4, 64, 0, st>>>(B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
+            bb_k_window_lane<5><<<lane_grid4, 64, 0, st>>>(B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
                                                           ctx->s_leafhist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(),
                                                           ctx->s_lwtab.as<uint16_t>(), cnt + 9, fb1, cnt + 10);
             bb_k_window_lane<BB_WIN_LW><<<lane_grid, 64, 0, st>>>(B, ctx->em, fb1, cnt + 10, ctx->seed, ctx->s_leafhist.as<uint2>(),

@@ -152,7 +152,7 @@ __device__ __forceinline__ void bb_window_of(int frag_len, unsigned long long se
 
 // One window alignment per thread; persistent lanes, all on the same step of the same phase.
 template <int LW>
-__global__ void __launch_bounds__(64, (LW <= 4 ? 8 : 4))
+__global__ void __launch_bounds__(64, (LW <= 5 ? 8 : 4))
 bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks_ptr, unsigned long long seed,
                  uint2 *hist_pool, uint8_t *tbuf_pool, uint16_t *wtab_pool, int *cursor, BBWinTask *fallback,
                  int *fallback_count) {
