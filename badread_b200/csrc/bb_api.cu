@@ -317,7 +317,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     const int k = ctx->em.k;
     ctx->h_reads.assign((size_t)n_reads, BBReadDev{});
     ctx->h_inlen.assign((size_t)n_reads, 0);
-    int64_t off = 0, peq_off = 0, log_off = 0, wres_off = 0;
+    int64_t off = 64, peq_off = 0, log_off = 0, wres_off = 0;  // lane kernels prefetch a few bytes around a fragment
     int max_len = 0;
     for (int32_t r = 0; r < n_reads; r++) {
         int64_t len = 0;

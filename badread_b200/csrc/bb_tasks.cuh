@@ -142,8 +142,14 @@ __global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues QN
 template <int LW>
 struct BBLanePass {
     uint32_t Pv[LW], Mv[LW], eA[LW], eC[LW], eG[LW], eT[LW];
+    uint32_t tw0, tw1, tw2;  // target characters: the aligned word in use and the next two in walking direction
     int wt, score, c;
 };
+
+// Aligned 32-bit word that holds byte address p.
+__device__ __forceinline__ uint32_t bb_word_at(const uint8_t *p) {
+    return *reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+}
 
 template <int LW>
 __device__ __forceinline__ void bb_lane_begin(BBLanePass<LW> &S, const BBProb &P) {
@@ -153,6 +159,10 @@ __device__ __forceinline__ void bb_lane_begin(BBLanePass<LW> &S, const BBProb &P
         bb_fetch_peq(P, 32 * x, S.eA[x], S.eC[x], S.eG[x], S.eT[x]);
     }
     S.wt = 0; S.score = 32 * LW; S.c = 0;
+    // every lane walks its own target: a load that is needed in the same step would stall the whole warp on that
+    // lane's cache miss, so characters are consumed from words fetched two words (8+ steps) ahead
+    const int dir = P.ts > 0 ? 4 : -4;
+    S.tw0 = bb_word_at(P.t); S.tw1 = bb_word_at(P.t + dir); S.tw2 = bb_word_at(P.t + 2 * dir);
 }
 
 // One column of the pass. hist / wtab (optional): LW history entries and the window top for this column.
@@ -173,7 +183,13 @@ __device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P,
         bb_fetch_peq(P, 32 * (S.wt + LW - 1), S.eA[LW - 1], S.eC[LW - 1], S.eG[LW - 1], S.eT[LW - 1]);
         S.score += 32;
     }
-    const uint32_t tc = P.t[(long long)c * P.ts];
+    const uint8_t *tptr = P.t + (long long)c * P.ts;
+    const uint32_t tsub = (uint32_t)(reinterpret_cast<uintptr_t>(tptr) & 3u);
+    const uint32_t tc = (S.tw0 >> (8 * tsub)) & 0xffu;
+    if (tsub == (P.ts > 0 ? 3u : 0u)) {  // last character of this word in walking direction: rotate the queue
+        S.tw0 = S.tw1; S.tw1 = S.tw2;
+        S.tw2 = bb_word_at(tptr + (P.ts > 0 ? 9 : -9));
+    }
     const uint32_t code = (tc >> 1) & 3u;  // A->0, C->1, T->2, G->3
     const bool acgt = ((0x47544341u >> (8 * code)) & 0xffu) == tc;
     uint32_t Eq[LW], Xv[LW], A[LW], Sm[LW], Ph[LW], Mh[LW];

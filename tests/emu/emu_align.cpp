@@ -45,8 +45,9 @@ int emu_align_path(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper
 extern "C" __attribute__((visibility("default")))
 int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int upper, uint8_t *ops, unsigned int *dcnt,
                     int *out5) {
-    std::vector<uint8_t> sq(seq, seq + n), fr(frag, frag + m);
-    sq.resize((size_t)n + 64, 0); fr.resize((size_t)m + 64, 0);
+    std::vector<uint8_t> sq(seq, seq + n), fr((size_t)m + 128, 0);
+    sq.resize((size_t)n + 64, 0);
+    std::memcpy(fr.data() + 64, frag, (size_t)m);  // the lane kernels prefetch a few bytes around the fragment
     std::vector<uint4> speq((size_t)bb_peq_words(n) + 8);
     BBReadDev rd;
     std::memset(&rd, 0, sizeof(rd));
@@ -54,7 +55,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     BBBatchDev B;
     std::memset(&B, 0, sizeof(B));
     unsigned long long ridx = 0;
-    B.n_reads = 1; B.read_index = &ridx; B.reads = &rd; B.frag = fr.data(); B.seq = sq.data(); B.ops = ops; B.dcnt = dcnt;
+    B.n_reads = 1; B.read_index = &ridx; B.reads = &rd; B.frag = fr.data() + 64; B.seq = sq.data(); B.ops = ops; B.dcnt = dcnt;
     B.speq = speq.data();
     std::memset(dcnt, 0, (size_t)n * sizeof(unsigned int));
     const int cap = 8192;
