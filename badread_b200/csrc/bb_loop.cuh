@@ -187,6 +187,10 @@ bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const
         if (__all_sync(BB_FULL, phase == 4)) break;
         for (int it = 0; it < 256; it++) {  // ''.join(new_fragment_bases[pos:pos2]) as it was after 25*a changes
             if (phase == 1) {
+                if ((jx & 7) == 0) {  // one sector of ordinals / bases ahead of the walk
+                    bb_prefetch(ctime + qpos + jx + 64);
+                    if ((jx & 31) == 0) bb_prefetch(frag + qpos + jx + 128);
+                }
                 const unsigned int ct = ctime[qpos + jx];
                 if (ct == 0u || ct > tmax) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = frag[qpos + jx]; tm++; }
                 else {
@@ -223,6 +227,10 @@ bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const
         for (int it = 0; it < 256; it++) {  // traceback (edlib's rule), counting '=' and 'D' columns
             if (phase == 3) {
                 if (ti >= 0 && tj >= 0) {
+                    if (tj >= 24) {  // the walk moves about one column per step: pull the history it will need
+                        bb_prefetch(hist + (long long)(tj - 24) * LW + ((ti >> 5) - (int)wtab[tj]));
+                        if ((tj & 15) == 0) bb_prefetch(wtab + tj - 24);
+                    }
                     const int x = (ti >> 5) - (int)wtab[tj];
                     if (x < 0 || x >= LW) { atomicOr(&B.reads[tk.r].flags, 1); ti = -1; tj = -1; }
                     else {

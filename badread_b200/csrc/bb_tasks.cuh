@@ -365,6 +365,10 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, uint16_t *wtab_pool, 
         for (int it = 0; it < 256; it++) {  // traceback moves (edlib's rule: 'I' > 'D' > diagonal)
             if (phase == 2) {
                 if (ti >= 0 && tj >= 0) {
+                    if (tj >= 24) {  // the walk moves about one column per step: pull the history it will need
+                        bb_prefetch(hist + (long long)(tj - 24) * LW + ((ti >> 5) - (int)wtab[tj]));
+                        if ((tj & 15) == 0) bb_prefetch(wtab + tj - 24);
+                    }
                     const int x = (ti >> 5) - (int)wtab[tj];
                     if (x < 0 || x >= LW) { atomicOr(&o.rd->flags, 1 << 8); ti = -1; tj = -1; }
                     else {
