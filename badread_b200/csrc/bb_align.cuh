@@ -68,15 +68,6 @@ struct BBProb {
     int *cols_out; int cols_lo;
 };
 
-// Non-blocking hint: bring the line that holds p towards the SM (lane kernels chase per-thread pointer streams).
-__device__ __forceinline__ void bb_prefetch(const void *p) {
-#ifndef BB_EMULATOR
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
-
 __device__ __forceinline__ void bb_band(int n, int m, int k, int &a, int &b) {
     // a path of cost <= k from (0,0) to (n,m) has at most (k-(n-m))/2 'D' and (k+(n-m))/2 'I' moves:
     // every cell (i,j) it can visit satisfies j - a <= i <= j + b

@@ -64,7 +64,7 @@ struct bb_ctx {
     // scratch
     int n_warps = 0;
     BBScratchPool pool{};
-    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist, s_lwtab;
+    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist;
     DevBuf d_ctime, d_chlog, d_wres, d_wtasks, d_wfallback, d_active;
     bool use_spec_loop = true;
     struct QueueBufs { DevBuf node[BBQ_NODE_CLASSES][2], leaf[2], count; } qbuf[2];  // [0] normal, [1] wide-root reads
@@ -152,7 +152,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order, &ctx->d_order_small, &ctx->d_order_large, &ctx->d_order_long,
                       &ctx->d_reads, &ctx->d_frag, &ctx->d_state, &ctx->d_seq, &ctx->d_ops, &ctx->d_dcnt,
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
-                      &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->s_lwtab, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
+                      &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
                       &ctx->d_wtasks, &ctx->d_wfallback, &ctx->d_active,
                       &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist};
     for (auto &qb : ctx->qbuf) {
@@ -317,7 +317,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     const int k = ctx->em.k;
     ctx->h_reads.assign((size_t)n_reads, BBReadDev{});
     ctx->h_inlen.assign((size_t)n_reads, 0);
-    int64_t off = 64, peq_off = 0, log_off = 0, wres_off = 0;  // lane kernels prefetch a few bytes around a fragment
+    int64_t off = 0, peq_off = 0, log_off = 0, wres_off = 0;
     int max_len = 0;
     for (int32_t r = 0; r < n_reads; r++) {
         int64_t len = 0;
@@ -380,7 +380,6 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
         const size_t lanes = (size_t)ctx->sm_count * 4 * 64;
         BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * lanes * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
         BB_CUDA(ctx, ctx->s_ltbuf.ensure(2 * lanes * BB_WIN_MAX_COLS));  // the 4-word window kernel runs 2x the lanes
-        BB_CUDA(ctx, ctx->s_lwtab.ensure(2 * lanes * BB_WIN_MAX_COLS * sizeof(uint16_t)));
     }
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->uploaded = true;
@@ -417,16 +416,15 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
         if (n_tasks > 0) {
             BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_wtasks.p, tasks.data(), (size_t)n_tasks * sizeof(BBWinTask), cudaMemcpyHostToDevice, st));
             BB_CUDA(ctx, cudaMemcpyAsync(cnt + 12, &n_tasks, sizeof(int), cudaMemcpyHostToDevice, st));
-            // 5-word windows first (bands up to 95 rows: almost every window); what does not fit falls through to
+            // 4-word windows first (bands up to 64 rows: almost every window); what does not fit falls through to
             // the 8-word build and from there to the warp kernel
             BBWinTask *fb1 = ctx->d_wfallback.as<BBWinTask>(), *fb2 = fb1 + n_tasks;
             const int lane_grid = std::min(lane_ctas, (n_tasks + 63) / 64);
             const int lane_grid4 = std::min(2 * lane_ctas, (n_tasks + 63) / 64);  // half the history per thread
-            bb_k_window_lane<5><<<lane_grid4, 64, 0, st>>>(B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
-                                                          ctx->s_leafhist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(),
-                                                          ctx->s_lwtab.as<uint16_t>(), cnt + 9, fb1, cnt + 10);
+            bb_k_window_lane<4><<<lane_grid4, 64, 0, st>>>(B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
+                                                          ctx->s_leafhist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), cnt + 9, fb1, cnt + 10);
             bb_k_window_lane<BB_WIN_LW><<<lane_grid, 64, 0, st>>>(B, ctx->em, fb1, cnt + 10, ctx->seed, ctx->s_leafhist.as<uint2>(),
-                                                                  ctx->s_ltbuf.as<uint8_t>(), ctx->s_lwtab.as<uint16_t>(), cnt + 13, fb2, cnt + 14);
+                                                                  ctx->s_ltbuf.as<uint8_t>(), cnt + 13, fb2, cnt + 14);
             bb_k_window_warp<<<ctx->sm_count * 2, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, fb2, cnt + 14, ctx->seed, cnt + 11);
             ctx->launches += 3;
         }
@@ -509,8 +507,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
     for (int s = 0; s < 2; s++) {
         cudaStream_t st = stream[s];
         bb_k_leaf_warp<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, cursor[s]++, warp_base[s]);
-        bb_k_leaf_lane<<<lane_ctas, 64, 0, st>>>(B, Q[s], ctx->s_leafhist.as<uint2>() + s * hist_per_pipe,
-                                                 ctx->s_lwtab.as<uint16_t>() + (size_t)s * lane_ctas * 64 * BB_LEAF_LANE_COLS, cursor[s]++);
+        bb_k_leaf_lane<<<lane_ctas, 64, 0, st>>>(B, Q[s], ctx->s_leafhist.as<uint2>() + s * hist_per_pipe, cursor[s]++);
         ctx->launches += 2;
     }
     BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, stream[1]));

@@ -152,15 +152,13 @@ __device__ __forceinline__ void bb_window_of(int frag_len, unsigned long long se
 
 // One window alignment per thread; persistent lanes, all on the same step of the same phase.
 template <int LW>
-__global__ void __launch_bounds__(64, (LW <= 5 ? 8 : 4))
+__global__ void __launch_bounds__(64, (LW <= 4 ? 8 : 4))
 bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks_ptr, unsigned long long seed,
-                 uint2 *hist_pool, uint8_t *tbuf_pool, uint16_t *wtab_pool, int *cursor, BBWinTask *fallback,
-                 int *fallback_count) {
+                 uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback, int *fallback_count) {
     const int n_tasks = *n_tasks_ptr;
     const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     uint2 *const hist = hist_pool + gl * (long long)(BB_WIN_MAX_COLS * LW);
     uint8_t *const tbuf = tbuf_pool + gl * (long long)BB_WIN_MAX_COLS;
-    uint16_t *const wtab = wtab_pool + gl * (long long)BB_WIN_MAX_COLS;
     BBLanePass<LW> S;
     BBProb P;
     BBWinTask tk = {0, 0};
@@ -187,10 +185,6 @@ bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const
         if (__all_sync(BB_FULL, phase == 4)) break;
         for (int it = 0; it < 256; it++) {  // ''.join(new_fragment_bases[pos:pos2]) as it was after 25*a changes
             if (phase == 1) {
-                if ((jx & 7) == 0) {  // one sector of ordinals / bases ahead of the walk
-                    bb_prefetch(ctime + qpos + jx + 64);
-                    if ((jx & 31) == 0) bb_prefetch(frag + qpos + jx + 128);
-                }
                 const unsigned int ct = ctime[qpos + jx];
                 if (ct == 0u || ct > tmax) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = frag[qpos + jx]; tm++; }
                 else {
@@ -220,18 +214,15 @@ bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const
         }
         for (int it = 0; it < 128; it++) {  // forward columns with history
             if (phase == 2) {
-                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW, wtab, (it & 31) == 0);
+                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
                 if (S.c >= tm) { ti = qn - 1; tj = tm - 1; matches = 0; dels = 0; phase = 3; }
             }
         }
         for (int it = 0; it < 256; it++) {  // traceback (edlib's rule), counting '=' and 'D' columns
             if (phase == 3) {
                 if (ti >= 0 && tj >= 0) {
-                    if (tj >= 24) {  // the walk moves about one column per step: pull the history it will need
-                        bb_prefetch(hist + (long long)(tj - 24) * LW + ((ti >> 5) - (int)wtab[tj]));
-                        if ((tj & 15) == 0) bb_prefetch(wtab + tj - 24);
-                    }
-                    const int x = (ti >> 5) - (int)wtab[tj];
+                    int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
+                    const int x = (ti >> 5) - wt;
                     if (x < 0 || x >= LW) { atomicOr(&B.reads[tk.r].flags, 1); ti = -1; tj = -1; }
                     else {
                         const uint2 e = hist[(long long)tj * LW + x];

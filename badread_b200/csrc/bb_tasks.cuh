@@ -142,14 +142,8 @@ __global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues QN
 template <int LW>
 struct BBLanePass {
     uint32_t Pv[LW], Mv[LW], eA[LW], eC[LW], eG[LW], eT[LW];
-    uint32_t tw0, tw1, tw2;  // target characters: the aligned word in use and the next two in walking direction
     int wt, score, c;
 };
-
-// Aligned 32-bit word that holds byte address p.
-__device__ __forceinline__ uint32_t bb_word_at(const uint8_t *p) {
-    return *reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-}
 
 template <int LW>
 __device__ __forceinline__ void bb_lane_begin(BBLanePass<LW> &S, const BBProb &P) {
@@ -159,20 +153,13 @@ __device__ __forceinline__ void bb_lane_begin(BBLanePass<LW> &S, const BBProb &P
         bb_fetch_peq(P, 32 * x, S.eA[x], S.eC[x], S.eG[x], S.eT[x]);
     }
     S.wt = 0; S.score = 32 * LW; S.c = 0;
-    // every lane walks its own target: a load that is needed in the same step would stall the whole warp on that
-    // lane's cache miss, so characters are consumed from words fetched two words (8+ steps) ahead
-    const int dir = P.ts > 0 ? 4 : -4;
-    S.tw0 = bb_word_at(P.t); S.tw1 = bb_word_at(P.t + dir); S.tw2 = bb_word_at(P.t + 2 * dir);
 }
 
-// One column of the pass. hist / wtab (optional): LW history entries and the window top for this column.
-// may_shift must be warp-uniform: sliding the window (register moves + a bitmap fetch) is a rare path per lane,
-// and taking it only at common points keeps it from being executed, mostly masked off, on every step.
+// One column of the pass. hist (optional): LW entries for this column.
 template <int LW, bool HIST>
-__device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P, uint2 *hist, uint16_t *wtab,
-                                             bool may_shift) {
+__device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P, uint2 *hist) {
     const int c = S.c;
-    if (may_shift && c - P.a >= 32 * (S.wt + 1)) {  // slide the window down one word
+    if (c - P.a >= 32 * (S.wt + 1)) {  // slide the window down one word
 #pragma unroll
         for (int x = 0; x + 1 < LW; x++) {
             S.Pv[x] = S.Pv[x + 1]; S.Mv[x] = S.Mv[x + 1];
@@ -183,13 +170,7 @@ __device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P,
         bb_fetch_peq(P, 32 * (S.wt + LW - 1), S.eA[LW - 1], S.eC[LW - 1], S.eG[LW - 1], S.eT[LW - 1]);
         S.score += 32;
     }
-    const uint8_t *tptr = P.t + (long long)c * P.ts;
-    const uint32_t tsub = (uint32_t)(reinterpret_cast<uintptr_t>(tptr) & 3u);
-    const uint32_t tc = (S.tw0 >> (8 * tsub)) & 0xffu;
-    if (tsub == (P.ts > 0 ? 3u : 0u)) {  // last character of this word in walking direction: rotate the queue
-        S.tw0 = S.tw1; S.tw1 = S.tw2;
-        S.tw2 = bb_word_at(tptr + (P.ts > 0 ? 9 : -9));
-    }
+    const uint32_t tc = P.t[(long long)c * P.ts];
     const uint32_t code = (tc >> 1) & 3u;  // A->0, C->1, T->2, G->3
     const bool acgt = ((0x47544341u >> (8 * code)) & 0xffu) == tc;
     uint32_t Eq[LW], Xv[LW], A[LW], Sm[LW], Ph[LW], Mh[LW];
@@ -224,7 +205,6 @@ __device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P,
         S.Mv[x] = phs & Xv[x];
         if (HIST) hist[x] = make_uint2(S.Pv[x], raw);
     }
-    if (HIST) wtab[c] = (uint16_t)S.wt;
     S.c = c + 1;
 }
 
@@ -289,7 +269,7 @@ bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
         // the hot loop: every lane advances its current pass by one column per iteration
         for (int it = 0; it < 128; it++) {
             if (phase == 1 || phase == 2) {
-                bb_lane_step<LW, false>(S, P, nullptr, nullptr, (it & 31) == 0);
+                bb_lane_step<LW, false>(S, P, nullptr);
                 if (S.c >= ncols) {
                     if (phase == 1) {
                         bb_lane_column_scores<LW>(S, nd.nn, loL, hiL, Lc);
@@ -320,13 +300,11 @@ bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
 
 // ---------------------------------------------------------------------------------------------- lane leaf kernel
 __global__ void __launch_bounds__(64)
-bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, uint16_t *wtab_pool, int *cursor) {
+bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
     constexpr int LW = BB_LEAF_LW;
     const BBNode *list = Q.leaf[0];
     const int count = min(Q.count[BBQ_LEAF_COUNT], Q.cap_leaf);
-    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    uint2 *const hist = hist_pool + gl * (long long)(BB_LEAF_LANE_COLS * LW);
-    uint16_t *const wtab = wtab_pool + gl * (long long)BB_LEAF_LANE_COLS;
+    uint2 *const hist = hist_pool + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * (long long)(BB_LEAF_LANE_COLS * LW);
     BBLanePass<LW> S;
     BBProb P;
     BBNode nd;
@@ -353,7 +331,7 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, uint16_t *wtab_pool, 
         if (__all_sync(BB_FULL, phase == 3)) break;
         for (int it = 0; it < 128; it++) {  // forward columns with history
             if (phase == 1) {
-                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW, wtab, (it & 31) == 0);
+                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
                 if (S.c >= nd.mm) {
                     const int d = bb_lane_column_scores<LW>(S, nd.nn, 0, -1, nullptr);
                     if (nd.best >= 0 && d != nd.best) atomicOr(&o.rd->flags, 8 << 8);
@@ -365,11 +343,8 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, uint16_t *wtab_pool, 
         for (int it = 0; it < 256; it++) {  // traceback moves (edlib's rule: 'I' > 'D' > diagonal)
             if (phase == 2) {
                 if (ti >= 0 && tj >= 0) {
-                    if (tj >= 24) {  // the walk moves about one column per step: pull the history it will need
-                        bb_prefetch(hist + (long long)(tj - 24) * LW + ((ti >> 5) - (int)wtab[tj]));
-                        if ((tj & 15) == 0) bb_prefetch(wtab + tj - 24);
-                    }
-                    const int x = (ti >> 5) - (int)wtab[tj];
+                    int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
+                    const int x = (ti >> 5) - wt;
                     if (x < 0 || x >= LW) { atomicOr(&o.rd->flags, 1 << 8); ti = -1; tj = -1; }
                     else {
                         const uint2 e = hist[(long long)tj * LW + x];

@@ -50,6 +50,24 @@ def align_path(query, target, k_upper=None, qabs_pad=0, maxl=16):
     return s, int(out5[2])
 
 
+def lane_align(query, target, k_upper, qabs_pad=0, lw=4):
+    """Lane-mode pass + traceback under the emulator -> (matches, dels, distance) or None if the band needs more
+    than lw window words."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(LIB))
+    q = query.encode('latin-1') if isinstance(query, str) else bytes(query)
+    t = target.encode('latin-1') if isinstance(target, str) else bytes(target)
+    out4 = np.zeros(4, dtype=np.int32)
+    rc = _lib.emu_lane_align(q, len(q), t, len(t), k_upper, qabs_pad, lw, out4.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        return None
+    if out4[3]:
+        raise RuntimeError(f'lane aligner error flags 0x{int(out4[3]):x}')
+    return int(out4[0]), int(out4[1]), int(out4[2])
+
+
 def tasks_align(seq, frag, upper):
     """The level-synchronous alignment task pipeline under the emulator -> expanded ops string."""
     global _lib

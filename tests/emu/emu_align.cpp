@@ -41,13 +41,46 @@ int emu_align_path(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper
 }
 
 
+// Lane-mode aligner (one problem per thread): every emulated lane solves the same problem, lane 0 reports.
+extern "C" __attribute__((visibility("default")))
+int emu_lane_align(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper, int qabs_pad, int lw, int *out4) {
+    std::vector<uint8_t> read((size_t)qabs_pad + n + 64, 'G');
+    std::memcpy(read.data() + qabs_pad, q, (size_t)n);
+    const int read_len = qabs_pad + n + 9;
+    std::vector<uint4> peq((size_t)bb_peq_words(read_len) + 8);
+    int a, b;
+    {
+        const int diff = n > m ? n - m : m - n;
+        if (k_upper < diff) k_upper = diff;
+        const int mx = n > m ? n : m;
+        if (k_upper > mx) k_upper = mx;
+    }
+    bb_band(n, m, k_upper, a, b);
+    if (bb_lane_words(a, b) > lw) return -1;
+    std::vector<uint2> hist((size_t)m * lw + 8);
+    int res[4] = {0, 0, 0, 0};
+    emu::run_warp([&]() {
+        bb_build_peq(read.data(), read_len, peq.data());
+        if (threadIdx.x != 0) return;
+        BBLaneProb P;
+        P.peq = peq.data(); P.peq_bit0 = qabs_pad + BB_PEQ_BIT0; P.q = read.data() + qabs_pad; P.n = n; P.t = t; P.m = m;
+        P.a = a; P.b = b; P.hist = hist.data();
+        int d, mt = 0, dl = 0, err = 0;
+        if (lw == 4) { d = bb_lane_pass<4>(P); bb_lane_traceback<4>(P, mt, dl, err); }
+        else { d = bb_lane_pass<8>(P); bb_lane_traceback<8>(P, mt, dl, err); }
+        res[0] = mt; res[1] = dl; res[2] = d; res[3] = err;
+    });
+    for (int i = 0; i < 4; i++) out4[i] = res[i];
+    return 0;
+}
+
+
 // The level-synchronous task pipeline (bb_tasks.cuh) for one read, every kernel as one emulated warp.
 extern "C" __attribute__((visibility("default")))
 int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int upper, uint8_t *ops, unsigned int *dcnt,
                     int *out5) {
-    std::vector<uint8_t> sq(seq, seq + n), fr((size_t)m + 128, 0);
-    sq.resize((size_t)n + 64, 0);
-    std::memcpy(fr.data() + 64, frag, (size_t)m);  // the lane kernels prefetch a few bytes around the fragment
+    std::vector<uint8_t> sq(seq, seq + n), fr(frag, frag + m);
+    sq.resize((size_t)n + 64, 0); fr.resize((size_t)m + 64, 0);
     std::vector<uint4> speq((size_t)bb_peq_words(n) + 8);
     BBReadDev rd;
     std::memset(&rd, 0, sizeof(rd));
@@ -55,7 +88,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     BBBatchDev B;
     std::memset(&B, 0, sizeof(B));
     unsigned long long ridx = 0;
-    B.n_reads = 1; B.read_index = &ridx; B.reads = &rd; B.frag = fr.data() + 64; B.seq = sq.data(); B.ops = ops; B.dcnt = dcnt;
+    B.n_reads = 1; B.read_index = &ridx; B.reads = &rd; B.frag = fr.data(); B.seq = sq.data(); B.ops = ops; B.dcnt = dcnt;
     B.speq = speq.data();
     std::memset(dcnt, 0, (size_t)n * sizeof(unsigned int));
     const int cap = 8192;
@@ -98,8 +131,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     }
     int *c3 = cursor++, *c4 = cursor++;
     emu::run_warp([&]() { bb_k_leaf_warp(B, Q, pool, c3, 0); });
-    std::vector<uint16_t> lwtab((size_t)32 * BB_LEAF_LANE_COLS);
-    emu::run_warp([&]() { bb_k_leaf_lane(B, Q, lhist.data(), lwtab.data(), c4); });
+    emu::run_warp([&]() { bb_k_leaf_lane(B, Q, lhist.data(), c4); });
     out5[0] = rd.matches; out5[1] = rd.dels; out5[2] = cnt[BBQ_OVERFLOW]; out5[3] = rd.lead_del; out5[4] = rd.flags;
     return 0;
 }

@@ -1,7 +1,7 @@
 """
 The DEVICE aligner code (badread_b200/csrc/*.cuh) compiled for the host through the warp emulator (tests/emu) and
-checked against the oracle on CPU: the warp wavefront (every L / K variant, strip fall-back) and the
-level-synchronous task pipeline with its lane-mode node and leaf kernels.  This is the same source the GPU runs; the GPU parity tests repeat it end to end.
+checked against the oracle on CPU: the warp wavefront (every L / K variant, strip fall-back), the lane aligner and
+the level-synchronous task pipeline.  This is the same source the GPU runs; the GPU parity tests repeat it end to end.
 """
 import random
 
@@ -49,6 +49,23 @@ def test_warp_aligner_hirschberg_wide_and_strip_fallback(emu):
     assert emu.align_path(random_dna(rnd, 3000), random_dna(rnd, 700), None, 9, 16)[1] == 2300 or True
     q, t = random_dna(rnd, 40), random_dna(rnd, 30000)
     assert emu.align_path(q, t, None, 0, 16) == O.align_path(q, t)         # wide leaf
+
+
+def test_lane_aligner(emu):
+    from oracle import oracle as O
+    rnd = random.Random(41)
+    checked = 0
+    for it in range(120):
+        n = rnd.choice([1, 2, 31, 32, 33, 100, 999, 1000])
+        a = random_dna(rnd, n, 'ACGT' if it % 5 else 'ACGTN')
+        b = mutate(rnd, a, rnd.choice([0, 0.01, 0.03, 0.06]))
+        ops, d = O.align_path(a, b)
+        for lw in (4, 8):
+            got = emu.lane_align(a, b, d + rnd.choice([0, 1, 5]), rnd.choice([0, 1, 40]), lw)
+            if got is not None:
+                assert got == (ops.count('='), ops.count('D'), d)
+                checked += 1
+    assert checked > 150
 
 
 def test_task_pipeline(emu):
