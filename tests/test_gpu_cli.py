@@ -85,3 +85,41 @@ def test_single_read_api_matches_oracle():
     qual, ident, by_q = get_qscores(seq, frag, qm)
     q2, m, c = orc.get_qscores(seq, frag, 77, read_index=0)
     assert qual == q2 and ident == m / c
+
+
+@pytest.mark.parametrize('extra', [
+    # BASELINE.json configs[2] flavour: nanopore2020 models, lower identity, heavy glitches
+    ['--error_model', 'nanopore2020', '--qscore_model', 'nanopore2020', '--identity', '90,98,5', '--glitches', '1000,100,100'],
+    # configs[3] flavour: pacbio2021 models, many chimeras
+    ['--error_model', 'pacbio2021', '--qscore_model', 'pacbio2021', '--chimeras', '10'],
+    # random / ideal models, normal-distributed qscore identities, junk and random reads
+    ['--error_model', 'random', '--qscore_model', 'ideal', '--identity', '12,3', '--junk_reads', '10', '--random_reads', '10'],
+])
+def test_simulate_config_variants_match_oracle(tmp_path, extra):
+    """Other corners of BASELINE.json's configs at small scale: every emitted read equals the oracle's."""
+    from badread_b200 import simulate as S
+    from badread_b200.error_model import ErrorModel
+    from badread_b200.fragment_lengths import FragmentLengths
+    from badread_b200.identities import Identities
+    from badread_b200.qscore_model import QScoreModel
+    from oracle import oracle as O
+    args, fastq, _ = _run(tmp_path, extra=['--quantity', '2x'] + extra)
+    lines = fastq.strip().split('\n')
+    records = {lines[i][1:].split(' ')[0]: (lines[i][1:], lines[i + 1], lines[i + 3]) for i in range(0, len(lines), 4)}
+    assert len(records) >= 10
+    sink = io.StringIO()
+    ref = S.Reference(args.reference, sink)
+    fl = FragmentLengths(args.mean_frag_length, args.frag_length_stdev, sink)
+    S.adjust_depths(ref, fl, args, np.random.RandomState(5))
+    planner = S.ReadPlanner(args, ref, fl, Identities(args.mean_identity, args.identity_stdev, args.max_identity, sink), 5)
+    orc = O.Oracle(ErrorModel(args.error_model, sink), QScoreModel(args.qscore_model, sink))
+    checked = 0
+    for idx in range(len(records) + 50):
+        pieces, info, ident, name = planner.plan(idx)
+        rec = records.get(str(name))
+        if rec is None:
+            continue
+        seq, qual, actual = orc.sequence_fragment(planner.materialise(pieces), ident, 5, read_index=idx)
+        assert (rec[1], rec[2]) == (seq, qual)
+        checked += 1
+    assert checked == len(records)
