@@ -342,7 +342,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
             rd.log_off = log_off; rd.wres_off = wres_off;
             log_off += cap; wres_off += cap / BB_ALIGNMENT_INTERVAL + 1;
             const double need = (double)rd.frag_len * (1.0 - target_identity[r]);
-            rd.horizon = (int)std::min<double>((double)cap, std::max(0.0, 1.12 * need) + 40.0);
+            rd.horizon = (int)std::min<double>((double)cap, std::max(0.0, 1.25 * need) + 48.0);
             rd.n_logged = 0; rd.n_resume = 0; rd.a_done = 0; rd.status = BB_READ_PENDING; rd.stop_reason = 0;
         }
         off += (rd.frag_len + 15) & ~15;
@@ -486,7 +486,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
             cudaStream_t st = stream[s];
             for (int c = 0; c < BBQ_NODE_CLASSES; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt[s] + c * 2 + (p ^ 1), 0, sizeof(int), st));
             if (s == 1) {
-                bb_k_node_pair<<<ctx->sm_count * 2, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
+                bb_k_node_pair<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
                 ctx->launches++;
             }
             bb_k_node_warp<4><<<grid_lean[s], BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, BBQ_NODE_LEAN, p, cursor[s]++, warp_base[s]);

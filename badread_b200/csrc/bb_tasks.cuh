@@ -422,7 +422,7 @@ __device__ __forceinline__ void bb_pair_sync(int id) {
 // Wide-band nodes: a PAIR of warps per node.  The even warp runs the forward pass over the left half of the target,
 // the odd warp the reverse pass over the right half, each as a full 32-lane wavefront (half the words per lane of
 // the paired single-warp variant, so the steps are half as long); the even warp then picks the split.
-__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 2)
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 1)
 bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
     __shared__ int s_task[BB_WARPS_PER_CTA / 2];
     const int lane = threadIdx.x & 31;
