@@ -66,7 +66,15 @@ struct BBProb {
                                           // read; rows ascend for qs > 0, descend for qs < 0)
     uint2 *hist; int nb_alloc;
     int *cols_out; int cols_lo;
+    uint32_t *esm = nullptr;              // SM variant only: the warp's shared-memory match-word cache, bb_esm_words(L)
 };
+
+// Shared-memory match cache of bb_band_pass<L, ., ., true>: lane l keeps the 4 x L match words of its current chunk
+// (already shifted / bit-reversed to the chunk's row order) at esm + l * (4 L + 4), component-major, so that a step
+// reads its L words with L/4 conflict-free 128-bit loads (the +4 pad staggers the lanes of a quarter warp over all
+// 32 banks) instead of L + 1 scattered global loads and L funnel shifts.
+__host__ __device__ constexpr int bb_esm_lane_stride(int L) { return 4 * L + 4; }
+__host__ __device__ constexpr int bb_esm_words(int L) { return 32 * bb_esm_lane_stride(L); }
 
 __device__ __forceinline__ void bb_band(int n, int m, int k, int &a, int &b) {
     // a path of cost <= k from (0,0) to (n,m) has at most (k-(n-m))/2 'D' and (k+(n-m))/2 'I' moves:
@@ -158,7 +166,7 @@ __device__ __forceinline__ void bb_add_words(const uint32_t (&A)[L], const uint3
 // path of cost <= the k the band was derived from and upper bounds elsewhere.
 // A chunk is handled as ONE 32L-bit Myers word: the only cross-word dependencies of a step are the carry chain
 // of the addition and the one-bit shifts, everything else is independent per word.
-template <int L, bool HIST, bool COLS>
+template <int L, bool HIST, bool COLS, bool SM = false>
 __device__ int bb_band_pass(const BBProb &P, int K) {
     const int lane = threadIdx.x & 31;
     const int slot = lane & (K - 1);
@@ -188,6 +196,7 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
     for (int x = 0; x < LR; x++) { eA[x] = eC[x] = eG[x] = eT[x] = 0u; }
     const uint32_t *const ewords = reinterpret_cast<const uint32_t *>(P.peq);
     const bool fwd = P.qs > 0;
+    uint32_t *const esm = (SM && STREAM) ? P.esm + lane * bb_esm_lane_stride(L) : nullptr;
     int eidx = 0, esh = 0, evalid = 0;  // bitmap word / shift of the chunk's first word; rows of the chunk below n
     int u = slot;
     int cs = max(0, CH * u - b), ce = min(ncols - 1, CH * u + CH - 1 + a);
@@ -214,6 +223,25 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
                     const int s0 = fwd ? P.peq_bit0 + u * CH : P.peq_bit0 - u * CH - 31;
                     eidx = s0 >> 5; esh = s0 & 31;
                     evalid = n - u * CH;
+                    if (SM) {  // cut the chunk's match words out of the bitmap once; the steps read them from smem
+                        uint4 w0 = P.peq[fwd ? eidx : eidx + 1];
+#pragma unroll 1
+                        for (int x = 0; x < L; x++) {
+                            const uint4 w1 = P.peq[fwd ? eidx + x + 1 : eidx - x];
+                            uint4 e;
+                            if (fwd) {
+                                e.x = __funnelshift_r(w0.x, w1.x, esh); e.y = __funnelshift_r(w0.y, w1.y, esh);
+                                e.z = __funnelshift_r(w0.z, w1.z, esh); e.w = __funnelshift_r(w0.w, w1.w, esh);
+                            } else {
+                                e.x = __brev(__funnelshift_r(w1.x, w0.x, esh)); e.y = __brev(__funnelshift_r(w1.y, w0.y, esh));
+                                e.z = __brev(__funnelshift_r(w1.z, w0.z, esh)); e.w = __brev(__funnelshift_r(w1.w, w0.w, esh));
+                            }
+                            const int v = evalid - 32 * x;
+                            const uint32_t keep = v >= 32 ? ~0u : (v <= 0 ? 0u : ((1u << v) - 1u));
+                            esm[x] = e.x & keep; esm[L + x] = e.y & keep; esm[2 * L + x] = e.z & keep; esm[3 * L + x] = e.w & keep;
+                            w0 = w1;
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int x = 0; x < LR; x++) bb_fetch_peq(P, u * CH + 32 * x, eA[x], eC[x], eG[x], eT[x]);
@@ -222,7 +250,14 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
             const uint32_t code = (tc >> 1) & 3u;  // A->0, C->1, T->2, G->3
             const bool acgt = ((0x47544341u >> (8 * code)) & 0xffu) == tc;
             uint32_t Eq[L], Xv[L], A[L], S[L];
-            if (STREAM) {
+            if (STREAM && SM) {
+                const uint4 *ep = reinterpret_cast<const uint4 *>(esm + (code ^ (code >> 1)) * L);
+#pragma unroll
+                for (int x = 0; x < L; x += 4) {
+                    const uint4 e = ep[x >> 2];
+                    if (x + 3 < L) { Eq[x] = e.x; Eq[x + 1] = e.y; Eq[x + 2] = e.z; Eq[x + 3] = e.w; }
+                }
+            } else if (STREAM) {
                 const uint32_t *ep = ewords + (code ^ (code >> 1));  // uint4 component: A, C, G, T
                 uint32_t wv[L + 1];
                 if (fwd) {
@@ -346,11 +381,11 @@ __device__ __forceinline__ int bb_pick_L(int a, int b, int K) {
     return 0;
 }
 
-template <bool HIST, bool COLS, int MAXL>
+template <bool HIST, bool COLS, int MAXL, bool SM = false>
 __device__ __forceinline__ int bb_band_dispatch(const BBProb &P, int K, int L) {
-    if (MAXL >= 32 && L == 32) return bb_band_pass<(MAXL >= 32 ? 32 : 1), HIST, COLS>(P, K);
-    if (MAXL >= 16 && L == 16) return bb_band_pass<(MAXL >= 16 ? 16 : 1), HIST, COLS>(P, K);
-    if (MAXL >= 8 && L == 8) return bb_band_pass<(MAXL >= 8 ? 8 : 1), HIST, COLS>(P, K);
+    if (MAXL >= 32 && L == 32) return bb_band_pass<(MAXL >= 32 ? 32 : 1), HIST, COLS, SM>(P, K);
+    if (MAXL >= 16 && L == 16) return bb_band_pass<(MAXL >= 16 ? 16 : 1), HIST, COLS, SM>(P, K);
+    if (MAXL >= 8 && L == 8) return bb_band_pass<(MAXL >= 8 ? 8 : 1), HIST, COLS, SM>(P, K);
     if (MAXL >= 4 && L == 4) return bb_band_pass<(MAXL >= 4 ? 4 : 1), HIST, COLS>(P, K);
     if (MAXL >= 2 && L == 2) return bb_band_pass<(MAXL >= 2 ? 2 : 1), HIST, COLS>(P, K);
     return bb_band_pass<1, HIST, COLS>(P, K);

@@ -135,6 +135,8 @@ extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
     for (int i = 0; from[i]; i++) comp[(uint8_t)from[i]] = (uint8_t)to[i];
     e = cudaMemcpyToSymbol(bb_c_comp, comp, 256);
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
+    e = cudaFuncSetAttribute(bb_k_node_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, BB_PAIR_SMEM_BYTES);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     // persistent warps: 4 CTAs of 4 warps per SM for the warp-per-read kernels
     ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
     if (const char *e = std::getenv("BADREAD_B200_ALIGN_TASKS")) ctx->use_tasks = (e[0] != '0');
@@ -486,7 +488,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
             cudaStream_t st = stream[s];
             for (int c = 0; c < BBQ_NODE_CLASSES; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt[s] + c * 2 + (p ^ 1), 0, sizeof(int), st));
             if (s == 1) {
-                bb_k_node_pair<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
+                bb_k_node_pair<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, BB_PAIR_SMEM_BYTES, st>>>(B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
                 ctx->launches++;
             }
             bb_k_node_warp<4><<<grid_lean[s], BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, BBQ_NODE_LEAN, p, cursor[s]++, warp_base[s]);

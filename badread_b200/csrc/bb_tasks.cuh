@@ -410,6 +410,8 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity
     }
 }
 
+#define BB_PAIR_SMEM_BYTES (BB_WARPS_PER_CTA * bb_esm_words(32) * 4)
+
 // Rendezvous of the two warps of a pair (named barrier `id`, 64 threads).
 __device__ __forceinline__ void bb_pair_sync(int id) {
 #ifdef BB_EMULATOR
@@ -425,6 +427,11 @@ __device__ __forceinline__ void bb_pair_sync(int id) {
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 1)
 bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
     __shared__ int s_task[BB_WARPS_PER_CTA / 2];
+#ifdef BB_EMULATOR
+    static uint32_t s_eq[BB_PAIR_SMEM_BYTES / 4];
+#else
+    extern __shared__ __align__(16) uint32_t s_eq[];  // BB_PAIR_SMEM_BYTES: one match-word cache per warp
+#endif
     const int lane = threadIdx.x & 31;
     const int wi = threadIdx.x >> 5;
     const int pair = wi >> 1;
@@ -461,7 +468,8 @@ bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
                 P.q = q + nd.q0 + nd.nn - 1; P.qs = -1; P.t = t + nd.t0 + nd.mm - 1; P.ts = -1; P.ncols = right_w;
                 P.peq_bit0 = nd.q0 + nd.nn - 1 + BB_PEQ_BIT0; P.cols_out = sc.R; P.cols_lo = loR;
             }
-            bb_band_dispatch<false, true, 32>(P, 32, L);
+            P.esm = s_eq + wi * bb_esm_words(32);
+            bb_band_dispatch<false, true, 32, true>(P, 32, L);
         }
         __threadfence_block();
         bb_pair_sync(pair + 1);
