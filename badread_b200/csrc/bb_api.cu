@@ -67,6 +67,8 @@ struct bb_ctx {
     DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist;
     DevBuf d_ctime, d_chlog, d_wres, d_wtasks, d_wfallback, d_active;
     bool use_spec_loop = true;
+    int lane8_cols = 4096, lane16_cols = 0;  // routing limits of the lane node kernels (tuning knobs)
+    int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
     struct QueueBufs { DevBuf node[BBQ_NODE_CLASSES][2], leaf[2], count; } qbuf[2];  // [0] normal, [1] wide-root reads
     bool use_tasks = true;
 
@@ -141,6 +143,9 @@ extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
     ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
     if (const char *e = std::getenv("BADREAD_B200_ALIGN_TASKS")) ctx->use_tasks = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_SPEC_LOOP")) ctx->use_spec_loop = (e[0] != '0');
+    if (const char *e = std::getenv("BADREAD_B200_LANE8_COLS")) ctx->lane8_cols = std::atoi(e);
+    if (const char *e = std::getenv("BADREAD_B200_LANE16_COLS")) ctx->lane16_cols = std::atoi(e);
+    if (const char *e = std::getenv("BADREAD_B200_PAIR_CTAS")) ctx->pair_ctas = (e[0] == '2') ? 2 : 1;
     *out = ctx;
     return BB_OK;
 }
@@ -469,6 +474,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
         BB_CUDA(ctx, qb.count.ensure(512 * sizeof(int)));
         cnt[s] = qb.count.as<int>();
         Q[s].count = cnt[s]; Q[s].overflow = cnt[s] + BBQ_OVERFLOW; Q[s].cap_node = cap_node; Q[s].cap_leaf = cap_leaf;
+        Q[s].lane8_cols = ctx->lane8_cols; Q[s].lane16_cols = ctx->lane16_cols;
         BB_CUDA(ctx, cudaMemsetAsync(cnt[s], 0, 512 * sizeof(int), stream[0]));
     }
     BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, ctx->h_order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream[0]));
@@ -480,7 +486,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
     BB_CUDA(ctx, cudaStreamWaitEvent(stream[1], ctx->ev_fork, 0));
     int *cursor[2] = {cnt[0] + 16, cnt[1] + 16};
     const int warp_base[2] = {0, ctx->n_warps / 2};
-    const int grid_lean[2] = {ctx->sm_count * 2, ctx->sm_count};
+    const int grid_lean[2] = {ctx->sm_count * 2, ctx->sm_count * 2};
     const int max_levels = 40;  // the target halves at every level: 2^40 columns is beyond any read
     for (int level = 0; level < max_levels; level++) {
         const int p = level & 1;
@@ -488,7 +494,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
             cudaStream_t st = stream[s];
             for (int c = 0; c < BBQ_NODE_CLASSES; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt[s] + c * 2 + (p ^ 1), 0, sizeof(int), st));
             if (s == 1) {
-                bb_k_node_pair<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, BB_PAIR_SMEM_BYTES, st>>>(B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
+                bb_k_node_pair<<<ctx->sm_count * ctx->pair_ctas, BB_WARPS_PER_CTA * 32, BB_PAIR_SMEM_BYTES, st>>>(B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
                 ctx->launches++;
             }
             bb_k_node_warp<4><<<grid_lean[s], BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, BBQ_NODE_LEAN, p, cursor[s]++, warp_base[s]);

@@ -35,6 +35,7 @@ struct BBQueues {
     int *count;          // node counts: [class*2 + parity]; leaf counts: [BBQ_LEAF_COUNT + which]
     int *overflow;
     int cap_node, cap_leaf;
+    int lane8_cols, lane16_cols;   // longest target a lane node task may have (longer ones go to the warp kernels)
 };
 
 struct BBAlignOut {      // where a read's alignment goes
@@ -80,9 +81,11 @@ __device__ void bb_push_task(const BBQueues &Q, int next_parity, const BBAlignOu
         if (idx >= Q.cap_leaf) { atomicExch(Q.overflow, 1); return; }
         Q.leaf[which][idx] = nd;
     } else {
-        const int cls = lw <= BB_NODE_LW_SMALL ? BBQ_NODE_LANE8
-                        : lw <= BB_NODE_LW ? BBQ_NODE_LANE16
-                                           : (a + b <= BB_WARP_LEAN_BAND ? BBQ_NODE_LEAN : BBQ_NODE_WIDE);
+        // a lane walks its node alone, one column after the other: only short nodes go there (they are the many
+        // ones); a long narrow node would hold a whole launch up and runs ~15x sooner as a warp wavefront
+        const int cls = (lw <= BB_NODE_LW_SMALL && nd.mm <= Q.lane8_cols) ? BBQ_NODE_LANE8
+                        : (lw <= BB_NODE_LW && nd.mm <= Q.lane16_cols) ? BBQ_NODE_LANE16
+                        : (a + b <= BB_WARP_LEAN_BAND ? BBQ_NODE_LEAN : BBQ_NODE_WIDE);
         const int idx = atomicAdd(&Q.count[cls * 2 + next_parity], 1);
         if (idx >= Q.cap_node) { atomicExch(Q.overflow, 1); return; }
         Q.node[cls][next_parity][idx] = nd;
@@ -424,7 +427,7 @@ __device__ __forceinline__ void bb_pair_sync(int id) {
 // Wide-band nodes: a PAIR of warps per node.  The even warp runs the forward pass over the left half of the target,
 // the odd warp the reverse pass over the right half, each as a full 32-lane wavefront (half the words per lane of
 // the paired single-warp variant, so the steps are half as long); the even warp then picks the split.
-__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 1)
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 2)
 bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
     __shared__ int s_task[BB_WARPS_PER_CTA / 2];
 #ifdef BB_EMULATOR

@@ -18,8 +18,10 @@ eng.upload_reference(ref.concat)
 eng.set_error_model(models[0])
 eng.set_qscore_model(models[1])
 eng.sequence_batch(batch)
-res, total = eng.sequence_batch(batch)
-print('total ms, stages', eng.last_run_ms())
+for _ in range(int(os.environ.get('READ_COST_REPEATS', '1'))):
+    res, total = eng.sequence_batch(batch)
+    t, st = eng.last_run_ms()
+    print('total ms %.1f' % t, {k: round(v, 1) for k, v in st.items() if v >= 0.5})
 rec = res.records
 L = np.array([rec[i].frag_len for i in range(len(plans))])
 ka = np.array([rec[i].align_kcycles for i in range(len(plans))], dtype=np.float64)
