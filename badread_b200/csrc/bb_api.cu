@@ -8,6 +8,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bb_kernels.cuh"
@@ -75,6 +76,15 @@ struct bb_ctx {
 
     cudaEvent_t ev[BB_N_STAGES + 1] = {};
     float stage_ms[BB_N_STAGES] = {};
+
+    // sub-batches: a context made by bb_create owns n_kids further worker contexts on the same device; a batch is
+    // dealt out over the workers (this context is worker 0) and their kernel chains run side by side on their
+    // own streams, so that one worker's tails and host round trips are covered by the others' kernels
+    std::vector<bb_ctx *> kids;
+    int n_split = 1;                          // workers the uploaded batch is spread over (1: this context alone)
+    std::vector<std::vector<int32_t>> part;   // part[w][i] = batch position of worker w's i-th read
+    std::vector<int64_t> part_base;           // offset of worker w's block in the fetched seq / qual buffers
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 };
 
 static thread_local std::string g_create_error;
@@ -101,9 +111,14 @@ extern "C" const char *bb_stage_name(int stage) {
     return (stage >= 0 && stage < BB_N_STAGES) ? kStageNames[stage] : "";
 }
 
-extern "C" int64_t bb_launch_count(const bb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t bb_launch_count(const bb_ctx *ctx) {
+    if (!ctx) return 0;
+    int64_t total = ctx->launches;
+    for (const bb_ctx *kid : ctx->kids) total += kid->launches;
+    return total;
+}
 
-extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
+static int create_worker(bb_ctx **out, int device, uint64_t seed) {
     if (!out) return BB_ERR_ARG;
     *out = nullptr;
     int n_dev = 0;
@@ -150,10 +165,32 @@ extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
     return BB_OK;
 }
 
+extern "C" int bb_destroy(bb_ctx *ctx);
+
+extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
+    int rc = create_worker(out, device, seed);
+    if (rc) return rc;
+    bb_ctx *ctx = *out;
+    int n_workers = 4;
+    if (const char *e = std::getenv("BADREAD_B200_SUBBATCHES")) n_workers = std::max(1, std::min(8, std::atoi(e)));
+    for (int w = 1; w < n_workers; w++) {
+        bb_ctx *kid = nullptr;
+        if ((rc = create_worker(&kid, device, seed))) { bb_destroy(ctx); *out = nullptr; return rc; }
+        ctx->kids.push_back(kid);
+    }
+    cudaEventCreate(&ctx->ev_t0);
+    cudaEventCreate(&ctx->ev_t1);
+    return BB_OK;
+}
+
 extern "C" int bb_destroy(bb_ctx *ctx) {
     if (!ctx) return BB_OK;
+    for (bb_ctx *kid : ctx->kids) bb_destroy(kid);
+    ctx->kids.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     DevBuf *bufs[] = {&ctx->ref, &ctx->em_k2r, &ctx->em_rowoff, &ctx->em_cum, &ctx->em_flags, &ctx->em_slots,
                       &ctx->em_pool, &ctx->qm_hkeys, &ctx->qm_hvals, &ctx->qm_rowoff, &ctx->qm_scores, &ctx->qm_cum,
                       &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order, &ctx->d_order_small, &ctx->d_order_large, &ctx->d_order_long,
@@ -190,6 +227,8 @@ extern "C" int bb_upload_reference(bb_ctx *ctx, const uint8_t *bases, int64_t n_
     if (rc) return rc;
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->ref_len = n_bases;
+    for (bb_ctx *kid : ctx->kids)
+        if ((rc = bb_upload_reference(kid, bases, n_bases))) return set_err(ctx, rc, kid->err);
     return BB_OK;
 }
 
@@ -219,6 +258,10 @@ extern "C" int bb_upload_error_model(bb_ctx *ctx, int k, int type, const int32_t
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_em = true;
     ctx->uploaded = false;
+    for (bb_ctx *kid : ctx->kids) {
+        const int rck = bb_upload_error_model(kid, k, type, kmer_to_row, n_index, n_rows, row_off, cum, flags, slots, pool, pool_len);
+        if (rck) return set_err(ctx, rck, kid->err);
+    }
     return BB_OK;
 }
 
@@ -252,6 +295,8 @@ extern "C" int bb_upload_qscore_model(bb_ctx *ctx, int kmer_size, int32_t n_keys
     ctx->qm.row_off = ctx->qm_rowoff.as<int32_t>(); ctx->qm.scores = ctx->qm_scores.as<uint8_t>();
     ctx->qm.cum = ctx->qm_cum.as<double>();
     ctx->have_qm = true;
+    for (bb_ctx *kid : ctx->kids)
+        if ((rc = bb_upload_qscore_model(kid, kmer_size, n_keys, keys, row_off, scores, cum))) return set_err(ctx, rc, kid->err);
     return BB_OK;
 }
 
@@ -313,9 +358,9 @@ static BBBatchDev batch_dev(bb_ctx *ctx) {
     return B;
 }
 
-extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_index, const int32_t *seg_off,
-                               const bb_segment *segs, const uint8_t *literal_pool, int64_t literal_len,
-                               const double *target_identity) {
+static int w_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_index, const int32_t *seg_off,
+                          const bb_segment *segs, const uint8_t *literal_pool, int64_t literal_len,
+                          const double *target_identity) {
     if (!ctx) return BB_ERR_ARG;
     if (n_reads <= 0 || !read_index || !seg_off || !segs || !target_identity || literal_len < 0)
         return set_err(ctx, BB_ERR_ARG, "bb_batch_upload: bad arguments");
@@ -527,7 +572,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
     return BB_OK;
 }
 
-extern "C" int bb_batch_run(bb_ctx *ctx) {
+static int w_batch_run(bb_ctx *ctx) {
     if (!ctx) return BB_ERR_ARG;
     if (!ctx->uploaded) return set_err(ctx, BB_ERR_STATE, "bb_batch_run: no batch uploaded");
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -643,10 +688,11 @@ extern "C" int bb_synchronize(bb_ctx *ctx) {
     if (!ctx) return BB_ERR_ARG;
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (bb_ctx *kid : ctx->kids) BB_CUDA(ctx, cudaStreamSynchronize(kid->stream));
     return BB_OK;
 }
 
-extern "C" int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms) {
+static int w_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms) {
     if (!ctx) return BB_ERR_ARG;
     if (!ctx->ran) return set_err(ctx, BB_ERR_STATE, "no run to time");
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -659,13 +705,13 @@ extern "C" int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms) {
     return BB_OK;
 }
 
-extern "C" int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t *seq_out, uint8_t *qual_out,
-                                   int64_t out_cap, int64_t *out_total) {
+// Worker-level fetch: the worker's packed block goes to seq_out / qual_out (already offset by the caller);
+// results[pos[i]] describes the worker's i-th read, its out_off shifted by `base`.
+static int w_fetch(bb_ctx *ctx, bb_read_result *results, const int32_t *pos, int64_t base, uint8_t *seq_out,
+                   uint8_t *qual_out) {
     if (!ctx) return BB_ERR_ARG;
     if (!ctx->ran) return set_err(ctx, BB_ERR_STATE, "bb_fetch_last_batch: nothing to fetch");
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (out_total) *out_total = ctx->out_total;
-    if (out_cap < ctx->out_total) return set_err(ctx, BB_ERR_CAPACITY, "output buffers too small");
     const int n = ctx->n_reads;
     std::vector<BBReadDev> reads((size_t)n);
     cudaStream_t st = ctx->stream;
@@ -680,8 +726,8 @@ extern "C" int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t
     for (int r = 0; r < n; r++) {
         const BBReadDev &rd = reads[(size_t)r];
         if (results) {
-            bb_read_result &o = results[r];
-            o.out_off = rd.out_off; o.out_len = rd.out_len; o.frag_len = ctx->h_inlen[(size_t)r];
+            bb_read_result &o = results[pos ? pos[r] : r];
+            o.out_off = base + rd.out_off; o.out_len = rd.out_len; o.frag_len = ctx->h_inlen[(size_t)r];
             o.matches = rd.matches; o.columns = rd.seq_len + rd.dels; o.loop_count = rd.loop_count;
             o.change_count = rd.change_count; o.n_alignments = rd.n_align; o.flags = rd.flags;
             o.loop_kcycles = rd.kc_loop; o.align_kcycles = rd.kc_align;
@@ -690,9 +736,146 @@ extern "C" int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t
     }
     if (bad) {
         char msg[160];
-        std::snprintf(msg, sizeof(msg), "device invariant violated: read %d flags 0x%x", bad_read, bad);
+        std::snprintf(msg, sizeof(msg), "device invariant violated: read %d flags 0x%x", pos ? pos[bad_read] : bad_read, bad);
         return set_err(ctx, BB_ERR_INTERNAL, msg);
     }
+    return BB_OK;
+}
+
+// ---- batch entry points: deal the reads out over the workers ---------------------------------------------
+static bb_ctx *worker_of(bb_ctx *ctx, int w) { return w == 0 ? ctx : ctx->kids[(size_t)w - 1]; }
+
+extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_index, const int32_t *seg_off,
+                               const bb_segment *segs, const uint8_t *literal_pool, int64_t literal_len,
+                               const double *target_identity) {
+    if (!ctx) return BB_ERR_ARG;
+    if (n_reads <= 0 || !read_index || !seg_off || !segs || !target_identity || literal_len < 0)
+        return set_err(ctx, BB_ERR_ARG, "bb_batch_upload: bad arguments");
+    const int n_workers = 1 + (int)ctx->kids.size();
+    ctx->n_split = (n_workers > 1 && n_reads >= 64 * n_workers) ? n_workers : 1;
+    if (ctx->n_split == 1)
+        return w_batch_upload(ctx, n_reads, read_index, seg_off, segs, literal_pool, literal_len, target_identity);
+    // deal the reads out longest first, so that every worker sees the same length distribution
+    const int S = ctx->n_split;
+    std::vector<int64_t> len((size_t)n_reads, 0);
+    for (int32_t r = 0; r < n_reads; r++) {
+        if (seg_off[r + 1] < seg_off[r]) return set_err(ctx, BB_ERR_ARG, "seg_off must be non-decreasing");
+        for (int32_t x = seg_off[r]; x < seg_off[r + 1]; x++) len[(size_t)r] += segs[x].len;
+    }
+    std::vector<int32_t> order((size_t)n_reads);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return len[(size_t)x] > len[(size_t)y]; });
+    ctx->part.assign((size_t)S, std::vector<int32_t>());
+    for (int32_t i = 0; i < n_reads; i++) ctx->part[(size_t)(i % S)].push_back(order[(size_t)i]);
+    std::vector<int> rcs((size_t)S, 0);
+    std::vector<std::thread> threads;
+    auto upload_part = [&](int w) {
+        std::vector<int32_t> &mine = ctx->part[(size_t)w];
+        std::sort(mine.begin(), mine.end());
+        std::vector<uint64_t> ridx; std::vector<int32_t> soff(1, 0); std::vector<bb_segment> sg; std::vector<uint8_t> lit;
+        std::vector<double> ident;
+        for (int32_t r : mine) {
+            ridx.push_back(read_index[r]);
+            ident.push_back(target_identity[r]);
+            for (int32_t x = seg_off[r]; x < seg_off[r + 1]; x++) {
+                bb_segment g = segs[x];
+                if (g.kind == BB_SEG_LITERAL) {
+                    if (g.len < 0 || g.src < 0 || g.src + g.len > literal_len) { rcs[(size_t)w] = -1; return; }
+                    const int64_t at = (int64_t)lit.size();
+                    lit.insert(lit.end(), literal_pool + g.src, literal_pool + g.src + g.len);
+                    g.src = at;
+                }
+                sg.push_back(g);
+            }
+            soff.push_back((int32_t)sg.size());
+        }
+        rcs[(size_t)w] = w_batch_upload(worker_of(ctx, w), (int32_t)mine.size(), ridx.data(), soff.data(), sg.data(),
+                                        lit.data(), (int64_t)lit.size(), ident.data());
+    };
+    for (int w = 1; w < S; w++) threads.emplace_back(upload_part, w);
+    upload_part(0);
+    for (auto &t : threads) t.join();
+    for (int w = 0; w < S; w++) {
+        if (rcs[(size_t)w] == -1) return set_err(ctx, BB_ERR_ARG, "literal segment out of range");
+        if (rcs[(size_t)w]) return w == 0 ? rcs[0] : set_err(ctx, rcs[(size_t)w], worker_of(ctx, w)->err);
+    }
+    return BB_OK;
+}
+
+extern "C" int bb_batch_run(bb_ctx *ctx) {
+    if (!ctx) return BB_ERR_ARG;
+    if (ctx->n_split == 1) return w_batch_run(ctx);
+    const int S = ctx->n_split;
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(worker_of(ctx, w)->stream, ctx->ev_t0, 0));
+    std::vector<int> rcs((size_t)S, 0);
+    std::vector<std::thread> threads;
+    for (int w = 1; w < S; w++) threads.emplace_back([&, w]() { rcs[(size_t)w] = w_batch_run(worker_of(ctx, w)); });
+    rcs[0] = w_batch_run(ctx);
+    for (auto &t : threads) t.join();
+    for (int w = 0; w < S; w++)
+        if (rcs[(size_t)w]) return w == 0 ? rcs[0] : set_err(ctx, rcs[(size_t)w], worker_of(ctx, w)->err);
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, worker_of(ctx, w)->ev[BB_N_STAGES - 1], 0));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+    return BB_OK;
+}
+
+// Whole-batch device time from the first worker's first kernel to the last worker's last one.  With several
+// workers the stages of different workers overlap in time: each stage is reported as its share of the summed
+// per-worker stage times, scaled to the whole-batch time.
+extern "C" int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms) {
+    if (!ctx) return BB_ERR_ARG;
+    if (ctx->n_split == 1) return w_last_run_ms(ctx, total_ms, stage_ms);
+    const int S = ctx->n_split;
+    float sum[BB_N_STAGES] = {};
+    for (int w = 0; w < S; w++) {
+        float t = 0.f, st[BB_N_STAGES];
+        const int rc = w_last_run_ms(worker_of(ctx, w), &t, st);
+        if (rc) return w == 0 ? rc : set_err(ctx, rc, worker_of(ctx, w)->err);
+        for (int i = 0; i < BB_N_STAGES; i++) sum[i] += st[i];
+    }
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    BB_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+    float total = 0.f;
+    BB_CUDA(ctx, cudaEventElapsedTime(&total, ctx->ev_t0, ctx->ev_t1));
+    const float scale = sum[BB_N_STAGES - 1] > 0.f ? total / sum[BB_N_STAGES - 1] : 0.f;
+    for (int i = 0; i < BB_N_STAGES - 1; i++) ctx->stage_ms[i] = sum[i] * scale;
+    ctx->stage_ms[BB_N_STAGES - 1] = total;
+    if (total_ms) *total_ms = total;
+    if (stage_ms) std::memcpy(stage_ms, ctx->stage_ms, sizeof(ctx->stage_ms));
+    return BB_OK;
+}
+
+extern "C" int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t *seq_out, uint8_t *qual_out,
+                                   int64_t out_cap, int64_t *out_total) {
+    if (!ctx) return BB_ERR_ARG;
+    const int S = ctx->n_split;
+    int64_t total = 0;
+    ctx->part_base.assign((size_t)S, 0);
+    for (int w = 0; w < S; w++) {
+        bb_ctx *wk = worker_of(ctx, w);
+        if (!wk->ran) return set_err(ctx, BB_ERR_STATE, "bb_fetch_last_batch: nothing to fetch");
+        ctx->part_base[(size_t)w] = total;
+        total += wk->out_total;
+    }
+    if (out_total) *out_total = total;
+    if (out_cap < total) return set_err(ctx, BB_ERR_CAPACITY, "output buffers too small");
+    if (total && (!seq_out || !qual_out)) return set_err(ctx, BB_ERR_ARG, "null output buffers");
+    if (S == 1) return w_fetch(ctx, results, nullptr, 0, seq_out, qual_out);
+    std::vector<int> rcs((size_t)S, 0);
+    std::vector<std::thread> threads;
+    auto fetch_part = [&](int w) {
+        const int64_t base = ctx->part_base[(size_t)w];
+        rcs[(size_t)w] = w_fetch(worker_of(ctx, w), results, ctx->part[(size_t)w].data(), base,
+                                 seq_out ? seq_out + base : nullptr, qual_out ? qual_out + base : nullptr);
+    };
+    for (int w = 1; w < S; w++) threads.emplace_back(fetch_part, w);
+    fetch_part(0);
+    for (auto &t : threads) t.join();
+    for (int w = 0; w < S; w++)
+        if (rcs[(size_t)w]) return w == 0 ? rcs[0] : set_err(ctx, rcs[(size_t)w], worker_of(ctx, w)->err);
     return BB_OK;
 }
 

@@ -56,7 +56,8 @@ typedef struct bb_segment {
 
 /* Per-read outputs besides the bases (header fields of simulate.py:73-75 come from these). */
 typedef struct bb_read_result {
-    int64_t out_off;      /* offset of this read's seq/qual in the output buffers */
+    int64_t out_off;      /* offset of this read's seq/qual in the output buffers (reads are packed without gaps,
+                           * but not necessarily in batch order) */
     int32_t out_len;      /* len(seq) after trimming; 0 => the reference skips the read (simulate.py:70) */
     int32_t frag_len;     /* len(fragment) before padding ("error-free_length") */
     int32_t matches;      /* '=' columns of the final alignment */
@@ -71,7 +72,9 @@ typedef struct bb_read_result {
 
 /* ---- lifecycle -------------------------------------------------------------------------------------- */
 /* Creates a context on CUDA device `device`. seed is `--seed` (simulate.py:34-36). Fails with BB_ERR_CUDA when
- * there is no usable GPU: there is no CPU path. */
+ * there is no usable GPU: there is no CPU path.
+ * A context holds BADREAD_B200_SUBBATCHES (environment, default 4, 1..8) workers on the device: large batches are
+ * dealt out over them and their kernel chains overlap on separate streams.  Results do not depend on it. */
 BB_API int bb_create(bb_ctx **ctx, int device, uint64_t seed);
 BB_API int bb_destroy(bb_ctx *ctx);
 BB_API const char *bb_last_error(const bb_ctx *ctx); /* ctx may be NULL for creation errors */
