@@ -60,6 +60,8 @@ def lib():
         'bb_batch_upload': (c.c_int, [vp, i32, vp, vp, vp, vp, i64, vp]),
         'bb_batch_run': (c.c_int, [vp]),
         'bb_synchronize': (c.c_int, [vp]),
+        'bb_host_alloc': (c.c_int, [P(vp), i64]),
+        'bb_host_free': (c.c_int, [vp]),
         'bb_last_run_ms': (c.c_int, [vp, P(c.c_float), P(c.c_float)]),
         'bb_stage_name': (c.c_char_p, [c.c_int]),
         'bb_launch_count': (i64, [vp]),
@@ -78,6 +80,6 @@ def lib():
 
 EXPORTED_SYMBOLS = ['bb_create', 'bb_destroy', 'bb_last_error', 'bb_version', 'bb_upload_reference',
                     'bb_upload_error_model', 'bb_upload_qscore_model', 'bb_sequence_batch',
-                    'bb_fetch_last_batch', 'bb_batch_upload', 'bb_batch_run', 'bb_synchronize',
+                    'bb_fetch_last_batch', 'bb_batch_upload', 'bb_batch_run', 'bb_synchronize', 'bb_host_alloc', 'bb_host_free',
                     'bb_last_run_ms', 'bb_stage_name', 'bb_launch_count', 'bb_get_qscores', 'bb_align_path',
                     'bb_host_align_kmers', 'bb_host_align_path']

@@ -684,6 +684,17 @@ static int w_batch_run(bb_ctx *ctx) {
     return BB_OK;
 }
 
+extern "C" int bb_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return BB_ERR_ARG;
+    *ptr = nullptr;
+    return cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable) == cudaSuccess ? BB_OK : BB_ERR_CUDA;
+}
+
+extern "C" int bb_host_free(void *ptr) {
+    if (!ptr) return BB_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? BB_OK : BB_ERR_CUDA;
+}
+
 extern "C" int bb_synchronize(bb_ctx *ctx) {
     if (!ctx) return BB_ERR_ARG;
     BB_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -103,9 +103,11 @@ class Engine(object):
         self.qscore_model = None
         self._out_cap = 0
         self._seq_buf = self._qual_buf = None
+        self._pinned = []
 
     def close(self):
         if getattr(self, '_ctx', None):
+            self._free_out()
             self._lib.bb_destroy(self._ctx)
             self._ctx = None
 
@@ -148,9 +150,23 @@ class Engine(object):
     def _ensure_out(self, cap):
         if cap > self._out_cap:
             cap = int(cap * 1.25) + 4096
-            self._seq_buf = np.empty(cap, dtype=np.uint8)
-            self._qual_buf = np.empty(cap, dtype=np.uint8)
+            self._free_out()
+            bufs = []
+            for _ in range(2):  # page-locked, so that the device-to-host copies run at link rate
+                p = ctypes.c_void_p()
+                if self._lib.bb_host_alloc(ctypes.byref(p), cap) != 0:
+                    raise EngineError(f'bb_host_alloc({cap}) failed')
+                self._pinned.append(p)
+                bufs.append(np.ctypeslib.as_array((ctypes.c_uint8 * cap).from_address(p.value)))
+            self._seq_buf, self._qual_buf = bufs
             self._out_cap = cap
+
+    def _free_out(self):
+        self._seq_buf = self._qual_buf = None
+        self._out_cap = 0
+        for p in self._pinned:
+            self._lib.bb_host_free(p)
+        self._pinned = []
 
     def upload_batch(self, batch):
         ri, so, segs, lit, lit_len, ti = batch.arrays()

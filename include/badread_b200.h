@@ -114,6 +114,11 @@ BB_API int bb_sequence_batch(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_
 BB_API int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t *seq_out, uint8_t *qual_out, int64_t out_cap,
                         int64_t *out_total);
 
+/* Page-locked host memory for the seq / qual output buffers (device-to-host copies into pageable memory go through
+ * a staging buffer at a fraction of the link rate).  Optional: any host pointer is accepted by the fetch calls. */
+BB_API int bb_host_alloc(void **ptr, int64_t bytes);
+BB_API int bb_host_free(void *ptr);
+
 /* Split form used by bench.py to time the device work with inputs already resident in HBM:
  * bb_batch_upload (H2D of descriptors) -> bb_batch_run (kernels only, asynchronous on the ctx stream;
  * may be called repeatedly on the same uploaded batch) -> bb_fetch_last_batch (D2H). */
