@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev e
     if (threadIdx.x == 0) running = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int cost = 0;  // sum of the exact edit distances base -> slot string: a tighter bound than the loop's count
     for (int base = 0; base < rd.frag_len; base += 256) {
         const int x = base + threadIdx.x;
         uint32_t st = BB_SLOT_NONE;
@@ -429,11 +430,29 @@ __global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev e
         const int off = running + woff + incl - len;
         if (x < rd.frag_len) {
             if (st == BB_SLOT_NONE) seq[off] = frag[x];
-            else for (int c = 0; c < len; c++) seq[off + c] = bb_slot_char(em, st, c);
+            else {
+                const uint8_t orig = frag[x];
+                int kept = 0;  // the original base survives inside the slot string: the rest are insertions
+                for (int c = 0; c < len; c++) {
+                    const uint8_t ch = bb_slot_char(em, st, c);
+                    seq[off + c] = ch;
+                    kept |= (ch == orig) ? 1 : 0;
+                }
+                cost += len == 0 ? 1 : len - kept;
+            }
         }
         __syncthreads();
         if (threadIdx.x == 255) running = off + len;
         __syncthreads();
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cost += __shfl_xor_sync(BB_FULL, cost, d);
+    if (lane == 0) warp_sum[wid] = cost;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tight = 0;
+        for (int w = 0; w < 8; w++) tight += warp_sum[w];
+        if (tight < rd.upper) B.reads[r].upper = tight;
     }
     uint4 *pq = B.speq + rd.speq_off;
     const int nwarps = blockDim.x >> 5;
