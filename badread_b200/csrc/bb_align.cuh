@@ -372,6 +372,174 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
     return result;
 }
 
+// Two columns per step: the distance-only variant of bb_band_pass for register-resident masks (L <= 4).  Chunk u
+// works on columns 2(step - u) and 2(step - u) + 1; one shuffle carries both horizontal deltas of the chunk above
+// and its score after the first of the two columns.  A step whose two columns are interior to the chunk (not its
+// first, not its last, both ACGT) runs two bare Myers steps; everything else takes the general per-column path.
+// Same outputs as bb_band_pass<L, false, COLS>.
+template <int L, bool COLS>
+__device__ int bb_band_pass2(const BBProb &P, int K) {
+    const int lane = threadIdx.x & 31;
+    const int slot = lane & (K - 1);
+    const int prev = (lane & ~(K - 1)) | ((slot + K - 1) & (K - 1));
+    constexpr int CH = 32 * L;
+    const int n = P.n, ncols = P.ncols, a = P.a, b = P.b, ts = P.ts;
+    int ulast = -1;
+    if (ncols > 0 && n > 0) {
+        ulast = (ncols - 1 + b) / CH;
+        const int nchunks = (n + CH - 1) / CH;
+        if (ulast > nchunks - 1) ulast = nchunks - 1;
+    }
+    const int T2 = __reduce_max_sync(BB_FULL, ulast >= 0 ? ((ncols - 1) >> 1) + ulast + 1 : 0);
+    const int cols_hi = min(n - 1, ncols - 1 + b);
+    uint32_t Pv[L], Mv[L], eA[L], eC[L], eG[L], eT[L];
+#pragma unroll
+    for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; eA[x] = eC[x] = eG[x] = eT[x] = 0u; }
+    int u = slot;
+    int cs = max(0, CH * u - b), ce = min(ncols - 1, CH * u + CH - 1 + a);
+    int ce_up = min(ncols - 1, CH * u - 1 + a);  // last column of the chunk above
+    int score = 0, result = BB_INF;
+    uint32_t outpack = 0, tcn0 = 0, tcn1 = 0;
+    const uint8_t *tp = P.t - 2ll * u * ts;  // tp + 2*step*ts is the first of this lane's two columns
+    if (u <= ulast) {
+        const int c0 = -2 * u;
+        if (c0 >= cs && c0 <= ce) tcn0 = tp[0];
+        if (c0 + 1 >= cs && c0 + 1 <= ce) tcn1 = tp[ts];
+    }
+    // one Myers step of the whole chunk on match words Eq with horizontal input hin; returns the horizontal output
+    auto myers = [&](uint32_t (&Eq)[L], int hin) -> int {
+        uint32_t Xv[L], A[L], S[L], Ph[L], Mh[L];
+        const uint32_t hin_neg = hin < 0 ? 1u : 0u;
+#pragma unroll
+        for (int x = 0; x < L; x++) Xv[x] = Eq[x] | Mv[x];
+        Eq[0] |= hin_neg;
+#pragma unroll
+        for (int x = 0; x < L; x++) A[x] = Eq[x] & Pv[x];
+        bb_add_words<L>(A, Pv, S);
+#pragma unroll
+        for (int x = 0; x < L; x++) {
+            const uint32_t Xh = (S[x] ^ Pv[x]) | Eq[x];
+            Ph[x] = Mv[x] | ~(Xh | Pv[x]);
+            Mh[x] = Pv[x] & Xh;
+        }
+        const int hout = (int)(Ph[L - 1] >> 31) - (int)(Mh[L - 1] >> 31);
+#pragma unroll
+        for (int x = L - 1; x >= 0; x--) {
+            const uint32_t ph_lo = x > 0 ? Ph[x - 1] : (hin > 0 ? 0x80000000u : 0u);
+            const uint32_t mh_lo = x > 0 ? Mh[x - 1] : (hin_neg << 31);
+            const uint32_t phs = __funnelshift_l(ph_lo, Ph[x], 1);
+            const uint32_t mhs = __funnelshift_l(mh_lo, Mh[x], 1);
+            Pv[x] = mhs | ~(Xv[x] | phs);
+            Mv[x] = phs & Xv[x];
+        }
+        return hout;
+    };
+    auto select = [&](uint32_t code, uint32_t (&Eq)[L]) {
+#pragma unroll
+        for (int x = 0; x < L; x++) Eq[x] = (code & 2u) ? ((code & 1u) ? eG[x] : eT[x]) : ((code & 1u) ? eC[x] : eA[x]);
+    };
+    // any column of the chunk (its first, its last, non-ACGT targets, the last column of the pass)
+    auto column = [&](int c, uint32_t tc, int hin, int above) -> int {
+        if (c == cs) {  // a chunk entering the band starts from the all-(+1) upper bound below chunk u-1
+            score = ((u == 0) ? cs : above - hin) + CH;
+#pragma unroll
+            for (int x = 0; x < L; x++) {
+                Pv[x] = ~0u; Mv[x] = 0u;
+                bb_fetch_peq(P, u * CH + 32 * x, eA[x], eC[x], eG[x], eT[x]);
+            }
+        }
+        const uint32_t code = (tc >> 1) & 3u;
+        uint32_t Eq[L];
+        select(code, Eq);
+        if (((0x47544341u >> (8 * code)) & 0xffu) != tc) {  // exact byte equality against every row of the chunk
+#pragma unroll
+            for (int x = 0; x < L; x++) {
+                Eq[x] = 0u;
+                const int row0 = u * CH + 32 * x;
+                for (int r = 0; r < 32; r++)
+                    if (row0 + r < n && P.q[(long long)(row0 + r) * P.qs] == tc) Eq[x] |= 1u << r;
+            }
+        }
+        const int hout = myers(Eq, hin);
+        score += hout;
+        if (c == ncols - 1) {
+            int run = score;
+#pragma unroll
+            for (int x = L - 1; x >= 0; x--) {
+                const int row0 = u * CH + 32 * x;
+                if (COLS) {
+                    int rr = run;
+                    for (int r = 31; r >= 0; r--) {
+                        const int row = row0 + r;
+                        if (row < n && row >= P.cols_lo && row <= cols_hi) P.cols_out[row - P.cols_lo] = rr;
+                        rr -= (int)((Pv[x] >> r) & 1u) - (int)((Mv[x] >> r) & 1u);
+                    }
+                }
+                if (row0 <= n - 1 && n - 1 < row0 + 32) {
+                    const int bit = (n - 1) - row0;
+                    const uint32_t up = bit == 31 ? 0u : (Pv[x] >> (bit + 1));
+                    const uint32_t um = bit == 31 ? 0u : (Mv[x] >> (bit + 1));
+                    result = run - __popc(up) + __popc(um);
+                }
+                run -= __popc(Pv[x]) - __popc(Mv[x]);
+            }
+        }
+        return hout;
+    };
+    auto take_over = [&]() {  // the band has moved past this chunk: chunk u + K is next
+        u += K;
+        cs = max(0, CH * u - b);
+        ce = min(ncols - 1, CH * u + CH - 1 + a);
+        ce_up = min(ncols - 1, CH * u - 1 + a);
+        tp -= 2ll * K * ts;
+    };
+    for (int s = 0; s < T2; s++) {
+        const uint32_t in = __shfl_sync(BB_FULL, outpack, prev);
+        const int c0 = 2 * (s - u), c1 = c0 + 1;
+        if (u <= ulast && c1 >= cs && c0 <= ce) {
+            const uint32_t tc0 = tcn0, tc1 = tcn1;
+            const int h0 = (u > 0 && c0 <= ce_up) ? (int)((in >> 22) & 3u) - 1 : 1;
+            const int h1 = (u > 0 && c1 <= ce_up) ? (int)((in >> 24) & 3u) - 1 : 1;
+            const uint32_t code0 = (tc0 >> 1) & 3u, code1 = (tc1 >> 1) & 3u;
+            const bool plain = ((0x47544341u >> (8 * code0)) & 0xffu) == tc0 && ((0x47544341u >> (8 * code1)) & 0xffu) == tc1;
+            int o0 = 0, o1 = 0, after0;
+            if (c0 > cs && c1 < ce && plain) {
+                uint32_t Eq[L];
+                select(code0, Eq);
+                o0 = myers(Eq, h0);
+                after0 = score + o0;
+                select(code1, Eq);
+                o1 = myers(Eq, h1);
+                score = after0 + o1;
+            } else {
+                const int above0 = (int)(in & BB_MAX_SCORE);  // the chunk above after column c0
+                bool moved = false;
+                after0 = score;
+                if (c0 >= cs) {  // c0 <= ce holds
+                    o0 = column(c0, tc0, h0, above0);
+                    after0 = score;
+                    if (c0 == ce) { take_over(); moved = true; }
+                }
+                if (!moved && c1 <= ce) {  // c1 >= cs holds
+                    o1 = column(c1, tc1, h1, above0 + h1);
+                    if (c0 < cs) after0 = score - o1;
+                    if (c1 == ce) take_over();
+                }
+            }
+            outpack = ((uint32_t)(o0 + 1) << 22) | ((uint32_t)(o1 + 1) << 24) | ((uint32_t)after0 & BB_MAX_SCORE);
+        }
+        if (u <= ulast) {
+            const int cn = 2 * (s + 1 - u);
+            if (cn >= cs && cn <= ce) tcn0 = tp[(long long)(2 * s + 2) * ts];
+            if (cn + 1 >= cs && cn + 1 <= ce) tcn1 = tp[(long long)(2 * s + 3) * ts];
+        }
+    }
+    const int owner = (lane & ~(K - 1)) | ((n > 0 ? (n - 1) / CH : 0) & (K - 1));
+    result = __shfl_sync(BB_FULL, result, owner);
+    __syncwarp();
+    return result;
+}
+
 // Smallest L in {1,2,4,...,MAXL} with (a + b) / (32 L) + 2 <= K, or 0 if none.  MAXL bounds the variants a kernel
 // instantiates (and with them its register footprint).
 template <int MAXL>
@@ -658,7 +826,7 @@ __device__ int bb_split_warp(const BBScratch &sc, int loL, int hiL, int loR, int
 // target character, the node is q[q0, q0+nn) x t[t0, t0+mm); band (a, b) must admit every optimal path.
 // best < 0 on entry (root): the minimum of forward + reverse scores over the split column is the edit distance and
 // is returned in best.  Returns 0 or an error code.
-template <int MAXL>
+template <int MAXL, bool CB2 = false>
 __device__ int bb_node_warp(const uint8_t *q, const uint8_t *t, int q0, int nn, int t0, int mm, int a, int b,
                             const BBScratch &sc, int &best, int &split, int &ls, int &rs, int qabs = 0) {
     const int lane = threadIdx.x & 31;
@@ -682,7 +850,13 @@ __device__ int bb_node_warp(const uint8_t *q, const uint8_t *t, int q0, int nn, 
         const int L2 = bb_pick_L<MAXL>(a, b, 16);
         if (L2 > 0) {  // forward and reverse pass side by side in two 16-lane groups
             const BBProb PG = make_prob(lane >= 16);
-            bb_band_dispatch<false, true, MAXL>(PG, 16, L2);
+            if (CB2 && MAXL <= 4) {  // two columns per step (register-resident masks only)
+                if (L2 == 4) bb_band_pass2<(MAXL >= 4 ? 4 : 1), true>(PG, 16);
+                else if (L2 == 2) bb_band_pass2<(MAXL >= 2 ? 2 : 1), true>(PG, 16);
+                else bb_band_pass2<1, true>(PG, 16);
+            } else {
+                bb_band_dispatch<false, true, MAXL>(PG, 16, L2);
+            }
         } else {
             const int L1 = bb_pick_L<MAXL>(a, b, 32);
             if (L1 > 0) {

@@ -397,7 +397,7 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity
         int a, b;
         bb_task_band(nd, rd->upper, a, b);
         int best = nd.best, split = 0, ls = 0, rs = 0;
-        const int err = bb_node_warp<MAXL>(q, t, nd.q0, nd.nn, nd.t0, nd.mm, a, b, sc, best, split, ls, rs);
+        const int err = bb_node_warp<MAXL, (MAXL <= 4)>(q, t, nd.q0, nd.nn, nd.t0, nd.mm, a, b, sc, best, split, ls, rs);
         __syncwarp();
         if (lane == 0) {
             if (err) atomicOr(&rd->flags, err << 8);

@@ -97,7 +97,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     BBQueues Q;
     for (int c = 0; c < BBQ_NODE_CLASSES; c++) for (int p = 0; p < 2; p++) { qn[c][p].resize(cap); Q.node[c][p] = qn[c][p].data(); }
     for (int w = 0; w < 2; w++) { ql[w].resize(cap); Q.leaf[w] = ql[w].data(); }
-    Q.count = cnt.data(); Q.overflow = cnt.data() + BBQ_OVERFLOW; Q.cap_node = cap; Q.cap_leaf = cap; Q.lane8_cols = 4096; Q.lane16_cols = 3072;
+    Q.count = cnt.data(); Q.overflow = cnt.data() + BBQ_OVERFLOW; Q.cap_node = cap; Q.cap_leaf = cap; Q.lane8_cols = 4096; Q.lane16_cols = 0;
     // scratch for the warp kernels (warp 0 only) and the lane leaf kernel
     const int big = std::max(n, m) + 64;
     const int NW = BB_WARPS_PER_CTA;  // scratch for every warp of one emulated CTA

@@ -79,3 +79,11 @@ def test_task_pipeline(emu):
         assert emu.tasks_align(b, a, int(O.align_path(b, a)[1] * 1.2) + 5) == O.align_path(b, a)[0]
     a = random_dna(rnd, 20000); b = mutate(rnd, a, 0.25)   # wide root: warp pairs
     assert emu.tasks_align(b, a, int(O.align_path(b, a)[1] * 1.1)) == O.align_path(b, a)[0]
+    # the two-columns-per-step wavefront of the lean warp kernel: odd / even lengths, every register-mask width
+    # (L = 1, 2, 4), loose and exact bounds, non-ACGT targets
+    for it in range(14):
+        n = rnd.randrange(2300, 7000)
+        a = random_dna(rnd, n, 'ACGTN' if it % 4 == 0 else 'ACGT')
+        b = mutate(rnd, a, rnd.choice([0.004, 0.02, 0.05, 0.1, 0.2]))
+        ops, d = O.align_path(b, a)
+        assert emu.tasks_align(b, a, d + rnd.choice([0, 1, 7, d // 5])) == ops
