@@ -27,6 +27,9 @@
 #define BB_OP_X 1
 #define BB_OP_I 2
 #define BB_MAX_SCORE 0x3fffff  // scores travel in 22 bits of the shuffle word
+#ifndef BB_NODE_CB
+#define BB_NODE_CB 2           // columns per wavefront step of the lean warp node kernel
+#endif
 #define BB_PEQ_PAD 34          // zero words in front of and behind a read's match bitmap (covers 32-word chunks)
 #define BB_PEQ_BIT0 (32 * BB_PEQ_PAD)  // bit index of the read's first base
 
@@ -372,13 +375,13 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
     return result;
 }
 
-// Two columns per step: the distance-only variant of bb_band_pass for register-resident masks (L <= 4).  Chunk u
-// works on columns 2(step - u) and 2(step - u) + 1; one shuffle carries both horizontal deltas of the chunk above
-// and its score after the first of the two columns.  A step whose two columns are interior to the chunk (not its
-// first, not its last, both ACGT) runs two bare Myers steps; everything else takes the general per-column path.
-// Same outputs as bb_band_pass<L, false, COLS>.
-template <int L, bool COLS>
-__device__ int bb_band_pass2(const BBProb &P, int K) {
+// CB columns per step: the distance-only variant of bb_band_pass for register-resident masks (L <= 4).  Chunk u
+// works on columns CB (step - u) ... CB (step - u) + CB - 1; one shuffle carries the CB horizontal deltas of the
+// chunk above (2 bits each) and its score after the first of those columns.  A step whose columns are all interior
+// to the chunk (not its first, not its last, all ACGT) runs CB bare Myers steps; everything else takes the general
+// per-column path.  Same outputs as bb_band_pass<L, false, COLS>.  CB <= 4 (22 + 2 CB bits in the shuffle word).
+template <int L, bool COLS, int CB>
+__device__ int bb_band_pass_cb(const BBProb &P, int K) {
     const int lane = threadIdx.x & 31;
     const int slot = lane & (K - 1);
     const int prev = (lane & ~(K - 1)) | ((slot + K - 1) & (K - 1));
@@ -390,7 +393,7 @@ __device__ int bb_band_pass2(const BBProb &P, int K) {
         const int nchunks = (n + CH - 1) / CH;
         if (ulast > nchunks - 1) ulast = nchunks - 1;
     }
-    const int T2 = __reduce_max_sync(BB_FULL, ulast >= 0 ? ((ncols - 1) >> 1) + ulast + 1 : 0);
+    const int T = __reduce_max_sync(BB_FULL, ulast >= 0 ? (ncols - 1) / CB + ulast + 1 : 0);
     const int cols_hi = min(n - 1, ncols - 1 + b);
     uint32_t Pv[L], Mv[L], eA[L], eC[L], eG[L], eT[L];
 #pragma unroll
@@ -399,12 +402,13 @@ __device__ int bb_band_pass2(const BBProb &P, int K) {
     int cs = max(0, CH * u - b), ce = min(ncols - 1, CH * u + CH - 1 + a);
     int ce_up = min(ncols - 1, CH * u - 1 + a);  // last column of the chunk above
     int score = 0, result = BB_INF;
-    uint32_t outpack = 0, tcn0 = 0, tcn1 = 0;
-    const uint8_t *tp = P.t - 2ll * u * ts;  // tp + 2*step*ts is the first of this lane's two columns
-    if (u <= ulast) {
-        const int c0 = -2 * u;
-        if (c0 >= cs && c0 <= ce) tcn0 = tp[0];
-        if (c0 + 1 >= cs && c0 + 1 <= ce) tcn1 = tp[ts];
+    uint32_t outpack = 0, tcn[CB];
+    const uint8_t *tp = P.t - (long long)CB * u * ts;  // tp + CB*step*ts is the first of this lane's columns
+#pragma unroll
+    for (int h = 0; h < CB; h++) {
+        tcn[h] = 0;
+        const int c = -CB * u + h;
+        if (u <= ulast && c >= cs && c <= ce) tcn[h] = tp[(long long)h * ts];
     }
     // one Myers step of the whole chunk on match words Eq with horizontal input hin; returns the horizontal output
     auto myers = [&](uint32_t (&Eq)[L], int hin) -> int {
@@ -486,52 +490,65 @@ __device__ int bb_band_pass2(const BBProb &P, int K) {
         }
         return hout;
     };
-    auto take_over = [&]() {  // the band has moved past this chunk: chunk u + K is next
-        u += K;
-        cs = max(0, CH * u - b);
-        ce = min(ncols - 1, CH * u + CH - 1 + a);
-        ce_up = min(ncols - 1, CH * u - 1 + a);
-        tp -= 2ll * K * ts;
-    };
-    for (int s = 0; s < T2; s++) {
+    for (int s = 0; s < T; s++) {
         const uint32_t in = __shfl_sync(BB_FULL, outpack, prev);
-        const int c0 = 2 * (s - u), c1 = c0 + 1;
-        if (u <= ulast && c1 >= cs && c0 <= ce) {
-            const uint32_t tc0 = tcn0, tc1 = tcn1;
-            const int h0 = (u > 0 && c0 <= ce_up) ? (int)((in >> 22) & 3u) - 1 : 1;
-            const int h1 = (u > 0 && c1 <= ce_up) ? (int)((in >> 24) & 3u) - 1 : 1;
-            const uint32_t code0 = (tc0 >> 1) & 3u, code1 = (tc1 >> 1) & 3u;
-            const bool plain = ((0x47544341u >> (8 * code0)) & 0xffu) == tc0 && ((0x47544341u >> (8 * code1)) & 0xffu) == tc1;
-            int o0 = 0, o1 = 0, after0;
-            if (c0 > cs && c1 < ce && plain) {
-                uint32_t Eq[L];
-                select(code0, Eq);
-                o0 = myers(Eq, h0);
-                after0 = score + o0;
-                select(code1, Eq);
-                o1 = myers(Eq, h1);
-                score = after0 + o1;
-            } else {
-                const int above0 = (int)(in & BB_MAX_SCORE);  // the chunk above after column c0
-                bool moved = false;
-                after0 = score;
-                if (c0 >= cs) {  // c0 <= ce holds
-                    o0 = column(c0, tc0, h0, above0);
-                    after0 = score;
-                    if (c0 == ce) { take_over(); moved = true; }
+        const int c0 = CB * (s - u), cl = c0 + CB - 1;
+        if (u <= ulast && cl >= cs && c0 <= ce) {
+            int hin[CB];
+            bool plain = true;
+#pragma unroll
+            for (int h = 0; h < CB; h++) {
+                hin[h] = (u > 0 && c0 + h <= ce_up) ? (int)((in >> (22 + 2 * h)) & 3u) - 1 : 1;
+                const uint32_t code = (tcn[h] >> 1) & 3u;
+                plain = plain && ((0x47544341u >> (8 * code)) & 0xffu) == tcn[h];
+            }
+            int o[CB];
+            int tail = 0;  // sum of the horizontal outputs of columns 1 .. CB-1
+            int last_score;
+            if (c0 > cs && cl < ce && plain) {
+#pragma unroll
+                for (int h = 0; h < CB; h++) {
+                    uint32_t Eq[L];
+                    select((tcn[h] >> 1) & 3u, Eq);
+                    o[h] = myers(Eq, hin[h]);
+                    score += o[h];
+                    if (h > 0) tail += o[h];
                 }
-                if (!moved && c1 <= ce) {  // c1 >= cs holds
-                    o1 = column(c1, tc1, h1, above0 + h1);
-                    if (c0 < cs) after0 = score - o1;
-                    if (c1 == ce) take_over();
+                last_score = score;
+            } else {
+                int above = (int)(in & BB_MAX_SCORE);  // the chunk above after column c0 + h
+                bool moved = false;
+                last_score = score;
+#pragma unroll
+                for (int h = 0; h < CB; h++) {
+                    const int c = c0 + h;
+                    o[h] = 0;
+                    if (h > 0) above += (int)((in >> (22 + 2 * h)) & 3u) - 1;
+                    if (!moved && c >= cs && c <= ce) {
+                        o[h] = column(c, tcn[h], hin[h], above);
+                        last_score = score;
+                        if (h > 0) tail += o[h];
+                        if (c == ce) {  // the band has moved past this chunk: chunk u + K is next
+                            u += K;
+                            cs = max(0, CH * u - b);
+                            ce = min(ncols - 1, CH * u + CH - 1 + a);
+                            ce_up = min(ncols - 1, CH * u - 1 + a);
+                            tp -= (long long)CB * K * ts;
+                            moved = true;
+                        }
+                    }
                 }
             }
-            outpack = ((uint32_t)(o0 + 1) << 22) | ((uint32_t)(o1 + 1) << 24) | ((uint32_t)after0 & BB_MAX_SCORE);
+            uint32_t pack = (uint32_t)(last_score - tail) & BB_MAX_SCORE;  // the score after column c0
+#pragma unroll
+            for (int h = 0; h < CB; h++) pack |= (uint32_t)(o[h] + 1) << (22 + 2 * h);
+            outpack = pack;
         }
         if (u <= ulast) {
-            const int cn = 2 * (s + 1 - u);
-            if (cn >= cs && cn <= ce) tcn0 = tp[(long long)(2 * s + 2) * ts];
-            if (cn + 1 >= cs && cn + 1 <= ce) tcn1 = tp[(long long)(2 * s + 3) * ts];
+            const int cn = CB * (s + 1 - u);
+#pragma unroll
+            for (int h = 0; h < CB; h++)
+                if (cn + h >= cs && cn + h <= ce) tcn[h] = tp[(long long)(CB * (s + 1) + h) * ts];
         }
     }
     const int owner = (lane & ~(K - 1)) | ((n > 0 ? (n - 1) / CH : 0) & (K - 1));
@@ -850,10 +867,10 @@ __device__ int bb_node_warp(const uint8_t *q, const uint8_t *t, int q0, int nn, 
         const int L2 = bb_pick_L<MAXL>(a, b, 16);
         if (L2 > 0) {  // forward and reverse pass side by side in two 16-lane groups
             const BBProb PG = make_prob(lane >= 16);
-            if (CB2 && MAXL <= 4) {  // two columns per step (register-resident masks only)
-                if (L2 == 4) bb_band_pass2<(MAXL >= 4 ? 4 : 1), true>(PG, 16);
-                else if (L2 == 2) bb_band_pass2<(MAXL >= 2 ? 2 : 1), true>(PG, 16);
-                else bb_band_pass2<1, true>(PG, 16);
+            if (CB2 && MAXL <= 4) {  // several columns per step (register-resident masks only)
+                if (L2 == 4) bb_band_pass_cb<(MAXL >= 4 ? 4 : 1), true, BB_NODE_CB>(PG, 16);
+                else if (L2 == 2) bb_band_pass_cb<(MAXL >= 2 ? 2 : 1), true, BB_NODE_CB>(PG, 16);
+                else bb_band_pass_cb<1, true, BB_NODE_CB>(PG, 16);
             } else {
                 bb_band_dispatch<false, true, MAXL>(PG, 16, L2);
             }
