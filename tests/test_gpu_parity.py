@@ -71,3 +71,36 @@ def test_sequence_batch_matches_oracle(engine, error_name, qscore_name):
         assert gq == q, (i, len(frag), ident)
         assert (rec.matches, rec.columns) == (st['matches'], st['columns'])
         assert rec.frag_len == len(frag)
+
+
+def test_large_batch_split_over_workers_matches_oracle(engine):
+    """A batch big enough to be dealt out over the context's sub-batch workers (>= 64 reads per worker): every read,
+    wherever it ran and wherever its block landed in the output buffers, equals the oracle's."""
+    from badread_b200.engine import FragmentBatch
+    em, qm = load_models('nanopore2023', 'nanopore2023')
+    O, orc = _oracle(em, qm)
+    engine.set_error_model(em)
+    engine.set_qscore_model(qm)
+    rnd = random.Random(20260924)
+    n_reads = 700
+    batch = FragmentBatch()
+    frags, idents = [], []
+    for i in range(n_reads):
+        n = rnd.choice([1, 40, 300, 900, 1500, 2600, 4000]) + rnd.randrange(0, 50)
+        frag = random_dna(rnd, n, 'ACGT' if i % 11 else 'ACGTN')
+        ident = rnd.choice([1.0, 0.98, 0.93, 0.88, 0.8])
+        frags.append(frag)
+        idents.append(ident)
+        batch.add_literal_read(5000 + 3 * i, frag, ident)
+    res, total = engine.sequence_batch(batch)
+    assert total == sum(res.records[i].out_len for i in range(n_reads))
+    spans = sorted((res.records[i].out_off, res.records[i].out_len) for i in range(n_reads) if res.records[i].out_len)
+    assert spans[0][0] == 0 and all(a + la == b for (a, la), (b, _) in zip(spans, spans[1:]))   # packed, no overlap
+    assert spans[-1][0] + spans[-1][1] == total
+    outs, _ = orc.sequence_batch(frags, idents, engine.seed, [5000 + 3 * i for i in range(n_reads)], n_threads=8)
+    for i in range(n_reads):
+        gs, gq = res.read(i)
+        assert (gs, gq) == (outs[i][0], outs[i][1]), (i, len(frags[i]), idents[i])
+        rec = res.records[i]
+        assert rec.frag_len == len(frags[i])
+        assert (rec.matches, rec.columns) == (outs[i][2], outs[i][3])
