@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -85,6 +86,7 @@ struct bb_ctx {
     std::vector<std::vector<int32_t>> part;   // part[w][i] = batch position of worker w's i-th read
     std::vector<int64_t> part_base;           // offset of worker w's block in the fetched seq / qual buffers
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    std::atomic<int> scan_ready{0};           // 1: out_total of the current run is known, -1: the run failed before that
 };
 
 static thread_local std::string g_create_error;
@@ -574,6 +576,7 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
 
 static int w_batch_run(bb_ctx *ctx) {
     if (!ctx) return BB_ERR_ARG;
+    ctx->scan_ready.store(0, std::memory_order_release);
     if (!ctx->uploaded) return set_err(ctx, BB_ERR_STATE, "bb_batch_run: no batch uploaded");
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -629,6 +632,7 @@ static int w_batch_run(bb_ctx *ctx) {
     }
     ctx->seq_total = seq_off;
     ctx->out_total = out_off;
+    ctx->scan_ready.store(1, std::memory_order_release);
     std::vector<int> small, large;  // work queues of the two final-alignment builds, longest fragments first
     for (int r : ctx->h_order) {
         const BBReadDev &rd = reads[(size_t)r];
@@ -896,8 +900,59 @@ extern "C" int bb_sequence_batch(bb_ctx *ctx, int32_t n_reads, const uint64_t *r
                                  uint8_t *qual_out, int64_t out_cap, int64_t *out_total) {
     int rc = bb_batch_upload(ctx, n_reads, read_index, seg_off, segs, literal_pool, literal_len, target_identity);
     if (rc) return rc;
-    if ((rc = bb_batch_run(ctx))) return rc;
-    return bb_fetch_last_batch(ctx, results, seq_out, qual_out, out_cap, out_total);
+    if (ctx->n_split == 1) {
+        if ((rc = bb_batch_run(ctx))) return rc;
+        return bb_fetch_last_batch(ctx, results, seq_out, qual_out, out_cap, out_total);
+    }
+    // several workers: each one copies its block out as soon as its own chain is done, while the others still compute
+    // (its offset only needs the output sizes of the workers before it, known since their host scans)
+    const int S = ctx->n_split;
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(worker_of(ctx, w)->stream, ctx->ev_t0, 0));
+    std::vector<int> rcs((size_t)S, 0);
+    ctx->part_base.assign((size_t)S, 0);
+    auto chain = [&](int w) {
+        bb_ctx *wk = worker_of(ctx, w);
+        int r = w_batch_run(wk);
+        if (wk->scan_ready.load(std::memory_order_acquire) == 0) wk->scan_ready.store(r ? -1 : 1, std::memory_order_release);
+        int64_t base = 0;
+        for (int v = 0; v < w && !r; v++) {
+            bb_ctx *o = worker_of(ctx, v);
+            int st;
+            while ((st = o->scan_ready.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+            if (st < 0) r = BB_ERR_STATE;  // that worker reports its own error
+            base += o->out_total;
+        }
+        if (!r) {
+            ctx->part_base[(size_t)w] = base;
+            if (base + wk->out_total > out_cap) r = BB_ERR_CAPACITY;
+            else r = w_fetch(wk, results, ctx->part[(size_t)w].data(), base, seq_out ? seq_out + base : nullptr,
+                             qual_out ? qual_out + base : nullptr);
+        }
+        rcs[(size_t)w] = r;
+    };
+    std::vector<std::thread> threads;
+    for (int w = 1; w < S; w++) threads.emplace_back(chain, w);
+    chain(0);
+    for (auto &t : threads) t.join();
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, worker_of(ctx, w)->ev[BB_N_STAGES - 1], 0));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+    int64_t total = 0;
+    bool capacity = false;
+    for (int w = 0; w < S; w++) {
+        const int r = rcs[(size_t)w];
+        if (r == BB_ERR_CAPACITY) capacity = true;
+        else if (r == BB_ERR_STATE && w > 0) continue;  // knocked on from another worker's failure
+        else if (r) return w == 0 ? r : set_err(ctx, r, worker_of(ctx, w)->err);
+        total += worker_of(ctx, w)->out_total;
+    }
+    for (int w = 0; w < S; w++)
+        if (rcs[(size_t)w] == BB_ERR_STATE) return set_err(ctx, BB_ERR_STATE, "a sub-batch worker failed");
+    if (out_total) *out_total = total;
+    if (capacity) return set_err(ctx, BB_ERR_CAPACITY, "output buffers too small");  // bb_fetch_last_batch can retry
+    return BB_OK;
 }
 
 // ---- single-pair entry points ------------------------------------------------------------------------

@@ -57,6 +57,16 @@ class FragmentBatch(object):
         self.end_read(read_index, target_identity)
 
     def arrays(self):
+        """The flat descriptor arrays bb_batch_upload takes (built once per batch state)."""
+        key = (len(self.read_index), len(self.seg_src), len(self.literals))
+        cached = getattr(self, '_arrays', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        out = self._build_arrays()
+        self._arrays = (key, out)
+        return out
+
+    def _build_arrays(self):
         n_seg = len(self.seg_src)
         segs = (Segment * max(n_seg, 1))()
         seg_np = np.frombuffer(segs, dtype=np.dtype([('src', np.int64), ('len', np.int32), ('kind', np.int32)]))
@@ -207,10 +217,24 @@ class Engine(object):
         return BatchResult(results, self._seq_buf, self._qual_buf, n), int(total.value)
 
     def sequence_batch(self, batch):
-        """bb_sequence_batch semantics (upload + run + fetch); returns (BatchResult, total_bases)."""
-        self.upload_batch(batch)
-        self.run_batch()
-        return self.fetch_batch()
+        """bb_sequence_batch (upload + run + fetch in one call: with several workers each block is copied out while
+        the other workers still compute); returns (BatchResult, total_bases)."""
+        ri, so, segs, lit, lit_len, ti = batch.arrays()
+        self._batch_keepalive = (ri, so, segs, lit, ti)
+        self._n = n = len(batch)
+        if self._seq_buf is None:
+            self._ensure_out(int(1.1 * sum(batch.seg_len)) + 4096)
+        results = (ReadResult * n)()
+        total = ctypes.c_int64(0)
+        rc = self._lib.bb_sequence_batch(self._ctx, n, _ptr(ri), _ptr(so), ctypes.cast(segs, ctypes.c_void_p), _ptr(lit),
+                                         lit_len, _ptr(ti), results, _ptr(self._seq_buf), _ptr(self._qual_buf),
+                                         self._out_cap, ctypes.byref(total))
+        if rc == _lib.BB_ERR_CAPACITY:
+            self._ensure_out(total.value)
+            rc = self._lib.bb_fetch_last_batch(self._ctx, results, _ptr(self._seq_buf), _ptr(self._qual_buf),
+                                               self._out_cap, ctypes.byref(total))
+        self._check(rc, 'bb_sequence_batch')
+        return BatchResult(results, self._seq_buf, self._qual_buf, n), int(total.value)
 
     # ---- single pair helpers
     def get_qscores(self, seq, frag, read_index=0):
