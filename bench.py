@@ -313,9 +313,21 @@ def main():
         traffic_src = 'profiles/r1c_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one step)'
     except Exception:
         pass
+    alu = None
+    try:  # integer ALU-pipe accounting: warp instructions of one step (committed ncu pass) over the measured step time
+        with open(os.path.join(ROOT, 'profiles', 'r1c_inst.json')) as f:
+            ginst = float(json.load(f)['warp_inst_G_per_step'])
+        sm_count, smsp = 148, 4
+        clk_ghz = (clocks.get('sm_mhz') or 1965.0) / 1e3
+        peak_alu = sm_count * smsp * clk_ghz * 0.5   # LOP3/IADD3/SHF: one warp instruction per 2 clocks per SMSP
+        ach = ginst / (dev_ms / a.steps * 1e-3)
+        alu = {'achieved': ach, 'peak': peak_alu, 'unit': 'G warp-inst/s', 'frac': ach / peak_alu,
+               'warp_inst_G_per_step': ginst, 'source': 'profiles/r1c_inst.json (ncu smsp__inst_executed.sum)'}
+    except Exception:
+        pass
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'kernel_ms': kernels[dom],
-                'algorithmic_bytes_per_step': alg_bytes_per_base * bases,
+                'algorithmic_bytes_per_step': alg_bytes_per_base * bases, 'alu_pipe': alu,
                 'note': 'stage = all kernels of the Hirschberg task pipeline (bb_k_node_warp<4> dominant); the path is '
                         'bit-vector DP bound by the integer ALU pipe (0.5 warp-inst/clk/SMSP), not by HBM: the HBM '
                         'fraction is small by construction, see DESIGN.md section 5 for the ALU-pipe accounting'}
