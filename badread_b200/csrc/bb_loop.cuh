@@ -122,6 +122,7 @@ bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work
                         if ((double)change_count > cc_limit) { stop = BB_STOP_COUNT; next_n0 = nL + 1; break; }
                     }
                 }
+                __syncwarp();  // every lane has read s_cc / s_n0 before lane 0 replaces them
                 if (lane == 0) { s_cc = change_count; s_stop = stop; s_n0 = next_n0; }
             }
             __syncthreads();
