@@ -184,17 +184,31 @@ bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const
             }
         }
         if (__all_sync(BB_FULL, phase == 4)) break;
-        for (int it = 0; it < 256; it++) {  // ''.join(new_fragment_bases[pos:pos2]) as it was after 25*a changes
+        for (int it = 0; it < 64; it++) {  // ''.join(new_fragment_bases[pos:pos2]) as it was after 25*a changes
             if (phase == 1) {
-                const unsigned int ct = ctime[qpos + jx];
-                if (ct == 0u || ct > tmax) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = frag[qpos + jx]; tm++; }
-                else {
-                    const uint32_t st = state[qpos + jx];
-                    const int sl = (int)(st & 0xff);
-                    for (int c = 0; c < sl; c++) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = bb_slot_char(em, st, c); tm++; }
-                    uw += sl < 1 ? 1 : sl;
+                // four slots per iteration: their loads are issued together, the (serial) appends follow
+                unsigned int ct4[4];
+                uint8_t fb4[4];
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    const int j = min(jx + h, qn - 1);
+                    ct4[h] = ctime[qpos + j];
+                    fb4[h] = frag[qpos + j];
                 }
-                if (++jx >= qn) {
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    if (jx < qn) {
+                        if (ct4[h] == 0u || ct4[h] > tmax) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = fb4[h]; tm++; }
+                        else {
+                            const uint32_t st = state[qpos + jx];
+                            const int sl = (int)(st & 0xff);
+                            for (int c = 0; c < sl; c++) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = bb_slot_char(em, st, c); tm++; }
+                            uw += sl < 1 ? 1 : sl;
+                        }
+                        jx++;
+                    }
+                }
+                if (jx >= qn) {
                     const int diff = qn > tm ? qn - tm : tm - qn;
                     if (uw < diff) uw = diff;
                     const int mx = qn > tm ? qn : tm;
