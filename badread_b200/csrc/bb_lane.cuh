@@ -142,3 +142,13 @@ __device__ void bb_lane_traceback(const BBLaneProb &P, int &matches, int &dels, 
     if (j >= 0) dl += j + 1;
     matches = mt; dels = dl;
 }
+
+// Traceback reads one history entry per step, each depending on the previous one, out of a per-lane history that no
+// longer sits in any cache: ask L2 for the line three lines down the path (the path moves at most one column a step).
+template <int LW>
+__device__ __forceinline__ void bb_prefetch_history(const uint2 *hist, int tj) {
+#if defined(__CUDA_ARCH__)
+    const long long e = (long long)tj * LW;
+    if ((e & 15) == 0 && e >= 48) asm volatile("prefetch.global.L2 [%0];" ::"l"(hist + (e - 48)));
+#endif
+}

@@ -240,6 +240,7 @@ bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const
                     const int x = (ti >> 5) - wt;
                     if (x < 0 || x >= LW) { atomicOr(&B.reads[tk.r].flags, 1); ti = -1; tj = -1; }
                     else {
+                        bb_prefetch_history<LW>(hist, tj);
                         const uint2 e = hist[(long long)tj * LW + x];
                         const int bit = ti & 31;
                         if ((e.x >> bit) & 1u) ti--;

@@ -350,6 +350,7 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
                     const int x = (ti >> 5) - wt;
                     if (x < 0 || x >= LW) { atomicOr(&o.rd->flags, 1 << 8); ti = -1; tj = -1; }
                     else {
+                        bb_prefetch_history<LW>(hist, tj);
                         const uint2 e = hist[(long long)tj * LW + x];
                         const int bit = ti & 31;
                         if ((e.x >> bit) & 1u) { o.ops[nd.q0 + ti] = BB_OP_I; ti--; }
