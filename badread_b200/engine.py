@@ -160,7 +160,7 @@ class Engine(object):
     def _ensure_out(self, cap):
         if cap > self._out_cap:
             cap = int(cap * 1.25) + 4096
-            self._free_out()
+            # earlier (smaller) buffers stay allocated until close(): BatchResults handed out before still view them
             bufs = []
             for _ in range(2):  # page-locked, so that the device-to-host copies run at link rate
                 p = ctypes.c_void_p()

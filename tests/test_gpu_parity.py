@@ -104,3 +104,26 @@ def test_large_batch_split_over_workers_matches_oracle(engine):
         rec = res.records[i]
         assert rec.frag_len == len(frags[i])
         assert (rec.matches, rec.columns) == (outs[i][2], outs[i][3])
+
+
+def test_output_buffers_grow_on_capacity_error(engine):
+    """bb_sequence_batch with buffers that are too small reports BB_ERR_CAPACITY and the needed size; the fetch is
+    repeated with larger buffers (single-worker and split batches), and the reads are unchanged."""
+    from badread_b200.engine import FragmentBatch
+    em, qm = load_models('random', 'ideal')
+    engine.set_error_model(em)
+    engine.set_qscore_model(qm)
+    rnd = random.Random(77)
+    for n_reads in (5, 300):
+        batch = FragmentBatch()
+        for i in range(n_reads):
+            batch.add_literal_read(i, random_dna(rnd, rnd.randrange(2000, 3000)), 0.9)
+        ref, total = engine.sequence_batch(batch)
+        want = [ref.read(i) for i in range(n_reads)]
+        engine._seq_buf = engine._qual_buf = None
+        engine._out_cap = 0
+        engine._ensure_out(16)                      # far too small for the batch
+        assert engine._out_cap < total
+        got, total2 = engine.sequence_batch(batch)
+        assert total2 == total and engine._out_cap >= total
+        assert [got.read(i) for i in range(n_reads)] == want
