@@ -217,3 +217,14 @@ def test_error_model_file_loading(tmp_path):
     assert list(flags) == [1, 0, 0, 0, 2]       # remainder entry appended because the row sums to 0.94
     flags = t['flags'][t['row_off'][1]:t['row_off'][2]]
     assert list(flags) == [1]                   # sums to 1.0: no remainder entry
+
+
+def test_library_rebuilds_when_any_device_header_changes():
+    """The in-tree build must pick up edits to every .cuh (a stale libbadread_b200.so silently runs old kernels)."""
+    import pathlib
+    csrc = pathlib.Path(__file__).resolve().parent.parent / 'badread_b200' / 'csrc'
+    rule = [ln for ln in (csrc / 'Makefile').read_text().splitlines() if ln.startswith('$(OUT):')]
+    assert len(rule) == 1
+    deps = rule[0]
+    assert '$(wildcard *.cuh)' in deps or all(h.name in deps for h in csrc.glob('*.cuh'))
+    assert 'bb_api.cu' in deps and 'bb_host.cpp' in deps and 'badread_b200.h' in deps
