@@ -448,7 +448,6 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
     const int n = ctx->n_reads;
     int *cnt = ctx->d_counter.as<int>();
     std::vector<int> active = ctx->h_order;  // longest fragments first
-    const int grid_warp = ctx->n_warps / BB_WARPS_PER_CTA;
     const int lane_ctas = ctx->sm_count * 4;
     std::vector<BBWinTask> tasks;
     for (int round = 0; !active.empty(); round++) {
