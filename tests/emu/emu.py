@@ -94,3 +94,16 @@ def tasks_align(seq, frag, upper):
     assert len(s) == n + out5[1], (len(s), n, out5)
     assert s.count('=') == out5[0], (s.count('='), out5)
     return s
+
+
+def compare_passes(query, target, k, cb=2):
+    """Mismatch count between the column-blocked (cb columns per step) and the single-column distance pass, both
+    directions of a Hirschberg node side by side; None if the band does not fit the lean kernel."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(LIB))
+    q = query.encode('latin-1') if isinstance(query, str) else bytes(query)
+    t = target.encode('latin-1') if isinstance(target, str) else bytes(target)
+    rc = _lib.emu_compare_passes(q, len(q), t, len(t), int(k), int(cb))
+    return None if rc < 0 else int(rc)

@@ -135,3 +135,58 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     out5[0] = rd.matches; out5[1] = rd.dels; out5[2] = cnt[BBQ_OVERFLOW]; out5[3] = rd.lead_del; out5[4] = rd.flags;
     return 0;
 }
+
+
+// The column-blocked distance pass against the single-column one on the same problem: both directions side by side in
+// two 16-lane groups (K = 16), as the lean warp node kernel runs them.  Returns the number of mismatching outputs
+// (column-score entries + the two corner scores), or -1 if the band does not fit L with K = 16.
+template <int L, int CB>
+static int emu_compare_passes_impl(const uint8_t *q, int n, const uint8_t *t, int m, int a, int b) {
+    std::vector<uint4> peq((size_t)bb_peq_words(n) + 8);
+    const int left_w = m / 2, right_w = m - left_w;
+    const int loL = std::max(0, left_w - 1 - a), loR = std::max(0, right_w - 1 - a);
+    std::vector<int> ref((size_t)2 * (n + 64), -7), got((size_t)2 * (n + 64), -7);
+    int corner_ref[2] = {0, 0}, corner_got[2] = {0, 0};
+    for (int variant = 0; variant < 2; variant++) {
+        std::vector<int> &out = variant ? got : ref;
+        int *corner = variant ? corner_got : corner_ref;
+        emu::run_warp([&]() {
+            const int lane = threadIdx.x & 31;
+            bb_build_peq(q, n, peq.data());
+            const bool rev = lane >= 16;
+            BBProb P;
+            P.n = n; P.a = a; P.b = b; P.peq = peq.data(); P.hist = nullptr; P.nb_alloc = 0;
+            if (!rev) {
+                P.q = q; P.qs = 1; P.t = t; P.ts = 1; P.ncols = left_w; P.peq_bit0 = BB_PEQ_BIT0;
+                P.cols_out = out.data(); P.cols_lo = loL;
+            } else {
+                P.q = q + n - 1; P.qs = -1; P.t = t + m - 1; P.ts = -1; P.ncols = right_w; P.peq_bit0 = n - 1 + BB_PEQ_BIT0;
+                P.cols_out = out.data() + n + 64; P.cols_lo = loR;
+            }
+            const int r = variant ? bb_band_pass_cb<L, true, CB>(P, 16) : bb_band_pass<L, false, true>(P, 16);
+            if (lane == 0) corner[0] = r;
+            if (lane == 16) corner[1] = r;
+        });
+    }
+    int bad = 0;
+    for (size_t i = 0; i < ref.size(); i++) bad += ref[i] != got[i];
+    bad += corner_ref[0] != corner_got[0];
+    bad += corner_ref[1] != corner_got[1];
+    return bad;
+}
+
+extern "C" __attribute__((visibility("default")))
+int emu_compare_passes(const uint8_t *q, int n, const uint8_t *t, int m, int k, int cb) {
+    int a, b;
+    bb_band(n, m, k, a, b);
+    const int L = bb_pick_L<4>(a, b, 16);
+    if (L <= 0) return -1;
+    if (cb == 2) {
+        if (L == 4) return emu_compare_passes_impl<4, 2>(q, n, t, m, a, b);
+        if (L == 2) return emu_compare_passes_impl<2, 2>(q, n, t, m, a, b);
+        return emu_compare_passes_impl<1, 2>(q, n, t, m, a, b);
+    }
+    if (L == 4) return emu_compare_passes_impl<4, 4>(q, n, t, m, a, b);
+    if (L == 2) return emu_compare_passes_impl<2, 4>(q, n, t, m, a, b);
+    return emu_compare_passes_impl<1, 4>(q, n, t, m, a, b);
+}
