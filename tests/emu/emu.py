@@ -107,3 +107,16 @@ def compare_passes(query, target, k, cb=2):
     t = target.encode('latin-1') if isinstance(target, str) else bytes(target)
     rc = _lib.emu_compare_passes(q, len(q), t, len(t), int(k), int(cb))
     return None if rc < 0 else int(rc)
+
+
+def compare_sm(query, target, k, L):
+    """Mismatch count between the wide wavefront pass with the shared-memory match-word cache and the streaming
+    variant (L = 8, 16 or 32 words per lane); None if the band does not fit."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(LIB))
+    q = query.encode('latin-1') if isinstance(query, str) else bytes(query)
+    t = target.encode('latin-1') if isinstance(target, str) else bytes(target)
+    rc = _lib.emu_compare_sm(q, len(q), t, len(t), int(k), int(L))
+    return None if rc < 0 else int(rc)

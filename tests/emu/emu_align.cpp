@@ -190,3 +190,50 @@ int emu_compare_passes(const uint8_t *q, int n, const uint8_t *t, int m, int k, 
     if (L == 2) return emu_compare_passes_impl<2, 4>(q, n, t, m, a, b);
     return emu_compare_passes_impl<1, 4>(q, n, t, m, a, b);
 }
+
+
+// The shared-memory match-word cache of the wide wavefront (bb_band_pass<L, ., ., true>) against the variant that
+// streams the words from the bitmap, forward and reverse pass of one node, one full warp each (K = 32).
+template <int L>
+static int emu_compare_sm_impl(const uint8_t *q, int n, const uint8_t *t, int m, int a, int b) {
+    std::vector<uint4> peq((size_t)bb_peq_words(n) + 8);
+    std::vector<uint32_t> esm((size_t)bb_esm_words(L) + 4);
+    const int left_w = m / 2, right_w = m - left_w;
+    const int loL = std::max(0, left_w - 1 - a), loR = std::max(0, right_w - 1 - a);
+    int bad = 0;
+    for (int rev = 0; rev < 2; rev++) {
+        std::vector<int> out[2] = {std::vector<int>((size_t)n + 64, -7), std::vector<int>((size_t)n + 64, -7)};
+        int corner[2] = {0, 0};
+        for (int variant = 0; variant < 2; variant++) {
+            emu::run_warp([&]() {
+                bb_build_peq(q, n, peq.data());
+                BBProb P;
+                P.n = n; P.a = a; P.b = b; P.peq = peq.data(); P.hist = nullptr; P.nb_alloc = 0;
+                P.cols_out = out[variant].data();
+                if (!rev) {
+                    P.q = q; P.qs = 1; P.t = t; P.ts = 1; P.ncols = left_w; P.peq_bit0 = BB_PEQ_BIT0; P.cols_lo = loL;
+                } else {
+                    P.q = q + n - 1; P.qs = -1; P.t = t + m - 1; P.ts = -1; P.ncols = right_w;
+                    P.peq_bit0 = n - 1 + BB_PEQ_BIT0; P.cols_lo = loR;
+                }
+                P.esm = esm.data();
+                const int r = variant ? bb_band_pass<L, false, true, true>(P, 32) : bb_band_pass<L, false, true, false>(P, 32);
+                if ((threadIdx.x & 31) == 0) corner[variant] = r;
+            });
+        }
+        for (size_t i = 0; i < out[0].size(); i++) bad += out[0][i] != out[1][i];
+        bad += corner[0] != corner[1];
+    }
+    return bad;
+}
+
+extern "C" __attribute__((visibility("default")))
+int emu_compare_sm(const uint8_t *q, int n, const uint8_t *t, int m, int k, int L) {
+    int a, b;
+    bb_band(n, m, k, a, b);
+    if ((a + b) / (32 * L) + 2 > 32) return -1;
+    if (L == 8) return emu_compare_sm_impl<8>(q, n, t, m, a, b);
+    if (L == 16) return emu_compare_sm_impl<16>(q, n, t, m, a, b);
+    if (L == 32) return emu_compare_sm_impl<32>(q, n, t, m, a, b);
+    return -1;
+}

@@ -110,3 +110,23 @@ def test_column_blocked_pass_equals_single_column_pass(emu):
                     assert bad == 0, (it, n, len(b), d, k, cb)
                     checked += 1
     assert checked > 250
+
+
+def test_shared_memory_match_cache_equals_streamed_words(emu):
+    """The warp-pair kernel's pass (match words cut out of the bitmap once per chunk into shared memory) equals the
+    pass that streams them every step, for 8 / 16 / 32 words per lane, forward and reverse, including chunks that
+    reach past the node's last row and non-ACGT targets."""
+    from oracle import oracle as O
+    rnd = random.Random(78)
+    checked = 0
+    for it in range(10):
+        n = rnd.choice([700, 1900, 3300, 5200])
+        a = random_dna(rnd, n, 'ACGTN' if it % 4 == 0 else 'ACGT')
+        b = mutate(rnd, a, rnd.choice([0.02, 0.1, 0.25]))
+        d = O.align_path(b, a)[1]
+        for L in (8, 16, 32):
+            bad = emu.compare_sm(b, a, d + rnd.choice([0, 3, 50]), L)
+            if bad is not None:
+                assert bad == 0, (it, n, len(b), d, L)
+                checked += 1
+    assert checked >= 25
