@@ -781,6 +781,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return len[(size_t)x] > len[(size_t)y]; });
     ctx->part.assign((size_t)S, std::vector<int32_t>());
     for (int32_t i = 0; i < n_reads; i++) ctx->part[(size_t)(i % S)].push_back(order[(size_t)i]);
+    constexpr int kBadLiteral = 1 << 20;  // not a bb_status value
     std::vector<int> rcs((size_t)S, 0);
     std::vector<std::thread> threads;
     auto upload_part = [&](int w) {
@@ -794,7 +795,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
             for (int32_t x = seg_off[r]; x < seg_off[r + 1]; x++) {
                 bb_segment g = segs[x];
                 if (g.kind == BB_SEG_LITERAL) {
-                    if (g.len < 0 || g.src < 0 || g.src + g.len > literal_len) { rcs[(size_t)w] = -1; return; }
+                    if (g.len < 0 || g.src < 0 || g.src + g.len > literal_len) { rcs[(size_t)w] = kBadLiteral; return; }
                     const int64_t at = (int64_t)lit.size();
                     lit.insert(lit.end(), literal_pool + g.src, literal_pool + g.src + g.len);
                     g.src = at;
@@ -810,7 +811,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     upload_part(0);
     for (auto &t : threads) t.join();
     for (int w = 0; w < S; w++) {
-        if (rcs[(size_t)w] == -1) return set_err(ctx, BB_ERR_ARG, "literal segment out of range");
+        if (rcs[(size_t)w] == kBadLiteral) return set_err(ctx, BB_ERR_ARG, "literal segment out of range");
         if (rcs[(size_t)w]) return w == 0 ? rcs[0] : set_err(ctx, rcs[(size_t)w], worker_of(ctx, w)->err);
     }
     return BB_OK;
