@@ -108,7 +108,7 @@ __device__ __forceinline__ int bb_last_block(int j, int b, int n) {
 // shifts without bounds checks.  Size: bb_peq_words(n).
 __host__ __device__ __forceinline__ int bb_peq_words(int n) { return ((n + 31) >> 5) + 2 * BB_PEQ_PAD; }
 
-__device__ void bb_build_peq(const uint8_t *q, int n, uint4 *peq) {
+static __device__ void bb_build_peq(const uint8_t *q, int n, uint4 *peq) {
     const int lane = threadIdx.x & 31;
     const int nw = (n + 31) >> 5;
     for (int w = lane; w < BB_PEQ_PAD; w += 32) {
@@ -800,7 +800,7 @@ __device__ __forceinline__ void bb_emit_all_deleted(int m, BBEmit em, int qbase,
 
 // edlib.cpp obtainAlignmentHirschberg's choice of the split row from the column scores in sc.L / sc.R, by one
 // warp.  best < 0 (root): every optimal path crosses the split column, so the minimum sum is the edit distance.
-__device__ int bb_split_warp(const BBScratch &sc, int loL, int hiL, int loR, int hiR, int nn, int left_w, int right_w,
+static __device__ int bb_split_warp(const BBScratch &sc, int loL, int hiL, int loR, int hiR, int nn, int left_w, int right_w,
                              int &best, int &split, int &ls, int &rs) {
     const int lane = threadIdx.x & 31;
     int rlo = max(loL, nn - 2 - hiR); if (rlo < 0) rlo = 0;

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "bb_kernels.cuh"
+#include "bb_launch.h"
 
 namespace {
 
@@ -57,7 +58,7 @@ struct bb_ctx {
     std::vector<BBReadDev> h_reads;
     std::vector<int32_t> h_inlen;
     int64_t frag_total = 0, seq_total = 0, out_total = 0;
-    DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_order_small, d_order_large, d_order_long, d_reads;
+    DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_reads;
     int n_lane_reads = 0, n_long_reads = 0;
     std::vector<int> h_order;
     DevBuf d_frag, d_state, d_seq, d_ops, d_dcnt, d_qual, d_out_seq, d_out_qual, d_counter, d_fpeq, d_speq, d_fallback;
@@ -68,11 +69,9 @@ struct bb_ctx {
     BBScratchPool pool{};
     DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist;
     DevBuf d_ctime, d_chlog, d_wres, d_wtasks, d_wfallback, d_active;
-    bool use_spec_loop = true;
     int lane8_cols = 4096, lane16_cols = 0;  // routing limits of the lane node kernels (tuning knobs)
     int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
     struct QueueBufs { DevBuf node[BBQ_NODE_CLASSES][2], leaf[2], count; } qbuf[2];  // [0] normal, [1] wide-root reads
-    bool use_tasks = true;
 
 
     cudaEvent_t ev[BB_N_STAGES + 1] = {};
@@ -154,12 +153,10 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed) {
     for (int i = 0; from[i]; i++) comp[(uint8_t)from[i]] = (uint8_t)to[i];
     e = cudaMemcpyToSymbol(bb_c_comp, comp, 256);
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
-    e = cudaFuncSetAttribute(bb_k_node_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, BB_PAIR_SMEM_BYTES);
+    e = bbl_node_pair_init();
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     // persistent warps: 4 CTAs of 4 warps per SM for the warp-per-read kernels
     ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
-    if (const char *e = std::getenv("BADREAD_B200_ALIGN_TASKS")) ctx->use_tasks = (e[0] != '0');
-    if (const char *e = std::getenv("BADREAD_B200_SPEC_LOOP")) ctx->use_spec_loop = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_LANE8_COLS")) ctx->lane8_cols = std::atoi(e);
     if (const char *e = std::getenv("BADREAD_B200_LANE16_COLS")) ctx->lane16_cols = std::atoi(e);
     if (const char *e = std::getenv("BADREAD_B200_PAIR_CTAS")) ctx->pair_ctas = (e[0] == '2') ? 2 : 1;
@@ -195,7 +192,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     DevBuf *bufs[] = {&ctx->ref, &ctx->em_k2r, &ctx->em_rowoff, &ctx->em_cum, &ctx->em_flags, &ctx->em_slots,
                       &ctx->em_pool, &ctx->qm_hkeys, &ctx->qm_hvals, &ctx->qm_rowoff, &ctx->qm_scores, &ctx->qm_cum,
-                      &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order, &ctx->d_order_small, &ctx->d_order_large, &ctx->d_order_long,
+                      &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order,
                       &ctx->d_reads, &ctx->d_frag, &ctx->d_state, &ctx->d_seq, &ctx->d_ops, &ctx->d_dcnt,
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
@@ -455,8 +452,7 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
         const int n_active = (int)active.size();
         BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, active.data(), (size_t)n_active * sizeof(int), cudaMemcpyHostToDevice, st));
         BB_CUDA(ctx, cudaMemsetAsync(cnt + 8, 0, 8 * sizeof(int), st));
-        bb_k_mutate<<<std::min(ctx->sm_count * 8, n_active), BB_WARPS_PER_CTA * 32, 0, st>>>(
-            B, ctx->em, ctx->seed, cnt + 8, ctx->d_active.as<int>(), n_active);
+        bbl_mutate(std::min(ctx->sm_count * 8, n_active), st, B, ctx->em, ctx->seed, cnt + 8, ctx->d_active.as<int>(), n_active);
         ctx->launches++;
         BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
         BB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -474,11 +470,11 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
             BBWinTask *fb1 = ctx->d_wfallback.as<BBWinTask>(), *fb2 = fb1 + n_tasks;
             const int lane_grid = std::min(lane_ctas, (n_tasks + 63) / 64);
             const int lane_grid4 = std::min(2 * lane_ctas, (n_tasks + 63) / 64);  // half the history per thread
-            bb_k_window_lane<4><<<lane_grid4, 64, 0, st>>>(B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
-                                                          ctx->s_leafhist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), cnt + 9, fb1, cnt + 10);
-            bb_k_window_lane<BB_WIN_LW><<<lane_grid, 64, 0, st>>>(B, ctx->em, fb1, cnt + 10, ctx->seed, ctx->s_leafhist.as<uint2>(),
-                                                                  ctx->s_ltbuf.as<uint8_t>(), cnt + 13, fb2, cnt + 14);
-            bb_k_window_warp<<<ctx->sm_count * 2, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, fb2, cnt + 14, ctx->seed, cnt + 11);
+            bbl_window_lane4(lane_grid4, st, B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
+                             ctx->s_leafhist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), cnt + 9, fb1, cnt + 10);
+            bbl_window_lane8(lane_grid, st, B, ctx->em, fb1, cnt + 10, ctx->seed, ctx->s_leafhist.as<uint2>(),
+                             ctx->s_ltbuf.as<uint8_t>(), cnt + 13, fb2, cnt + 14);
+            bbl_window_warp(ctx->sm_count * 2, st, B, ctx->em, ctx->pool, fb2, cnt + 14, ctx->seed, cnt + 11);
             ctx->launches += 3;
         }
         bb_k_replay<<<(n_active + 127) / 128, 128, 0, st>>>(B, ctx->d_active.as<int>(), n_active, ctx->em.k);
@@ -540,12 +536,12 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
             cudaStream_t st = stream[s];
             for (int c = 0; c < BBQ_NODE_CLASSES; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt[s] + c * 2 + (p ^ 1), 0, sizeof(int), st));
             if (s == 1) {
-                bb_k_node_pair<<<ctx->sm_count * ctx->pair_ctas, BB_WARPS_PER_CTA * 32, BB_PAIR_SMEM_BYTES, st>>>(B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
+                bbl_node_pair(ctx->sm_count * ctx->pair_ctas, st, B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
                 ctx->launches++;
             }
-            bb_k_node_warp<4><<<grid_lean[s], BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, BBQ_NODE_LEAN, p, cursor[s]++, warp_base[s]);
-            bb_k_node_lane<BB_NODE_LW><<<lane_ctas, 64, 0, st>>>(B, Q[s], p, cursor[s]++);
-            bb_k_node_lane<BB_NODE_LW_SMALL><<<ctx->sm_count * 6, 64, 0, st>>>(B, Q[s], p, cursor[s]++);
+            bbl_node_warp4(grid_lean[s], st, B, Q[s], ctx->pool, BBQ_NODE_LEAN, p, cursor[s]++, warp_base[s]);
+            bbl_node_lane16(lane_ctas, st, B, Q[s], p, cursor[s]++);
+            bbl_node_lane8(ctx->sm_count * 6, st, B, Q[s], p, cursor[s]++);
             ctx->launches += 3;
         }
         if (level >= 3 && (level & 3) == 3) {  // every few levels: stop as soon as all queues are empty
@@ -560,8 +556,8 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
     }
     for (int s = 0; s < 2; s++) {
         cudaStream_t st = stream[s];
-        bb_k_leaf_warp<<<ctx->sm_count, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q[s], ctx->pool, cursor[s]++, warp_base[s]);
-        bb_k_leaf_lane<<<lane_ctas, 64, 0, st>>>(B, Q[s], ctx->s_leafhist.as<uint2>() + s * hist_per_pipe, cursor[s]++);
+        bbl_leaf_warp(ctx->sm_count, st, B, Q[s], ctx->pool, cursor[s]++, warp_base[s]);
+        bbl_leaf_lane(lane_ctas, st, B, Q[s], ctx->s_leafhist.as<uint2>() + s * hist_per_pipe, cursor[s]++);
         ctx->launches += 2;
     }
     BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, stream[1]));
@@ -575,14 +571,12 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
 
 static int w_batch_run(bb_ctx *ctx) {
     if (!ctx) return BB_ERR_ARG;
-    ctx->scan_ready.store(0, std::memory_order_release);
     if (!ctx->uploaded) return set_err(ctx, BB_ERR_STATE, "bb_batch_run: no batch uploaded");
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n = ctx->n_reads;
     BBBatchDev B = batch_dev(ctx);
     int *counters = ctx->d_counter.as<int>();
-    const int grid_warp = ctx->n_warps / BB_WARPS_PER_CTA;
 
     // the per-read records start from the uploaded state on every run (bb_batch_run may be repeated)
     BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, ctx->h_reads.data(), (size_t)n * sizeof(BBReadDev),
@@ -594,16 +588,9 @@ static int w_batch_run(bb_ctx *ctx) {
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // one thread per read; reads whose windows exceed the lane-mode limits are redone by the warp kernel
     std::vector<BBReadDev> reads((size_t)n);
-    if (ctx->use_spec_loop) {
+    {
         int rcl = run_spec_loop(ctx, B, reads);
         if (rcl) return rcl;
-    } else {
-        // sequential variant: one warp per read interleaves the k-mer loop with its window alignments
-        const int h_n = n;
-        BB_CUDA(ctx, cudaMemcpyAsync(counters + 6, &h_n, sizeof(int), cudaMemcpyHostToDevice, st));
-        bb_k_error_loop<<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->em, ctx->pool, ctx->seed, counters + 5,
-                                                                     ctx->d_order.as<int>(), counters + 6, 0, 0);
-        ctx->launches++;
     }
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     // host scan of the joined lengths -> offsets of the per-read regions in seq / ops / dcnt / qual / out
@@ -632,15 +619,6 @@ static int w_batch_run(bb_ctx *ctx) {
     ctx->seq_total = seq_off;
     ctx->out_total = out_off;
     ctx->scan_ready.store(1, std::memory_order_release);
-    std::vector<int> small, large;  // work queues of the two final-alignment builds, longest fragments first
-    for (int r : ctx->h_order) {
-        const BBReadDev &rd = reads[(size_t)r];
-        const int bound = std::min(rd.upper, std::max(rd.seq_len, rd.frag_len));
-        (bound <= 1900 ? small : large).push_back(r);
-    }
-    const int grid_large = std::max(1, std::min(ctx->sm_count * 2, ((int)large.size() + BB_WARPS_PER_CTA - 1) / BB_WARPS_PER_CTA));
-    if ((rc0 = upload(ctx, ctx->d_order_small, small.data(), small.size()))) return rc0;
-    if ((rc0 = upload(ctx, ctx->d_order_large, large.data(), large.size()))) return rc0;
     BB_CUDA(ctx, ctx->d_seq.ensure((size_t)seq_off + 16));
     BB_CUDA(ctx, ctx->d_ops.ensure((size_t)seq_off + 16));
     BB_CUDA(ctx, ctx->d_dcnt.ensure(((size_t)seq_off + 16) * sizeof(unsigned int)));
@@ -657,23 +635,10 @@ static int w_batch_run(bb_ctx *ctx) {
     bb_k_join<<<n, 256, 0, st>>>(B, ctx->em);
     ctx->launches++;
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    if (ctx->use_tasks) {
+    {
         int rc2 = run_align_tasks(ctx, B, reads);
         if (rc2) return rc2;
         BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-    } else {
-        // depth-first variant: one warp walks the whole Hirschberg tree of a read (kept for comparison / testing)
-        if (!large.empty()) {
-            bb_k_final_align<16><<<grid_large, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 1,
-                                                                             ctx->d_order_large.as<int>(), (int)large.size(), 0);
-            ctx->launches++;
-        }
-        BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-        if (!small.empty()) {
-            bb_k_final_align<2><<<grid_warp, BB_WARPS_PER_CTA * 32, 0, st>>>(B, ctx->pool, counters + 2,
-                                                                           ctx->d_order_small.as<int>(), (int)small.size(), 0);
-            ctx->launches++;
-        }
     }
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
     bb_k_qscores<<<n, 256, 0, st>>>(B, ctx->qm, ctx->seed);
@@ -819,8 +784,10 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
 
 extern "C" int bb_batch_run(bb_ctx *ctx) {
     if (!ctx) return BB_ERR_ARG;
+    ctx->scan_ready.store(0, std::memory_order_release);
     if (ctx->n_split == 1) return w_batch_run(ctx);
     const int S = ctx->n_split;
+    for (int w = 1; w < S; w++) worker_of(ctx, w)->scan_ready.store(0, std::memory_order_release);
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
     for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(worker_of(ctx, w)->stream, ctx->ev_t0, 0));
@@ -907,6 +874,9 @@ extern "C" int bb_sequence_batch(bb_ctx *ctx, int32_t n_reads, const uint64_t *r
     // several workers: each one copies its block out as soon as its own chain is done, while the others still compute
     // (its offset only needs the output sizes of the workers before it, known since their host scans)
     const int S = ctx->n_split;
+    // every worker's "output size known" flag is cleared here, before any chain thread exists: a chain polls the
+    // flags of the workers in front of it and must never see the value a previous batch left behind
+    for (int w = 0; w < S; w++) worker_of(ctx, w)->scan_ready.store(0, std::memory_order_release);
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
     for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(worker_of(ctx, w)->stream, ctx->ev_t0, 0));
@@ -967,8 +937,8 @@ static int align_pair_device(bb_ctx *ctx, const uint8_t *q, int n, const uint8_t
     if ((rc = ensure_scratch(ctx, std::max(n, m), std::max(n, m), std::max(n, m)))) return rc;
     BB_CUDA(ctx, cudaMemsetAsync(ddcnt.p, 0, ((size_t)n + 16) * sizeof(unsigned int), ctx->stream));
     BB_CUDA(ctx, cudaMemsetAsync(dout.p, 0, 8 * sizeof(int), ctx->stream));
-    bb_k_align_pair<<<1, 32, 0, ctx->stream>>>(dq.as<uint8_t>(), n, dt.as<uint8_t>(), m, std::max(n, m), ctx->pool,
-                                                dops.as<uint8_t>(), ddcnt.as<unsigned int>(), dout.as<int>());
+    bbl_align_pair(ctx->stream, dq.as<uint8_t>(), n, dt.as<uint8_t>(), m, std::max(n, m), ctx->pool, dops.as<uint8_t>(),
+                   ddcnt.as<unsigned int>(), dout.as<int>());
     ctx->launches++;
     BB_CUDA(ctx, cudaMemcpyAsync(out5, dout.p, 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -112,6 +112,7 @@ struct BBScratchPool {
 __constant__ uint8_t bb_c_comp[256];  // misc.REV_COMP_DICT, unknown -> 'N' (misc.py:56-67)
 
 // ------------------------------------------------------------------------------------------------ K1
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(256) bb_k_build_fragments(BBBatchDev B, const uint8_t *__restrict__ ref, int k,
                                                             unsigned long long seed) {
     const int r = blockIdx.x;
@@ -177,7 +178,7 @@ __device__ __forceinline__ uint8_t bb_slot_char(const BBErrorModelDev &em, uint3
 
 // ''.join(new_fragment_bases[lo:lo+count]) into out (warp-cooperative). Returns the joined length; *upper gets
 // the number of edits that turn the original slice into the joined one (an upper bound on their edit distance).
-__device__ int bb_join_slots(const BBErrorModelDev &em, const uint8_t *frag, const uint32_t *state, int lo, int count,
+static __device__ int bb_join_slots(const BBErrorModelDev &em, const uint8_t *frag, const uint32_t *state, int lo, int count,
                              uint8_t *out, int *upper) {
     const int lane = threadIdx.x & 31;
     int total = 0, up = 0;
@@ -253,152 +254,8 @@ __device__ __forceinline__ void bb_eval_iteration(const BBErrorModelDev &em, con
     kind = 2; rpos = p;
 }
 
-__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 4)
-bb_k_error_loop(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, unsigned long long seed, int *work_counter,
-                const int *order, const int *n_items_ptr, int reinit, int warp_base) {
-    const int lane = threadIdx.x & 31;
-    const int warp = warp_base + blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
-    BBScratch sc = pool.for_warp(warp);
-    uint8_t *tbuf = pool.tbuf + (long long)warp * pool.tbuf_stride;
-    const int k = em.k;
-    const int n_items = *n_items_ptr;
-    BBEmit no_emit = {nullptr, nullptr, nullptr};
-    for (;;) {
-        int w = 0;
-        if (lane == 0) w = atomicAdd(work_counter, 1);
-        w = __shfl_sync(BB_FULL, w, 0);
-        if (w >= n_items) break;
-        const int r = order[w];
-        BBReadDev *rd = &B.reads[r];
-        const long long clk0 = clock64();
-        const uint8_t *frag = B.frag + rd->frag_off;
-        uint32_t *state = B.state + rd->frag_off;
-        const int frag_len = rd->frag_len;
-        const unsigned long long read = B.read_index[r];
-        const double target = B.target[r];
-        const double fl = (double)frag_len;
-        const int max_kmer_index = frag_len - 1 - k;
-        const long long limit = 100ll * frag_len;  // loop_count > 100 * frag_len stops the loop (simulate.py:279)
-        double errors = 0.0;
-        int change_count = 0, n_align = 0, upper = 0, flags = 0;
-        long long loop_count = 0, n0 = 0;
-        const double est_needed = __dmul_rn(fl, __dsub_rn(1.0, target));
-        bool done = est_needed < 0.5;
-        if (!done && 1.0 <= target) { done = true; loop_count = 1; }
-        __syncwarp();
-        sc.peq = B.fpeq + rd->fpeq_off;  // match bitmap of the padded fragment (built by bb_k_build_fragments)
-        if (reinit) {                    // a read handed over by the lane kernel starts again from pristine slots
-            for (int x = lane; x < frag_len; x += 32) state[x] = BB_SLOT_NONE;
-            __syncwarp();
-        }
-        while (!done) {
-            const long long n = n0 + lane;
-            int kind = 0, pos_i = 0, rpos = 0;
-            uint32_t payload = 0;
-            if (n < limit) bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
-            __syncwarp();
-            uint32_t cmask = __ballot_sync(BB_FULL, kind != 0);
-            while (cmask && !done) {
-                const int L = __ffs(cmask) - 1;
-                cmask &= cmask - 1;
-                const int bi = __shfl_sync(BB_FULL, pos_i, L);
-                const int bkind = __shfl_sync(BB_FULL, kind, L);
-                const uint32_t bpay = __shfl_sync(BB_FULL, payload, L);
-                const int brpos = __shfl_sync(BB_FULL, rpos, L);
-                // estimated_identity of this iteration (simulate.py:290); errors are scaled by its 1.5th power
-                // computed as x*sqrt(x): two correctly rounded operations, identical on host and device
-                const double est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl));
-                const double scale = __dmul_rn(est_id, __dsqrt_rn(est_id));
-                uint32_t enc = 0;
-                bool app = false;
-                if (lane < k) {
-                    const uint8_t fb = frag[bi + lane];
-                    enc = bkind == 1 ? em.slots[(long long)bpay * k + lane]
-                                     : (lane == brpos ? bpay : bb_slot_inline(1, fb, 0));
-                    const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
-                    app = differs && state[bi + lane] == BB_SLOT_NONE;  // simulate.py:309
-                }
-                uint32_t amask = __ballot_sync(BB_FULL, app);
-                while (amask) {
-                    const int j = __ffs(amask) - 1;
-                    amask &= amask - 1;
-                    const uint32_t e = __shfl_sync(BB_FULL, enc, j);
-                    if (lane == j) state[bi + j] = e;
-                    __syncwarp();
-                    const int len = (int)(e & 0xff);
-                    change_count++;
-                    upper += len < 1 ? 1 : len;
-                    const int new_errors = len < 2 ? 1 : len - 1;
-                    errors = __dadd_rn(errors, __dmul_rn((double)new_errors, scale));  // simulate.py:321
-                    if (change_count % BB_ALIGNMENT_INTERVAL == 0) {  // simulate.py:325-346
-                        __syncwarp();
-                        int qpos = 0, qn = frag_len;
-                        if (frag_len > BB_ALIGNMENT_SIZE) {
-                            BBRng wr;
-                            wr.init(seed, read);
-                            wr.stream(BB_PURPOSE_WINDOW, (uint32_t)n_align);
-                            qpos = (int)wr.randbelow((uint32_t)(frag_len - BB_ALIGNMENT_SIZE + 1));
-                            qn = BB_ALIGNMENT_SIZE;
-                        }
-                        int uw = 0;
-                        const int tm = bb_join_slots(em, frag, state, qpos, qn, tbuf, &uw);
-                        BBAlnCounts cnt = {0, 0, 0, 0};
-                        bb_align<false, 1>(frag + qpos, qn, tbuf, tm, uw, sc, no_emit, qpos, cnt);
-                        flags |= cnt.err;
-                        const int cols = qn + cnt.dels;
-                        const double actual = cols ? __ddiv_rn((double)cnt.matches, (double)cols) : 0.0;
-                        if (frag_len <= BB_ALIGNMENT_SIZE) {
-                            errors = __dmul_rn(__dsub_rn(1.0, actual), fl);
-                        } else {
-                            const double est_err = __dmul_rn(__dsub_rn(1.0, actual), fl);
-                            const double weight = __ddiv_rn((double)BB_ALIGNMENT_SIZE, fl);
-                            errors = __dadd_rn(__dmul_rn(est_err, weight), __dmul_rn(errors, __dsub_rn(1.0, weight)));
-                        }
-                        n_align++;
-                        __syncwarp();
-                    }
-                }
-                // the checks at the top of the next iteration (simulate.py:285-292) can only change after a commit
-                const long long nL = n0 + L;
-                if ((double)change_count > __dmul_rn(0.9, fl)) { done = true; loop_count = nL + 2; }
-                else {
-                    const double est = __dsub_rn(1.0, __ddiv_rn(errors, fl));
-                    if (est <= target) { done = true; loop_count = nL + 2; }
-                }
-                if (flags) { done = true; }
-            }
-            if (!done) {
-                n0 += 32;
-                if (n0 >= limit) { done = true; loop_count = limit + 1; }
-            }
-        }
-        __syncwarp();
-        // lengths of the joined read and of the two pad regions (simulate.py:348-351)
-        int total = 0, st_trim = 0, en_trim = 0;
-        for (int base = 0; base < frag_len; base += 32) {
-            const int x = base + lane;
-            int len = 0;
-            if (x < frag_len) { const uint32_t st = state[x]; len = st == BB_SLOT_NONE ? 1 : (int)(st & 0xff); }
-            total += len;
-            if (x < k) st_trim += len;
-            if (x < frag_len && x >= frag_len - k) en_trim += len;
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            total += __shfl_xor_sync(BB_FULL, total, d);
-            st_trim += __shfl_xor_sync(BB_FULL, st_trim, d);
-            en_trim += __shfl_xor_sync(BB_FULL, en_trim, d);
-        }
-        if (lane == 0) {
-            rd->seq_len = total; rd->start_trim = st_trim; rd->end_trim = en_trim; rd->upper = upper;
-            rd->loop_count = (int)(loop_count > 0x7fffffff ? 0x7fffffff : loop_count);
-            rd->change_count = change_count; rd->n_align = n_align; rd->flags = flags;
-            rd->kc_loop = (int)((clock64() - clk0) >> 10);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ K3
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev em) {
     const int r = blockIdx.x;
     if (r >= B.n_reads) return;
@@ -470,40 +327,6 @@ __global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev e
     }
 }
 
-// ------------------------------------------------------------------------------------------------ K4
-// MAXL bounds the band-pass variants (words per lane) the kernel instantiates: reads whose edit bound fits
-// 32*MAXL*30 rows go to the lean MAXL = 2 build, the few long / noisy ones to MAXL = 16 (more registers).
-template <int MAXL>
-__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (MAXL <= 2 ? 4 : 2))
-bb_k_final_align(BBBatchDev B, BBScratchPool pool, int *work_counter, const int *order, int n_items, int warp_base) {
-    const int lane = threadIdx.x & 31;
-    const int warp = warp_base + blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
-    BBScratch sc = pool.for_warp(warp);
-    for (;;) {
-        int w = 0;
-        if (lane == 0) w = atomicAdd(work_counter, 1);
-        w = __shfl_sync(BB_FULL, w, 0);
-        if (w >= n_items) break;
-        const int r = order[w];
-        BBReadDev *rd = &B.reads[r];
-        const long long clk0 = clock64();
-        sc.peq = B.speq + rd->speq_off;  // match bitmap of the joined read (built by bb_k_join)
-        BBEmit em;
-        em.ops = B.ops + rd->seq_off;
-        em.dcnt = B.dcnt + rd->seq_off;
-        em.lead_del = &rd->lead_del;
-        BBAlnCounts cnt = {0, 0, 0, 0};
-        // query = mutated read, target = original fragment (qscore_model.py:37)
-        bb_align<true, MAXL>(B.seq + rd->seq_off, rd->seq_len, B.frag + rd->frag_off, rd->frag_len, rd->upper, sc, em,
-                             0, cnt);
-        __syncwarp();
-        if (lane == 0) {
-            rd->matches = cnt.matches; rd->dels = cnt.dels; rd->flags |= cnt.err << 8;
-            rd->kc_align = (int)((clock64() - clk0) >> 10);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ K5
 __device__ __forceinline__ int bb_qm_find(const BBQScoreModelDev &qm, unsigned long long key) {
     const uint32_t mask = (1u << qm.hbits) - 1u;
@@ -551,6 +374,7 @@ __device__ __forceinline__ uint8_t bb_qscore_base(const BBQScoreModelDev &qm, co
     return (uint8_t)(qm.scores[e0 + pick] + 33);
 }
 
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(256) bb_k_qscores(BBBatchDev B, BBQScoreModelDev qm, unsigned long long seed) {
     const int r = blockIdx.x;
     const BBReadDev rd = B.reads[r];
@@ -564,6 +388,7 @@ __global__ void __launch_bounds__(256) bb_k_qscores(BBBatchDev B, BBQScoreModelD
 }
 
 // ------------------------------------------------------------------------------------------------ K6
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(256) bb_k_compact(BBBatchDev B) {
     const int r = blockIdx.x;
     const BBReadDev rd = B.reads[r];
@@ -578,6 +403,7 @@ __global__ void __launch_bounds__(256) bb_k_compact(BBBatchDev B) {
 
 // ------------------------------------------------------------------------------------------------ single-pair entry points
 // edlib.align(query, target, task='path') for one pair (diagnostics / tests): ops + dcnt + lead_del + counts.
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(32) bb_k_align_pair(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper,
                                                       BBScratchPool pool, uint8_t *ops, unsigned int *dcnt, int *out4) {
     const BBScratch sc = pool.for_warp(0);
@@ -592,6 +418,7 @@ __global__ void __launch_bounds__(32) bb_k_align_pair(const uint8_t *q, int n, c
     if ((threadIdx.x & 31) == 0) { out4[0] = cnt.matches; out4[1] = cnt.dels; out4[2] = cnt.dist; out4[4] = cnt.err; }
 }
 
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(256) bb_k_qscores_pair(const uint8_t *ops, const unsigned int *dcnt, int n,
                                                          BBQScoreModelDev qm, unsigned long long seed,
                                                          unsigned long long read, uint8_t *qual) {

@@ -33,6 +33,7 @@ struct BBWinTask { int r, a; };  // read, alignment ordinal (1-based: after 25*a
 // One CTA (4 warps) per read: every step the 128 threads evaluate 128 consecutive loop iterations (position, k-mer,
 // model draw: chains of dependent loads, independent across iterations), then warp 0 commits the iterations that
 // change something, in order.
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
 bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter, const int *order,
             int n_items) {
@@ -258,6 +259,7 @@ bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const
 }
 
 // Windows beyond the lane limits: one warp each, with the general aligner.
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 4)
 bb_k_window_warp(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, const BBWinTask *tasks, const int *n_tasks_ptr,
                  unsigned long long seed, int *cursor) {
@@ -324,6 +326,7 @@ bb_k_window_warp(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, const BBW
 
 // ------------------------------------------------------------------------------------------------ replay
 // One thread per read: the scalar recurrence of simulate.py:290-346 over the change log.
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(128)
 bb_k_replay(BBBatchDev B, const int *order, int n_items, int k) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;

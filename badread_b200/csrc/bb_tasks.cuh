@@ -62,7 +62,7 @@ __device__ __forceinline__ void bb_task_band(const BBNode &nd, int upper, int &a
 }
 
 // Queue a child (or finish it on the spot when one side is empty, edlib.cpp obtainAlignment).
-__device__ void bb_push_task(const BBQueues &Q, int next_parity, const BBAlignOut &o, const BBNode &nd, int upper) {
+static __device__ void bb_push_task(const BBQueues &Q, int next_parity, const BBAlignOut &o, const BBNode &nd, int upper) {
     if (nd.nn == 0) {
         atomicAdd(&o.rd->dels, nd.mm);
         bb_add_dels(o, nd.q0 - 1, nd.mm);
@@ -95,7 +95,7 @@ __device__ void bb_push_task(const BBQueues &Q, int next_parity, const BBAlignOu
 // edlib.cpp obtainAlignmentHirschberg's choice of the split row from the two column-score arrays
 // (L[r - loL] = D(q[0..r], t[0..left_w)), R[x - loR] = D(rq[0..x], rt[0..right_w))), sequential version.
 // best < 0 (root): the minimum over all splits is the edit distance.  Returns false if no split matches.
-__device__ bool bb_choose_split_seq(const int *L, int loL, int hiL, const int *R, int loR, int hiR, int nn, int left_w,
+static __device__ bool bb_choose_split_seq(const int *L, int loL, int hiL, const int *R, int loR, int hiR, int nn, int left_w,
                                     int right_w, int &best, int &split, int &ls, int &rs) {
     int rlo = max(loL, nn - 2 - hiR); if (rlo < 0) rlo = 0;
     int rhi = min(hiL, nn - 2 - loR); if (rhi > nn - 2) rhi = nn - 2;
@@ -126,6 +126,7 @@ __device__ bool bb_choose_split_seq(const int *L, int loL, int hiL, const int *R
 // Roots of all reads of the batch (same routing rule as every other task).
 // Reads whose root has a wide band form their own pipeline (QW): its levels are not held up by, and do not hold
 // up, the levels of all other reads (QN).
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues QN, BBQueues QW, const int *order) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B.n_reads) return;
@@ -302,6 +303,7 @@ bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
 }
 
 // ---------------------------------------------------------------------------------------------- lane leaf kernel
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(64)
 bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
     constexpr int LW = BB_LEAF_LW;
@@ -428,6 +430,7 @@ __device__ __forceinline__ void bb_pair_sync(int id) {
 // Wide-band nodes: a PAIR of warps per node.  The even warp runs the forward pass over the left half of the target,
 // the odd warp the reverse pass over the right half, each as a full 32-lane wavefront (half the words per lane of
 // the paired single-warp variant, so the steps are half as long); the even warp then picks the split.
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 2)
 bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
     __shared__ int s_task[BB_WARPS_PER_CTA / 2];
@@ -500,6 +503,7 @@ bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
 }
 
 // One leaf per warp (bands or lengths beyond the lane kernel's limits).
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 2)
 bb_k_leaf_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int *cursor, int warp_base) {
     const int lane = threadIdx.x & 31;

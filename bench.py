@@ -149,26 +149,31 @@ class ClockSampler(object):
         return out
 
 
-def cpu_port_rate(planner, models, plans, indices, budget_s, n_threads):
-    """Times the CPU oracle port on a bounded sample of the workload; returns (gbases_per_s, description)."""
+def cpu_port_run(planner, models, plans, indices, n_threads, n_reads=None):
+    """Runs the CPU oracle port (Philox mode, pthreads over reads) over the first n_reads reads of the workload (all of
+    them by default).  Returns (outputs, bases, seconds, description); outputs[i] = (seq, qual, matches, columns)."""
     from oracle import oracle as O
     orc = O.Oracle(*models)
-    frs = [planner.materialise(p[0]) for p in plans[:min(len(plans), 4096)]]
-    ids = [p[2] for p in plans[:len(frs)]]
-    probe_n = min(len(frs), max(2 * n_threads, 16))
+    n = len(plans) if n_reads is None else min(len(plans), n_reads)
+    frs = [planner.materialise(p[0]) for p in plans[:n]]
+    ids = [p[2] for p in plans[:n]]
     t0 = time.perf_counter()
-    _, bases = orc.sequence_batch(frs[:probe_n], ids[:probe_n], SEED, indices[:probe_n], n_threads=n_threads)
+    outs, bases = orc.sequence_batch(frs, ids, SEED, indices[:n], n_threads=n_threads)
     dt = time.perf_counter() - t0
-    rate = bases / dt if dt > 0 else 1e6
-    n = probe_n
-    mean_len = max(1.0, bases / probe_n)
-    want = int(rate * budget_s / mean_len)
-    if want > probe_n * 2:
-        n = min(len(frs), want)
-        t0 = time.perf_counter()
-        _, bases = orc.sequence_batch(frs[:n], ids[:n], SEED, indices[:n], n_threads=n_threads)
-        dt = time.perf_counter() - t0
-    return bases / dt / 1e9, f'first {n} reads of the workload ({bases} bases) in {dt:.1f} s on {n_threads} threads', bases, dt
+    what = 'the whole workload' if n == len(plans) else f'the first {n} of {len(plans)} reads of the workload'
+    return outs, bases, dt, f'{what}: {n} reads, {bases} bases in {dt:.2f} s on {n_threads} threads'
+
+
+def parity_check(res, outs):
+    """GPU reads (BatchResult) against the oracle's for the same read indices: sequences, quality strings, alignment
+    counts.  Returns the parity object of the JSON line."""
+    bad = []
+    for i, o in enumerate(outs):
+        rec = res.records[i]
+        if res.read(i) != (o[0], o[1]) or (rec.matches, rec.columns) != (o[2], o[3]):
+            bad.append(i)
+    return {'reads_checked': len(outs), 'bases_checked': int(sum(len(o[0]) for o in outs)), 'mismatches': len(bad),
+            'first_mismatching_reads': bad[:8], 'against': 'oracle/badread_oracle.c (Philox mode), same read indices'}
 
 
 def peaks():
@@ -188,7 +193,6 @@ def main():
     ap.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
     ap.add_argument('--reads', type=int, default=None, help='override the number of reads per rank (debugging)')
     ap.add_argument('--profile', action='store_true', help='skip the e2e and CPU legs (for runs under ncu)')
-    ap.add_argument('--cpu_seconds', type=float, default=15.0, help='budget of the CPU baseline sample')
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -201,13 +205,12 @@ def main():
     if a.impl == 'reference':
         if rank != 0:
             return 0
-        planner, ref, models, plans, indices = build_workload(0, 1, n_reads_override=a.reads or 2048)
+        planner, ref, models, plans, indices = build_workload(0, 1, n_reads_override=a.reads)
         values = []
-        per_step = max(3.0, min(30.0, a.cpu_seconds))
-        for s in range(a.warmup + a.steps):
-            g, desc, bases, dt = cpu_port_rate(planner, models, plans, indices, per_step if s >= a.warmup else 1.0, n_cores)
-            if s >= a.warmup:
-                values.append((g, bases, dt, desc))
+        for s_ in range(a.warmup + a.steps):   # every step = the same reads the GPU arm processes per step
+            _, bases, dt, desc = cpu_port_run(planner, models, plans, indices, n_cores)
+            if s_ >= a.warmup:
+                values.append((bases / dt / 1e9, bases, dt, desc))
         tot_b = sum(v[1] for v in values)
         tot_t = sum(v[2] for v in values)
         val = tot_b / tot_t / 1e9
@@ -331,9 +334,11 @@ def main():
                 'note': 'stage = all kernels of the Hirschberg task pipeline (bb_k_node_warp<4> dominant); the path is '
                         'bit-vector DP bound by the integer ALU pipe (0.5 warp-inst/clk/SMSP), not by HBM: the HBM '
                         'fraction is small by construction, see DESIGN.md section 5 for the ALU-pipe accounting'}
-    cpu_g, cpu_desc = None, 'skipped (--profile)'
+    cpu_g, cpu_desc, parity = None, 'skipped (--profile)', None
     if not a.profile:
-        cpu_g, cpu_desc, _, _ = cpu_port_rate(planner, models, plans, indices, a.cpu_seconds, n_cores)
+        outs, cpu_bases, cpu_dt, cpu_desc = cpu_port_run(planner, models, plans, indices, n_cores)
+        cpu_g = cpu_bases / cpu_dt / 1e9
+        parity = parity_check(res, outs)   # res: the reads fetched by the last end-to-end step
     line = {'metric': 'simulated Gbases/sec', 'value': value, 'unit': 'Gbases/s', 'n_gpus': world, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': max_elapsed / a.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u8/int32 (+f64 identity estimate)', 'data': 'synthetic', 'config': config,
@@ -343,11 +348,15 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'Gbases/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': int(launches),
             'roofline': roofline,
-            'cpu_baseline': {'value': cpu_g, 'unit': 'Gbases/s', 'cores': n_cores, 'kind': 'port', 'sample': cpu_desc}}
+            'cpu_baseline': {'value': cpu_g, 'unit': 'Gbases/s', 'cores': n_cores, 'kind': 'port', 'sample': cpu_desc},
+            'parity': parity}
     print(json.dumps(line), flush=True)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+    if parity is not None and parity['mismatches']:
+        log(f'PARITY FAILURE: {parity}')
+        return 3
     return 0
 
 

@@ -127,3 +127,67 @@ def test_output_buffers_grow_on_capacity_error(engine):
         got, total2 = engine.sequence_batch(batch)
         assert total2 == total and engine._out_cap >= total
         assert [got.read(i) for i in range(n_reads)] == want
+
+
+def _np_dna(seed, n):
+    import numpy as np
+    return np.frombuffer(b'ACGT', dtype=np.uint8)[np.random.RandomState(seed).randint(0, 4, n)].tobytes().decode('ascii')
+
+
+# Long reads: the regime that carries most of the benchmark's bases (58 % of configs[1] sits in reads > 20 kb; the
+# longest is ~150 kb) and all of config 5.  Lengths x identities are chosen to reach both final-alignment pipelines
+# (lean single-warp nodes; wide roots by warp pairs with 8-, 16- and 32-word chunks) and the strip fallback
+# (a + b > 30 * 1024 rows: 150 kb at identity 0.75).
+LONG_CASES = [(25000, 0.95), (25000, 0.8), (40000, 0.9), (40000, 0.95), (60000, 0.95), (60000, 0.8), (100000, 0.9),
+              (100000, 0.95), (150000, 0.95), (150000, 0.9), (150000, 0.8), (150000, 0.75), (131072, 0.99), (33000, 1.0)]
+
+
+@pytest.mark.parametrize('error_name,qscore_name', [('nanopore2023', 'nanopore2023'), ('nanopore2020', 'nanopore2020')])
+def test_long_reads_match_oracle(engine, error_name, qscore_name):
+    from badread_b200.engine import FragmentBatch
+    em, qm = load_models(error_name, qscore_name)
+    O, orc = _oracle(em, qm)
+    engine.set_error_model(em)
+    engine.set_qscore_model(qm)
+    batch = FragmentBatch()
+    frags, idents, ridx = [], [], []
+    for i, (n, ident) in enumerate(LONG_CASES):
+        frags.append(_np_dna(977 + i, n))
+        idents.append(ident)
+        ridx.append(90000 + 7 * i)
+        batch.add_literal_read(ridx[-1], frags[-1], ident)
+    res, total = engine.sequence_batch(batch)
+    outs, _ = orc.sequence_batch(frags, idents, engine.seed, ridx, n_threads=max(1, min(16, len(frags))))
+    for i in range(len(frags)):
+        gs, gq = res.read(i)
+        rec = res.records[i]
+        assert rec.flags == 0
+        assert gs == outs[i][0], (i, LONG_CASES[i])
+        assert gq == outs[i][1], (i, LONG_CASES[i])
+        assert (rec.matches, rec.columns) == (outs[i][2], outs[i][3]), (i, LONG_CASES[i])
+    assert total == sum(len(o[0]) for o in outs)
+
+
+def test_long_reads_in_a_split_batch_match_oracle(engine):
+    """Long reads inside a batch that is dealt out over the sub-batch workers (>= 64 reads per worker): the wide-root
+    pipeline runs next to the lean one on every worker, as in the benchmark."""
+    from badread_b200.engine import FragmentBatch
+    em, qm = load_models('nanopore2023', 'nanopore2023')
+    O, orc = _oracle(em, qm)
+    engine.set_error_model(em)
+    engine.set_qscore_model(qm)
+    rnd = random.Random(4242)
+    lens = [rnd.choice([300, 2500, 9000]) + rnd.randrange(100) for _ in range(280)]
+    lens += [22000, 31000, 48000, 75000, 120000, 149690]
+    batch = FragmentBatch()
+    frags, idents, ridx = [], [], []
+    for i, n in enumerate(lens):
+        frags.append(_np_dna(5000 + i, n))
+        idents.append(rnd.choice([0.99, 0.96, 0.93, 0.87]))
+        ridx.append(2 * i + 1)
+        batch.add_literal_read(ridx[-1], frags[-1], idents[-1])
+    res, total = engine.sequence_batch(batch)
+    outs, _ = orc.sequence_batch(frags, idents, engine.seed, ridx, n_threads=16)
+    bad = [i for i in range(len(frags)) if res.read(i) != (outs[i][0], outs[i][1])
+           or (res.records[i].matches, res.records[i].columns) != (outs[i][2], outs[i][3])]
+    assert not bad, [(i, lens[i], idents[i]) for i in bad[:10]]

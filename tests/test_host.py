@@ -220,11 +220,14 @@ def test_error_model_file_loading(tmp_path):
 
 
 def test_library_rebuilds_when_any_device_header_changes():
-    """The in-tree build must pick up edits to every .cuh (a stale libbadread_b200.so silently runs old kernels)."""
+    """The in-tree build must pick up edits to every header (a stale libbadread_b200.so silently runs old kernels):
+    every object depends on all .cuh / .h files, and the library on every object."""
     import pathlib
     csrc = pathlib.Path(__file__).resolve().parent.parent / 'badread_b200' / 'csrc'
-    rule = [ln for ln in (csrc / 'Makefile').read_text().splitlines() if ln.startswith('$(OUT):')]
-    assert len(rule) == 1
-    deps = rule[0]
-    assert '$(wildcard *.cuh)' in deps or all(h.name in deps for h in csrc.glob('*.cuh'))
-    assert 'bb_api.cu' in deps and 'bb_host.cpp' in deps and 'badread_b200.h' in deps
+    mk = (csrc / 'Makefile').read_text()
+    hdrs = [ln for ln in mk.splitlines() if ln.startswith('HDRS')]
+    assert len(hdrs) == 1 and '$(wildcard *.cuh)' in hdrs[0] and '$(wildcard *.h)' in hdrs[0] and 'badread_b200.h' in hdrs[0]
+    obj_rules = [ln for ln in mk.splitlines() if ln.startswith('$(BUILD)/') and ':' in ln]
+    assert obj_rules and all('$(HDRS)' in ln for ln in obj_rules)
+    assert '$(wildcard bb_tu_*.cu)' in mk and 'bb_api.cu' in mk and 'bb_host.cpp' in mk
+    assert [ln for ln in mk.splitlines() if ln.startswith('$(OUT): $(OBJS)')]
