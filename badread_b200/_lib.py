@@ -28,6 +28,32 @@ class ReadResult(ctypes.Structure):
                 ('loop_kcycles', ctypes.c_int32), ('align_kcycles', ctypes.c_int32)]
 
 
+class PlanConfig(ctypes.Structure):
+    """bb_plan_config (include/badread_b200.h)."""
+    _fields_ = [('seed', ctypes.c_uint64), ('n_contigs', ctypes.c_int32), ('contig_len', ctypes.c_void_p),
+                ('contig_weight', ctypes.c_void_p), ('contig_flags', ctypes.c_void_p), ('contig_names', ctypes.c_char_p),
+                ('contig_name_off', ctypes.c_void_p),
+                ('frag_mean', ctypes.c_double), ('frag_stdev', ctypes.c_double), ('gamma_k', ctypes.c_double),
+                ('gamma_t', ctypes.c_double),
+                ('identity_type', ctypes.c_int32), ('id_mean', ctypes.c_double), ('id_stdev', ctypes.c_double),
+                ('id_max', ctypes.c_double), ('beta_a', ctypes.c_double), ('beta_b', ctypes.c_double),
+                ('start_adapter', ctypes.c_char_p), ('start_adapter_len', ctypes.c_int32),
+                ('start_adapter_rate', ctypes.c_double), ('start_adapter_amount', ctypes.c_double),
+                ('end_adapter', ctypes.c_char_p), ('end_adapter_len', ctypes.c_int32),
+                ('end_adapter_rate', ctypes.c_double), ('end_adapter_amount', ctypes.c_double),
+                ('junk_rate', ctypes.c_double), ('random_rate', ctypes.c_double), ('chimera_rate', ctypes.c_double),
+                ('chimera_end_adapter_chance', ctypes.c_double), ('chimera_start_adapter_chance', ctypes.c_double),
+                ('glitch_rate', ctypes.c_double), ('glitch_size', ctypes.c_double), ('glitch_skip', ctypes.c_double)]
+
+
+class PlanView(ctypes.Structure):
+    """bb_plan_view (include/badread_b200.h)."""
+    _fields_ = [('n_reads', ctypes.c_int32), ('read_index', ctypes.c_void_p), ('seg_off', ctypes.c_void_p),
+                ('segs', ctypes.c_void_p), ('literals', ctypes.c_void_p), ('literal_len', ctypes.c_int64),
+                ('target_identity', ctypes.c_void_p), ('read_names', ctypes.c_void_p), ('info_off', ctypes.c_void_p),
+                ('info', ctypes.c_void_p), ('frag_len', ctypes.c_void_p)]
+
+
 class LibraryMissing(RuntimeError):
     pass
 
@@ -69,6 +95,13 @@ def lib():
         'bb_align_path': (c.c_int, [vp, vp, i32, vp, i32, vp, i64, P(i64), P(i32)]),
         'bb_host_align_kmers': (c.c_int, [c.c_int, i32, vp, vp, vp, vp, vp, vp, i64, P(i64)]),
         'bb_host_align_path': (c.c_int, [vp, i32, vp, i32, vp, i64, P(i64), P(i32)]),
+        'bb_planner_create': (c.c_int, [P(vp), P(PlanConfig)]),
+        'bb_planner_destroy': (c.c_int, [vp]),
+        'bb_planner_plan': (c.c_int, [vp, u64, u64, i32, i32]),
+        'bb_planner_view': (c.c_int, [vp, P(PlanView)]),
+        'bb_planner_error': (c.c_char_p, [vp]),
+        'bb_fastq_format': (c.c_int, [P(PlanView), vp, vp, vp, i32, i64, i64, i32, vp, i64, P(i64), P(i32), P(i64), P(i32)]),
+        'bb_fastq_format_sharded': (c.c_int, [i32, vp, vp, vp, vp, i32, i64, i64, i32, vp, i64, P(i64), P(i32), P(i64), P(i32)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -82,4 +115,5 @@ EXPORTED_SYMBOLS = ['bb_create', 'bb_destroy', 'bb_last_error', 'bb_version', 'b
                     'bb_upload_error_model', 'bb_upload_qscore_model', 'bb_sequence_batch',
                     'bb_fetch_last_batch', 'bb_batch_upload', 'bb_batch_run', 'bb_synchronize', 'bb_host_alloc', 'bb_host_free',
                     'bb_last_run_ms', 'bb_stage_name', 'bb_launch_count', 'bb_get_qscores', 'bb_align_path',
-                    'bb_host_align_kmers', 'bb_host_align_path']
+                    'bb_host_align_kmers', 'bb_host_align_path', 'bb_planner_create', 'bb_planner_destroy',
+                    'bb_planner_plan', 'bb_planner_view', 'bb_planner_error', 'bb_fastq_format', 'bb_fastq_format_sharded']

@@ -20,15 +20,18 @@ namespace {
 struct DevBuf {  // grow-only device allocation
     void *p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;  // p belongs to another context (the workers of a context share its reference and tables)
+    void borrow(const DevBuf &o) { release(); p = o.p; cap = o.cap; borrowed = true; }
     cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
+        if (bytes <= cap && !borrowed) return cudaSuccess;
+        if (borrowed) { p = nullptr; cap = 0; borrowed = false; }
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -226,8 +229,7 @@ extern "C" int bb_upload_reference(bb_ctx *ctx, const uint8_t *bases, int64_t n_
     if (rc) return rc;
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->ref_len = n_bases;
-    for (bb_ctx *kid : ctx->kids)
-        if ((rc = bb_upload_reference(kid, bases, n_bases))) return set_err(ctx, rc, kid->err);
+    for (bb_ctx *kid : ctx->kids) { kid->ref.borrow(ctx->ref); kid->ref_len = n_bases; }  // one copy per GPU
     return BB_OK;
 }
 
@@ -257,10 +259,7 @@ extern "C" int bb_upload_error_model(bb_ctx *ctx, int k, int type, const int32_t
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_em = true;
     ctx->uploaded = false;
-    for (bb_ctx *kid : ctx->kids) {
-        const int rck = bb_upload_error_model(kid, k, type, kmer_to_row, n_index, n_rows, row_off, cum, flags, slots, pool, pool_len);
-        if (rck) return set_err(ctx, rck, kid->err);
-    }
+    for (bb_ctx *kid : ctx->kids) { kid->em = ctx->em; kid->have_em = true; kid->uploaded = false; }  // shared tables
     return BB_OK;
 }
 
@@ -294,8 +293,7 @@ extern "C" int bb_upload_qscore_model(bb_ctx *ctx, int kmer_size, int32_t n_keys
     ctx->qm.row_off = ctx->qm_rowoff.as<int32_t>(); ctx->qm.scores = ctx->qm_scores.as<uint8_t>();
     ctx->qm.cum = ctx->qm_cum.as<double>();
     ctx->have_qm = true;
-    for (bb_ctx *kid : ctx->kids)
-        if ((rc = bb_upload_qscore_model(kid, kmer_size, n_keys, keys, row_off, scores, cum))) return set_err(ctx, rc, kid->err);
+    for (bb_ctx *kid : ctx->kids) { kid->qm = ctx->qm; kid->have_qm = true; }  // shared tables
     return BB_OK;
 }
 

@@ -56,6 +56,9 @@ class FragmentBatch(object):
         self.add_literal_segment(fragment)
         self.end_read(read_index, target_identity)
 
+    def frag_bases(self):
+        return sum(self.seg_len)
+
     def arrays(self):
         """The flat descriptor arrays bb_batch_upload takes (built once per batch state)."""
         key = (len(self.read_index), len(self.seg_src), len(self.literals))
@@ -223,7 +226,7 @@ class Engine(object):
         self._batch_keepalive = (ri, so, segs, lit, ti)
         self._n = n = len(batch)
         if self._seq_buf is None:
-            self._ensure_out(int(1.1 * sum(batch.seg_len)) + 4096)
+            self._ensure_out(int(1.1 * batch.frag_bases()) + 4096)
         results = (ReadResult * n)()
         total = ctypes.c_int64(0)
         rc = self._lib.bb_sequence_batch(self._ctx, n, _ptr(ri), _ptr(so), ctypes.cast(segs, ctypes.c_void_p), _ptr(lit),

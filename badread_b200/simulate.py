@@ -439,64 +439,81 @@ def simulate(args, output=sys.stderr, stdout=None):
     print('', file=output)
 
     n_gpus = max(1, int(getattr(args, 'gpus', 1) or 1))
-    engines = []
+    run_batches(args, ref, frag_lengths, identities, error_model, qscore_model, seed, target_size, n_gpus, output, stdout)
+    print('\n', file=output)
+
+
+def _write_fastq(stdout, buf):
+    """FASTQ bytes to the caller's stream: the binary layer of a real file / pipe, or a text stream (tests)."""
+    raw = getattr(stdout, 'buffer', None)
+    if raw is not None:
+        stdout.flush()
+        raw.write(memoryview(buf))
+    else:
+        stdout.write(bytes(buf).decode('latin-1'))
+
+
+def run_batches(args, ref, frag_lengths, identities, error_model, qscore_model, seed, target_size, n_gpus, output, stdout):
+    """The driver loop of simulate.py:63-86 over batches of reads.  Reads are numbered 0, 1, 2, ...; a batch of B
+    indices is dealt out over the GPUs (GPU g takes indices = g mod G), planned by the native planner, sequenced on
+    the GPUs side by side (one host thread each) and written in index order until the total reaches the target, so
+    the FASTQ is independent of the batch size and of the number of GPUs."""
+    from .planner import NativePlanner, fastq_format_sharded
+    from ._lib import ReadResult
+    import os
+    engines, planners = [], []
+    threads_each = max(1, (os.cpu_count() or 1) // n_gpus)
     for g in range(n_gpus):
         eng = Engine(device=g, seed=seed)
         eng.upload_reference(ref.concat)
         eng.set_error_model(error_model)
         eng.set_qscore_model(qscore_model)
         engines.append(eng)
+        planners.append(NativePlanner(args, ref, frag_lengths, identities, seed, n_threads=threads_each))
 
     count, total_size, next_index = 0, 0, 0
     mean_len = max(1.0, float(args.mean_frag_length))
     max_batch = int(getattr(args, 'batch_reads', 0) or 16384) * n_gpus
+    out_buf = None
+    empty = np.zeros(1, dtype=np.uint8)
     print_progress(count, total_size, target_size, output)
-    while total_size < target_size:
-        want = int((target_size - total_size) / mean_len * 1.05) + 8
-        n_batch = max(1, min(max_batch, want))
-        plans = [planner.plan(next_index + i) for i in range(n_batch)]
-        results = [None] * n_gpus
+    try:
+        while total_size < target_size:
+            want = int((target_size - total_size) / mean_len * 1.05) + 8
+            n_batch = max(1, min(max_batch, want))
+            planned, results, errors = [None] * n_gpus, [None] * n_gpus, [None] * n_gpus
 
-        def work(g):
-            batch = FragmentBatch()
-            mine = list(range(g, n_batch, n_gpus))
-            for i in mine:
-                planner.add_to_batch(batch, next_index + i, plans[i][0], plans[i][2])
-            results[g] = (mine, engines[g].sequence_batch(batch)[0]) if mine else (mine, None)
+            def work(g):
+                try:
+                    n_g = len(range(g, n_batch, n_gpus))
+                    planned[g] = planners[g].plan(next_index + g, n_g, stride=n_gpus)
+                    results[g] = engines[g].sequence_batch(planned[g])[0] if n_g else None
+                except BaseException as e:   # re-raised on the main thread (a worker thread would swallow it)
+                    errors[g] = e
 
-        if n_gpus == 1:
-            work(0)
-        else:
-            threads = [threading.Thread(target=work, args=(g,)) for g in range(n_gpus)]
-            for t in threads:
-                t.start()
-            for t in threads:
-                t.join()
-        where = {}
-        for g in range(n_gpus):
-            mine, res = results[g]
-            for j, i in enumerate(mine):
-                where[i] = (res, j)
-        for i in range(n_batch):
-            if total_size >= target_size:
-                break
-            res, j = where[i]
-            seq, quals = res.read(j)
-            if len(seq) == 0:
-                continue
-            pieces, info, _, read_name = plans[i]
-            info = list(info)
-            info.append(f'length={len(seq)}')
-            info.append(f'error-free_length={res.records[j].frag_len}')
-            info.append(f'read_identity={res.identity(j) * 100.0:.3f}%')
-            print(f'@{read_name} {" ".join(info)}', file=stdout)
-            print(seq, file=stdout)
-            print('+', file=stdout)
-            print(quals, file=stdout)
-            total_size += len(seq)
-            count += 1
+            if n_gpus == 1:
+                work(0)
+            else:
+                threads = [threading.Thread(target=work, args=(g,)) for g in range(n_gpus)]
+                for t in threads:
+                    t.start()
+                for t in threads:
+                    t.join()
+            for e in errors:
+                if e is not None:
+                    raise e
+            recs = [r.records if r is not None else (ReadResult * 1)() for r in results]
+            seqs = [r.seq if r is not None else empty for r in results]
+            quals = [r.qual if r is not None else empty for r in results]
+            buf, n_emit, bases, _, out_buf = fastq_format_sharded(planned, recs, seqs, quals, 0, total_size, target_size,
+                                                                  out=out_buf)
+            _write_fastq(stdout, buf)
+            total_size += bases
+            count += n_emit
             print_progress(count, total_size, target_size, output)
-        next_index += n_batch
-    for eng in engines:
-        eng.close()
-    print('\n', file=output)
+            next_index += n_batch
+    finally:
+        for eng in engines:
+            eng.close()
+        for pl in planners:
+            pl.close()

@@ -155,6 +155,75 @@ BB_API int bb_host_align_kmers(int k, int32_t n_alts, const uint8_t *kmers, cons
 BB_API int bb_host_align_path(const uint8_t *query, int32_t q_len, const uint8_t *target, int32_t t_len, uint8_t *ops_out,
                        int64_t ops_cap, int64_t *n_ops, int32_t *distance);
 
+
+/* ---- fragment builder and FASTQ assembly on the host (no GPU needed) -------------------------------- */
+/* The steps either side of the hot path, as native multi-threaded host code.  bb_planner_plan replaces the per-read
+ * Python of build_fragment (badread/simulate.py:91-115), get_fragment / get_real_fragment / get_junk_fragment
+ * (:148-253), the adapters (:361-394), add_glitches (:459-482), FragmentLengths.get_fragment_length
+ * (fragment_lengths.py:47-64) and Identities.get_identity (identities.py:76-94); it emits fragment DESCRIPTORS in
+ * exactly the layout bb_batch_upload / bb_sequence_batch take.  Every read draws from its own random.Random /
+ * numpy RandomState keyed by (seed, read index), restated bit for bit. */
+typedef struct bb_planner bb_planner;
+
+typedef struct bb_plan_config {
+    uint64_t seed;
+    /* reference (misc.load_fasta, simulate.py:118-121): contigs in file order */
+    int32_t n_contigs;
+    const int64_t *contig_len;
+    const double *contig_weight;     /* depth * length after adjust_depths (simulate.py:516-536) */
+    const uint8_t *contig_flags;     /* bit 0 circular, bit 1 hairpin_left, bit 2 hairpin_right */
+    const char *contig_names;        /* concatenated; contig i is [contig_name_off[i], contig_name_off[i+1]) */
+    const int64_t *contig_name_off;
+    /* fragment lengths (fragment_lengths.py): stdev == 0 => constant */
+    double frag_mean, frag_stdev, gamma_k, gamma_t;
+    /* identities (identities.py): type 0 beta (mean, max as fractions), 1 normal (mean, stdev as qscores) */
+    int32_t identity_type;
+    double id_mean, id_stdev, id_max, beta_a, beta_b;
+    /* adapters (simulate.py:361-394): rate / amount as fractions */
+    const uint8_t *start_adapter; int32_t start_adapter_len; double start_adapter_rate, start_adapter_amount;
+    const uint8_t *end_adapter; int32_t end_adapter_len; double end_adapter_rate, end_adapter_amount;
+    /* read types (simulate.py:168-180) and chimeras (:101-110), as fractions */
+    double junk_rate, random_rate, chimera_rate, chimera_end_adapter_chance, chimera_start_adapter_chance;
+    /* glitches (simulate.py:459-482) */
+    double glitch_rate, glitch_size, glitch_skip;
+} bb_plan_config;
+
+/* The last plan of a planner (pointers stay valid until the next bb_planner_plan / bb_planner_destroy). */
+typedef struct bb_plan_view {
+    int32_t n_reads;
+    const uint64_t *read_index;      /* [n] */
+    const int32_t *seg_off;          /* [n+1] */
+    const bb_segment *segs;
+    const uint8_t *literals;
+    int64_t literal_len;
+    const double *target_identity;   /* [n] */
+    const uint8_t *read_names;       /* [n][16]: uuid.UUID(int=random.getrandbits(128)).bytes (simulate.py:77) */
+    const int64_t *info_off;         /* [n+1] into info */
+    const char *info;                /* ' '.join(info) of simulate.py:97-113, before the length fields */
+    const int32_t *frag_len;         /* [n] len(fragment) */
+} bb_plan_view;
+
+BB_API int bb_planner_create(bb_planner **planner, const bb_plan_config *config);
+BB_API int bb_planner_destroy(bb_planner *planner);
+/* Plans reads first_index, first_index + stride, ... (n_reads of them) with n_threads host threads.
+ * BB_ERR_STATE: a read could not be built (the reference exits with bb_planner_error()'s message, simulate.py:164). */
+BB_API int bb_planner_plan(bb_planner *planner, uint64_t first_index, uint64_t stride, int32_t n_reads, int32_t n_threads);
+BB_API int bb_planner_view(const bb_planner *planner, bb_plan_view *view);
+BB_API const char *bb_planner_error(const bb_planner *planner);
+
+/* FASTQ records of simulate.py:70-86 for reads [first, n) of a finished batch in plan order, into out: empty reads
+ * are skipped; stops after the read with which bases_so_far + emitted bases reaches target_bases.  *out_len = bytes
+ * needed (BB_ERR_CAPACITY if out_cap is smaller), *next_read = first read not consumed. */
+BB_API int bb_fastq_format(const bb_plan_view *view, const bb_read_result *results, const uint8_t *seq, const uint8_t *qual,
+                    int32_t first, int64_t bases_so_far, int64_t target_bases, int32_t n_threads, uint8_t *out,
+                    int64_t out_cap, int64_t *out_len, int32_t *n_emitted, int64_t *bases_emitted, int32_t *next_read);
+/* The same for a batch dealt out over n_shards contexts (GPUs): read j of the batch is read j / n_shards of shard
+ * j % n_shards (views[g], results[g], seq[g], qual[g]); records come out in read-index order, independent of n_shards. */
+BB_API int bb_fastq_format_sharded(int32_t n_shards, const bb_plan_view *const *views, const bb_read_result *const *results,
+                            const uint8_t *const *seq, const uint8_t *const *qual, int32_t first, int64_t bases_so_far,
+                            int64_t target_bases, int32_t n_threads, uint8_t *out, int64_t out_cap, int64_t *out_len,
+                            int32_t *n_emitted, int64_t *bases_emitted, int32_t *next_read);
+
 #ifdef __cplusplus
 }
 #endif
