@@ -229,5 +229,5 @@ def test_library_rebuilds_when_any_device_header_changes():
     assert len(hdrs) == 1 and '$(wildcard *.cuh)' in hdrs[0] and '$(wildcard *.h)' in hdrs[0] and 'badread_b200.h' in hdrs[0]
     obj_rules = [ln for ln in mk.splitlines() if ln.startswith('$(BUILD)/') and ':' in ln]
     assert obj_rules and all('$(HDRS)' in ln for ln in obj_rules)
-    assert '$(wildcard bb_tu_*.cu)' in mk and 'bb_api.cu' in mk and 'bb_host.cpp' in mk
+    assert '$(wildcard bb_tu_*.cu)' in mk and 'bb_api.cu' in mk and 'bb_host.o' in mk and 'bb_planner.o' in mk
     assert [ln for ln in mk.splitlines() if ln.startswith('$(OUT): $(OBJS)')]
