@@ -2,6 +2,10 @@
 Command line of badread_b200: `python -m badread_b200 simulate ...` with the flags, defaults and validation
 messages of `badread simulate` (/root/reference/badread/__main__.py:83-147, 239-336). Additive flags: --gpus,
 --batch_reads. The model-building and plotting subcommands of Badread are outside this package's scope.
+
+Derived from Badread (Copyright 2018 Ryan Wick, rrwick@gmail.com, https://github.com/rrwick/Badread), which is free
+software under the GNU General Public License version 3 or later; this file mirrors the named parts of the
+reference's interface and is distributed under the same licence (see LICENSE and NOTICE at the repository root).
 """
 import argparse
 import pathlib

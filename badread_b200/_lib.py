@@ -91,6 +91,7 @@ def lib():
         'bb_last_run_ms': (c.c_int, [vp, P(c.c_float), P(c.c_float)]),
         'bb_stage_name': (c.c_char_p, [c.c_int]),
         'bb_launch_count': (i64, [vp]),
+        'bb_trace_dump': (c.c_int, [vp, c.c_char_p]),
         'bb_get_qscores': (c.c_int, [vp, u64, vp, i32, vp, i32, vp, P(i32), P(i32)]),
         'bb_align_path': (c.c_int, [vp, vp, i32, vp, i32, vp, i64, P(i64), P(i32)]),
         'bb_host_align_kmers': (c.c_int, [c.c_int, i32, vp, vp, vp, vp, vp, vp, i64, P(i64)]),
@@ -114,6 +115,6 @@ def lib():
 EXPORTED_SYMBOLS = ['bb_create', 'bb_destroy', 'bb_last_error', 'bb_version', 'bb_upload_reference',
                     'bb_upload_error_model', 'bb_upload_qscore_model', 'bb_sequence_batch',
                     'bb_fetch_last_batch', 'bb_batch_upload', 'bb_batch_run', 'bb_synchronize', 'bb_host_alloc', 'bb_host_free',
-                    'bb_last_run_ms', 'bb_stage_name', 'bb_launch_count', 'bb_get_qscores', 'bb_align_path',
+                    'bb_last_run_ms', 'bb_stage_name', 'bb_launch_count', 'bb_trace_dump', 'bb_get_qscores', 'bb_align_path',
                     'bb_host_align_kmers', 'bb_host_align_path', 'bb_planner_create', 'bb_planner_destroy',
                     'bb_planner_plan', 'bb_planner_view', 'bb_planner_error', 'bb_fastq_format', 'bb_fastq_format_sharded']

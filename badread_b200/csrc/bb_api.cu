@@ -72,6 +72,7 @@ struct bb_ctx {
     BBScratchPool pool{};
     DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist;
     DevBuf d_ctime, d_chlog, d_wres, d_wtasks, d_wfallback, d_active;
+    DevBuf p_q, p_t, p_ops, p_dcnt, p_out, p_qual;  // single-pair entry points (bb_align_path / bb_get_qscores): kept between calls
     int lane8_cols = 4096, lane16_cols = 0;  // routing limits of the lane node kernels (tuning knobs)
     int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
     struct QueueBufs { DevBuf node[BBQ_NODE_CLASSES][2], leaf[2], count; } qbuf[2];  // [0] normal, [1] wide-root reads
@@ -89,7 +90,27 @@ struct bb_ctx {
     std::vector<int64_t> part_base;           // offset of worker w's block in the fetched seq / qual buffers
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     std::atomic<int> scan_ready{0};           // 1: out_total of the current run is known, -1: the run failed before that
+
+    // launch trace (BADREAD_B200_TRACE=1): an event after every launch / host step of a run, dumped by bb_trace_dump
+    bool trace = false;
+    struct Mark { const char *name; int stream; cudaEvent_t ev; };
+    std::vector<Mark> marks;
+    std::vector<cudaEvent_t> mark_pool;
+    size_t mark_used = 0;
 };
+
+// Records "the work enqueued on `st` up to here is done" under `name` (tracing only).
+static void mark(bb_ctx *ctx, cudaStream_t st, const char *name) {
+    if (!ctx->trace) return;
+    if (ctx->mark_used == ctx->mark_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        ctx->mark_pool.push_back(e);
+    }
+    cudaEvent_t e = ctx->mark_pool[ctx->mark_used++];
+    cudaEventRecord(e, st);
+    ctx->marks.push_back(bb_ctx::Mark{name, st == ctx->stream2 ? 1 : 0, e});
+}
 
 static thread_local std::string g_create_error;
 
@@ -160,6 +181,7 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed) {
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     // persistent warps: 4 CTAs of 4 warps per SM for the warp-per-read kernels
     ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
+    if (const char *e = std::getenv("BADREAD_B200_TRACE")) ctx->trace = (e[0] == '1');
     if (const char *e = std::getenv("BADREAD_B200_LANE8_COLS")) ctx->lane8_cols = std::atoi(e);
     if (const char *e = std::getenv("BADREAD_B200_LANE16_COLS")) ctx->lane16_cols = std::atoi(e);
     if (const char *e = std::getenv("BADREAD_B200_PAIR_CTAS")) ctx->pair_ctas = (e[0] == '2') ? 2 : 1;
@@ -200,7 +222,8 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
                       &ctx->d_wtasks, &ctx->d_wfallback, &ctx->d_active,
-                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist};
+                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist,
+                      &ctx->p_q, &ctx->p_t, &ctx->p_ops, &ctx->p_dcnt, &ctx->p_out, &ctx->p_qual};
     for (auto &qb : ctx->qbuf) {
         for (auto &cl : qb.node) for (auto &d : cl) d.release();
         qb.leaf[0].release(); qb.leaf[1].release(); qb.count.release();
@@ -452,6 +475,7 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
         BB_CUDA(ctx, cudaMemsetAsync(cnt + 8, 0, 8 * sizeof(int), st));
         bbl_mutate(std::min(ctx->sm_count * 8, n_active), st, B, ctx->em, ctx->seed, cnt + 8, ctx->d_active.as<int>(), n_active);
         ctx->launches++;
+        mark(ctx, st, "mutate");
         BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
         BB_CUDA(ctx, cudaStreamSynchronize(st));
         tasks.clear();
@@ -468,15 +492,20 @@ static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev
             BBWinTask *fb1 = ctx->d_wfallback.as<BBWinTask>(), *fb2 = fb1 + n_tasks;
             const int lane_grid = std::min(lane_ctas, (n_tasks + 63) / 64);
             const int lane_grid4 = std::min(2 * lane_ctas, (n_tasks + 63) / 64);  // half the history per thread
+            mark(ctx, st, "host:window_tasks");
             bbl_window_lane4(lane_grid4, st, B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
                              ctx->s_leafhist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), cnt + 9, fb1, cnt + 10);
+            mark(ctx, st, "window_lane4");
             bbl_window_lane8(lane_grid, st, B, ctx->em, fb1, cnt + 10, ctx->seed, ctx->s_leafhist.as<uint2>(),
                              ctx->s_ltbuf.as<uint8_t>(), cnt + 13, fb2, cnt + 14);
+            mark(ctx, st, "window_lane8");
             bbl_window_warp(ctx->sm_count * 2, st, B, ctx->em, ctx->pool, fb2, cnt + 14, ctx->seed, cnt + 11);
+            mark(ctx, st, "window_warp");
             ctx->launches += 3;
         }
         bb_k_replay<<<(n_active + 127) / 128, 128, 0, st>>>(B, ctx->d_active.as<int>(), n_active, ctx->em.k);
         ctx->launches++;
+        mark(ctx, st, "replay");
         BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
         BB_CUDA(ctx, cudaStreamSynchronize(st));
         std::vector<int> next;
@@ -536,10 +565,14 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
             if (s == 1) {
                 bbl_node_pair(ctx->sm_count * ctx->pair_ctas, st, B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
                 ctx->launches++;
+                mark(ctx, st, "node_pair");
             }
             bbl_node_warp4(grid_lean[s], st, B, Q[s], ctx->pool, BBQ_NODE_LEAN, p, cursor[s]++, warp_base[s]);
+            mark(ctx, st, "node_warp4");
             bbl_node_lane16(lane_ctas, st, B, Q[s], p, cursor[s]++);
+            mark(ctx, st, "node_lane16");
             bbl_node_lane8(ctx->sm_count * 6, st, B, Q[s], p, cursor[s]++);
+            mark(ctx, st, "node_lane8");
             ctx->launches += 3;
         }
         if (level >= 3 && (level & 3) == 3) {  // every few levels: stop as soon as all queues are empty
@@ -555,7 +588,9 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
     for (int s = 0; s < 2; s++) {
         cudaStream_t st = stream[s];
         bbl_leaf_warp(ctx->sm_count, st, B, Q[s], ctx->pool, cursor[s]++, warp_base[s]);
+        mark(ctx, st, "leaf_warp");
         bbl_leaf_lane(lane_ctas, st, B, Q[s], ctx->s_leafhist.as<uint2>() + s * hist_per_pipe, cursor[s]++);
+        mark(ctx, st, "leaf_lane");
         ctx->launches += 2;
     }
     BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, stream[1]));
@@ -581,8 +616,11 @@ static int w_batch_run(bb_ctx *ctx) {
                                  cudaMemcpyHostToDevice, st));
     BB_CUDA(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(int), st));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    ctx->marks.clear(); ctx->mark_used = 0;
+    mark(ctx, st, "begin");
     bb_k_build_fragments<<<n, 256, 0, st>>>(B, ctx->ref.as<uint8_t>(), ctx->em.k, ctx->seed);
     ctx->launches++;
+    mark(ctx, st, "build_fragments");
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // one thread per read; reads whose windows exceed the lane-mode limits are redone by the warp kernel
     std::vector<BBReadDev> reads((size_t)n);
@@ -630,8 +668,10 @@ static int w_batch_run(bb_ctx *ctx) {
     BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, reads.data(), (size_t)n * sizeof(BBReadDev), cudaMemcpyHostToDevice, st));
     BB_CUDA(ctx, cudaMemsetAsync(ctx->d_dcnt.p, 0, ((size_t)seq_off + 16) * sizeof(unsigned int), st));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    mark(ctx, st, "host:scan");
     bb_k_join<<<n, 256, 0, st>>>(B, ctx->em);
     ctx->launches++;
+    mark(ctx, st, "join");
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
     {
         int rc2 = run_align_tasks(ctx, B, reads);
@@ -639,11 +679,14 @@ static int w_batch_run(bb_ctx *ctx) {
         BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
     }
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+    mark(ctx, st, "align_tail");
     bb_k_qscores<<<n, 256, 0, st>>>(B, ctx->qm, ctx->seed);
     ctx->launches++;
+    mark(ctx, st, "qscores");
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
     bb_k_compact<<<n, 256, 0, st>>>(B);
     ctx->launches++;
+    mark(ctx, st, "compact");
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
     BB_CUDA(ctx, cudaGetLastError());
     ctx->ran = true;
@@ -828,6 +871,34 @@ extern "C" int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms) {
     return BB_OK;
 }
 
+// Launch trace of the last run (BADREAD_B200_TRACE=1) as CSV: worker, stream, name, begin_ms, end_ms relative to the
+// first worker's first mark; "begin" is the previous mark on the same worker and stream.
+extern "C" int bb_trace_dump(bb_ctx *ctx, const char *path) {
+    if (!ctx || !path) return BB_ERR_ARG;
+    if (!ctx->trace || ctx->marks.empty()) return set_err(ctx, BB_ERR_STATE, "no trace (set BADREAD_B200_TRACE=1 before bb_create)");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    BB_CUDA(ctx, cudaDeviceSynchronize());
+    FILE *f = std::fopen(path, "w");
+    if (!f) return set_err(ctx, BB_ERR_ARG, "cannot open trace file");
+    std::fprintf(f, "worker,stream,name,begin_ms,end_ms\n");
+    const cudaEvent_t base = ctx->marks[0].ev;
+    const int S = ctx->n_split;
+    for (int w = 0; w < S; w++) {
+        bb_ctx *wk = w == 0 ? ctx : ctx->kids[(size_t)w - 1];
+        float prev[2] = {0.f, 0.f};
+        bool have[2] = {false, false};
+        for (const bb_ctx::Mark &m : wk->marks) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, base, m.ev) != cudaSuccess) continue;
+            const float b = have[m.stream] ? prev[m.stream] : (have[0] ? prev[0] : t);
+            std::fprintf(f, "%d,%d,%s,%.4f,%.4f\n", w, m.stream, m.name, b, t);
+            prev[m.stream] = t; have[m.stream] = true;
+        }
+    }
+    std::fclose(f);
+    return BB_OK;
+}
+
 extern "C" int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t *seq_out, uint8_t *qual_out,
                                    int64_t out_cap, int64_t *out_total) {
     if (!ctx) return BB_ERR_ARG;
@@ -953,7 +1024,7 @@ extern "C" int bb_align_path(bb_ctx *ctx, const uint8_t *query, int32_t q_len, c
     if (!ctx) return BB_ERR_ARG;
     if (!query || !target || q_len <= 0 || t_len <= 0) return set_err(ctx, BB_ERR_ARG, "bb_align_path: empty sequence");
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
-    DevBuf dq, dt, dops, ddcnt, dout;
+    DevBuf &dq = ctx->p_q, &dt = ctx->p_t, &dops = ctx->p_ops, &ddcnt = ctx->p_dcnt, &dout = ctx->p_out;
     int out5[5] = {0, 0, 0, 0, 0};
     int rc = align_pair_device(ctx, query, q_len, target, t_len, dq, dt, dops, ddcnt, dout, out5);
     std::vector<uint8_t> ops((size_t)q_len);
@@ -962,7 +1033,6 @@ extern "C" int bb_align_path(bb_ctx *ctx, const uint8_t *query, int32_t q_len, c
         cudaMemcpy(ops.data(), dops.p, (size_t)q_len, cudaMemcpyDeviceToHost);
         cudaMemcpy(dcnt.data(), ddcnt.p, (size_t)q_len * sizeof(unsigned int), cudaMemcpyDeviceToHost);
     }
-    dq.release(); dt.release(); dops.release(); ddcnt.release(); dout.release();
     if (rc) return rc;
     const int64_t total = (int64_t)q_len + out5[1];
     if (n_ops) *n_ops = total;
@@ -986,7 +1056,7 @@ extern "C" int bb_get_qscores(bb_ctx *ctx, uint64_t read_index, const uint8_t *s
     if (!seq || !frag || seq_len <= 0 || frag_len <= 0 || !qual_out) return set_err(ctx, BB_ERR_ARG, "bb_get_qscores: bad arguments");
     if (!ctx->have_qm) return set_err(ctx, BB_ERR_STATE, "upload the qscore model first");
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
-    DevBuf dq, dt, dops, ddcnt, dout, dqual;
+    DevBuf &dq = ctx->p_q, &dt = ctx->p_t, &dops = ctx->p_ops, &ddcnt = ctx->p_dcnt, &dout = ctx->p_out, &dqual = ctx->p_qual;
     int out5[5] = {0, 0, 0, 0, 0};
     int rc = align_pair_device(ctx, seq, seq_len, frag, frag_len, dq, dt, dops, ddcnt, dout, out5);
     if (rc == BB_OK) {
@@ -1001,7 +1071,6 @@ extern "C" int bb_get_qscores(bb_ctx *ctx, uint64_t read_index, const uint8_t *s
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = set_err(ctx, BB_ERR_CUDA, cudaGetErrorString(e));
     }
-    dq.release(); dt.release(); dops.release(); ddcnt.release(); dout.release(); dqual.release();
     if (rc) return rc;
     if (matches) *matches = out5[0];
     if (columns) *columns = seq_len + out5[1];

@@ -205,6 +205,10 @@ class Engine(object):
     def launch_count(self):
         return int(self._lib.bb_launch_count(self._ctx))
 
+    def trace_dump(self, path):
+        """Timeline of the last run (needs BADREAD_B200_TRACE=1 in the environment before the Engine is created)."""
+        self._check(self._lib.bb_trace_dump(self._ctx, str(path).encode()), 'bb_trace_dump')
+
     def fetch_batch(self):
         n = self._n
         results = (ReadResult * n)()

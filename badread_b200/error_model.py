@@ -17,6 +17,10 @@ Table layout (shared by the CUDA path and the CPU oracle):
                     slots  k encoded slot strings: len | chars << 8 for len <= 3, else len | pool_offset << 8
 The slot strings come from align_kmers (error_model.py:179-229), run for the whole file by the host helper
 `bb_host_align_kmers` (csrc/bb_host.cpp).
+
+Derived from Badread (Copyright 2018 Ryan Wick, rrwick@gmail.com, https://github.com/rrwick/Badread), which is free
+software under the GNU General Public License version 3 or later; this file mirrors the named parts of the
+reference's interface and is distributed under the same licence (see LICENSE and NOTICE at the repository root).
 """
 import ctypes
 import itertools

@@ -3,6 +3,10 @@ FragmentLengths - gamma-distributed fragment lengths, same surface as
 /root/reference/badread/fragment_lengths.py:25-64 (`FragmentLengths(mean, stdev, output)`,
 `get_fragment_length()`, `gamma_k`, `gamma_t`). The N50 line of the banner needs scipy and is printed when scipy
 imports; the ASCII histogram of the reference's banner is presentation only and is not reproduced.
+
+Derived from Badread (Copyright 2018 Ryan Wick, rrwick@gmail.com, https://github.com/rrwick/Badread), which is free
+software under the GNU General Public License version 3 or later; this file mirrors the named parts of the
+reference's interface and is distributed under the same licence (see LICENSE and NOTICE at the repository root).
 """
 import sys
 

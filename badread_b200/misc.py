@@ -2,6 +2,10 @@
 Small host-side helpers with the semantics of /root/reference/badread/misc.py that the `simulate` surface needs:
 FASTA loading (misc.py:122-153), reverse complement (misc.py:56-71), the random helpers (misc.py:156-182),
 identity_from_edlib_cigar (misc.py:228-240) and number formatting (misc.py:192-202).
+
+Derived from Badread (Copyright 2018 Ryan Wick, rrwick@gmail.com, https://github.com/rrwick/Badread), which is free
+software under the GNU General Public License version 3 or later; this file mirrors the named parts of the
+reference's interface and is distributed under the same licence (see LICENSE and NOTICE at the repository root).
 """
 import collections
 import contextlib

@@ -7,6 +7,10 @@ plus `to_device_tables()` for `bb_upload_qscore_model`, and the module-level `ge
 Device table layout: every CIGAR key over {=,X,I,D} is packed two bits per symbol ('='=0, 'X'=1, 'I'=2, 'D'=3)
 under a leading 1 bit (so keys of different lengths never collide; at most 31 symbols); row_off / scores / cum per
 key, cum = list(itertools.accumulate(probabilities)) as random.choices builds it (qscore_model.py:283).
+
+Derived from Badread (Copyright 2018 Ryan Wick, rrwick@gmail.com, https://github.com/rrwick/Badread), which is free
+software under the GNU General Public License version 3 or later; this file mirrors the named parts of the
+reference's interface and is distributed under the same licence (see LICENSE and NOTICE at the repository root).
 """
 import ctypes
 import itertools
@@ -171,10 +175,12 @@ class QScoreModel(object):
 
 def get_qscores(seq, frag, qscore_model):
     """qscore_model.py:32-75 on the GPU: returns (qual, actual_identity, identity_by_qscores)."""
-    from .engine import default_engine
+    from .engine import default_engine, next_read_index
     assert len(seq) > 0
     eng = default_engine(qscore_model=qscore_model)
-    qual, matches, columns = eng.get_qscores(seq, frag)
+    # every call draws from the Philox streams of a fresh read index (successive calls are independent, like the
+    # reference's advancing `random` stream; sequence_fragment() numbers its reads from the same counter)
+    qual, matches, columns = eng.get_qscores(seq, frag, read_index=next_read_index())
     actual_identity = matches / columns if columns else 0.0
     identity_by_qscores = 1.0 - statistics.mean(qscore_char_to_error_prob(q) for q in qual)
     return qual, actual_identity, identity_by_qscores

@@ -2,6 +2,10 @@
 Constants of the hot path, mirroring /root/reference/badread/settings.py:24-51 (same names, same values).
 ALIGNMENT_INTERVAL / ALIGNMENT_SIZE are compiled into the kernels (csrc/bb_kernels.cuh); they are listed here
 because the reference exposes them as module attributes.
+
+Derived from Badread (Copyright 2018 Ryan Wick, rrwick@gmail.com, https://github.com/rrwick/Badread), which is free
+software under the GNU General Public License version 3 or later; this file mirrors the named parts of the
+reference's interface and is distributed under the same licence (see LICENSE and NOTICE at the repository root).
 """
 ALIGNMENT_INTERVAL = 25
 ALIGNMENT_SIZE = 1000

@@ -14,6 +14,10 @@ What runs where:
     data-dependent per read and cannot be reproduced in parallel; with per-read streams the FASTQ depends only
     on --seed, never on batch size or GPU count.  Reads are emitted in index order until the total reaches the
     target (simulate.py:63), skipping empty reads (simulate.py:70).
+
+Derived from Badread (Copyright 2018 Ryan Wick, rrwick@gmail.com, https://github.com/rrwick/Badread), which is free
+software under the GNU General Public License version 3 or later; this file mirrors the named parts of the
+reference's interface and is distributed under the same licence (see LICENSE and NOTICE at the repository root).
 """
 import random
 import statistics

@@ -412,6 +412,9 @@ def main():
     elapsed = wall if nb == 1 else run_s   # several batches: only the bb_batch_run spans count (see the docstring)
     clocks = sampler.stop()
     launches = eng.launch_count() - launches0
+    if os.environ.get('BADREAD_B200_TRACE') == '1':   # diagnostics: timeline of the last timed run
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        eng.trace_dump(os.path.join(ROOT, 'gpurun_out', f'trace_config{a.config}_rank{rank}.csv'))
     dev_ms = state['dev_ms']
 
     # ---- end to end through bb_sequence_batch: host descriptors in, host seq/qual out, every step

@@ -134,6 +134,9 @@ BB_API int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms);
 BB_API const char *bb_stage_name(int stage);
 /* Number of kernel launches issued by this context so far. */
 BB_API int64_t bb_launch_count(const bb_ctx *ctx);
+/* Diagnostics: with BADREAD_B200_TRACE=1 in the environment at bb_create, every launch of a run is followed by a CUDA
+ * event; this writes the last run's timeline (worker, stream, name, begin_ms, end_ms) as CSV. */
+BB_API int bb_trace_dump(bb_ctx *ctx, const char *path);
 
 /* get_qscores(seq, frag, qscore_model) on its own (qscore_model.py:32-75) for one pair; qual_out has seq_len bytes. */
 BB_API int bb_get_qscores(bb_ctx *ctx, uint64_t read_index, const uint8_t *seq, int32_t seq_len, const uint8_t *frag,

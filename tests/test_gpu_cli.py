@@ -83,8 +83,10 @@ def test_single_read_api_matches_oracle():
     frag = random_dna(rnd, 800)
     seq = frag[:300] + 'A' + frag[300:500] + frag[503:]
     qual, ident, by_q = get_qscores(seq, frag, qm)
-    q2, m, c = orc.get_qscores(seq, frag, 77, read_index=0)
+    q2, m, c = orc.get_qscores(seq, frag, 77, read_index=3)    # the module-level counter: three reads came before
     assert qual == q2 and ident == m / c
+    qual_b, _, _ = get_qscores(seq, frag, qm)
+    assert qual_b == orc.get_qscores(seq, frag, 77, read_index=4)[0] and qual_b != qual   # successive calls are independent
 
 
 @pytest.mark.parametrize('extra', [
