@@ -52,7 +52,7 @@ struct bb_ctx {
     // reference + models
     DevBuf ref; int64_t ref_len = 0;
     bool have_em = false, have_qm = false;
-    BBErrorModelDev em{}; DevBuf em_k2r, em_rowoff, em_cum, em_flags, em_slots, em_pool;
+    BBErrorModelDev em{}; DevBuf em_k2r, em_rowoff, em_cum, em_flags, em_slots, em_pool, em_rowinfo;
     BBQScoreModelDev qm{}; DevBuf qm_hkeys, qm_hvals, qm_rowoff, qm_scores, qm_cum;
 
     // batch
@@ -64,7 +64,7 @@ struct bb_ctx {
     DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_reads;
     int n_lane_reads = 0, n_long_reads = 0;
     std::vector<int> h_order;
-    DevBuf d_frag, d_state, d_seq, d_ops, d_dcnt, d_qual, d_out_seq, d_out_qual, d_counter, d_fpeq, d_speq, d_fallback;
+    DevBuf d_kidx, d_frag, d_state, d_seq, d_ops, d_dcnt, d_qual, d_out_seq, d_out_qual, d_counter, d_fpeq, d_speq, d_fallback;
     int64_t fpeq_total = 0;
 
     // scratch
@@ -216,9 +216,9 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     DevBuf *bufs[] = {&ctx->ref, &ctx->em_k2r, &ctx->em_rowoff, &ctx->em_cum, &ctx->em_flags, &ctx->em_slots,
-                      &ctx->em_pool, &ctx->qm_hkeys, &ctx->qm_hvals, &ctx->qm_rowoff, &ctx->qm_scores, &ctx->qm_cum,
+                      &ctx->em_pool, &ctx->em_rowinfo, &ctx->qm_hkeys, &ctx->qm_hvals, &ctx->qm_rowoff, &ctx->qm_scores, &ctx->qm_cum,
                       &ctx->d_read_index, &ctx->d_seg_off, &ctx->d_segs, &ctx->d_lit, &ctx->d_target, &ctx->d_order,
-                      &ctx->d_reads, &ctx->d_frag, &ctx->d_state, &ctx->d_seq, &ctx->d_ops, &ctx->d_dcnt,
+                      &ctx->d_reads, &ctx->d_kidx, &ctx->d_frag, &ctx->d_state, &ctx->d_seq, &ctx->d_ops, &ctx->d_dcnt,
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
                       &ctx->d_wtasks, &ctx->d_wfallback, &ctx->d_active,
@@ -275,9 +275,20 @@ extern "C" int bb_upload_error_model(bb_ctx *ctx, int k, int type, const int32_t
         if ((rc = upload(ctx, ctx->em_flags, flags, (size_t)ne))) return rc;
         if ((rc = upload(ctx, ctx->em_slots, slots, (size_t)ne * k))) return rc;
         if ((rc = upload(ctx, ctx->em_pool, pool, (size_t)pool_len))) return rc;
+        std::vector<BBRowInfo> info((size_t)n_rows);
+        for (int32_t r = 0; r < n_rows; r++) {
+            const int32_t e0 = row_off[r], ne = row_off[r + 1] - e0;
+            if (ne <= 0) return set_err(ctx, BB_ERR_ARG, "error model: empty table row");
+            BBRowInfo &ri = info[(size_t)r];
+            ri.cum_last = cum[e0 + ne - 1]; ri.cum0 = cum[e0]; ri.e0 = e0; ri.ne = ne;
+            ri.first_is_identity = flags[e0] == 1 ? 1 : 0; ri.pad = 0;
+        }
+        if ((rc = upload(ctx, ctx->em_rowinfo, info.data(), info.size()))) return rc;
+        BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `info` is about to go out of scope
         ctx->em.kmer_to_row = ctx->em_k2r.as<int32_t>(); ctx->em.row_off = ctx->em_rowoff.as<int32_t>();
         ctx->em.cum = ctx->em_cum.as<double>(); ctx->em.flags = ctx->em_flags.as<uint8_t>();
         ctx->em.slots = ctx->em_slots.as<uint32_t>(); ctx->em.pool = ctx->em_pool.as<uint8_t>();
+        ctx->em.rowinfo = ctx->em_rowinfo.as<BBRowInfo>();
     }
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->have_em = true;
@@ -364,6 +375,7 @@ static BBBatchDev batch_dev(bb_ctx *ctx) {
     B.reads = ctx->d_reads.as<BBReadDev>();
     B.frag = ctx->d_frag.as<uint8_t>();
     B.state = ctx->d_state.as<uint32_t>();
+    B.kidx = ctx->d_kidx.as<int>();
     B.seq = ctx->d_seq.as<uint8_t>();
     B.ops = ctx->d_ops.as<uint8_t>();
     B.dcnt = ctx->d_dcnt.as<unsigned int>();
@@ -437,6 +449,7 @@ static int w_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_ind
     if ((rc = upload(ctx, ctx->d_reads, ctx->h_reads.data(), (size_t)n_reads))) return rc;
     BB_CUDA(ctx, ctx->d_frag.ensure((size_t)off + 16));
     BB_CUDA(ctx, ctx->d_state.ensure(((size_t)off + 16) * sizeof(uint32_t)));
+    BB_CUDA(ctx, ctx->d_kidx.ensure(((size_t)off + 16) * sizeof(int)));
     BB_CUDA(ctx, ctx->d_counter.ensure(16 * sizeof(int)));
     BB_CUDA(ctx, ctx->d_fpeq.ensure(((size_t)peq_off + 4) * sizeof(uint4)));
     BB_CUDA(ctx, ctx->d_fallback.ensure(((size_t)n_reads + 4) * sizeof(int)));
@@ -618,7 +631,7 @@ static int w_batch_run(bb_ctx *ctx) {
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     ctx->marks.clear(); ctx->mark_used = 0;
     mark(ctx, st, "begin");
-    bb_k_build_fragments<<<n, 256, 0, st>>>(B, ctx->ref.as<uint8_t>(), ctx->em.k, ctx->seed);
+    bb_k_build_fragments<<<n, 256, 0, st>>>(B, ctx->ref.as<uint8_t>(), ctx->em.k, ctx->seed, ctx->em.type == 1 ? ctx->em.kmer_to_row : nullptr);
     ctx->launches++;
     mark(ctx, st, "build_fragments");
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));

@@ -23,6 +23,16 @@
 #define BB_ALIGNMENT_SIZE 1000    // settings.py:25
 #define BB_WARPS_PER_CTA 4
 
+// Everything the common outcome of a model draw needs, in one 32-byte record per table row: random.choices picks
+// entry 0 - the unchanged k-mer, p ~ 0.92 (nanopore) ... 0.99 (pacbio) - iff random() * cum_last < cum0.
+struct __align__(32) BBRowInfo {
+    double cum_last;   // cum[e0 + ne - 1]
+    double cum0;       // cum[e0]
+    int32_t e0, ne;    // entry range of the row
+    int32_t first_is_identity;  // flags[e0] == 1: ''.join(alt) == kmer and not the remainder entry
+    int32_t pad;
+};
+
 struct BBErrorModelDev {
     int k, type;
     const int32_t *kmer_to_row;
@@ -31,6 +41,7 @@ struct BBErrorModelDev {
     const uint8_t *flags;
     const uint32_t *slots;
     const uint8_t *pool;
+    const BBRowInfo *rowinfo;
 };
 
 struct BBQScoreModelDev {
@@ -86,6 +97,7 @@ struct BBBatchDev {
     uint8_t *qual;
     uint8_t *out_seq, *out_qual;
     uint4 *fpeq, *speq;
+    int *kidx;             // per fragment position: table row of the k-mer that starts there (-1: not in the model)
     unsigned int *ctime;   // per slot: ordinal of the change that rewrote it (0 = pristine)
     uint2 *chlog;          // per read: (iteration, position) of every applied change, in order
     int2 *wres;            // per read: (matches, columns) of every window alignment
@@ -114,7 +126,7 @@ __constant__ uint8_t bb_c_comp[256];  // misc.REV_COMP_DICT, unknown -> 'N' (mis
 // ------------------------------------------------------------------------------------------------ K1
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(256) bb_k_build_fragments(BBBatchDev B, const uint8_t *__restrict__ ref, int k,
-                                                            unsigned long long seed) {
+                                                            unsigned long long seed, const int32_t *__restrict__ kmer_to_row) {
     const int r = blockIdx.x;
     if (r >= B.n_reads) return;
     const BBReadDev rd = B.reads[r];
@@ -147,6 +159,20 @@ __global__ void __launch_bounds__(256) bb_k_build_fragments(BBBatchDev B, const 
     for (int x = threadIdx.x; x < flen; x += blockDim.x) { st[x] = BB_SLOT_NONE; ct[x] = 0u; }
     // match bitmap of the padded fragment (bb_build_peq layout), one ballot group per 32 bases
     __syncthreads();
+    if (kmer_to_row) {  // table row of every k-mer of the fragment: the loop looks a position up with one load
+        int *kx = B.kidx + rd.frag_off;
+        for (int x = threadIdx.x; x + k <= flen; x += blockDim.x) {
+            int idx = 0;
+            bool ok = true;
+            for (int j = 0; j < k; j++) {
+                const uint8_t c = f[x + j];
+                const int code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+                if (code < 0) ok = false;
+                idx = idx * 4 + (code & 3);
+            }
+            kx[x] = ok ? kmer_to_row[idx] : -1;
+        }
+    }
     uint4 *pq = B.fpeq + rd.fpeq_off;
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int fw = (flen + 31) >> 5;
@@ -213,8 +239,8 @@ static __device__ int bb_join_slots(const BBErrorModelDev &em, const uint8_t *fr
 // One speculative evaluation of simulate.py:294-296 for loop iteration n: position, k-mer, model draw.
 // kind 0: ''.join(new_kmer) == kmer (nothing to do); 1: table entry `payload`; 2: one random change where
 // slot `rpos` becomes the inline-encoded string `payload` (error_model.py:163-176).
-__device__ __forceinline__ void bb_eval_iteration(const BBErrorModelDev &em, const uint8_t *frag, int max_kmer_index,
-                                                  unsigned long long seed, unsigned long long read,
+__device__ __forceinline__ void bb_eval_iteration(const BBErrorModelDev &em, const uint8_t *frag, const int *kidx,
+                                                  int max_kmer_index, unsigned long long seed, unsigned long long read,
                                                   unsigned int n, int &kind, int &pos_i, uint32_t &payload,
                                                   int &rpos) {
     BBRng rng;
@@ -225,19 +251,26 @@ __device__ __forceinline__ void bb_eval_iteration(const BBErrorModelDev &em, con
     pos_i = i;
     bool random_change = (em.type == 0);
     if (!random_change) {
-        int idx = 0;
-        bool ok = true;
-        for (int j = 0; j < k; j++) {
-            const int c = bb_base_code(frag[i + j]);
-            if (c < 0) ok = false;
-            idx = idx * 4 + (c & 3);
-        }
-        const int row = ok ? em.kmer_to_row[idx] : -1;
-        if (row < 0) random_change = true;  // kmer not in self.alternatives (error_model.py:143-144)
+        const int row = kidx[i];  // kmer -> row, -1: not in self.alternatives (error_model.py:143-144) or non-ACGT
+        if (row < 0) random_change = true;
         else {
-            const int e0 = em.row_off[row], ne = em.row_off[row + 1] - e0;
-            const int e = e0 + bb_choices(rng, em.cum + e0, ne);
-            const uint8_t fl = em.flags[e];
+            const BBRowInfo ri = em.rowinfo[row];
+            // random.choices: bisect_right(cum, random() * cum[-1]); entry 0 answers whenever the product is below cum[0]
+            const double x = __dmul_rn(rng.random(), ri.cum_last);
+            int e = ri.e0;
+            uint8_t fl;
+            if (x < ri.cum0) fl = ri.first_is_identity ? 1 : em.flags[e];
+            else {
+                const double *cum = em.cum + ri.e0;
+                int lo = 1, hi = ri.ne - 1;
+                if (lo > hi) lo = hi;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (x < cum[mid]) hi = mid; else lo = mid + 1;
+                }
+                e += lo;
+                fl = em.flags[e];
+            }
             if (fl & 2) random_change = true;  // alt is None (error_model.py:157-158)
             else { kind = (fl & 1) ? 0 : 1; payload = (uint32_t)e; rpos = 0; return; }
         }

@@ -57,6 +57,7 @@ bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work
         const uint8_t *frag = B.frag + rd->frag_off;
         uint32_t *state = B.state + rd->frag_off;
         unsigned int *ctime = B.ctime + rd->frag_off;
+        const int *kidx = B.kidx + rd->frag_off;
         uint2 *chlog = B.chlog + rd->log_off;
         const int frag_len = rd->frag_len;
         const unsigned long long read = B.read_index[r];
@@ -85,7 +86,7 @@ bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work
                 const long long n = n0 + threadIdx.x;
                 int kind = 0, pos_i = 0, rpos = 0;
                 uint32_t payload = 0;
-                if (n < limit) bb_eval_iteration(em, frag, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
+                if (n < limit) bb_eval_iteration(em, frag, kidx, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
                 s_kind[threadIdx.x] = kind; s_pos[threadIdx.x] = pos_i; s_rpos[threadIdx.x] = rpos; s_pay[threadIdx.x] = payload;
             }
             __syncthreads();
