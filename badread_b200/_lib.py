@@ -14,7 +14,7 @@ LIB_PATH = _HERE / 'libbadread_b200.so'
 BB_OK = 0
 BB_ERR_CUDA, BB_ERR_ARG, BB_ERR_STATE, BB_ERR_CAPACITY, BB_ERR_INTERNAL = -1, -2, -3, -4, -5
 BB_SEG_REF_FWD, BB_SEG_REF_REV, BB_SEG_LITERAL = 0, 1, 2
-BB_N_STAGES = 9
+BB_N_STAGES = 8
 
 
 class Segment(ctypes.Structure):

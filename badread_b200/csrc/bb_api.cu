@@ -35,8 +35,8 @@ struct DevBuf {  // grow-only device allocation
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-const char *kStageNames[BB_N_STAGES] = {"build_fragments", "error_loop", "host_scan", "join", "final_align",
-                                        "final_align_dfs_lean", "qscores", "compact", "total"};
+const char *kStageNames[BB_N_STAGES] = {"build_fragments", "error_loop", "scan", "join", "final_align", "qscores",
+                                        "compact", "total"};
 
 }  // namespace
 
@@ -60,7 +60,23 @@ struct bb_ctx {
     bool uploaded = false, ran = false;
     std::vector<BBReadDev> h_reads;
     std::vector<int32_t> h_inlen;
-    int64_t frag_total = 0, seq_total = 0, out_total = 0;
+    std::vector<double> h_target;
+    int64_t frag_total = 0, out_total = 0;
+    int64_t seq_cap = 0, out_cap = 0, speq_cap = 0;  // capacities of the per-batch buffers (from the fragment lengths)
+    int64_t log_total = 0, wres_total = 0;
+    int max_len = 0;
+    // sizing knobs a retry raises (bb_k_scan / the node kernels flag what did not fit; see w_finish)
+    double slack = 1.25;       // joined reads may be this much longer than their fragments in total
+    int n_rounds = 3;          // mutate -> windows -> replay rounds enqueued without asking the device in between
+    int n_levels = 0;          // Hirschberg levels enqueued (from the longest fragment)
+    int extra_levels = 0;
+    bool lr_worst = false;     // size the split-score scratch for the worst case instead of the expected edit count
+    struct RunInfo { BBScanOut scan; int counters[256]; int qcount[2][32]; } *h_info = nullptr;  // pinned
+    std::vector<BBReadDev> h_res;  // per-read records of the finished run
+    bool finished = false;
+    bool reran = false;        // w_finish had to run the batch again (copies enqueued before that are stale)
+    DevBuf d_scan;
+    cudaEvent_t ev_scan = nullptr;
     DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_reads;
     int n_lane_reads = 0, n_long_reads = 0;
     std::vector<int> h_order;
@@ -89,7 +105,6 @@ struct bb_ctx {
     std::vector<std::vector<int32_t>> part;   // part[w][i] = batch position of worker w's i-th read
     std::vector<int64_t> part_base;           // offset of worker w's block in the fetched seq / qual buffers
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
-    std::atomic<int> scan_ready{0};           // 1: out_total of the current run is known, -1: the run failed before that
 
     // launch trace (BADREAD_B200_TRACE=1): an event after every launch / host step of a run, dumped by bb_trace_dump
     bool trace = false;
@@ -169,6 +184,10 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed) {
     cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming);
+    if (cudaHostAlloc((void **)&ctx->h_info, sizeof(bb_ctx::RunInfo), cudaHostAllocPortable) != cudaSuccess) {
+        g_create_error = "cudaHostAlloc failed"; delete ctx; return BB_ERR_CUDA;
+    }
     // misc.REV_COMP_DICT (misc.py:56-61); anything else complements to 'N' (misc.py:64-68)
     uint8_t comp[256];
     std::memset(comp, 'N', sizeof(comp));
@@ -222,7 +241,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
                       &ctx->d_wtasks, &ctx->d_wfallback, &ctx->d_active,
-                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist,
+                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->d_scan,
                       &ctx->p_q, &ctx->p_t, &ctx->p_ops, &ctx->p_dcnt, &ctx->p_out, &ctx->p_qual};
     for (auto &qb : ctx->qbuf) {
         for (auto &cl : qb.node) for (auto &d : cl) d.release();
@@ -234,6 +253,9 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_scan) cudaEventDestroy(ctx->ev_scan);
+    if (ctx->h_info) cudaFreeHost(ctx->h_info);
+    for (cudaEvent_t e : ctx->mark_pool) cudaEventDestroy(e);
     delete ctx;
     return BB_OK;
 }
@@ -390,6 +412,80 @@ static BBBatchDev batch_dev(bb_ctx *ctx) {
     return B;
 }
 
+// Counters of a run live in d_counter (256 ints, cleared once per run): [0, 16) spare; round r of the error loop owns
+// the 16 ints from BB_ROUND_BASE(r).
+#define BB_N_COUNTERS 256
+#define BB_MAX_ROUNDS 15
+#define BB_ROUND_BASE(r) (16 + 16 * (r))
+enum { BBC_MUTATE = 0, BBC_NTASKS = 1, BBC_LANE4 = 2, BBC_FB1 = 3, BBC_LANE8 = 4, BBC_FB2 = 5, BBC_WARP = 6, BBC_PENDING = 7 };
+
+// Hirschberg levels a fragment of max_len bases can need: a node is split while edlib's traceback estimate
+// 20 ceil(nn/64) mm + 8 mm reaches 1 MiB; mm halves per level and nn <= 2 mm + 64 bounds the query side generously.
+static int level_bound(int max_len, double slack) {
+    long long mm = (long long)(max_len * slack) + 64;
+    int d = 0;
+    while (20ll * ((2 * mm + 64 + 63) / 64) * mm + 8ll * mm >= 1048576ll) { mm = (mm + 1) / 2; d++; }
+    return d + 1;
+}
+
+// Every allocation a run needs, sized from the fragment lengths: a run is pure enqueueing, nothing on the host
+// depends on a value the device computes.  What turns out too small is flagged by the kernels and w_finish grows
+// the knobs (slack, n_rounds, levels, lr_worst) and runs the batch again.
+static int w_prepare(bb_ctx *ctx) {
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = ctx->n_reads;
+    const int64_t off = ctx->frag_total;
+    ctx->seq_cap = (int64_t)((double)off * ctx->slack) + 16ll * n + 65536;
+    ctx->out_cap = ctx->seq_cap;
+    ctx->speq_cap = ctx->seq_cap / 32 + (2ll * BB_PEQ_PAD + 2) * n + 64;
+    BB_CUDA(ctx, ctx->d_frag.ensure((size_t)off + 16));
+    BB_CUDA(ctx, ctx->d_state.ensure(((size_t)off + 16) * sizeof(uint32_t)));
+    BB_CUDA(ctx, ctx->d_kidx.ensure(((size_t)off + 16) * sizeof(int)));
+    BB_CUDA(ctx, ctx->d_counter.ensure(BB_N_COUNTERS * sizeof(int)));
+    BB_CUDA(ctx, ctx->d_scan.ensure(sizeof(BBScanOut)));
+    BB_CUDA(ctx, ctx->d_fpeq.ensure(((size_t)ctx->fpeq_total + 4) * sizeof(uint4)));
+    BB_CUDA(ctx, ctx->d_ctime.ensure(((size_t)off + 16) * sizeof(unsigned int)));
+    BB_CUDA(ctx, ctx->d_chlog.ensure(((size_t)ctx->log_total + 16) * sizeof(uint2)));
+    BB_CUDA(ctx, ctx->d_wres.ensure(((size_t)ctx->wres_total + 16) * sizeof(int2)));
+    BB_CUDA(ctx, ctx->d_wtasks.ensure(((size_t)ctx->wres_total + 16) * sizeof(BBWinTask)));
+    BB_CUDA(ctx, ctx->d_wfallback.ensure((2 * (size_t)ctx->wres_total + 16) * sizeof(BBWinTask)));
+    BB_CUDA(ctx, ctx->d_seq.ensure((size_t)ctx->seq_cap + 16));
+    BB_CUDA(ctx, ctx->d_ops.ensure((size_t)ctx->seq_cap + 16));
+    BB_CUDA(ctx, ctx->d_dcnt.ensure(((size_t)ctx->seq_cap + 16) * sizeof(unsigned int)));
+    BB_CUDA(ctx, ctx->d_qual.ensure((size_t)ctx->seq_cap + 16));
+    BB_CUDA(ctx, ctx->d_speq.ensure(((size_t)ctx->speq_cap + 4) * sizeof(uint4)));
+    BB_CUDA(ctx, ctx->d_out_seq.ensure((size_t)ctx->out_cap + 16));
+    BB_CUDA(ctx, ctx->d_out_qual.ensure((size_t)ctx->out_cap + 16));
+    const int lane_ctas = ctx->sm_count * 4;  // 64-thread CTAs of the lane kernels
+    {   // lane pools shared by the window aligner and the leaf aligner: history of 2048 columns x 8 words per thread
+        const size_t lanes = (size_t)lane_ctas * 64;
+        BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * lanes * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
+        BB_CUDA(ctx, ctx->s_ltbuf.ensure(2 * lanes * BB_WIN_MAX_COLS));  // the 4-word window kernel runs 2x the lanes
+    }
+    // per-warp scratch: strip carries / bitmaps for the longest joined read; split-score arrays for the widest band
+    // (expected: a few times the injected edits; worst case: the whole read)
+    const int len_b = (int)std::min<double>((double)ctx->max_len * ctx->slack + 64.0, (double)(1 << 24));
+    int lr_need = 4096;
+    for (int r = 0; r < n; r++) {
+        const double len = (double)ctx->h_reads[(size_t)r].frag_len;
+        const double worst = len * ctx->slack + 64.0;
+        const double expect = 3.0 * (1.0 - ctx->h_target[(size_t)r]) * len + 0.02 * len + 512.0;
+        lr_need = std::max(lr_need, (int)std::min(worst, ctx->lr_worst ? worst : expect));
+    }
+    int rc = ensure_scratch(ctx, len_b, lr_need, len_b);
+    if (rc) return rc;
+    const int cap_node = (int)std::min<int64_t>(ctx->seq_cap / 256 + 4ll * n + 1024, 0x7ffffff0);
+    for (int s = 0; s < 2; s++) {
+        auto &qb = ctx->qbuf[s];
+        for (int c = 0; c < BBQ_NODE_CLASSES; c++)
+            for (int p = 0; p < 2; p++) BB_CUDA(ctx, qb.node[c][p].ensure((size_t)cap_node * sizeof(BBNode)));
+        for (int w = 0; w < 2; w++) BB_CUDA(ctx, qb.leaf[w].ensure((size_t)cap_node * sizeof(BBNode)));
+        BB_CUDA(ctx, qb.count.ensure(512 * sizeof(int)));
+    }
+    ctx->n_levels = std::min(48, level_bound(ctx->max_len, ctx->slack) + ctx->extra_levels);
+    return BB_OK;
+}
+
 static int w_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_index, const int32_t *seg_off,
                           const bb_segment *segs, const uint8_t *literal_pool, int64_t literal_len,
                           const double *target_identity) {
@@ -401,6 +497,7 @@ static int w_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_ind
     const int k = ctx->em.k;
     ctx->h_reads.assign((size_t)n_reads, BBReadDev{});
     ctx->h_inlen.assign((size_t)n_reads, 0);
+    ctx->h_target.assign(target_identity, target_identity + n_reads);
     int64_t off = 0, peq_off = 0, log_off = 0, wres_off = 0;
     int max_len = 0;
     for (int32_t r = 0; r < n_reads; r++) {
@@ -432,7 +529,8 @@ static int w_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_ind
         off += (rd.frag_len + 15) & ~15;
         max_len = std::max(max_len, rd.frag_len);
     }
-    ctx->frag_total = off;
+    ctx->frag_total = off; ctx->fpeq_total = peq_off; ctx->log_total = log_off; ctx->wres_total = wres_off;
+    ctx->max_len = max_len;
     std::vector<int> order((size_t)n_reads);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(),
@@ -447,120 +545,71 @@ static int w_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_ind
     if ((rc = upload(ctx, ctx->d_target, target_identity, (size_t)n_reads))) return rc;
     if ((rc = upload(ctx, ctx->d_order, order.data(), (size_t)n_reads))) return rc;
     if ((rc = upload(ctx, ctx->d_reads, ctx->h_reads.data(), (size_t)n_reads))) return rc;
-    BB_CUDA(ctx, ctx->d_frag.ensure((size_t)off + 16));
-    BB_CUDA(ctx, ctx->d_state.ensure(((size_t)off + 16) * sizeof(uint32_t)));
-    BB_CUDA(ctx, ctx->d_kidx.ensure(((size_t)off + 16) * sizeof(int)));
-    BB_CUDA(ctx, ctx->d_counter.ensure(16 * sizeof(int)));
-    BB_CUDA(ctx, ctx->d_fpeq.ensure(((size_t)peq_off + 4) * sizeof(uint4)));
-    BB_CUDA(ctx, ctx->d_fallback.ensure(((size_t)n_reads + 4) * sizeof(int)));
-    ctx->fpeq_total = peq_off;
-    if ((rc = ensure_scratch(ctx, max_len, 4096, max_len))) return rc;
-    BB_CUDA(ctx, ctx->d_ctime.ensure(((size_t)off + 16) * sizeof(unsigned int)));
-    BB_CUDA(ctx, ctx->d_chlog.ensure(((size_t)log_off + 16) * sizeof(uint2)));
-    BB_CUDA(ctx, ctx->d_wres.ensure(((size_t)wres_off + 16) * sizeof(int2)));
-    BB_CUDA(ctx, ctx->d_wtasks.ensure(((size_t)wres_off + 16) * sizeof(BBWinTask)));
-    BB_CUDA(ctx, ctx->d_wfallback.ensure((2 * (size_t)wres_off + 16) * sizeof(BBWinTask)));
-    BB_CUDA(ctx, ctx->d_active.ensure(((size_t)n_reads + 16) * sizeof(int)));
-    {   // lane pools shared by the window aligner and the leaf aligner: history of 2048 columns x 8 words per thread
-        const size_t lanes = (size_t)ctx->sm_count * 4 * 64;
-        BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * lanes * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
-        BB_CUDA(ctx, ctx->s_ltbuf.ensure(2 * lanes * BB_WIN_MAX_COLS));  // the 4-word window kernel runs 2x the lanes
-    }
+    if ((rc = w_prepare(ctx))) return rc;
     BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->uploaded = true;
     ctx->ran = false;
+    ctx->finished = false;
     return BB_OK;
 }
 
-// The error loop decoupled from its identity re-measurements (bb_loop.cuh): mutate ahead -> all window alignments
-// as independent lane tasks -> scalar replay; reads whose horizon was too short go round again.
-static int run_spec_loop(bb_ctx *ctx, const BBBatchDev &B, std::vector<BBReadDev> &reads) {
+// The error loop decoupled from its identity re-measurements (bb_loop.cuh): mutate ahead -> task list -> all window
+// alignments as independent lane tasks -> scalar replay, n_rounds times back to back.  A round after the last read
+// has finished costs six launches that find nothing to do; a read that is still pending after the last round is
+// reported by the replay kernel's counter and w_finish runs the batch again with more rounds.
+static int enqueue_error_loop(bb_ctx *ctx, const BBBatchDev &B) {
     cudaStream_t st = ctx->stream;
     const int n = ctx->n_reads;
     int *cnt = ctx->d_counter.as<int>();
-    std::vector<int> active = ctx->h_order;  // longest fragments first
     const int lane_ctas = ctx->sm_count * 4;
-    std::vector<BBWinTask> tasks;
-    for (int round = 0; !active.empty(); round++) {
-        if (round >= 12) return set_err(ctx, BB_ERR_INTERNAL, "error loop did not converge");
-        const int n_active = (int)active.size();
-        BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, active.data(), (size_t)n_active * sizeof(int), cudaMemcpyHostToDevice, st));
-        BB_CUDA(ctx, cudaMemsetAsync(cnt + 8, 0, 8 * sizeof(int), st));
-        bbl_mutate(std::min(ctx->sm_count * 8, n_active), st, B, ctx->em, ctx->seed, cnt + 8, ctx->d_active.as<int>(), n_active);
-        ctx->launches++;
+    const int *order = ctx->d_order.as<int>();
+    BBWinTask *tasks = ctx->d_wtasks.as<BBWinTask>();
+    BBWinTask *fb1 = ctx->d_wfallback.as<BBWinTask>(), *fb2 = fb1 + ctx->wres_total + 8;
+    for (int round = 0; round < ctx->n_rounds; round++) {
+        int *c = cnt + BB_ROUND_BASE(round);
+        bbl_mutate(std::min(ctx->sm_count * 8, n), st, B, ctx->em, ctx->seed, c + BBC_MUTATE, order, n);
         mark(ctx, st, "mutate");
-        BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
-        BB_CUDA(ctx, cudaStreamSynchronize(st));
-        tasks.clear();
-        for (int r : active) {
-            const BBReadDev &rd = reads[(size_t)r];
-            for (int a = rd.a_done + 1; a <= rd.n_logged / BB_ALIGNMENT_INTERVAL; a++) tasks.push_back(BBWinTask{r, a});
-        }
-        const int n_tasks = (int)tasks.size();
-        if (n_tasks > 0) {
-            BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_wtasks.p, tasks.data(), (size_t)n_tasks * sizeof(BBWinTask), cudaMemcpyHostToDevice, st));
-            BB_CUDA(ctx, cudaMemcpyAsync(cnt + 12, &n_tasks, sizeof(int), cudaMemcpyHostToDevice, st));
-            // 4-word windows first (bands up to 64 rows: almost every window); what does not fit falls through to
-            // the 8-word build and from there to the warp kernel
-            BBWinTask *fb1 = ctx->d_wfallback.as<BBWinTask>(), *fb2 = fb1 + n_tasks;
-            const int lane_grid = std::min(lane_ctas, (n_tasks + 63) / 64);
-            const int lane_grid4 = std::min(2 * lane_ctas, (n_tasks + 63) / 64);  // half the history per thread
-            mark(ctx, st, "host:window_tasks");
-            bbl_window_lane4(lane_grid4, st, B, ctx->em, ctx->d_wtasks.as<BBWinTask>(), cnt + 12, ctx->seed,
-                             ctx->s_leafhist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), cnt + 9, fb1, cnt + 10);
-            mark(ctx, st, "window_lane4");
-            bbl_window_lane8(lane_grid, st, B, ctx->em, fb1, cnt + 10, ctx->seed, ctx->s_leafhist.as<uint2>(),
-                             ctx->s_ltbuf.as<uint8_t>(), cnt + 13, fb2, cnt + 14);
-            mark(ctx, st, "window_lane8");
-            bbl_window_warp(ctx->sm_count * 2, st, B, ctx->em, ctx->pool, fb2, cnt + 14, ctx->seed, cnt + 11);
-            mark(ctx, st, "window_warp");
-            ctx->launches += 3;
-        }
-        bb_k_replay<<<(n_active + 127) / 128, 128, 0, st>>>(B, ctx->d_active.as<int>(), n_active, ctx->em.k);
-        ctx->launches++;
+        bb_k_window_tasks<<<(n + 255) / 256, 256, 0, st>>>(B, order, n, tasks, c + BBC_NTASKS);
+        mark(ctx, st, "window_tasks");
+        // 4-word windows first (bands up to 64 rows: almost every window); what does not fit falls through to the
+        // 8-word build and from there to the warp kernel
+        bbl_window_lane4(2 * lane_ctas, st, B, ctx->em, tasks, c + BBC_NTASKS, ctx->seed, ctx->s_leafhist.as<uint2>(),
+                         ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE4, fb1, c + BBC_FB1);
+        mark(ctx, st, "window_lane4");
+        bbl_window_lane8(lane_ctas, st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed, ctx->s_leafhist.as<uint2>(),
+                         ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE8, fb2, c + BBC_FB2);
+        mark(ctx, st, "window_lane8");
+        bbl_window_warp(ctx->sm_count * 2, st, B, ctx->em, ctx->pool, fb2, c + BBC_FB2, ctx->seed, c + BBC_WARP);
+        mark(ctx, st, "window_warp");
+        bb_k_replay<<<(n + 127) / 128, 128, 0, st>>>(B, order, n, ctx->em.k, c + BBC_PENDING);
         mark(ctx, st, "replay");
-        BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
-        BB_CUDA(ctx, cudaStreamSynchronize(st));
-        std::vector<int> next;
-        for (int r : active)
-            if (reads[(size_t)r].status != BB_READ_DONE) next.push_back(r);
-        active.swap(next);
+        ctx->launches += 6;
     }
     return BB_OK;
 }
 
-// Final alignment as level-synchronous tasks (bb_tasks.cuh): roots are classified here, every level of all
-// reads' Hirschberg trees is three launches (wide-warp, lean-warp, lane nodes), leaves run at the end.
-static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<BBReadDev> &reads) {
-    (void)reads;
+// Final alignment as level-synchronous tasks (bb_tasks.cuh): every level of all reads' Hirschberg trees is a few
+// launches (warp-pair, lean-warp and lane nodes), leaves run at the end.  The number of levels comes from the longest
+// fragment; nodes left over after the last level are reported by the queue counters (w_finish adds levels).
+static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
     cudaStream_t stream[2] = {ctx->stream, ctx->stream2};
     const int n = ctx->n_reads;
-    const int cap_node = (int)std::min<int64_t>(ctx->seq_total / 256 + 4ll * n + 1024, 0x7ffffff0);
-    const int cap_leaf = cap_node;
-    const int lane_ctas = ctx->sm_count * 4;  // 64-thread CTAs of the lane kernels
+    const int cap_node = (int)std::min<int64_t>(ctx->seq_cap / 256 + 4ll * n + 1024, 0x7ffffff0);
+    const int lane_ctas = ctx->sm_count * 4;
     const size_t hist_per_pipe = (size_t)lane_ctas * 64 * BB_LEAF_LANE_COLS * BB_LEAF_LW;
-    BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * hist_per_pipe * sizeof(uint2)));
     BBQueues Q[2];
     int *cnt[2];
     for (int s = 0; s < 2; s++) {
         auto &qb = ctx->qbuf[s];
         for (int c = 0; c < BBQ_NODE_CLASSES; c++)
-            for (int p = 0; p < 2; p++) {
-                BB_CUDA(ctx, qb.node[c][p].ensure((size_t)cap_node * sizeof(BBNode)));
-                Q[s].node[c][p] = qb.node[c][p].as<BBNode>();
-            }
-        for (int w = 0; w < 2; w++) {
-            BB_CUDA(ctx, qb.leaf[w].ensure((size_t)cap_leaf * sizeof(BBNode)));
-            Q[s].leaf[w] = qb.leaf[w].as<BBNode>();
-        }
-        BB_CUDA(ctx, qb.count.ensure(512 * sizeof(int)));
+            for (int p = 0; p < 2; p++) Q[s].node[c][p] = qb.node[c][p].as<BBNode>();
+        for (int w = 0; w < 2; w++) Q[s].leaf[w] = qb.leaf[w].as<BBNode>();
         cnt[s] = qb.count.as<int>();
-        Q[s].count = cnt[s]; Q[s].overflow = cnt[s] + BBQ_OVERFLOW; Q[s].cap_node = cap_node; Q[s].cap_leaf = cap_leaf;
+        Q[s].count = cnt[s]; Q[s].overflow = cnt[s] + BBQ_OVERFLOW; Q[s].cap_node = cap_node; Q[s].cap_leaf = cap_node;
         Q[s].lane8_cols = ctx->lane8_cols; Q[s].lane16_cols = ctx->lane16_cols;
         BB_CUDA(ctx, cudaMemsetAsync(cnt[s], 0, 512 * sizeof(int), stream[0]));
     }
-    BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, ctx->h_order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream[0]));
-    bb_k_push_roots<<<(n + 255) / 256, 256, 0, stream[0]>>>(B, Q[0], Q[1], ctx->d_active.as<int>());
+    bb_k_push_roots<<<(n + 255) / 256, 256, 0, stream[0]>>>(B, Q[0], Q[1], ctx->d_order.as<int>());
     ctx->launches++;
     // pipeline 0 (stream 0): every read whose root band fits the lean / lane kernels; pipeline 1 (stream 1): reads
     // with a wide root (long or noisy reads).  The two never wait for each other's levels.
@@ -569,12 +618,11 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
     int *cursor[2] = {cnt[0] + 16, cnt[1] + 16};
     const int warp_base[2] = {0, ctx->n_warps / 2};
     const int grid_lean[2] = {ctx->sm_count * 2, ctx->sm_count * 2};
-    const int max_levels = 40;  // the target halves at every level: 2^40 columns is beyond any read
-    for (int level = 0; level < max_levels; level++) {
+    for (int level = 0; level < ctx->n_levels; level++) {
         const int p = level & 1;
         for (int s = 0; s < 2; s++) {
             cudaStream_t st = stream[s];
-            for (int c = 0; c < BBQ_NODE_CLASSES; c++) BB_CUDA(ctx, cudaMemsetAsync(cnt[s] + c * 2 + (p ^ 1), 0, sizeof(int), st));
+            BB_CUDA(ctx, cudaMemsetAsync(cnt[s] + BBQ_COUNT(0, p ^ 1), 0, BBQ_NODE_CLASSES * sizeof(int), st));
             if (s == 1) {
                 bbl_node_pair(ctx->sm_count * ctx->pair_ctas, st, B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
                 ctx->launches++;
@@ -582,20 +630,14 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
             }
             bbl_node_warp4(grid_lean[s], st, B, Q[s], ctx->pool, BBQ_NODE_LEAN, p, cursor[s]++, warp_base[s]);
             mark(ctx, st, "node_warp4");
-            bbl_node_lane16(lane_ctas, st, B, Q[s], p, cursor[s]++);
-            mark(ctx, st, "node_lane16");
+            if (ctx->lane16_cols > 0) {
+                bbl_node_lane16(lane_ctas, st, B, Q[s], p, cursor[s]++);
+                ctx->launches++;
+                mark(ctx, st, "node_lane16");
+            }
             bbl_node_lane8(ctx->sm_count * 6, st, B, Q[s], p, cursor[s]++);
             mark(ctx, st, "node_lane8");
-            ctx->launches += 3;
-        }
-        if (level >= 3 && (level & 3) == 3) {  // every few levels: stop as soon as all queues are empty
-            int h[2][2 * BBQ_NODE_CLASSES];
-            for (int s = 0; s < 2; s++) BB_CUDA(ctx, cudaMemcpyAsync(h[s], cnt[s], sizeof(h[s]), cudaMemcpyDeviceToHost, stream[s]));
-            for (int s = 0; s < 2; s++) BB_CUDA(ctx, cudaStreamSynchronize(stream[s]));
-            int pending = 0;
-            for (int s = 0; s < 2; s++)
-                for (int c = 0; c < BBQ_NODE_CLASSES; c++) pending += h[s][c * 2 + (p ^ 1)];
-            if (pending == 0) break;
+            ctx->launches += 2;
         }
     }
     for (int s = 0; s < 2; s++) {
@@ -608,101 +650,107 @@ static int run_align_tasks(bb_ctx *ctx, const BBBatchDev &B, const std::vector<B
     }
     BB_CUDA(ctx, cudaEventRecord(ctx->ev_join, stream[1]));
     BB_CUDA(ctx, cudaStreamWaitEvent(stream[0], ctx->ev_join, 0));
-    int h_over[2] = {0, 0};
-    for (int s = 0; s < 2; s++) BB_CUDA(ctx, cudaMemcpyAsync(&h_over[s], Q[s].overflow, sizeof(int), cudaMemcpyDeviceToHost, stream[0]));
-    BB_CUDA(ctx, cudaStreamSynchronize(stream[0]));
-    if (h_over[0] || h_over[1]) return set_err(ctx, BB_ERR_INTERNAL, "alignment task queue overflow");
+    for (int s = 0; s < 2; s++)
+        BB_CUDA(ctx, cudaMemcpyAsync(ctx->h_info->qcount[s], cnt[s], 32 * sizeof(int), cudaMemcpyDeviceToHost, stream[0]));
     return BB_OK;
 }
 
-static int w_batch_run(bb_ctx *ctx) {
+// Enqueues the whole hot path of the uploaded batch on the worker's streams and returns: no host round trip inside.
+static int w_enqueue(bb_ctx *ctx) {
     if (!ctx) return BB_ERR_ARG;
     if (!ctx->uploaded) return set_err(ctx, BB_ERR_STATE, "bb_batch_run: no batch uploaded");
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n = ctx->n_reads;
     BBBatchDev B = batch_dev(ctx);
-    int *counters = ctx->d_counter.as<int>();
-
+    ctx->finished = false;
     // the per-read records start from the uploaded state on every run (bb_batch_run may be repeated)
-    BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, ctx->h_reads.data(), (size_t)n * sizeof(BBReadDev),
-                                 cudaMemcpyHostToDevice, st));
-    BB_CUDA(ctx, cudaMemsetAsync(counters, 0, 16 * sizeof(int), st));
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, ctx->h_reads.data(), (size_t)n * sizeof(BBReadDev), cudaMemcpyHostToDevice, st));
+    BB_CUDA(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, BB_N_COUNTERS * sizeof(int), st));
     ctx->marks.clear(); ctx->mark_used = 0;
     mark(ctx, st, "begin");
-    bb_k_build_fragments<<<n, 256, 0, st>>>(B, ctx->ref.as<uint8_t>(), ctx->em.k, ctx->seed, ctx->em.type == 1 ? ctx->em.kmer_to_row : nullptr);
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    bb_k_build_fragments<<<n, 256, 0, st>>>(B, ctx->ref.as<uint8_t>(), ctx->em.k, ctx->seed,
+                                             ctx->em.type == 1 ? ctx->em.kmer_to_row : nullptr);
     ctx->launches++;
     mark(ctx, st, "build_fragments");
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    // one thread per read; reads whose windows exceed the lane-mode limits are redone by the warp kernel
-    std::vector<BBReadDev> reads((size_t)n);
-    {
-        int rcl = run_spec_loop(ctx, B, reads);
-        if (rcl) return rcl;
-    }
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-    // host scan of the joined lengths -> offsets of the per-read regions in seq / ops / dcnt / qual / out
-    BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
-    BB_CUDA(ctx, cudaStreamSynchronize(st));
-    int64_t seq_off = 0, out_off = 0, speq_off = 0;
-    int rc0 = 0;
-    int lr_need = 0, hbuf_need = 0, len_need = 0;
-    for (int r = 0; r < n; r++) {
-        BBReadDev &rd = reads[(size_t)r];
-        rd.seq_off = seq_off;
-        rd.out_off = out_off;
-        rd.speq_off = speq_off;
-        speq_off += bb_peq_words(rd.seq_len);
-        int out_len = rd.seq_len - rd.start_trim - rd.end_trim;  // seq[start_trim:-end_trim]
-        if (out_len < 0) out_len = 0;
-        rd.out_len = out_len;
-        rd.lead_del = 0; rd.matches = 0; rd.dels = 0;
-        seq_off += (rd.seq_len + 15) & ~15;
-        out_off += out_len;
-        const int mx = std::max(rd.seq_len, rd.frag_len);
-        lr_need = std::max(lr_need, std::min(rd.seq_len, std::min(rd.upper, mx) + 2));
-        hbuf_need = std::max(hbuf_need, rd.frag_len);
-        len_need = std::max(len_need, mx);
-    }
-    ctx->seq_total = seq_off;
-    ctx->out_total = out_off;
-    ctx->scan_ready.store(1, std::memory_order_release);
-    BB_CUDA(ctx, ctx->d_seq.ensure((size_t)seq_off + 16));
-    BB_CUDA(ctx, ctx->d_ops.ensure((size_t)seq_off + 16));
-    BB_CUDA(ctx, ctx->d_dcnt.ensure(((size_t)seq_off + 16) * sizeof(unsigned int)));
-    BB_CUDA(ctx, ctx->d_qual.ensure((size_t)seq_off + 16));
-    BB_CUDA(ctx, ctx->d_speq.ensure(((size_t)speq_off + 4) * sizeof(uint4)));
-    BB_CUDA(ctx, ctx->d_out_seq.ensure((size_t)out_off + 16));
-    BB_CUDA(ctx, ctx->d_out_qual.ensure((size_t)out_off + 16));
-    int rc = ensure_scratch(ctx, hbuf_need, lr_need, len_need);
+    int rc = enqueue_error_loop(ctx, B);
     if (rc) return rc;
-    B = batch_dev(ctx);
-    BB_CUDA(ctx, cudaMemcpyAsync(ctx->d_reads.p, reads.data(), (size_t)n * sizeof(BBReadDev), cudaMemcpyHostToDevice, st));
-    BB_CUDA(ctx, cudaMemsetAsync(ctx->d_dcnt.p, 0, ((size_t)seq_off + 16) * sizeof(unsigned int), st));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    // offsets of the per-read regions of the joined reads, on the device
+    bb_k_scan<<<1, 1024, 0, st>>>(B, n, ctx->seq_cap, ctx->out_cap, ctx->speq_cap, ctx->d_scan.as<BBScanOut>());
+    ctx->launches++;
+    BB_CUDA(ctx, cudaMemcpyAsync(&ctx->h_info->scan, ctx->d_scan.p, sizeof(BBScanOut), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev_scan, st));  // from here on the host can learn the size of this worker's output
+    BB_CUDA(ctx, cudaMemsetAsync(ctx->d_dcnt.p, 0, ((size_t)ctx->seq_cap + 16) * sizeof(unsigned int), st));
+    mark(ctx, st, "scan");
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    mark(ctx, st, "host:scan");
     bb_k_join<<<n, 256, 0, st>>>(B, ctx->em);
     ctx->launches++;
     mark(ctx, st, "join");
     BB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    {
-        int rc2 = run_align_tasks(ctx, B, reads);
-        if (rc2) return rc2;
-        BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-    }
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+    if ((rc = enqueue_align_tasks(ctx, B))) return rc;
     mark(ctx, st, "align_tail");
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
     bb_k_qscores<<<n, 256, 0, st>>>(B, ctx->qm, ctx->seed);
     ctx->launches++;
     mark(ctx, st, "qscores");
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
     bb_k_compact<<<n, 256, 0, st>>>(B);
     ctx->launches++;
     mark(ctx, st, "compact");
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
+    BB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+    BB_CUDA(ctx, cudaMemcpyAsync(ctx->h_info->counters, ctx->d_counter.p, BB_N_COUNTERS * sizeof(int), cudaMemcpyDeviceToHost, st));
     BB_CUDA(ctx, cudaGetLastError());
     ctx->ran = true;
+    return BB_OK;
+}
+
+// Waits for the worker's run and checks what the device reported.  Returns BB_OK when the results are final; when
+// something did not fit (buffers sized from the fragment lengths, rounds, levels, split-score scratch) the knob is
+// raised and the batch runs again - the results do not depend on any of them.
+static int w_finish(bb_ctx *ctx) {
+    if (!ctx) return BB_ERR_ARG;
+    if (!ctx->ran) return set_err(ctx, BB_ERR_STATE, "no run to finish");
+    if (ctx->finished) return BB_OK;
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = ctx->n_reads;
+    for (int attempt = 0;; attempt++) {
+        ctx->h_res.resize((size_t)n);
+        BB_CUDA(ctx, cudaMemcpyAsync(ctx->h_res.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, ctx->stream));
+        BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const bb_ctx::RunInfo &info = *ctx->h_info;
+        bool again = false;
+        std::string why;
+        if (info.counters[BB_ROUND_BASE(ctx->n_rounds - 1) + BBC_PENDING] > 0 || info.scan.n_pending > 0) {
+            ctx->n_rounds = std::min(BB_MAX_ROUNDS, ctx->n_rounds + 3); again = true; why += " error-loop rounds";
+        }
+        if (info.scan.n_nospace > 0) {  // (reads still pending after the last round are counted separately)
+            const double need = (double)std::max(info.scan.seq_total, info.scan.out_total) / (double)std::max<int64_t>(1, ctx->frag_total);
+            ctx->slack = std::max(ctx->slack * 1.5, need * 1.1 + 0.05); again = true; why += " buffer slack";
+        }
+        const int last_parity = ctx->n_levels & 1;  // the queues the level after the last one would read
+        int left = 0, overflow = 0;
+        for (int s = 0; s < 2; s++) {
+            for (int c = 0; c < BBQ_NODE_CLASSES; c++) left += info.qcount[s][BBQ_COUNT(c, last_parity)];
+            overflow += info.qcount[s][BBQ_OVERFLOW];
+        }
+        if (left > 0) { ctx->extra_levels += 8; again = true; why += " levels"; }
+        if (overflow) { ctx->slack *= 1.5; again = true; why += " task queues"; }
+        for (int r = 0; r < n && !ctx->lr_worst; r++) {
+            const int f = (ctx->h_res[(size_t)r].flags & ~BB_FLAG_NOSPACE) >> 8;
+            if (f & (16 | 4 | 2)) { ctx->lr_worst = true; ctx->slack *= 1.25; again = true; why += " alignment scratch"; }
+        }
+        if (!again) break;
+        ctx->reran = true;
+        if (attempt >= 3) return set_err(ctx, BB_ERR_INTERNAL, "batch did not fit after growing:" + why);
+        int rc = w_prepare(ctx);
+        if (rc) return rc;
+        if ((rc = w_enqueue(ctx))) return rc;
+    }
+    ctx->out_total = ctx->h_info->scan.out_total;
+    ctx->finished = true;
     return BB_OK;
 }
 
@@ -738,26 +786,24 @@ static int w_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms) {
     return BB_OK;
 }
 
-// Worker-level fetch: the worker's packed block goes to seq_out / qual_out (already offset by the caller);
-// results[pos[i]] describes the worker's i-th read, its out_off shifted by `base`.
-static int w_fetch(bb_ctx *ctx, bb_read_result *results, const int32_t *pos, int64_t base, uint8_t *seq_out,
-                   uint8_t *qual_out) {
-    if (!ctx) return BB_ERR_ARG;
-    if (!ctx->ran) return set_err(ctx, BB_ERR_STATE, "bb_fetch_last_batch: nothing to fetch");
+// Enqueues the device-to-host copies of a finished (or at least scanned) worker's packed block on its stream.
+static int w_copy_out(bb_ctx *ctx, int64_t base, uint8_t *seq_out, uint8_t *qual_out) {
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int n = ctx->n_reads;
-    std::vector<BBReadDev> reads((size_t)n);
-    cudaStream_t st = ctx->stream;
-    BB_CUDA(ctx, cudaMemcpyAsync(reads.data(), ctx->d_reads.p, (size_t)n * sizeof(BBReadDev), cudaMemcpyDeviceToHost, st));
-    if (ctx->out_total) {
+    const int64_t total = ctx->h_info->scan.out_total;
+    if (total > 0) {
         if (!seq_out || !qual_out) return set_err(ctx, BB_ERR_ARG, "null output buffers");
-        BB_CUDA(ctx, cudaMemcpyAsync(seq_out, ctx->d_out_seq.p, (size_t)ctx->out_total, cudaMemcpyDeviceToHost, st));
-        BB_CUDA(ctx, cudaMemcpyAsync(qual_out, ctx->d_out_qual.p, (size_t)ctx->out_total, cudaMemcpyDeviceToHost, st));
+        BB_CUDA(ctx, cudaMemcpyAsync(seq_out + base, ctx->d_out_seq.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+        BB_CUDA(ctx, cudaMemcpyAsync(qual_out + base, ctx->d_out_qual.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    BB_CUDA(ctx, cudaStreamSynchronize(st));
+    return BB_OK;
+}
+
+// results[pos[i]] describes the worker's i-th read, its out_off shifted by `base` (from the records w_finish fetched).
+static int w_results(bb_ctx *ctx, bb_read_result *results, const int32_t *pos, int64_t base) {
+    const int n = ctx->n_reads;
     int bad = 0, bad_read = -1;
     for (int r = 0; r < n; r++) {
-        const BBReadDev &rd = reads[(size_t)r];
+        const BBReadDev &rd = ctx->h_res[(size_t)r];
         if (results) {
             bb_read_result &o = results[pos ? pos[r] : r];
             o.out_off = base + rd.out_off; o.out_len = rd.out_len; o.frag_len = ctx->h_inlen[(size_t)r];
@@ -836,23 +882,18 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     return BB_OK;
 }
 
+// Asynchronous: the kernel chains of all workers are enqueued from this thread and overlap on the device.
 extern "C" int bb_batch_run(bb_ctx *ctx) {
     if (!ctx) return BB_ERR_ARG;
-    ctx->scan_ready.store(0, std::memory_order_release);
-    if (ctx->n_split == 1) return w_batch_run(ctx);
     const int S = ctx->n_split;
-    for (int w = 1; w < S; w++) worker_of(ctx, w)->scan_ready.store(0, std::memory_order_release);
+    for (int w = 0; w < S; w++) worker_of(ctx, w)->reran = false;
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
     for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(worker_of(ctx, w)->stream, ctx->ev_t0, 0));
-    std::vector<int> rcs((size_t)S, 0);
-    std::vector<std::thread> threads;
-    for (int w = 1; w < S; w++) threads.emplace_back([&, w]() { rcs[(size_t)w] = w_batch_run(worker_of(ctx, w)); });
-    rcs[0] = w_batch_run(ctx);
-    for (auto &t : threads) t.join();
-    for (int w = 0; w < S; w++)
-        if (rcs[(size_t)w]) return w == 0 ? rcs[0] : set_err(ctx, rcs[(size_t)w], worker_of(ctx, w)->err);
-    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int w = 0; w < S; w++) {
+        const int rc = w_enqueue(worker_of(ctx, w));
+        if (rc) return w == 0 ? rc : set_err(ctx, rc, worker_of(ctx, w)->err);
+    }
     for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, worker_of(ctx, w)->ev[BB_N_STAGES - 1], 0));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
     return BB_OK;
@@ -863,7 +904,6 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
 // per-worker stage times, scaled to the whole-batch time.
 extern "C" int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms) {
     if (!ctx) return BB_ERR_ARG;
-    if (ctx->n_split == 1) return w_last_run_ms(ctx, total_ms, stage_ms);
     const int S = ctx->n_split;
     float sum[BB_N_STAGES] = {};
     for (int w = 0; w < S; w++) {
@@ -912,35 +952,48 @@ extern "C" int bb_trace_dump(bb_ctx *ctx, const char *path) {
     return BB_OK;
 }
 
-extern "C" int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t *seq_out, uint8_t *qual_out,
-                                   int64_t out_cap, int64_t *out_total) {
-    if (!ctx) return BB_ERR_ARG;
+// Finishes every worker's run, packs their blocks back to back in the caller's buffers and fills the results.
+// eager: the copies of a worker were already enqueued behind its kernels with these bases (bb_sequence_batch).
+static int fetch_all(bb_ctx *ctx, bb_read_result *results, uint8_t *seq_out, uint8_t *qual_out, int64_t out_cap,
+                     int64_t *out_total, const std::vector<int64_t> *eager_bases) {
     const int S = ctx->n_split;
+    std::vector<int64_t> base((size_t)S, 0);
     int64_t total = 0;
-    ctx->part_base.assign((size_t)S, 0);
+    bool moved = false;  // a worker's output size changed after the eager copies were placed (it had to run again)
     for (int w = 0; w < S; w++) {
         bb_ctx *wk = worker_of(ctx, w);
         if (!wk->ran) return set_err(ctx, BB_ERR_STATE, "bb_fetch_last_batch: nothing to fetch");
-        ctx->part_base[(size_t)w] = total;
+        const int rc = w_finish(wk);
+        if (rc) return w == 0 ? rc : set_err(ctx, rc, wk->err);
+        if (wk->reran) moved = true;
+        base[(size_t)w] = total;
         total += wk->out_total;
     }
+    ctx->part_base = base;
     if (out_total) *out_total = total;
     if (out_cap < total) return set_err(ctx, BB_ERR_CAPACITY, "output buffers too small");
     if (total && (!seq_out || !qual_out)) return set_err(ctx, BB_ERR_ARG, "null output buffers");
-    if (S == 1) return w_fetch(ctx, results, nullptr, 0, seq_out, qual_out);
-    std::vector<int> rcs((size_t)S, 0);
-    std::vector<std::thread> threads;
-    auto fetch_part = [&](int w) {
-        const int64_t base = ctx->part_base[(size_t)w];
-        rcs[(size_t)w] = w_fetch(worker_of(ctx, w), results, ctx->part[(size_t)w].data(), base,
-                                 seq_out ? seq_out + base : nullptr, qual_out ? qual_out + base : nullptr);
-    };
-    for (int w = 1; w < S; w++) threads.emplace_back(fetch_part, w);
-    fetch_part(0);
-    for (auto &t : threads) t.join();
-    for (int w = 0; w < S; w++)
-        if (rcs[(size_t)w]) return w == 0 ? rcs[0] : set_err(ctx, rcs[(size_t)w], worker_of(ctx, w)->err);
+    const bool have_eager = eager_bases && !moved && *eager_bases == base;
+    if (!have_eager) {
+        for (int w = 0; w < S; w++) {
+            const int rc = w_copy_out(worker_of(ctx, w), base[(size_t)w], seq_out, qual_out);
+            if (rc) return w == 0 ? rc : set_err(ctx, rc, worker_of(ctx, w)->err);
+        }
+    }
+    for (int w = 0; w < S; w++) {
+        bb_ctx *wk = worker_of(ctx, w);
+        BB_CUDA(ctx, cudaSetDevice(wk->device));
+        BB_CUDA(ctx, cudaStreamSynchronize(wk->stream));
+        const int rc = w_results(wk, results, S == 1 ? nullptr : ctx->part[(size_t)w].data(), base[(size_t)w]);
+        if (rc) return w == 0 ? rc : set_err(ctx, rc, wk->err);
+    }
     return BB_OK;
+}
+
+extern "C" int bb_fetch_last_batch(bb_ctx *ctx, bb_read_result *results, uint8_t *seq_out, uint8_t *qual_out,
+                                   int64_t out_cap, int64_t *out_total) {
+    if (!ctx) return BB_ERR_ARG;
+    return fetch_all(ctx, results, seq_out, qual_out, out_cap, out_total, nullptr);
 }
 
 extern "C" int bb_sequence_batch(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_index, const int32_t *seg_off,
@@ -949,62 +1002,23 @@ extern "C" int bb_sequence_batch(bb_ctx *ctx, int32_t n_reads, const uint64_t *r
                                  uint8_t *qual_out, int64_t out_cap, int64_t *out_total) {
     int rc = bb_batch_upload(ctx, n_reads, read_index, seg_off, segs, literal_pool, literal_len, target_identity);
     if (rc) return rc;
-    if (ctx->n_split == 1) {
-        if ((rc = bb_batch_run(ctx))) return rc;
-        return bb_fetch_last_batch(ctx, results, seq_out, qual_out, out_cap, out_total);
-    }
-    // several workers: each one copies its block out as soon as its own chain is done, while the others still compute
-    // (its offset only needs the output sizes of the workers before it, known since their host scans)
+    if ((rc = bb_batch_run(ctx))) return rc;
+    // each worker's block is copied out as soon as its own chain is done, while the others still compute: its place
+    // in the caller's buffers only needs the output sizes of the workers before it, known since their scans
     const int S = ctx->n_split;
-    // every worker's "output size known" flag is cleared here, before any chain thread exists: a chain polls the
-    // flags of the workers in front of it and must never see the value a previous batch left behind
-    for (int w = 0; w < S; w++) worker_of(ctx, w)->scan_ready.store(0, std::memory_order_release);
-    BB_CUDA(ctx, cudaSetDevice(ctx->device));
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
-    for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(worker_of(ctx, w)->stream, ctx->ev_t0, 0));
-    std::vector<int> rcs((size_t)S, 0);
-    ctx->part_base.assign((size_t)S, 0);
-    auto chain = [&](int w) {
-        bb_ctx *wk = worker_of(ctx, w);
-        int r = w_batch_run(wk);
-        if (wk->scan_ready.load(std::memory_order_acquire) == 0) wk->scan_ready.store(r ? -1 : 1, std::memory_order_release);
-        int64_t base = 0;
-        for (int v = 0; v < w && !r; v++) {
-            bb_ctx *o = worker_of(ctx, v);
-            int st;
-            while ((st = o->scan_ready.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
-            if (st < 0) r = BB_ERR_STATE;  // that worker reports its own error
-            base += o->out_total;
-        }
-        if (!r) {
-            ctx->part_base[(size_t)w] = base;
-            if (base + wk->out_total > out_cap) r = BB_ERR_CAPACITY;
-            else r = w_fetch(wk, results, ctx->part[(size_t)w].data(), base, seq_out ? seq_out + base : nullptr,
-                             qual_out ? qual_out + base : nullptr);
-        }
-        rcs[(size_t)w] = r;
-    };
-    std::vector<std::thread> threads;
-    for (int w = 1; w < S; w++) threads.emplace_back(chain, w);
-    chain(0);
-    for (auto &t : threads) t.join();
-    BB_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, worker_of(ctx, w)->ev[BB_N_STAGES - 1], 0));
-    BB_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+    std::vector<int64_t> base((size_t)S, 0);
     int64_t total = 0;
-    bool capacity = false;
-    for (int w = 0; w < S; w++) {
-        const int r = rcs[(size_t)w];
-        if (r == BB_ERR_CAPACITY) capacity = true;
-        else if (r == BB_ERR_STATE && w > 0) continue;  // knocked on from another worker's failure
-        else if (r) return w == 0 ? r : set_err(ctx, r, worker_of(ctx, w)->err);
-        total += worker_of(ctx, w)->out_total;
+    bool eager = true;
+    for (int w = 0; w < S && eager; w++) {
+        bb_ctx *wk = worker_of(ctx, w);
+        BB_CUDA(ctx, cudaSetDevice(wk->device));
+        BB_CUDA(ctx, cudaEventSynchronize(wk->ev_scan));
+        base[(size_t)w] = total;
+        total += wk->h_info->scan.out_total;
+        if (wk->h_info->scan.n_nospace > 0 || total > out_cap) { eager = false; break; }
+        if ((rc = w_copy_out(wk, base[(size_t)w], seq_out, qual_out))) { eager = false; break; }
     }
-    for (int w = 0; w < S; w++)
-        if (rcs[(size_t)w] == BB_ERR_STATE) return set_err(ctx, BB_ERR_STATE, "a sub-batch worker failed");
-    if (out_total) *out_total = total;
-    if (capacity) return set_err(ctx, BB_ERR_CAPACITY, "output buffers too small");  // bb_fetch_last_batch can retry
-    return BB_OK;
+    return fetch_all(ctx, results, seq_out, qual_out, out_cap, out_total, eager ? &base : nullptr);
 }
 
 // ---- single-pair entry points ------------------------------------------------------------------------

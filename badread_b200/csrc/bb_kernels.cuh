@@ -22,6 +22,7 @@
 #define BB_ALIGNMENT_INTERVAL 25  // settings.py:24
 #define BB_ALIGNMENT_SIZE 1000    // settings.py:25
 #define BB_WARPS_PER_CTA 4
+enum { BB_READ_PENDING = 0, BB_READ_DONE = 1 };  // BBReadDev::status: the error loop of the read has finished
 
 // Everything the common outcome of a model draw needs, in one 32-byte record per table row: random.choices picks
 // entry 0 - the unchanged k-mer, p ~ 0.92 (nanopore) ... 0.99 (pacbio) - iff random() * cum_last < cum0.
@@ -287,12 +288,100 @@ __device__ __forceinline__ void bb_eval_iteration(const BBErrorModelDev &em, con
     kind = 2; rpos = p;
 }
 
+// ------------------------------------------------------------------------------------------------ scan
+// Offsets of the per-read regions in seq / ops / dcnt / qual (16-byte aligned), the match bitmaps of the joined reads
+// and the packed outputs: three exclusive prefix sums over the reads in batch order, by one CTA (a few ten thousand
+// reads).  A read whose regions do not fit the buffers (sized from the fragment lengths before the run) is flagged
+// BB_FLAG_NOSPACE and left empty; the host grows the buffers and runs the batch again.
+#define BB_FLAG_NOSPACE 0x40000000
+struct BBScanOut {
+    long long seq_total, out_total, speq_total;
+    int n_nospace, max_seq_len, max_upper, n_pending;
+};
+
+template <int BB_TU_ = 0>
+__global__ void __launch_bounds__(1024)
+bb_k_scan(BBBatchDev B, int n, long long seq_cap, long long out_cap, long long speq_cap, BBScanOut *out) {
+    __shared__ long long s_w[3][32];
+    __shared__ long long s_run[3];
+    __shared__ int s_bad, s_maxlen, s_maxup, s_pend;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_run[0] = s_run[1] = s_run[2] = 0; s_bad = 0; s_maxlen = 0; s_maxup = 0; s_pend = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int r = base + threadIdx.x;
+        long long v[3] = {0, 0, 0};
+        int out_len = 0, seq_len = 0;
+        bool pending = false;  // the error loop of this read has not finished (too few rounds enqueued): skipped like a
+                               // read without room, the host runs the batch again with more rounds
+        if (r < n && B.reads[r].status != BB_READ_DONE) pending = true;
+        if (r < n && !pending) {
+            const BBReadDev &rd = B.reads[r];
+            seq_len = rd.seq_len;
+            out_len = seq_len - rd.start_trim - rd.end_trim;  // seq[start_trim:-end_trim]
+            if (out_len < 0) out_len = 0;
+            v[0] = (seq_len + 15) & ~15; v[1] = out_len; v[2] = bb_peq_words(seq_len);
+        }
+        long long incl[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            long long x = v[c];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long y = __shfl_up_sync(BB_FULL, x, d);
+                if (lane >= d) x += y;
+            }
+            incl[c] = x;
+            if (lane == 31) s_w[c][wid] = x;
+        }
+        __syncthreads();
+        if (wid == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                long long x = s_w[c][lane];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const long long y = __shfl_up_sync(BB_FULL, x, d);
+                    if (lane >= d) x += y;
+                }
+                s_w[c][lane] = x;  // inclusive over warps
+            }
+        }
+        __syncthreads();
+        long long off[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) off[c] = s_run[c] + (wid ? s_w[c][wid - 1] : 0) + incl[c] - v[c];
+        if (r < n) {
+            BBReadDev &rd = B.reads[r];
+            const bool fits = !pending && off[0] + v[0] <= seq_cap && off[1] + v[1] <= out_cap && off[2] + v[2] <= speq_cap;
+            rd.seq_off = fits ? off[0] : 0; rd.out_off = fits ? off[1] : 0; rd.speq_off = fits ? off[2] : 0;
+            rd.out_len = fits ? out_len : 0;
+            rd.lead_del = 0; rd.matches = 0; rd.dels = 0;
+            if (!fits) { rd.flags |= BB_FLAG_NOSPACE; atomicAdd(pending ? &s_pend : &s_bad, 1); }
+            if (pending) { rd.seq_len = 0; rd.start_trim = 0; rd.end_trim = 0; }
+            atomicMax(&s_maxlen, seq_len);
+            atomicMax(&s_maxup, rd.upper);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) s_run[c] += s_w[c][31];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out->seq_total = s_run[0]; out->out_total = s_run[1]; out->speq_total = s_run[2];
+        out->n_nospace = s_bad; out->max_seq_len = s_maxlen; out->max_upper = s_maxup; out->n_pending = s_pend;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K3
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(256) bb_k_join(BBBatchDev B, BBErrorModelDev em) {
     const int r = blockIdx.x;
     if (r >= B.n_reads) return;
     const BBReadDev rd = B.reads[r];
+    if (rd.flags & BB_FLAG_NOSPACE) return;
     const uint8_t *frag = B.frag + rd.frag_off;
     const uint32_t *state = B.state + rd.frag_off;
     uint8_t *seq = B.seq + rd.seq_off;
@@ -411,6 +500,7 @@ template <int BB_TU_ = 0>  // a template: only the translation unit that launche
 __global__ void __launch_bounds__(256) bb_k_qscores(BBBatchDev B, BBQScoreModelDev qm, unsigned long long seed) {
     const int r = blockIdx.x;
     const BBReadDev rd = B.reads[r];
+    if (rd.flags & BB_FLAG_NOSPACE) return;
     const int n = rd.seq_len;
     const uint8_t *ops = B.ops + rd.seq_off;
     const unsigned int *dcnt = B.dcnt + rd.seq_off;

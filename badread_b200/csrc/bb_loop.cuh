@@ -22,7 +22,6 @@
 #include "bb_lane.cuh"
 
 enum { BB_STOP_HORIZON = 0, BB_STOP_LIMIT = 1, BB_STOP_COUNT = 2, BB_STOP_NOLOOP = 3 };
-enum { BB_READ_PENDING = 0, BB_READ_DONE = 1 };
 
 #define BB_WIN_LW 8          // window words of the lane window aligner (bands up to 32*6 rows)
 #define BB_WIN_MAX_COLS 2048 // joined window length a lane can keep
@@ -53,6 +52,7 @@ bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work
         if (w >= n_items) break;
         const int r = order[w];
         BBReadDev *rd = &B.reads[r];
+        if (rd->status == BB_READ_DONE) continue;  // later rounds: only reads whose horizon was too short go on
         const long long clk0 = clock64();
         const uint8_t *frag = B.frag + rd->frag_off;
         uint32_t *state = B.state + rd->frag_off;
@@ -137,6 +137,23 @@ bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work
         }
         __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------------------------------------ window task list
+// One thread per read: the identity re-measurements its newly logged changes call for ("after 25 a changes", a from
+// a_done + 1 to n_logged / 25) become tasks.  Built on the device so that a round of the loop needs no host round trip.
+template <int BB_TU_ = 0>
+__global__ void __launch_bounds__(256)
+bb_k_window_tasks(BBBatchDev B, const int *order, int n_items, BBWinTask *tasks, int *n_tasks) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_items) return;
+    const int r = order[w];
+    const BBReadDev *rd = &B.reads[r];
+    if (rd->status == BB_READ_DONE) return;
+    const int a0 = rd->a_done + 1, a1 = rd->n_logged / BB_ALIGNMENT_INTERVAL;
+    if (a1 < a0) return;
+    const int base = atomicAdd(n_tasks, a1 - a0 + 1);
+    for (int a = a0; a <= a1; a++) tasks[base + a - a0] = BBWinTask{r, a};
 }
 
 // ------------------------------------------------------------------------------------------------ window alignments
@@ -329,7 +346,7 @@ bb_k_window_warp(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, const BBW
 // One thread per read: the scalar recurrence of simulate.py:290-346 over the change log.
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(128)
-bb_k_replay(BBBatchDev B, const int *order, int n_items, int k) {
+bb_k_replay(BBBatchDev B, const int *order, int n_items, int k, int *n_pending) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_items) return;
     const int r = order[w];
@@ -389,6 +406,7 @@ bb_k_replay(BBBatchDev B, const int *order, int n_items, int k) {
     if (!stopped) {  // the horizon was too short: log more changes and come back
         rd->horizon = n_logged + max(64, n_logged / 2);
         rd->a_done = n_logged / BB_ALIGNMENT_INTERVAL;
+        atomicAdd(n_pending, 1);
         return;
     }
     for (int x = kstop; x < n_logged; x++) {  // changes logged past the stop never happened

@@ -24,6 +24,7 @@
 #define BB_WARP_LEAN_BAND 1792  // a + b the MAXL = 4 warp build can pair (448 * 4)
 
 enum { BBQ_NODE_LANE8 = 0, BBQ_NODE_LANE16 = 1, BBQ_NODE_LEAN = 2, BBQ_NODE_WIDE = 3, BBQ_NODE_CLASSES = 4 };
+#define BBQ_COUNT(cls, parity) ((parity) * BBQ_NODE_CLASSES + (cls))  // Q.count index of a node queue's length
 #define BBQ_LEAF_COUNT 8   // Q.count index of the leaf counters (lane, warp)
 #define BBQ_OVERFLOW 10
 
@@ -32,7 +33,7 @@ struct BBNode { int r, q0, nn, t0, mm, best; };  // best < 0: root (band from th
 struct BBQueues {
     BBNode *node[BBQ_NODE_CLASSES][2];  // [class][level parity]
     BBNode *leaf[2];     // lane, warp
-    int *count;          // node counts: [class*2 + parity]; leaf counts: [BBQ_LEAF_COUNT + which]
+    int *count;          // node counts: [BBQ_COUNT(class, parity)]; leaf counts: [BBQ_LEAF_COUNT + which]
     int *overflow;
     int cap_node, cap_leaf;
     int lane8_cols, lane16_cols;   // longest target a lane node task may have (longer ones go to the warp kernels)
@@ -86,7 +87,7 @@ static __device__ void bb_push_task(const BBQueues &Q, int next_parity, const BB
         const int cls = (lw <= BB_NODE_LW_SMALL && nd.mm <= Q.lane8_cols) ? BBQ_NODE_LANE8
                         : (lw <= BB_NODE_LW && nd.mm <= Q.lane16_cols) ? BBQ_NODE_LANE16
                         : (a + b <= BB_WARP_LEAN_BAND ? BBQ_NODE_LEAN : BBQ_NODE_WIDE);
-        const int idx = atomicAdd(&Q.count[cls * 2 + next_parity], 1);
+        const int idx = atomicAdd(&Q.count[BBQ_COUNT(cls, next_parity)], 1);
         if (idx >= Q.cap_node) { atomicExch(Q.overflow, 1); return; }
         Q.node[cls][next_parity][idx] = nd;
     }
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues QN
     if (i >= B.n_reads) return;
     const int r = order[i];  // longest fragments first, so the biggest nodes start early
     BBReadDev *rd = &B.reads[r];
+    if (rd->flags & BB_FLAG_NOSPACE) return;  // no room for this read (bb_k_scan): the host runs the batch again
     BBAlignOut o;
     o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
     const BBNode nd = {r, 0, rd->seq_len, 0, rd->frag_len, -1};
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(64, (LW <= 8 ? 6 : 4))
 bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
     constexpr int CLS = LW <= BB_NODE_LW_SMALL ? BBQ_NODE_LANE8 : BBQ_NODE_LANE16;
     const BBNode *list = Q.node[CLS][parity];
-    const int count = min(Q.count[CLS * 2 + parity], Q.cap_node);
+    const int count = min(Q.count[BBQ_COUNT(CLS, parity)], Q.cap_node);
     BBLanePass<LW> S;
     BBProb P;
     BBNode nd;
@@ -385,7 +387,7 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity
     const int warp = warp_base + blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
     BBScratch sc = pool.for_warp(warp);
     const BBNode *list = Q.node[cls][parity];
-    const int count = min(Q.count[cls * 2 + parity], Q.cap_node);
+    const int count = min(Q.count[BBQ_COUNT(cls, parity)], Q.cap_node);
     for (;;) {
         int w = 0;
         if (lane == 0) w = atomicAdd(cursor, 1);
@@ -446,7 +448,7 @@ bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
     // both warps of a pair use the even warp's scratch (L and R live there)
     BBScratch sc = pool.for_warp(warp_base + blockIdx.x * BB_WARPS_PER_CTA + (wi & ~1));
     const BBNode *list = Q.node[BBQ_NODE_WIDE][parity];
-    const int count = min(Q.count[BBQ_NODE_WIDE * 2 + parity], Q.cap_node);
+    const int count = min(Q.count[BBQ_COUNT(BBQ_NODE_WIDE, parity)], Q.cap_node);
     for (;;) {
         if (!rev && lane == 0) s_task[pair] = atomicAdd(cursor, 1);
         bb_pair_sync(pair + 1);

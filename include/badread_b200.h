@@ -129,7 +129,7 @@ BB_API int bb_batch_run(bb_ctx *ctx);
 BB_API int bb_synchronize(bb_ctx *ctx);
 /* CUDA-event time (ms) of the last bb_batch_run on the ctx stream, total and per stage
  * (stage_ms[BB_N_STAGES], see bb_stage_name). Synchronizes. */
-#define BB_N_STAGES 9
+#define BB_N_STAGES 8
 BB_API int bb_last_run_ms(bb_ctx *ctx, float *total_ms, float *stage_ms);
 BB_API const char *bb_stage_name(int stage);
 /* Number of kernel launches issued by this context so far. */

@@ -15,6 +15,9 @@
 
 #define __device__
 #define __global__
+#ifndef __align__
+#define __align__(n) alignas(n)
+#endif
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
@@ -200,6 +203,7 @@ inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 inline int atomicOr(int *p, int v) { const int o = *p; *p = o | v; return o; }
 inline int atomicExch(int *p, int v) { const int o = *p; *p = v; return o; }
+inline int atomicMax(int *p, int v) { const int o = *p; if (v > o) *p = v; return o; }
 inline long long clock64() { return 0; }
 inline void __syncthreads() { emu::block_barrier(); }
 inline void __threadfence_block() {}

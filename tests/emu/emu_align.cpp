@@ -119,14 +119,14 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     int *cursor = cnt.data() + 16;
     for (int level = 0; level < 40; level++) {
         const int p = level & 1;
-        for (int c = 0; c < BBQ_NODE_CLASSES; c++) cnt[c * 2 + (p ^ 1)] = 0;
+        for (int c = 0; c < BBQ_NODE_CLASSES; c++) cnt[BBQ_COUNT(c, p ^ 1)] = 0;
         int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++, *c2b = cursor++;
         emu::run_block(BB_WARPS_PER_CTA * 32, [&]() { bb_k_node_pair(B, Q, pool, p, c0, 0); });
         emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, BBQ_NODE_LEAN, p, c1, 0); });
         emu::run_warp([&]() { bb_k_node_lane<BB_NODE_LW>(B, Q, p, c2); });
         emu::run_warp([&]() { bb_k_node_lane<BB_NODE_LW_SMALL>(B, Q, p, c2b); });
         int pending = 0;
-        for (int c = 0; c < BBQ_NODE_CLASSES; c++) pending += cnt[c * 2 + (p ^ 1)];
+        for (int c = 0; c < BBQ_NODE_CLASSES; c++) pending += cnt[BBQ_COUNT(c, p ^ 1)];
         if (pending == 0) break;
     }
     int *c3 = cursor++, *c4 = cursor++;
