@@ -45,6 +45,8 @@ struct bb_ctx {
     int sm_count = 0;
     uint64_t seed = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaStream_t side[2][4] = {};   // per alignment pipeline: the streams of the node classes that run next to the main one
+    cudaEvent_t ev_side[2][4] = {}, ev_level[2] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int64_t launches = 0;
@@ -85,11 +87,11 @@ struct bb_ctx {
 
     // scratch
     int n_warps = 0;
-    BBScratchPool pool{};
-    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist;
+    BBScratchPool pool{}, pool_lean{};  // pool_lean: split-score arrays of the single-warp node kernels (bands < 2048 rows)
+    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist, s_lr_lean;
     DevBuf d_ctime, d_chlog, d_wres, d_wtasks, d_wfallback, d_active;
     DevBuf p_q, p_t, p_ops, p_dcnt, p_out, p_qual;  // single-pair entry points (bb_align_path / bb_get_qscores): kept between calls
-    int lane8_cols = 4096, lane16_cols = 0;  // routing limits of the lane node kernels (tuning knobs)
+    int lane8_cols = 4096;  // routing limit of the lane node kernel (tuning knob)
     int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
     struct QueueBufs { DevBuf node[BBQ_NODE_CLASSES][2], leaf[2], count; } qbuf[2];  // [0] normal, [1] wide-root reads
 
@@ -124,7 +126,11 @@ static void mark(bb_ctx *ctx, cudaStream_t st, const char *name) {
     }
     cudaEvent_t e = ctx->mark_pool[ctx->mark_used++];
     cudaEventRecord(e, st);
-    ctx->marks.push_back(bb_ctx::Mark{name, st == ctx->stream2 ? 1 : 0, e});
+    int id = st == ctx->stream ? 0 : st == ctx->stream2 ? 1 : -1;
+    for (int p = 0; p < 2 && id < 0; p++)
+        for (int x = 0; x < 4; x++)
+            if (st == ctx->side[p][x]) id = 2 + 4 * p + x;
+    ctx->marks.push_back(bb_ctx::Mark{name, id < 0 ? 0 : id, e});
 }
 
 static thread_local std::string g_create_error;
@@ -185,6 +191,13 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming);
+    for (int p = 0; p < 2; p++) {
+        cudaEventCreateWithFlags(&ctx->ev_level[p], cudaEventDisableTiming);
+        for (int x = 0; x < 4; x++) {
+            cudaStreamCreateWithFlags(&ctx->side[p][x], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&ctx->ev_side[p][x], cudaEventDisableTiming);
+        }
+    }
     if (cudaHostAlloc((void **)&ctx->h_info, sizeof(bb_ctx::RunInfo), cudaHostAllocPortable) != cudaSuccess) {
         g_create_error = "cudaHostAlloc failed"; delete ctx; return BB_ERR_CUDA;
     }
@@ -202,7 +215,6 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed) {
     ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
     if (const char *e = std::getenv("BADREAD_B200_TRACE")) ctx->trace = (e[0] == '1');
     if (const char *e = std::getenv("BADREAD_B200_LANE8_COLS")) ctx->lane8_cols = std::atoi(e);
-    if (const char *e = std::getenv("BADREAD_B200_LANE16_COLS")) ctx->lane16_cols = std::atoi(e);
     if (const char *e = std::getenv("BADREAD_B200_PAIR_CTAS")) ctx->pair_ctas = (e[0] == '2') ? 2 : 1;
     *out = ctx;
     return BB_OK;
@@ -241,7 +253,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
                       &ctx->d_wtasks, &ctx->d_wfallback, &ctx->d_active,
-                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->d_scan,
+                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->s_lr_lean, &ctx->d_scan,
                       &ctx->p_q, &ctx->p_t, &ctx->p_ops, &ctx->p_dcnt, &ctx->p_out, &ctx->p_qual};
     for (auto &qb : ctx->qbuf) {
         for (auto &cl : qb.node) for (auto &d : cl) d.release();
@@ -254,6 +266,13 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_scan) cudaEventDestroy(ctx->ev_scan);
+    for (int p = 0; p < 2; p++) {
+        if (ctx->ev_level[p]) cudaEventDestroy(ctx->ev_level[p]);
+        for (int x = 0; x < 4; x++) {
+            if (ctx->side[p][x]) cudaStreamDestroy(ctx->side[p][x]);
+            if (ctx->ev_side[p][x]) cudaEventDestroy(ctx->ev_side[p][x]);
+        }
+    }
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
     for (cudaEvent_t e : ctx->mark_pool) cudaEventDestroy(e);
     delete ctx;
@@ -382,6 +401,12 @@ static int ensure_scratch(bb_ctx *ctx, int hbuf_need, int lr_need, int len_need)
     p.stack = ctx->s_stack.as<int>(); p.stack_cap = stack_cap;
     p.tbuf = ctx->s_tbuf.as<uint8_t>(); p.tbuf_stride = tbuf_stride;
     p.peq = ctx->s_peq.as<uint4>(); p.peq_stride = peq_cap; p.peq_cap = peq_cap;
+    // the single-warp node kernels (2 pipelines x 3 widths, all resident at once) only touch the split-score arrays
+    constexpr int lean_cap = 2048;  // > a + b + 1 of the widest lean class (bb_pick_L<4>(a, b, 16) > 0: a + b < 1920)
+    const size_t lean_warps = 2 * (size_t)ctx->sm_count * (2 + 3 + 3) * BB_WARPS_PER_CTA;
+    BB_CUDA(ctx, ctx->s_lr_lean.ensure(lean_warps * lean_cap * 2 * sizeof(int)));
+    ctx->pool_lean = p;
+    ctx->pool_lean.lr = ctx->s_lr_lean.as<int>(); ctx->pool_lean.lr_stride = 2ll * lean_cap; ctx->pool_lean.lr_cap = lean_cap;
     return BB_OK;
 }
 
@@ -606,7 +631,7 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
         for (int w = 0; w < 2; w++) Q[s].leaf[w] = qb.leaf[w].as<BBNode>();
         cnt[s] = qb.count.as<int>();
         Q[s].count = cnt[s]; Q[s].overflow = cnt[s] + BBQ_OVERFLOW; Q[s].cap_node = cap_node; Q[s].cap_leaf = cap_node;
-        Q[s].lane8_cols = ctx->lane8_cols; Q[s].lane16_cols = ctx->lane16_cols;
+        Q[s].lane8_cols = ctx->lane8_cols;
         BB_CUDA(ctx, cudaMemsetAsync(cnt[s], 0, 512 * sizeof(int), stream[0]));
     }
     bb_k_push_roots<<<(n + 255) / 256, 256, 0, stream[0]>>>(B, Q[0], Q[1], ctx->d_order.as<int>());
@@ -617,27 +642,47 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
     BB_CUDA(ctx, cudaStreamWaitEvent(stream[1], ctx->ev_fork, 0));
     int *cursor[2] = {cnt[0] + 16, cnt[1] + 16};
     const int warp_base[2] = {0, ctx->n_warps / 2};
-    const int grid_lean[2] = {ctx->sm_count * 2, ctx->sm_count * 2};
+    const int w4 = ctx->sm_count * 2 * BB_WARPS_PER_CTA, w2 = ctx->sm_count * 3 * BB_WARPS_PER_CTA;  // warps of the lean kernels
+    const int lean_base[2] = {0, w4 + 2 * w2};
+    // The node classes of a level read the same queues and push into the next level's: they are independent and run
+    // side by side on their own streams; the level ends when all of them have finished.
     for (int level = 0; level < ctx->n_levels; level++) {
         const int p = level & 1;
         for (int s = 0; s < 2; s++) {
             cudaStream_t st = stream[s];
             BB_CUDA(ctx, cudaMemsetAsync(cnt[s] + BBQ_COUNT(0, p ^ 1), 0, BBQ_NODE_CLASSES * sizeof(int), st));
+            BB_CUDA(ctx, cudaEventRecord(ctx->ev_level[s], st));
+            int n_side = 0;
+            auto on_side = [&]() -> cudaStream_t {
+                cudaStream_t x = ctx->side[s][n_side++];
+                cudaStreamWaitEvent(x, ctx->ev_level[s], 0);
+                mark(ctx, x, "fork");
+                return x;
+            };
             if (s == 1) {
-                bbl_node_pair(ctx->sm_count * ctx->pair_ctas, st, B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
+                cudaStream_t x = on_side();
+                bbl_node_pair(ctx->sm_count * ctx->pair_ctas, x, B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
                 ctx->launches++;
-                mark(ctx, st, "node_pair");
+                mark(ctx, x, "node_pair");
             }
-            bbl_node_warp4(grid_lean[s], st, B, Q[s], ctx->pool, BBQ_NODE_LEAN, p, cursor[s]++, warp_base[s]);
+            {
+                cudaStream_t x = on_side();
+                bbl_node_warp(2, ctx->sm_count * 3, x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4);
+                mark(ctx, x, "node_warp2");
+                x = on_side();
+                bbl_node_warp(1, ctx->sm_count * 3, x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4 + w2);
+                mark(ctx, x, "node_warp1");
+                x = on_side();
+                bbl_node_lane8(ctx->sm_count * 6, x, B, Q[s], p, cursor[s]++);
+                mark(ctx, x, "node_lane8");
+            }
+            bbl_node_warp(4, ctx->sm_count * 2, st, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s]);
             mark(ctx, st, "node_warp4");
-            if (ctx->lane16_cols > 0) {
-                bbl_node_lane16(lane_ctas, st, B, Q[s], p, cursor[s]++);
-                ctx->launches++;
-                mark(ctx, st, "node_lane16");
+            ctx->launches += 4;
+            for (int x = 0; x < n_side; x++) {
+                BB_CUDA(ctx, cudaEventRecord(ctx->ev_side[s][x], ctx->side[s][x]));
+                BB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_side[s][x], 0));
             }
-            bbl_node_lane8(ctx->sm_count * 6, st, B, Q[s], p, cursor[s]++);
-            mark(ctx, st, "node_lane8");
-            ctx->launches += 2;
         }
     }
     for (int s = 0; s < 2; s++) {
@@ -938,8 +983,8 @@ extern "C" int bb_trace_dump(bb_ctx *ctx, const char *path) {
     const int S = ctx->n_split;
     for (int w = 0; w < S; w++) {
         bb_ctx *wk = w == 0 ? ctx : ctx->kids[(size_t)w - 1];
-        float prev[2] = {0.f, 0.f};
-        bool have[2] = {false, false};
+        float prev[10] = {};
+        bool have[10] = {};
         for (const bb_ctx::Mark &m : wk->marks) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, base, m.ev) != cudaSuccess) continue;

@@ -17,9 +17,8 @@ void bbl_window_lane8(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev e
                       int *fallback_count);
 void bbl_window_warp(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, const BBWinTask *tasks,
                      const int *n_tasks, unsigned long long seed, int *cursor);
-void bbl_node_warp4(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity, int *cursor,
-                    int warp_base);
-void bbl_node_lane16(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, int parity, int *cursor);
+void bbl_node_warp(int words, int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor,
+                   int warp_base);  // words per lane: 1, 2 or 4 (class BBQ_NODE_LEAN1 / 2 / 4)
 void bbl_node_lane8(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, int parity, int *cursor);
 cudaError_t bbl_node_pair_init();
 void bbl_node_pair(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor,

@@ -17,16 +17,17 @@
 #include "bb_align.cuh"
 #include "bb_lane.cuh"
 
-#define BB_NODE_LW 16        // window words of the wider lane node kernel (bands up to 32*14 rows)
-#define BB_NODE_LW_SMALL 8   // window words of the narrow lane node kernel
+#define BB_NODE_LW_SMALL 8   // window words of the lane node kernel (bands up to 32*6 rows)
 #define BB_LEAF_LW 8         // window words of the lane leaf kernel
 #define BB_LEAF_LANE_COLS 2048
-#define BB_WARP_LEAN_BAND 1792  // a + b the MAXL = 4 warp build can pair (448 * 4)
 
-enum { BBQ_NODE_LANE8 = 0, BBQ_NODE_LANE16 = 1, BBQ_NODE_LEAN = 2, BBQ_NODE_WIDE = 3, BBQ_NODE_CLASSES = 4 };
+// Node classes, one queue (per level parity) and one kernel each: lane mode for narrow short nodes; single warps with
+// the forward and the reverse pass in its two 16-lane halves, 1 / 2 / 4 words per lane (one build per width: the
+// narrow ones need a third of the registers of the wide one and run at three times the occupancy); warp pairs beyond.
+enum { BBQ_NODE_LANE8 = 0, BBQ_NODE_LEAN1 = 1, BBQ_NODE_LEAN2 = 2, BBQ_NODE_LEAN4 = 3, BBQ_NODE_WIDE = 4, BBQ_NODE_CLASSES = 5 };
 #define BBQ_COUNT(cls, parity) ((parity) * BBQ_NODE_CLASSES + (cls))  // Q.count index of a node queue's length
-#define BBQ_LEAF_COUNT 8   // Q.count index of the leaf counters (lane, warp)
-#define BBQ_OVERFLOW 10
+#define BBQ_LEAF_COUNT 10  // Q.count index of the leaf counters (lane, warp)
+#define BBQ_OVERFLOW 12
 
 struct BBNode { int r, q0, nn, t0, mm, best; };  // best < 0: root (band from the read's edit bound)
 
@@ -36,7 +37,7 @@ struct BBQueues {
     int *count;          // node counts: [BBQ_COUNT(class, parity)]; leaf counts: [BBQ_LEAF_COUNT + which]
     int *overflow;
     int cap_node, cap_leaf;
-    int lane8_cols, lane16_cols;   // longest target a lane node task may have (longer ones go to the warp kernels)
+    int lane8_cols;      // longest target a lane node task may have (longer ones go to the warp kernels)
 };
 
 struct BBAlignOut {      // where a read's alignment goes
@@ -84,9 +85,9 @@ static __device__ void bb_push_task(const BBQueues &Q, int next_parity, const BB
     } else {
         // a lane walks its node alone, one column after the other: only short nodes go there (they are the many
         // ones); a long narrow node would hold a whole launch up and runs ~15x sooner as a warp wavefront
+        const int L2 = bb_pick_L<4>(a, b, 16);  // words per lane that let two 16-lane groups share a warp (0: too wide)
         const int cls = (lw <= BB_NODE_LW_SMALL && nd.mm <= Q.lane8_cols) ? BBQ_NODE_LANE8
-                        : (lw <= BB_NODE_LW && nd.mm <= Q.lane16_cols) ? BBQ_NODE_LANE16
-                        : (a + b <= BB_WARP_LEAN_BAND ? BBQ_NODE_LEAN : BBQ_NODE_WIDE);
+                        : L2 == 1 ? BBQ_NODE_LEAN1 : L2 == 2 ? BBQ_NODE_LEAN2 : L2 == 4 ? BBQ_NODE_LEAN4 : BBQ_NODE_WIDE;
         const int idx = atomicAdd(&Q.count[BBQ_COUNT(cls, next_parity)], 1);
         if (idx >= Q.cap_node) { atomicExch(Q.overflow, 1); return; }
         Q.node[cls][next_parity][idx] = nd;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) bb_k_push_roots(BBBatchDev B, BBQueues QN
     const BBNode nd = {r, 0, rd->seq_len, 0, rd->frag_len, -1};
     int a, b;
     bb_task_band(nd, rd->upper, a, b);
-    const bool wide = !bb_uses_traceback(nd.nn, nd.mm) && bb_lane_words(a, b) > BB_NODE_LW && a + b > BB_WARP_LEAN_BAND;
+    const bool wide = !bb_uses_traceback(nd.nn, nd.mm) && bb_pick_L<4>(a, b, 16) == 0;
     bb_push_task(wide ? QW : QN, 0, o, nd, rd->upper);
 }
 
@@ -238,9 +239,9 @@ __device__ int bb_lane_column_scores(const BBLanePass<LW> &S, int n, int lo, int
 
 // ---------------------------------------------------------------------------------------------- lane node kernel
 template <int LW>
-__global__ void __launch_bounds__(64, (LW <= 8 ? 6 : 4))
+__global__ void __launch_bounds__(64, 6)
 bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
-    constexpr int CLS = LW <= BB_NODE_LW_SMALL ? BBQ_NODE_LANE8 : BBQ_NODE_LANE16;
+    constexpr int CLS = BBQ_NODE_LANE8;
     const BBNode *list = Q.node[CLS][parity];
     const int count = min(Q.count[BBQ_COUNT(CLS, parity)], Q.cap_node);
     BBLanePass<LW> S;
@@ -379,15 +380,18 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
 }
 
 // ---------------------------------------------------------------------------------------------- warp kernels
-// One Hirschberg node per warp with the wavefront passes of bb_align.cuh (MAXL bounds the instantiated variants).
-template <int MAXL>
-__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (MAXL <= 4 ? 3 : 1))
-bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity, int *cursor, int warp_base) {
+// One Hirschberg node per warp: the forward pass over the left half of the target and the reverse pass over the right
+// half run side by side in the warp's two 16-lane groups with exactly L words per lane (class BBQ_NODE_LEAN<L>), several
+// columns per wavefront step (bb_band_pass_cb); then the split row by edlib's rule.
+template <int L>
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (L == 1 ? 6 : L == 2 ? 5 : 3))
+bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
+    constexpr int CLS = L == 1 ? BBQ_NODE_LEAN1 : L == 2 ? BBQ_NODE_LEAN2 : BBQ_NODE_LEAN4;
     const int lane = threadIdx.x & 31;
     const int warp = warp_base + blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
     BBScratch sc = pool.for_warp(warp);
-    const BBNode *list = Q.node[cls][parity];
-    const int count = min(Q.count[BBQ_COUNT(cls, parity)], Q.cap_node);
+    const BBNode *list = Q.node[CLS][parity];
+    const int count = min(Q.count[BBQ_COUNT(CLS, parity)], Q.cap_node);
     for (;;) {
         int w = 0;
         if (lane == 0) w = atomicAdd(cursor, 1);
@@ -401,15 +405,31 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int cls, int parity
         const uint8_t *q = B.seq + rd->seq_off, *t = B.frag + rd->frag_off;
         int a, b;
         bb_task_band(nd, rd->upper, a, b);
-        int best = nd.best, split = 0, ls = 0, rs = 0;
-        const int err = bb_node_warp<MAXL, (MAXL <= 4)>(q, t, nd.q0, nd.nn, nd.t0, nd.mm, a, b, sc, best, split, ls, rs);
+        const int left_w = nd.mm / 2, right_w = nd.mm - left_w;
+        const int loL = max(0, left_w - 1 - a), hiL = min(nd.nn - 1, left_w - 1 + b);
+        const int loR = max(0, right_w - 1 - a), hiR = min(nd.nn - 1, right_w - 1 + b);
+        int best = nd.best, split = 0, ls = 0, rs = 0, err = 0;
+        if (hiL - loL + 1 > sc.lr_cap || hiR - loR + 1 > sc.lr_cap) err = 16;
+        else {
+            BBProb P;
+            P.n = nd.nn; P.a = a; P.b = b; P.peq = sc.peq; P.hist = nullptr; P.nb_alloc = 0;
+            if (lane < 16) {
+                P.q = q + nd.q0; P.qs = 1; P.t = t + nd.t0; P.ts = 1; P.ncols = left_w;
+                P.peq_bit0 = nd.q0 + BB_PEQ_BIT0; P.cols_out = sc.L; P.cols_lo = loL;
+            } else {
+                P.q = q + nd.q0 + nd.nn - 1; P.qs = -1; P.t = t + nd.t0 + nd.mm - 1; P.ts = -1; P.ncols = right_w;
+                P.peq_bit0 = nd.q0 + nd.nn - 1 + BB_PEQ_BIT0; P.cols_out = sc.R; P.cols_lo = loR;
+            }
+            bb_band_pass_cb<L, true, BB_NODE_CB>(P, 16);
+            __syncwarp();
+            err = bb_split_warp(sc, loL, hiL, loR, hiR, nd.nn, left_w, right_w, best, split, ls, rs);
+        }
         __syncwarp();
         if (lane == 0) {
             if (err) atomicOr(&rd->flags, err << 8);
             else {
-                const int left_w = nd.mm / 2;
                 BBNode c0 = {nd.r, nd.q0, split + 1, nd.t0, left_w, ls};
-                BBNode c1 = {nd.r, nd.q0 + split + 1, nd.nn - split - 1, nd.t0 + left_w, nd.mm - left_w, rs};
+                BBNode c1 = {nd.r, nd.q0 + split + 1, nd.nn - split - 1, nd.t0 + left_w, right_w, rs};
                 bb_push_task(Q, parity ^ 1, o, c0, rd->upper);
                 bb_push_task(Q, parity ^ 1, o, c1, rd->upper);
             }

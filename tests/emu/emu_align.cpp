@@ -97,7 +97,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     BBQueues Q;
     for (int c = 0; c < BBQ_NODE_CLASSES; c++) for (int p = 0; p < 2; p++) { qn[c][p].resize(cap); Q.node[c][p] = qn[c][p].data(); }
     for (int w = 0; w < 2; w++) { ql[w].resize(cap); Q.leaf[w] = ql[w].data(); }
-    Q.count = cnt.data(); Q.overflow = cnt.data() + BBQ_OVERFLOW; Q.cap_node = cap; Q.cap_leaf = cap; Q.lane8_cols = 4096; Q.lane16_cols = 0;
+    Q.count = cnt.data(); Q.overflow = cnt.data() + BBQ_OVERFLOW; Q.cap_node = cap; Q.cap_leaf = cap; Q.lane8_cols = 4096;
     // scratch for the warp kernels (warp 0 only) and the lane leaf kernel
     const int big = std::max(n, m) + 64;
     const int NW = BB_WARPS_PER_CTA;  // scratch for every warp of one emulated CTA
@@ -120,10 +120,11 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     for (int level = 0; level < 40; level++) {
         const int p = level & 1;
         for (int c = 0; c < BBQ_NODE_CLASSES; c++) cnt[BBQ_COUNT(c, p ^ 1)] = 0;
-        int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++, *c2b = cursor++;
+        int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++, *c2b = cursor++, *c2c = cursor++;
         emu::run_block(BB_WARPS_PER_CTA * 32, [&]() { bb_k_node_pair(B, Q, pool, p, c0, 0); });
-        emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, BBQ_NODE_LEAN, p, c1, 0); });
-        emu::run_warp([&]() { bb_k_node_lane<BB_NODE_LW>(B, Q, p, c2); });
+        emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, p, c1, 0); });
+        emu::run_warp([&]() { bb_k_node_warp<2>(B, Q, pool, p, c2, 0); });
+        emu::run_warp([&]() { bb_k_node_warp<1>(B, Q, pool, p, c2c, 0); });
         emu::run_warp([&]() { bb_k_node_lane<BB_NODE_LW_SMALL>(B, Q, p, c2b); });
         int pending = 0;
         for (int c = 0; c < BBQ_NODE_CLASSES; c++) pending += cnt[BBQ_COUNT(c, p ^ 1)];
