@@ -8,6 +8,10 @@ import ctypes
 import os
 import pathlib
 
+# every worker of a context drives several CUDA streams; with the default of 8 hardware queues they would serialize
+# behind each other (must be set before CUDA is initialized in this process; the library sets the same default)
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 _HERE = pathlib.Path(os.path.dirname(os.path.realpath(__file__)))
 LIB_PATH = _HERE / 'libbadread_b200.so'
 

@@ -93,6 +93,7 @@ struct bb_ctx {
     DevBuf p_q, p_t, p_ops, p_dcnt, p_out, p_qual;  // single-pair entry points (bb_align_path / bb_get_qscores): kept between calls
     int lane8_cols = 4096;  // routing limit of the lane node kernel (tuning knob)
     int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
+    bool head_worker = true;  // worker 0 = the longest reads only (see bb_batch_upload)
     struct QueueBufs { DevBuf node[BBQ_NODE_CLASSES][2], leaf[2], count; } qbuf[2];  // [0] normal, [1] wide-root reads
 
 
@@ -134,6 +135,16 @@ static void mark(bb_ctx *ctx, cudaStream_t st, const char *name) {
 }
 
 static thread_local std::string g_create_error;
+
+// A context drives up to 7 streams per worker (4 workers by default).  CUDA multiplexes streams onto
+// CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue serialize behind each other's
+// pending waits.  Ask for the maximum unless the user chose a value; it only takes effect if CUDA is not initialized yet
+// in this process (badread_b200/_lib.py and bench.py set it before anything touches CUDA).
+namespace {
+struct ConnectionsDefault {
+    ConnectionsDefault() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_connections_default;
+}  // namespace
 
 #define BB_CUDA(ctx, call)                                                                                   \
     do {                                                                                                     \
@@ -216,6 +227,7 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed) {
     if (const char *e = std::getenv("BADREAD_B200_TRACE")) ctx->trace = (e[0] == '1');
     if (const char *e = std::getenv("BADREAD_B200_LANE8_COLS")) ctx->lane8_cols = std::atoi(e);
     if (const char *e = std::getenv("BADREAD_B200_PAIR_CTAS")) ctx->pair_ctas = (e[0] == '2') ? 2 : 1;
+    if (const char *e = std::getenv("BADREAD_B200_HEAD_WORKER")) ctx->head_worker = (e[0] != '0');
     *out = ctx;
     return BB_OK;
 }
@@ -666,10 +678,9 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
                 mark(ctx, x, "node_pair");
             }
             {
-                cudaStream_t x = on_side();
+                cudaStream_t x = on_side();   // the two narrow single-warp classes share a stream
                 bbl_node_warp(2, ctx->sm_count * 3, x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4);
                 mark(ctx, x, "node_warp2");
-                x = on_side();
                 bbl_node_warp(1, ctx->sm_count * 3, x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4 + w2);
                 mark(ctx, x, "node_warp1");
                 x = on_side();
@@ -890,7 +901,23 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return len[(size_t)x] > len[(size_t)y]; });
     ctx->part.assign((size_t)S, std::vector<int32_t>());
-    for (int32_t i = 0; i < n_reads; i++) ctx->part[(size_t)(i % S)].push_back(order[(size_t)i]);
+    // The chain of Hirschberg levels of the longest reads is the longest dependent chain of the batch.  Worker 0 is a
+    // small HEAD batch of the longest reads: its error loop is short, so their alignment starts early and overlaps the
+    // other workers' error loops instead of trailing the step.  The other workers share the rest evenly.
+    int32_t n_head = 0;
+    if (S >= 3 && ctx->head_worker) {
+        int64_t total = 0, hb = 0;
+        for (int32_t r = 0; r < n_reads; r++) total += len[(size_t)r];
+        const int64_t longest = len[(size_t)order[0]];
+        while (n_head < n_reads / 16 && hb < total / S &&
+               (10 * len[(size_t)order[(size_t)n_head]] >= 6 * longest || hb < total / (4 * S))) {
+            hb += len[(size_t)order[(size_t)n_head]];
+            ctx->part[0].push_back(order[(size_t)n_head++]);
+        }
+        if (n_head < 16) { ctx->part[0].clear(); n_head = 0; }
+    }
+    if (n_head > 0) for (int32_t i = n_head; i < n_reads; i++) ctx->part[(size_t)(1 + (i - n_head) % (S - 1))].push_back(order[(size_t)i]);
+    else for (int32_t i = 0; i < n_reads; i++) ctx->part[(size_t)(i % S)].push_back(order[(size_t)i]);
     constexpr int kBadLiteral = 1 << 20;  // not a bb_status value
     std::vector<int> rcs((size_t)S, 0);
     std::vector<std::thread> threads;

@@ -41,6 +41,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.realpath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')   # before torch / the library initialize CUDA (see _lib.py)
 
 SEED = 1
 PARITY_PREFIX = 10000   # first 10 000 read indices for the sharded configs
