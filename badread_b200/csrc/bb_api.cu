@@ -45,8 +45,8 @@ struct bb_ctx {
     int sm_count = 0;
     uint64_t seed = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaStream_t side[2][4] = {};   // per alignment pipeline: the streams of the node classes that run next to the main one
-    cudaEvent_t ev_side[2][4] = {}, ev_level[2] = {};
+    cudaStream_t side[2][3] = {};   // per alignment pipeline: the streams of the node classes that run next to the main one
+    cudaEvent_t ev_side[2][3] = {}, ev_level[2] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int64_t launches = 0;
@@ -129,7 +129,7 @@ static void mark(bb_ctx *ctx, cudaStream_t st, const char *name) {
     cudaEventRecord(e, st);
     int id = st == ctx->stream ? 0 : st == ctx->stream2 ? 1 : -1;
     for (int p = 0; p < 2 && id < 0; p++)
-        for (int x = 0; x < 4; x++)
+        for (int x = 0; x < 3; x++)
             if (st == ctx->side[p][x]) id = 2 + 4 * p + x;
     ctx->marks.push_back(bb_ctx::Mark{name, id < 0 ? 0 : id, e});
 }
@@ -175,7 +175,7 @@ extern "C" int64_t bb_launch_count(const bb_ctx *ctx) {
     return total;
 }
 
-static int create_worker(bb_ctx **out, int device, uint64_t seed) {
+static int create_worker(bb_ctx **out, int device, uint64_t seed, bool high_priority = false) {
     if (!out) return BB_ERR_ARG;
     *out = nullptr;
     int n_dev = 0;
@@ -195,17 +195,22 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed) {
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
-    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    // worker 0 carries the longest reads of a split batch (bb_batch_upload): their dependent chain of stages bounds the
+    // step from below, so its kernels go first whenever the block scheduler has a choice
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const int prio = high_priority ? prio_hi : prio_lo;
+    e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio);
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
-    cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming);
     for (int p = 0; p < 2; p++) {
         cudaEventCreateWithFlags(&ctx->ev_level[p], cudaEventDisableTiming);
-        for (int x = 0; x < 4; x++) {
-            cudaStreamCreateWithFlags(&ctx->side[p][x], cudaStreamNonBlocking);
+        for (int x = 0; x < 3; x++) {
+            cudaStreamCreateWithPriority(&ctx->side[p][x], cudaStreamNonBlocking, prio);
             cudaEventCreateWithFlags(&ctx->ev_side[p][x], cudaEventDisableTiming);
         }
     }
@@ -235,7 +240,9 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed) {
 extern "C" int bb_destroy(bb_ctx *ctx);
 
 extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
-    int rc = create_worker(out, device, seed);
+    bool prio = true;
+    if (const char *e = std::getenv("BADREAD_B200_HEAD_PRIORITY")) prio = (e[0] != '0');
+    int rc = create_worker(out, device, seed, prio);
     if (rc) return rc;
     bb_ctx *ctx = *out;
     int n_workers = 4;
@@ -280,7 +287,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
     if (ctx->ev_scan) cudaEventDestroy(ctx->ev_scan);
     for (int p = 0; p < 2; p++) {
         if (ctx->ev_level[p]) cudaEventDestroy(ctx->ev_level[p]);
-        for (int x = 0; x < 4; x++) {
+        for (int x = 0; x < 3; x++) {
             if (ctx->side[p][x]) cudaStreamDestroy(ctx->side[p][x]);
             if (ctx->ev_side[p][x]) cudaEventDestroy(ctx->ev_side[p][x]);
         }

@@ -29,17 +29,35 @@ enum { BB_STOP_HORIZON = 0, BB_STOP_LIMIT = 1, BB_STOP_COUNT = 2, BB_STOP_NOLOOP
 struct BBWinTask { int r, a; };  // read, alignment ordinal (1-based: after 25*a changes)
 
 // ------------------------------------------------------------------------------------------------ mutate
-// One CTA (4 warps) per read: every step the 128 threads evaluate 128 consecutive loop iterations (position, k-mer,
-// model draw: chains of dependent loads, independent across iterations), then warp 0 commits the iterations that
-// change something, in order.
+// One CTA (4 warps) per read.  A step covers BB_MUT_ITERS consecutive loop iterations:
+//   1. every thread evaluates its iterations (position, k-mer row, model draw: chains of dependent loads, independent
+//      across iterations);
+//   2. the iterations that change something are compacted, in order, into a candidate list;
+//   3. all threads prefetch what committing a candidate needs - the k encoded slot strings, whether each differs from
+//      the original base, whether the slot is still pristine - into shared memory, k lanes per candidate;
+//   4. warp 0 commits the candidates in iteration order out of shared memory.  A slot rewritten earlier in the same
+//      step is recognised through a small position bitmap and re-read from global memory (the only serial loads left).
+// The commit is the reference's `if new_fragment_bases[i+j] is None` (simulate.py:309) in iteration order: identical
+// results, but the serial part costs tens of nanoseconds per change instead of a global round trip.
+#define BB_MUT_IPT 2                                        // iterations per thread and step
+#define BB_MUT_ITERS (BB_WARPS_PER_CTA * 32 * BB_MUT_IPT)   // iterations per step
+#define BB_MUT_KMAX 16                                      // slots per candidate in shared memory (k <= 12)
+#define BB_MUT_DIRTY_WORDS 128                              // bitmap over positions mod 4096
+
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
 bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter, const int *order,
             int n_items) {
-    constexpr int NT = BB_WARPS_PER_CTA * 32;
-    __shared__ int s_kind[NT], s_pos[NT], s_rpos[NT];
-    __shared__ uint32_t s_pay[NT];
-    __shared__ int s_w, s_stop, s_cc;
+    constexpr int NT = BB_WARPS_PER_CTA * 32, NI = BB_MUT_ITERS, NG = NI / 32;
+    __shared__ int s_pos[NI];
+    __shared__ uint32_t s_pay[NI];
+    __shared__ uint8_t s_kind[NI], s_rpos[NI];
+    __shared__ unsigned short s_cidx[NI];
+    __shared__ uint32_t s_enc[NI][BB_MUT_KMAX];
+    __shared__ uint8_t s_flag[NI][BB_MUT_KMAX];   // 0: same as the original base, 1: differs but the slot is taken, 2: differs, pristine
+    __shared__ uint32_t s_dirty[BB_MUT_DIRTY_WORDS];
+    __shared__ int s_gcount[NG];
+    __shared__ int s_w, s_stop, s_cc, s_ncand;
     __shared__ long long s_n0;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -82,47 +100,82 @@ bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work
                 __syncthreads();
                 break;
             }
-            {
-                const long long n = n0 + threadIdx.x;
+            // 1. evaluate: slot i of the step is iteration n0 + i; thread t owns slots t, t + NT, ...
+#pragma unroll
+            for (int j = 0; j < BB_MUT_IPT; j++) {
+                const int i = j * NT + threadIdx.x;
+                const long long n = n0 + i;
                 int kind = 0, pos_i = 0, rpos = 0;
                 uint32_t payload = 0;
                 if (n < limit) bb_eval_iteration(em, frag, kidx, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
-                s_kind[threadIdx.x] = kind; s_pos[threadIdx.x] = pos_i; s_rpos[threadIdx.x] = rpos; s_pay[threadIdx.x] = payload;
+                s_kind[i] = (uint8_t)kind; s_pos[i] = pos_i; s_rpos[i] = (uint8_t)rpos; s_pay[i] = payload;
+            }
+            if (threadIdx.x < BB_MUT_DIRTY_WORDS) s_dirty[threadIdx.x] = 0u;
+            __syncthreads();
+            // 2. candidate list in iteration order
+            for (int g = warp; g < NG; g += BB_WARPS_PER_CTA) {
+                const uint32_t m = __ballot_sync(BB_FULL, s_kind[32 * g + lane] != 0);
+                if (lane == 0) s_gcount[g] = __popc(m);
             }
             __syncthreads();
+            for (int g = warp; g < NG; g += BB_WARPS_PER_CTA) {
+                int off = 0;
+                for (int h = 0; h < g; h++) off += s_gcount[h];
+                const bool c = s_kind[32 * g + lane] != 0;
+                const uint32_t m = __ballot_sync(BB_FULL, c);
+                if (c) s_cidx[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(32 * g + lane);
+                if (g == NG - 1 && lane == 0) s_ncand = off + __popc(m);
+            }
+            __syncthreads();
+            const int ncand = s_ncand;
+            // 3. prefetch, BB_MUT_KMAX lanes per candidate
+            for (int c = threadIdx.x / BB_MUT_KMAX; c < ncand; c += NT / BB_MUT_KMAX) {
+                const int l = threadIdx.x % BB_MUT_KMAX;
+                if (l < k) {
+                    const int i = s_cidx[c];
+                    const int bi = s_pos[i];
+                    const uint8_t fb = frag[bi + l];
+                    const uint32_t enc = s_kind[i] == 1 ? em.slots[(long long)s_pay[i] * k + l]
+                                                        : (l == s_rpos[i] ? s_pay[i] : bb_slot_inline(1, fb, 0));
+                    const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
+                    s_enc[c][l] = enc;
+                    s_flag[c][l] = differs ? (state[bi + l] == BB_SLOT_NONE ? 2 : 1) : 0;
+                }
+            }
+            __syncthreads();
+            // 4. ordered commit by warp 0
             if (warp == 0) {
                 int change_count = s_cc, stop = -1;
-                long long next_n0 = n0 + NT;
-                for (int g = 0; g < BB_WARPS_PER_CTA && stop < 0; g++) {
-                    uint32_t cmask = __ballot_sync(BB_FULL, s_kind[32 * g + lane] != 0);
-                    while (cmask) {
-                        const int L = 32 * g + __ffs(cmask) - 1;
-                        cmask &= cmask - 1;
-                        const long long nL = n0 + L;
-                        if (change_count >= horizon) { stop = BB_STOP_HORIZON; next_n0 = nL; break; }  // pause at an iteration top
-                        const int bi = s_pos[L], bkind = s_kind[L], brpos = s_rpos[L];
-                        const uint32_t bpay = s_pay[L];
-                        uint32_t enc = 0;
-                        bool app = false;
-                        if (lane < k) {
-                            const uint8_t fb = frag[bi + lane];
-                            enc = bkind == 1 ? em.slots[(long long)bpay * k + lane]
-                                             : (lane == brpos ? bpay : bb_slot_inline(1, fb, 0));
-                            const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
-                            app = differs && state[bi + lane] == BB_SLOT_NONE;  // simulate.py:309
+                long long next_n0 = n0 + NI;
+                for (int c = 0; c < ncand; c++) {
+                    const int i = s_cidx[c];
+                    const long long nL = n0 + i;
+                    if (change_count >= horizon) { stop = BB_STOP_HORIZON; next_n0 = nL; break; }  // pause at an iteration top
+                    const int bi = s_pos[i];
+                    uint32_t enc = 0;
+                    bool app = false;
+                    if (lane < k) {
+                        const int pos = bi + lane;
+                        enc = s_enc[c][lane];
+                        const int fg = s_flag[c][lane];
+                        if (fg) {
+                            const bool dirty = (s_dirty[(pos >> 5) & (BB_MUT_DIRTY_WORDS - 1)] >> (pos & 31)) & 1u;
+                            app = dirty ? (state[pos] == BB_SLOT_NONE) : (fg == 2);  // simulate.py:309
                         }
-                        const uint32_t amask = __ballot_sync(BB_FULL, app);
-                        if (app) {  // slots of one k-mer are distinct positions: applied together, ordinals in slot order
-                            const int ord = change_count + __popc(amask & ((1u << lane) - 1u)) + 1;
-                            state[bi + lane] = enc;
-                            ctime[bi + lane] = (unsigned int)ord;
-                            chlog[ord - 1] = make_uint2((unsigned int)nL, (unsigned int)(bi + lane) | ((enc & 0xffu) << 24));
-                        }
-                        change_count += __popc(amask);
-                        __syncwarp();
-                        // the guard at the top of the next iteration (simulate.py:285) can only change after a commit
-                        if ((double)change_count > cc_limit) { stop = BB_STOP_COUNT; next_n0 = nL + 1; break; }
                     }
+                    const uint32_t amask = __ballot_sync(BB_FULL, app);
+                    if (app) {  // slots of one k-mer are distinct positions: applied together, ordinals in slot order
+                        const int pos = bi + lane;
+                        const int ord = change_count + __popc(amask & ((1u << lane) - 1u)) + 1;
+                        state[pos] = enc;
+                        ctime[pos] = (unsigned int)ord;
+                        chlog[ord - 1] = make_uint2((unsigned int)nL, (unsigned int)pos | ((enc & 0xffu) << 24));
+                        atomicOr(&s_dirty[(pos >> 5) & (BB_MUT_DIRTY_WORDS - 1)], 1u << (pos & 31));
+                    }
+                    change_count += __popc(amask);
+                    __syncwarp();
+                    // the guard at the top of the next iteration (simulate.py:285) can only change after a commit
+                    if ((double)change_count > cc_limit) { stop = BB_STOP_COUNT; next_n0 = nL + 1; break; }
                 }
                 __syncwarp();  // every lane has read s_cc / s_n0 before lane 0 replaces them
                 if (lane == 0) { s_cc = change_count; s_stop = stop; s_n0 = next_n0; }

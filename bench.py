@@ -260,6 +260,46 @@ def parity_check(res, picks, outs):
     return bad
 
 
+def reference_shim_rate(cfg, n_procs, quantity_bases):
+    """BASELINE.md's primary CPU baseline: the UNMODIFIED reference (`badread.simulate.simulate`, installed from
+    /root/reference into baseline/_ref) with `edlib` provided by oracle/edlib_shim (the oracle's aligner; the real wheel
+    is absent), run the way its README recommends for parallelism: n independent processes with --quantity target/n and
+    different seeds.  Returns the cpu_baseline-style object, or None with a reason."""
+    ref_dir = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'badread')):
+        return {'value': None, 'kind': 'reference', 'sample': 'baseline/_ref is not installed'}
+    try:
+        fd, fasta = tempfile.mkstemp(suffix='.fasta')
+        with os.fdopen(fd, 'wb') as f:
+            for name, n, seed, depth, circ in cfg['contigs']:
+                hdr = f'>{name}' + (f' depth={depth:g}' if depth != 1.0 else '') + (' circular=true' if circ else '')
+                f.write(hdr.encode() + b'\n' + _synth_contig(seed, n).tobytes() + b'\n')
+        env = dict(os.environ)
+        env['PYTHONPATH'] = os.pathsep.join([os.path.join(ROOT, 'oracle', 'edlib_shim'), ref_dir, env.get('PYTHONPATH', '')])
+        runner = ('import sys\nfrom badread.__main__ import main\nmain()\n')
+        t0 = time.perf_counter()
+        procs = []
+        for i in range(n_procs):
+            argv = [sys.executable, '-c', runner, 'simulate', '--reference', fasta, '--quantity', str(quantity_bases),
+                    '--seed', str(SEED + i)] + cfg['extra']
+            procs.append(subprocess.Popen(argv, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL))
+        bases = 0
+        for p in procs:
+            out, _ = p.communicate()
+            if p.returncode != 0:
+                raise RuntimeError(f'reference process exited with {p.returncode}')
+            lines = out.split(b'\n')
+            bases += sum(len(lines[j]) for j in range(1, len(lines), 4))
+        dt = time.perf_counter() - t0
+        os.unlink(fasta)
+        return {'value': bases / dt / 1e9, 'unit': 'Gbases/s', 'cores': n_procs, 'kind': 'reference',
+                'sample': f'unmodified badread.simulate (baseline/_ref) + oracle/edlib_shim: {n_procs} processes x --quantity '
+                          f'{quantity_bases} with seeds {SEED}..{SEED + n_procs - 1}, {bases} bases in {dt:.1f} s wall of the '
+                          f'slowest (model loading, ~3 s per process, included)'}
+    except Exception as e:   # a reported baseline, never a reason to fail the bench
+        return {'value': None, 'kind': 'reference', 'sample': f'failed: {e}'}
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -298,6 +338,8 @@ def main():
     ap.add_argument('--batch_reads', type=int, default=32768, help='reads per device batch')
     ap.add_argument('--profile', action='store_true', help='skip the e2e, parity and CPU legs (for runs under ncu)')
     ap.add_argument('--no_parity', action='store_true', help='skip the parity + CPU baseline leg')
+    ap.add_argument('--ref_shim_bases', type=int, default=1500000,
+                    help='bases per process of the reference-with-shim baseline leg (0: skip it)')
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -460,6 +502,10 @@ def main():
                   'scope': 'whole workload' if limit is None else f'first {limit} read indices (SURVEY.md 8d)',
                   'against': 'oracle/badread_oracle.c (Philox mode), same read indices: seq, qual, matches/columns'}
 
+    ref_shim = None
+    if rank == 0 and world == 1 and not a.profile and not a.no_parity and a.ref_shim_bases > 0:
+        ref_shim = reference_shim_rate(cfg, n_cores, a.ref_shim_bases)
+
     tot_bases, max_elapsed, max_e2e = float(bases), elapsed, e2e_elapsed
     if dist is not None:
         import torch
@@ -527,6 +573,7 @@ def main():
             'gpu_launches': int(launches),
             'roofline': roofline,
             'cpu_baseline': {'value': cpu_g, 'unit': 'Gbases/s', 'cores': max(1, n_cores // world), 'kind': 'port', 'sample': cpu_desc},
+            'cpu_baseline_reference': ref_shim,
             'parity': parity}
     print(json.dumps(line), flush=True)
     eng.close()
