@@ -94,6 +94,9 @@ struct bb_ctx {
     int lane8_cols = 4096;  // routing limit of the lane node kernel (tuning knob)
     int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
     bool head_worker = true;  // worker 0 = the longest reads only (see bb_batch_upload)
+    bool is_head = false;     // this worker holds the head batch of the current upload
+    int grid_div_env = 0;
+    int grid_div = 1;         // persistent grids are launched at 1/grid_div of their full size (the workers of a split batch share the SMs)
     struct QueueBufs { DevBuf node[BBQ_NODE_CLASSES][2], leaf[2], count; } qbuf[2];  // [0] normal, [1] wide-root reads
 
 
@@ -233,6 +236,7 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed, bool high_prio
     if (const char *e = std::getenv("BADREAD_B200_LANE8_COLS")) ctx->lane8_cols = std::atoi(e);
     if (const char *e = std::getenv("BADREAD_B200_PAIR_CTAS")) ctx->pair_ctas = (e[0] == '2') ? 2 : 1;
     if (const char *e = std::getenv("BADREAD_B200_HEAD_WORKER")) ctx->head_worker = (e[0] != '0');
+    if (const char *e = std::getenv("BADREAD_B200_GRID_DIV")) ctx->grid_div_env = std::atoi(e);
     *out = ctx;
     return BB_OK;
 }
@@ -597,6 +601,13 @@ static int w_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_ind
     return BB_OK;
 }
 
+// Persistent grids (CTAs that pull work from a queue until it is empty) of `per_sm` CTAs per SM at full size.  The
+// workers of a split batch run side by side: each launches its share, so that their kernels are resident together
+// instead of queueing behind each other's long-running CTAs.
+static int pgrid(const bb_ctx *ctx, int per_sm) {
+    return std::max(ctx->sm_count / 2, (ctx->sm_count * per_sm + ctx->grid_div - 1) / ctx->grid_div);
+}
+
 // The error loop decoupled from its identity re-measurements (bb_loop.cuh): mutate ahead -> task list -> all window
 // alignments as independent lane tasks -> scalar replay, n_rounds times back to back.  A round after the last read
 // has finished costs six launches that find nothing to do; a read that is still pending after the last round is
@@ -611,21 +622,21 @@ static int enqueue_error_loop(bb_ctx *ctx, const BBBatchDev &B) {
     BBWinTask *fb1 = ctx->d_wfallback.as<BBWinTask>(), *fb2 = fb1 + ctx->wres_total + 8;
     for (int round = 0; round < ctx->n_rounds; round++) {
         int *c = cnt + BB_ROUND_BASE(round);
-        bbl_mutate(std::min(ctx->sm_count * 8, n), st, B, ctx->em, ctx->seed, c + BBC_MUTATE, order, n);
+        bbl_mutate(std::min(pgrid(ctx, 8), n), st, B, ctx->em, ctx->seed, c + BBC_MUTATE, order, n, ctx->is_head);
         mark(ctx, st, "mutate");
         bb_k_window_tasks<<<(n + 255) / 256, 256, 0, st>>>(B, order, n, tasks, c + BBC_NTASKS);
         mark(ctx, st, "window_tasks");
         // 4-word windows first (bands up to 64 rows: almost every window); what does not fit falls through to the
         // 8-word build and from there to the warp kernel
-        bbl_window_lane4(2 * lane_ctas, st, B, ctx->em, tasks, c + BBC_NTASKS, ctx->seed, ctx->s_leafhist.as<uint2>(),
+        bbl_window_lane4(pgrid(ctx, 8), st, B, ctx->em, tasks, c + BBC_NTASKS, ctx->seed, ctx->s_leafhist.as<uint2>(),
                          ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE4, fb1, c + BBC_FB1);
         mark(ctx, st, "window_lane4");
-        bbl_window_lane8(lane_ctas, st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed, ctx->s_leafhist.as<uint2>(),
+        bbl_window_lane8(pgrid(ctx, 4), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed, ctx->s_leafhist.as<uint2>(),
                          ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE8, fb2, c + BBC_FB2);
         mark(ctx, st, "window_lane8");
-        bbl_window_warp(ctx->sm_count * 2, st, B, ctx->em, ctx->pool, fb2, c + BBC_FB2, ctx->seed, c + BBC_WARP);
+        bbl_window_warp(pgrid(ctx, 2), st, B, ctx->em, ctx->pool, fb2, c + BBC_FB2, ctx->seed, c + BBC_WARP);
         mark(ctx, st, "window_warp");
-        bb_k_replay<<<(n + 127) / 128, 128, 0, st>>>(B, order, n, ctx->em.k, c + BBC_PENDING);
+        bb_k_replay<<<(n + 3) / 4, 128, 0, st>>>(B, order, n, ctx->em.k, c + BBC_PENDING);
         mark(ctx, st, "replay");
         ctx->launches += 6;
     }
@@ -686,15 +697,15 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
             }
             {
                 cudaStream_t x = on_side();   // the two narrow single-warp classes share a stream
-                bbl_node_warp(2, ctx->sm_count * 3, x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4);
+                bbl_node_warp(2, pgrid(ctx, 3), x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4);
                 mark(ctx, x, "node_warp2");
-                bbl_node_warp(1, ctx->sm_count * 3, x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4 + w2);
+                bbl_node_warp(1, pgrid(ctx, 3), x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4 + w2);
                 mark(ctx, x, "node_warp1");
                 x = on_side();
-                bbl_node_lane8(ctx->sm_count * 6, x, B, Q[s], p, cursor[s]++);
+                bbl_node_lane8(pgrid(ctx, 6), x, B, Q[s], p, cursor[s]++);
                 mark(ctx, x, "node_lane8");
             }
-            bbl_node_warp(4, ctx->sm_count * 2, st, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s]);
+            bbl_node_warp(4, pgrid(ctx, 2), st, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s]);
             mark(ctx, st, "node_warp4");
             ctx->launches += 4;
             for (int x = 0; x < n_side; x++) {
@@ -707,7 +718,7 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
         cudaStream_t st = stream[s];
         bbl_leaf_warp(ctx->sm_count, st, B, Q[s], ctx->pool, cursor[s]++, warp_base[s]);
         mark(ctx, st, "leaf_warp");
-        bbl_leaf_lane(lane_ctas, st, B, Q[s], ctx->s_leafhist.as<uint2>() + s * hist_per_pipe, cursor[s]++);
+        bbl_leaf_lane(pgrid(ctx, 4), st, B, Q[s], ctx->s_leafhist.as<uint2>() + s * hist_per_pipe, cursor[s]++);
         mark(ctx, st, "leaf_lane");
         ctx->launches += 2;
     }
@@ -895,8 +906,11 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
         return set_err(ctx, BB_ERR_ARG, "bb_batch_upload: bad arguments");
     const int n_workers = 1 + (int)ctx->kids.size();
     ctx->n_split = (n_workers > 1 && n_reads >= 64 * n_workers) ? n_workers : 1;
-    if (ctx->n_split == 1)
+    if (ctx->n_split == 1) {
+        ctx->is_head = false;
+        ctx->grid_div = 1;
         return w_batch_upload(ctx, n_reads, read_index, seg_off, segs, literal_pool, literal_len, target_identity);
+    }
     // deal the reads out longest first, so that every worker sees the same length distribution
     const int S = ctx->n_split;
     std::vector<int64_t> len((size_t)n_reads, 0);
@@ -922,6 +936,11 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
             ctx->part[0].push_back(order[(size_t)n_head++]);
         }
         if (n_head < 16) { ctx->part[0].clear(); n_head = 0; }
+    }
+    ctx->is_head = n_head > 0;
+    {   // share of the SMs each worker's persistent kernels ask for (BADREAD_B200_GRID_DIV overrides; 1 = all of them)
+        int div = ctx->grid_div_env > 0 ? ctx->grid_div_env : 2;
+        for (int w = 0; w < S; w++) worker_of(ctx, w)->grid_div = div;
     }
     if (n_head > 0) for (int32_t i = n_head; i < n_reads; i++) ctx->part[(size_t)(1 + (i - n_head) % (S - 1))].push_back(order[(size_t)i]);
     else for (int32_t i = 0; i < n_reads; i++) ctx->part[(size_t)(i % S)].push_back(order[(size_t)i]);

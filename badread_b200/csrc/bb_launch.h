@@ -8,7 +8,7 @@
 #include "bb_kernels.cuh"
 
 void bbl_mutate(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter,
-                const int *order, int n_items);
+                const int *order, int n_items, bool chain);  // chain: the low-latency build (bb_k_mutate_chain)
 void bbl_window_lane4(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks,
                       unsigned long long seed, uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback,
                       int *fallback_count);

@@ -29,6 +29,121 @@ enum { BB_STOP_HORIZON = 0, BB_STOP_LIMIT = 1, BB_STOP_COUNT = 2, BB_STOP_NOLOOP
 struct BBWinTask { int r, a; };  // read, alignment ordinal (1-based: after 25*a changes)
 
 // ------------------------------------------------------------------------------------------------ mutate
+// One CTA (4 warps) per read: every step the 128 threads evaluate 128 consecutive loop iterations (position, k-mer,
+// model draw: chains of dependent loads, independent across iterations), then warp 0 commits the iterations that
+// change something, in order.
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
+__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
+bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter, const int *order,
+            int n_items) {
+    constexpr int NT = BB_WARPS_PER_CTA * 32;
+    __shared__ int s_kind[NT], s_pos[NT], s_rpos[NT];
+    __shared__ uint32_t s_pay[NT];
+    __shared__ int s_w, s_stop, s_cc;
+    __shared__ long long s_n0;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int k = em.k;
+    for (;;) {
+        if (threadIdx.x == 0) s_w = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int w = s_w;
+        __syncthreads();
+        if (w >= n_items) break;
+        const int r = order[w];
+        BBReadDev *rd = &B.reads[r];
+        if (rd->status == BB_READ_DONE) continue;  // later rounds: only reads whose horizon was too short go on
+        const long long clk0 = clock64();
+        const uint8_t *frag = B.frag + rd->frag_off;
+        uint32_t *state = B.state + rd->frag_off;
+        unsigned int *ctime = B.ctime + rd->frag_off;
+        const int *kidx = B.kidx + rd->frag_off;
+        uint2 *chlog = B.chlog + rd->log_off;
+        const int frag_len = rd->frag_len;
+        const unsigned long long read = B.read_index[r];
+        const double target = B.target[r];
+        const double fl = (double)frag_len;
+        const int max_kmer_index = frag_len - 1 - k;
+        const long long limit = 100ll * frag_len;  // loop_count > 100 * frag_len stops the loop (simulate.py:279)
+        const double cc_limit = __dmul_rn(0.9, fl);
+        const int horizon = rd->horizon;
+        if (threadIdx.x == 0) {
+            int stop = -1;
+            if (__dmul_rn(fl, __dsub_rn(1.0, target)) < 0.5) stop = BB_STOP_NOLOOP;  // simulate.py:274
+            else if ((double)rd->n_logged > cc_limit) stop = BB_STOP_COUNT;
+            s_stop = stop; s_cc = rd->n_logged; s_n0 = rd->n_resume;
+        }
+        __syncthreads();
+        while (s_stop < 0) {
+            const long long n0 = s_n0;
+            if (n0 >= limit) {
+                __syncthreads();
+                if (threadIdx.x == 0) s_stop = BB_STOP_LIMIT;
+                __syncthreads();
+                break;
+            }
+            {
+                const long long n = n0 + threadIdx.x;
+                int kind = 0, pos_i = 0, rpos = 0;
+                uint32_t payload = 0;
+                if (n < limit) bb_eval_iteration(em, frag, kidx, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
+                s_kind[threadIdx.x] = kind; s_pos[threadIdx.x] = pos_i; s_rpos[threadIdx.x] = rpos; s_pay[threadIdx.x] = payload;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int change_count = s_cc, stop = -1;
+                long long next_n0 = n0 + NT;
+                for (int g = 0; g < BB_WARPS_PER_CTA && stop < 0; g++) {
+                    uint32_t cmask = __ballot_sync(BB_FULL, s_kind[32 * g + lane] != 0);
+                    while (cmask) {
+                        const int L = 32 * g + __ffs(cmask) - 1;
+                        cmask &= cmask - 1;
+                        const long long nL = n0 + L;
+                        if (change_count >= horizon) { stop = BB_STOP_HORIZON; next_n0 = nL; break; }  // pause at an iteration top
+                        const int bi = s_pos[L], bkind = s_kind[L], brpos = s_rpos[L];
+                        const uint32_t bpay = s_pay[L];
+                        uint32_t enc = 0;
+                        bool app = false;
+                        if (lane < k) {
+                            const uint8_t fb = frag[bi + lane];
+                            enc = bkind == 1 ? em.slots[(long long)bpay * k + lane]
+                                             : (lane == brpos ? bpay : bb_slot_inline(1, fb, 0));
+                            const bool differs = !((enc & 0xff) == 1 && ((enc >> 8) & 0xff) == fb);
+                            app = differs && state[bi + lane] == BB_SLOT_NONE;  // simulate.py:309
+                        }
+                        const uint32_t amask = __ballot_sync(BB_FULL, app);
+                        if (app) {  // slots of one k-mer are distinct positions: applied together, ordinals in slot order
+                            const int ord = change_count + __popc(amask & ((1u << lane) - 1u)) + 1;
+                            state[bi + lane] = enc;
+                            ctime[bi + lane] = (unsigned int)ord;
+                            chlog[ord - 1] = make_uint2((unsigned int)nL, (unsigned int)(bi + lane) | ((enc & 0xffu) << 24));
+                        }
+                        change_count += __popc(amask);
+                        __syncwarp();
+                        // the guard at the top of the next iteration (simulate.py:285) can only change after a commit
+                        if ((double)change_count > cc_limit) { stop = BB_STOP_COUNT; next_n0 = nL + 1; break; }
+                    }
+                }
+                __syncwarp();  // every lane has read s_cc / s_n0 before lane 0 replaces them
+                if (lane == 0) { s_cc = change_count; s_stop = stop; s_n0 = next_n0; }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            rd->n_logged = s_cc;
+            rd->n_resume = (int)(s_n0 > 0x7fffffff ? 0x7fffffff : s_n0);
+            rd->stop_reason = s_stop;
+            rd->kc_loop += (int)((clock64() - clk0) >> 10);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ mutate (latency build)
+// The same loop as bb_k_mutate for the reads whose dependent chain of stages bounds the step: the HEAD batch of the
+// longest reads (bb_batch_upload).  bb_k_mutate commits a change with a global round trip (~1 us each, thousands of
+// them in a row for a 150 kb read) but has the higher throughput when tens of CTAs share an SM; this build takes the
+// round trips out of the serial part:
 // One CTA (4 warps) per read.  A step covers BB_MUT_ITERS consecutive loop iterations:
 //   1. every thread evaluates its iterations (position, k-mer row, model draw: chains of dependent loads, independent
 //      across iterations);
@@ -46,7 +161,7 @@ struct BBWinTask { int r, a; };  // read, alignment ordinal (1-based: after 25*a
 
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
-bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter, const int *order,
+bb_k_mutate_chain(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter, const int *order,
             int n_items) {
     constexpr int NT = BB_WARPS_PER_CTA * 32, NI = BB_MUT_ITERS, NG = NI / 32;
     __shared__ int s_pos[NI];
@@ -396,11 +511,14 @@ bb_k_window_warp(BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, const BBW
 }
 
 // ------------------------------------------------------------------------------------------------ replay
-// One thread per read: the scalar recurrence of simulate.py:290-346 over the change log.
+// One warp per read: the scalar recurrence of simulate.py:290-346 over the change log.  The recurrence itself is serial
+// (every lane computes it redundantly); the log is read 32 entries at a time, coalesced, and handed round by shuffles,
+// so the dependent chain of a long read is arithmetic only.
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(128)
 bb_k_replay(BBBatchDev B, const int *order, int n_items, int k, int *n_pending) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= n_items) return;
     const int r = order[w];
     BBReadDev *rd = &B.reads[r];
@@ -414,20 +532,35 @@ bb_k_replay(BBBatchDev B, const int *order, int n_items, int k, int *n_pending) 
     const double cc_limit = __dmul_rn(0.9, fl);
     const long long limit = 100ll * frag_len;
     const int n_logged = rd->n_logged;
-    double errors = 0.0, est_id = 1.0;
+    const int stop_reason = rd->stop_reason, n_resume = rd->n_resume;
+    double errors = 0.0, est_id = 1.0, scale = 1.0;
     int total = frag_len, st_trim = k, en_trim = k, upper = 0;
     long long loop_count = -1;
     int kstop = n_logged;  // changes that survive
     bool stopped = false;
-    if (rd->stop_reason == BB_STOP_NOLOOP) { stopped = true; loop_count = 0; kstop = 0; }
+    if (stop_reason == BB_STOP_NOLOOP) { stopped = true; loop_count = 0; kstop = 0; }
     else if (1.0 <= target) { stopped = true; loop_count = 1; kstop = 0; }  // first check of the first iteration
-    int c = 0;
-    while (!stopped && c < n_logged) {
-        // all changes of one iteration (est_id is the value from the top of that iteration, simulate.py:290,321)
-        const unsigned int n = chlog[c].x;
-        const double scale = __dmul_rn(est_id, __dsqrt_rn(est_id));
-        while (c < n_logged && chlog[c].x == n) {
-            const unsigned int py = chlog[c].y;
+    long long cur_n = -1;  // iteration whose changes are being applied (-1: none yet)
+    // the checks at the top of iteration cur_n + 1 (simulate.py:278-292), after `c` changes
+    auto close_group = [&](int c) {
+        est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl));
+        if (cur_n + 1 >= limit) { stopped = true; loop_count = limit + 1; kstop = c; }
+        else if ((double)c > cc_limit || est_id <= target) { stopped = true; loop_count = cur_n + 2; kstop = c; }
+    };
+    for (int c0 = 0; c0 < n_logged && !stopped; c0 += 32) {
+        uint2 mine = make_uint2(0u, 0u);
+        if (c0 + lane < n_logged) mine = chlog[c0 + lane];
+        const int m = min(32, n_logged - c0);
+        for (int j = 0; j < m && !stopped; j++) {
+            const unsigned int n = __shfl_sync(BB_FULL, mine.x, j);
+            const unsigned int py = __shfl_sync(BB_FULL, mine.y, j);
+            int c = c0 + j;  // changes applied before this one
+            if ((long long)n != cur_n) {
+                if (cur_n >= 0) { close_group(c); if (stopped) break; }
+                cur_n = n;
+                // all changes of one iteration use est_id from the top of that iteration (simulate.py:290,321)
+                scale = __dmul_rn(est_id, __dsqrt_rn(est_id));
+            }
             const int pos = (int)(py & 0xffffffu), len = (int)(py >> 24);
             c++;
             upper += len < 1 ? 1 : len;
@@ -447,26 +580,27 @@ bb_k_replay(BBBatchDev B, const int *order, int n_items, int k, int *n_pending) 
                 }
             }
         }
-        // the checks at the top of iteration n + 1 (simulate.py:278-292)
-        est_id = __dsub_rn(1.0, __ddiv_rn(errors, fl));
-        if ((long long)n + 1 >= limit) { stopped = true; loop_count = limit + 1; kstop = c; }
-        else if ((double)c > cc_limit || est_id <= target) { stopped = true; loop_count = (long long)n + 2; kstop = c; }
     }
+    if (!stopped && cur_n >= 0) close_group(n_logged);
     if (!stopped) {
-        if (rd->stop_reason == BB_STOP_LIMIT) { stopped = true; loop_count = limit + 1; kstop = n_logged; }
-        else if (rd->stop_reason == BB_STOP_COUNT) { stopped = true; loop_count = (long long)rd->n_resume + 1; kstop = n_logged; }
+        if (stop_reason == BB_STOP_LIMIT) { stopped = true; loop_count = limit + 1; kstop = n_logged; }
+        else if (stop_reason == BB_STOP_COUNT) { stopped = true; loop_count = (long long)n_resume + 1; kstop = n_logged; }
     }
     if (!stopped) {  // the horizon was too short: log more changes and come back
-        rd->horizon = n_logged + max(64, n_logged / 2);
-        rd->a_done = n_logged / BB_ALIGNMENT_INTERVAL;
-        atomicAdd(n_pending, 1);
+        if (lane == 0) {
+            rd->horizon = n_logged + max(64, n_logged / 2);
+            rd->a_done = n_logged / BB_ALIGNMENT_INTERVAL;
+            atomicAdd(n_pending, 1);
+        }
         return;
     }
-    for (int x = kstop; x < n_logged; x++) {  // changes logged past the stop never happened
+    for (int x = kstop + lane; x < n_logged; x += 32) {  // changes logged past the stop never happened
         state[chlog[x].y & 0xffffffu] = BB_SLOT_NONE;
     }
-    rd->seq_len = total; rd->start_trim = st_trim; rd->end_trim = en_trim; rd->upper = upper;
-    rd->loop_count = (int)(loop_count > 0x7fffffff ? 0x7fffffff : loop_count);
-    rd->change_count = kstop; rd->n_align = kstop / BB_ALIGNMENT_INTERVAL;
-    rd->status = BB_READ_DONE;
+    if (lane == 0) {
+        rd->seq_len = total; rd->start_trim = st_trim; rd->end_trim = en_trim; rd->upper = upper;
+        rd->loop_count = (int)(loop_count > 0x7fffffff ? 0x7fffffff : loop_count);
+        rd->change_count = kstop; rd->n_align = kstop / BB_ALIGNMENT_INTERVAL;
+        rd->status = BB_READ_DONE;
+    }
 }

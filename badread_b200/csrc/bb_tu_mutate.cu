@@ -1,7 +1,8 @@
-// bb_tu_mutate.cu — compiles bb_k_mutate (bb_loop.cuh).
+// bb_tu_mutate.cu — compiles bb_k_mutate and bb_k_mutate_chain (bb_loop.cuh).
 #include "bb_launch.h"
 
 void bbl_mutate(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter,
-                const int *order, int n_items) {
-    bb_k_mutate<<<grid, BB_WARPS_PER_CTA * 32, 0, st>>>(B, em, seed, work_counter, order, n_items);
+                const int *order, int n_items, bool chain) {
+    if (chain) bb_k_mutate_chain<<<grid, BB_WARPS_PER_CTA * 32, 0, st>>>(B, em, seed, work_counter, order, n_items);
+    else bb_k_mutate<<<grid, BB_WARPS_PER_CTA * 32, 0, st>>>(B, em, seed, work_counter, order, n_items);
 }
