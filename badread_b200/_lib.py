@@ -100,6 +100,12 @@ def lib():
         'bb_align_path': (c.c_int, [vp, vp, i32, vp, i32, vp, i64, P(i64), P(i32)]),
         'bb_host_align_kmers': (c.c_int, [c.c_int, i32, vp, vp, vp, vp, vp, vp, i64, P(i64)]),
         'bb_host_align_path': (c.c_int, [vp, i32, vp, i32, vp, i64, P(i64), P(i32)]),
+        'bb_nccl_available': (c.c_int, []),
+        'bb_comm_unique_id': (c.c_int, [vp]),
+        'bb_comm_init_rank': (c.c_int, [vp, vp, c.c_int, c.c_int]),
+        'bb_comm_init_all': (c.c_int, [P(vp), c.c_int]),
+        'bb_allreduce_bases': (c.c_int, [vp, i64, P(i64)]),
+        'bb_allreduce_bases_all': (c.c_int, [P(vp), c.c_int, P(i64), P(i64)]),
         'bb_planner_create': (c.c_int, [P(vp), P(PlanConfig)]),
         'bb_planner_destroy': (c.c_int, [vp]),
         'bb_planner_plan': (c.c_int, [vp, u64, u64, i32, i32]),
@@ -120,5 +126,6 @@ EXPORTED_SYMBOLS = ['bb_create', 'bb_destroy', 'bb_last_error', 'bb_version', 'b
                     'bb_upload_error_model', 'bb_upload_qscore_model', 'bb_sequence_batch',
                     'bb_fetch_last_batch', 'bb_batch_upload', 'bb_batch_run', 'bb_synchronize', 'bb_host_alloc', 'bb_host_free',
                     'bb_last_run_ms', 'bb_stage_name', 'bb_launch_count', 'bb_trace_dump', 'bb_get_qscores', 'bb_align_path',
-                    'bb_host_align_kmers', 'bb_host_align_path', 'bb_planner_create', 'bb_planner_destroy',
+                    'bb_host_align_kmers', 'bb_host_align_path', 'bb_nccl_available', 'bb_comm_unique_id', 'bb_comm_init_rank',
+                    'bb_comm_init_all', 'bb_allreduce_bases', 'bb_allreduce_bases_all', 'bb_planner_create', 'bb_planner_destroy',
                     'bb_planner_plan', 'bb_planner_view', 'bb_planner_error', 'bb_fastq_format', 'bb_fastq_format_sharded']

@@ -375,6 +375,171 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
     return result;
 }
 
+// The wavefront of bb_band_pass spread over the WARPS warps of a CTA group (K = 32 WARPS lane slots, one problem):
+// a band that needs L words per lane on one warp needs L / WARPS here, so a step is WARPS times shorter and the
+// warps issue on different schedulers.  Distance only, column scores out (the node passes of the Hirschberg recursion).
+// Lane 31 of a warp hands its chunk's horizontal deltas to lane 0 of the next warp through a double-buffered mailbox
+// in shared memory; one named barrier (`bar_id`, 32 WARPS threads) per step orders the hand-over.  All warps of the
+// group must call this with the same problem; `wg` is the warp's index in the group.
+template <int L, int WARPS>
+__device__ void bb_band_pass_mw(const BBProb &P, int wg, volatile uint32_t *mbox, int bar_id) {
+    constexpr int K = 32 * WARPS;
+    constexpr int CH = 32 * L;
+    const int lane = threadIdx.x & 31;
+    const int slot = wg * 32 + lane;
+    const int n = P.n, ncols = P.ncols, a = P.a, b = P.b, ts = P.ts;
+    int ulast = -1;
+    if (ncols > 0 && n > 0) {
+        ulast = (ncols - 1 + b) / CH;
+        const int nchunks = (n + CH - 1) / CH;
+        if (ulast > nchunks - 1) ulast = nchunks - 1;
+    }
+    const int T = ulast >= 0 ? ncols + ulast : 0;  // the same for every lane of the group
+    const int cols_hi = min(n - 1, ncols - 1 + b);
+    constexpr bool STREAM = (L >= 8);
+    constexpr int LR = STREAM ? 1 : L;
+    uint32_t Pv[L], Mv[L], eA[LR], eC[LR], eG[LR], eT[LR];
+#pragma unroll
+    for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; }
+#pragma unroll
+    for (int x = 0; x < LR; x++) { eA[x] = eC[x] = eG[x] = eT[x] = 0u; }
+    const bool fwd = P.qs > 0;
+    uint32_t *const esm = STREAM ? P.esm + lane * bb_esm_lane_stride(L) : nullptr;
+    int u = slot;
+    int cs = max(0, CH * u - b), ce = min(ncols - 1, CH * u + CH - 1 + a);
+    int ce_up = min(ncols - 1, CH * u - 1 + a);  // last column of the chunk above
+    int score = 0;
+    uint32_t outpack = 0;
+    uint32_t tcn = 0;
+    const uint8_t *tp = P.t - (long long)u * ts;  // tp + tau*ts is this lane's column at step tau
+    if (u <= ulast && 0 - u >= cs && 0 - u <= ce) tcn = *tp;
+    for (int tau = 0; tau < T; tau++) {
+        // the previous slot's output of step tau - 1: from the lane below, or from the warp before through the mailbox
+        uint32_t in = __shfl_up_sync(BB_FULL, outpack, 1);
+        if (lane == 31) mbox[wg * 2 + (tau & 1)] = outpack;
+#ifdef BB_EMULATOR
+        emu::named_barrier(bar_id, K);
+#else
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(K) : "memory");
+#endif
+        if (lane == 0) in = mbox[((wg + WARPS - 1) % WARPS) * 2 + (tau & 1)];
+        const int c = tau - u;
+        const bool active = (u <= ulast) && c >= cs && c <= ce;
+        if (active) {
+            const uint32_t tc = tcn;
+            int hin = 1;
+            if (u > 0 && c <= ce_up) hin = (int)((in >> 22) & 3u) - 1;
+            if (c == cs) {  // a chunk entering the band starts from the all-(+1) upper bound below chunk u-1
+                const int base = (u == 0) ? cs : (int)(in & BB_MAX_SCORE) - hin;
+                score = base + CH;
+#pragma unroll
+                for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; }
+                if (STREAM) {  // cut the chunk's match words out of the bitmap once; the steps read them from smem
+                    const int s0 = fwd ? P.peq_bit0 + u * CH : P.peq_bit0 - u * CH - 31;
+                    const int eidx = s0 >> 5, esh = s0 & 31;
+                    const int evalid = n - u * CH;
+                    uint4 w0 = P.peq[fwd ? eidx : eidx + 1];
+#pragma unroll 1
+                    for (int x = 0; x < L; x++) {
+                        const uint4 w1 = P.peq[fwd ? eidx + x + 1 : eidx - x];
+                        uint4 e;
+                        if (fwd) {
+                            e.x = __funnelshift_r(w0.x, w1.x, esh); e.y = __funnelshift_r(w0.y, w1.y, esh);
+                            e.z = __funnelshift_r(w0.z, w1.z, esh); e.w = __funnelshift_r(w0.w, w1.w, esh);
+                        } else {
+                            e.x = __brev(__funnelshift_r(w1.x, w0.x, esh)); e.y = __brev(__funnelshift_r(w1.y, w0.y, esh));
+                            e.z = __brev(__funnelshift_r(w1.z, w0.z, esh)); e.w = __brev(__funnelshift_r(w1.w, w0.w, esh));
+                        }
+                        const int v = evalid - 32 * x;
+                        const uint32_t keep = v >= 32 ? ~0u : (v <= 0 ? 0u : ((1u << v) - 1u));
+                        esm[x] = e.x & keep; esm[L + x] = e.y & keep; esm[2 * L + x] = e.z & keep; esm[3 * L + x] = e.w & keep;
+                        w0 = w1;
+                    }
+                } else {
+#pragma unroll
+                    for (int x = 0; x < LR; x++) bb_fetch_peq(P, u * CH + 32 * x, eA[x], eC[x], eG[x], eT[x]);
+                }
+            }
+            const uint32_t code = (tc >> 1) & 3u;  // A->0, C->1, T->2, G->3
+            const bool acgt = ((0x47544341u >> (8 * code)) & 0xffu) == tc;
+            uint32_t Eq[L], Xv[L], A[L], S[L];
+            if (STREAM) {
+                const uint4 *ep = reinterpret_cast<const uint4 *>(esm + (code ^ (code >> 1)) * L);
+#pragma unroll
+                for (int x = 0; x < L; x += 4) {
+                    const uint4 e = ep[x >> 2];
+                    if (x + 3 < L) { Eq[x] = e.x; Eq[x + 1] = e.y; Eq[x + 2] = e.z; Eq[x + 3] = e.w; }
+                }
+            } else {
+#pragma unroll
+                for (int x = 0; x < L; x++) {
+                    const int y = x < LR ? x : 0;
+                    Eq[x] = (code & 2u) ? ((code & 1u) ? eG[y] : eT[y]) : ((code & 1u) ? eC[y] : eA[y]);
+                }
+            }
+            if (!acgt) {  // non-ACGT target character: exact byte equality against every row of the chunk
+#pragma unroll
+                for (int x = 0; x < L; x++) {
+                    Eq[x] = 0u;
+                    const int row0 = u * CH + 32 * x;
+                    for (int r = 0; r < 32; r++)
+                        if (row0 + r < n && P.q[(long long)(row0 + r) * P.qs] == tc) Eq[x] |= 1u << r;
+                }
+            }
+            const uint32_t hin_neg = hin < 0 ? 1u : 0u;
+#pragma unroll
+            for (int x = 0; x < L; x++) Xv[x] = Eq[x] | Mv[x];
+            Eq[0] |= hin_neg;
+#pragma unroll
+            for (int x = 0; x < L; x++) A[x] = Eq[x] & Pv[x];
+            bb_add_words<L>(A, Pv, S);
+            uint32_t Ph[L], Mh[L];
+#pragma unroll
+            for (int x = 0; x < L; x++) {
+                const uint32_t Xh = (S[x] ^ Pv[x]) | Eq[x];
+                Ph[x] = Mv[x] | ~(Xh | Pv[x]);
+                Mh[x] = Pv[x] & Xh;
+            }
+            const int hout = (int)(Ph[L - 1] >> 31) - (int)(Mh[L - 1] >> 31);
+#pragma unroll
+            for (int x = L - 1; x >= 0; x--) {
+                const uint32_t ph_lo = x > 0 ? Ph[x - 1] : (hin > 0 ? 0x80000000u : 0u);
+                const uint32_t mh_lo = x > 0 ? Mh[x - 1] : (hin_neg << 31);
+                const uint32_t phs = __funnelshift_l(ph_lo, Ph[x], 1);
+                const uint32_t mhs = __funnelshift_l(mh_lo, Mh[x], 1);
+                Pv[x] = mhs | ~(Xv[x] | phs);
+                Mv[x] = phs & Xv[x];
+            }
+            score += hout;
+            outpack = ((uint32_t)(hout + 1) << 22) | ((uint32_t)score & BB_MAX_SCORE);
+            if (c == ncols - 1) {
+                int run = score;
+#pragma unroll
+                for (int x = L - 1; x >= 0; x--) {
+                    const int row0 = u * CH + 32 * x;
+                    int rr = run;
+                    for (int r = 31; r >= 0; r--) {
+                        const int row = row0 + r;
+                        if (row < n && row >= P.cols_lo && row <= cols_hi) P.cols_out[row - P.cols_lo] = rr;
+                        rr -= (int)((Pv[x] >> r) & 1u) - (int)((Mv[x] >> r) & 1u);
+                    }
+                    run -= __popc(Pv[x]) - __popc(Mv[x]);
+                }
+            }
+            if (c == ce) {  // the band has moved past this chunk: take over chunk u + K
+                u += K;
+                cs = max(0, CH * u - b);
+                ce = min(ncols - 1, CH * u + CH - 1 + a);
+                ce_up = min(ncols - 1, CH * u - 1 + a);
+                tp -= (long long)K * ts;
+            }
+        }
+        const int cn = tau + 1 - u;
+        if (u <= ulast && cn >= cs && cn <= ce) tcn = tp[(long long)(tau + 1) * ts];
+    }
+    __syncwarp();
+}
+
 // CB columns per step: the distance-only variant of bb_band_pass for register-resident masks (L <= 4).  Chunk u
 // works on columns CB (step - u) ... CB (step - u) + CB - 1; one shuffle carries the CB horizontal deltas of the
 // chunk above (2 bits each) and its score after the first of those columns.  A step whose columns are all interior

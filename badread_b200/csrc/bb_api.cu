@@ -1,6 +1,7 @@
 // bb_api.cu — C ABI of libbadread_b200.so (see include/badread_b200.h): context, one-time uploads, batch
 // orchestration. All hot-path work is done by the kernels in bb_kernels.cuh; there is no CPU path here.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -78,6 +79,8 @@ struct bb_ctx {
     bool finished = false;
     bool reran = false;        // w_finish had to run the batch again (copies enqueued before that are stale)
     DevBuf d_scan;
+    void *nccl_comm = nullptr;   // ncclComm_t of this context's device (bb_comm_init_rank / bb_comm_init_all)
+    DevBuf d_red;                // two int64: send, receive of bb_allreduce_bases
     cudaEvent_t ev_scan = nullptr;
     DevBuf d_read_index, d_seg_off, d_segs, d_lit, d_target, d_order, d_reads;
     int n_lane_reads = 0, n_long_reads = 0;
@@ -95,6 +98,7 @@ struct bb_ctx {
     int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
     bool head_worker = true;  // worker 0 = the longest reads only (see bb_batch_upload)
     bool is_head = false;     // this worker holds the head batch of the current upload
+    bool use_quad = true;     // wide nodes by 8-warp CTAs (bb_k_node_quad) instead of warp pairs
     int grid_div_env = 0;
     int grid_div = 1;         // persistent grids are launched at 1/grid_div of their full size (the workers of a split batch share the SMs)
     struct QueueBufs { DevBuf node[BBQ_NODE_CLASSES][2], leaf[2], count; } qbuf[2];  // [0] normal, [1] wide-root reads
@@ -229,6 +233,7 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed, bool high_prio
     e = cudaMemcpyToSymbol(bb_c_comp, comp, 256);
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     e = bbl_node_pair_init();
+    if (e == cudaSuccess) e = bbl_node_quad_init();
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     // persistent warps: 4 CTAs of 4 warps per SM for the warp-per-read kernels
     ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
@@ -237,11 +242,13 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed, bool high_prio
     if (const char *e = std::getenv("BADREAD_B200_PAIR_CTAS")) ctx->pair_ctas = (e[0] == '2') ? 2 : 1;
     if (const char *e = std::getenv("BADREAD_B200_HEAD_WORKER")) ctx->head_worker = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_GRID_DIV")) ctx->grid_div_env = std::atoi(e);
+    if (const char *e = std::getenv("BADREAD_B200_QUAD")) ctx->use_quad = (e[0] != '0');
     *out = ctx;
     return BB_OK;
 }
 
 extern "C" int bb_destroy(bb_ctx *ctx);
+static void (*nccl_destroy)(void *) = nullptr;  // set once NCCL is loaded (bb_comm_init_*)
 
 extern "C" int bb_create(bb_ctx **out, int device, uint64_t seed) {
     bool prio = true;
@@ -276,7 +283,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
                       &ctx->d_wtasks, &ctx->d_wfallback, &ctx->d_active,
-                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->s_lr_lean, &ctx->d_scan,
+                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->s_lr_lean, &ctx->d_scan, &ctx->d_red,
                       &ctx->p_q, &ctx->p_t, &ctx->p_ops, &ctx->p_dcnt, &ctx->p_out, &ctx->p_qual};
     for (auto &qb : ctx->qbuf) {
         for (auto &cl : qb.node) for (auto &d : cl) d.release();
@@ -297,6 +304,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
         }
     }
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
+    if (ctx->nccl_comm && nccl_destroy) nccl_destroy(ctx->nccl_comm);
     for (cudaEvent_t e : ctx->mark_pool) cudaEventDestroy(e);
     delete ctx;
     return BB_OK;
@@ -691,9 +699,10 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
             };
             if (s == 1) {
                 cudaStream_t x = on_side();
-                bbl_node_pair(ctx->sm_count * ctx->pair_ctas, x, B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
+                if (ctx->use_quad) bbl_node_quad(ctx->sm_count, x, B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
+                else bbl_node_pair(ctx->sm_count * ctx->pair_ctas, x, B, Q[s], ctx->pool, p, cursor[s]++, warp_base[s]);
                 ctx->launches++;
-                mark(ctx, x, "node_pair");
+                mark(ctx, x, ctx->use_quad ? "node_quad" : "node_pair");
             }
             {
                 cudaStream_t x = on_side();   // the two narrow single-warp classes share a stream
@@ -939,7 +948,7 @@ extern "C" int bb_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *rea
     }
     ctx->is_head = n_head > 0;
     {   // share of the SMs each worker's persistent kernels ask for (BADREAD_B200_GRID_DIV overrides; 1 = all of them)
-        int div = ctx->grid_div_env > 0 ? ctx->grid_div_env : 2;
+        int div = ctx->grid_div_env > 0 ? ctx->grid_div_env : 1;
         for (int w = 0; w < S; w++) worker_of(ctx, w)->grid_div = div;
     }
     if (n_head > 0) for (int32_t i = n_head; i < n_reads; i++) ctx->part[(size_t)(1 + (i - n_head) % (S - 1))].push_back(order[(size_t)i]);
@@ -1199,5 +1208,134 @@ extern "C" int bb_get_qscores(bb_ctx *ctx, uint64_t read_index, const uint8_t *s
     if (rc) return rc;
     if (matches) *matches = out5[0];
     if (columns) *columns = seq_len + out5[1];
+    return BB_OK;
+}
+
+// ---- the one collective of the path: SUM of emitted bases over the GPUs (stop condition, simulate.py:63) ----------
+// Reads shard over GPUs by read index and never exchange data; the only thing the GPUs have to agree on is the running
+// total of emitted bases that ends the simulation.  NCCL is loaded at run time (the process's own libnccl.so.2 if one
+// is already mapped - e.g. PyTorch's - else the system library), so the library has no link-time dependency on it.
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, bb_nccl_id, int) = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+
+NcclApi &nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return api;
+    api.lib = h;
+    api.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void **, int, bb_nccl_id, int))dlsym(h, "ncclCommInitRank");
+    api.CommInitAll = (int (*)(void **, int, const int *))dlsym(h, "ncclCommInitAll");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
+    api.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    api.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+    api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    nccl_destroy = (void (*)(void *))api.CommDestroy;
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.AllReduce && api.GroupStart && api.GroupEnd;
+    return api;
+}
+constexpr int kNcclInt64 = 4, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+int nccl_err(bb_ctx *ctx, const char *what, int rc) {
+    const char *msg = nccl().GetErrorString ? nccl().GetErrorString(rc) : "?";
+    return set_err(ctx, BB_ERR_CUDA, std::string(what) + ": " + msg);
+}
+}  // namespace
+
+extern "C" int bb_nccl_available(void) { return nccl().ok ? 1 : 0; }
+
+extern "C" int bb_comm_unique_id(bb_nccl_id *id) {
+    if (!id) return BB_ERR_ARG;
+    if (!nccl().ok) return BB_ERR_STATE;
+    return nccl().GetUniqueId(id) == 0 ? BB_OK : BB_ERR_CUDA;
+}
+
+extern "C" int bb_comm_init_rank(bb_ctx *ctx, const bb_nccl_id *id, int rank, int world) {
+    if (!ctx || !id || rank < 0 || rank >= world) return BB_ERR_ARG;
+    if (!nccl().ok) return set_err(ctx, BB_ERR_STATE, "libnccl.so.2 could not be loaded");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->nccl_comm && nccl().CommDestroy) { nccl().CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+    const int rc = nccl().CommInitRank(&ctx->nccl_comm, world, *id, rank);
+    if (rc) return nccl_err(ctx, "ncclCommInitRank", rc);
+    BB_CUDA(ctx, ctx->d_red.ensure(2 * sizeof(long long)));
+    return BB_OK;
+}
+
+extern "C" int bb_comm_init_all(bb_ctx **ctxs, int n) {
+    if (!ctxs || n <= 0) return BB_ERR_ARG;
+    if (!nccl().ok) return set_err(ctxs[0], BB_ERR_STATE, "libnccl.so.2 could not be loaded");
+    std::vector<int> devs((size_t)n);
+    std::vector<void *> comms((size_t)n, nullptr);
+    for (int i = 0; i < n; i++) { if (!ctxs[i]) return BB_ERR_ARG; devs[(size_t)i] = ctxs[i]->device; }
+    const int rc = nccl().CommInitAll(comms.data(), n, devs.data());
+    if (rc) return nccl_err(ctxs[0], "ncclCommInitAll", rc);
+    for (int i = 0; i < n; i++) {
+        ctxs[i]->nccl_comm = comms[(size_t)i];
+        BB_CUDA(ctxs[i], cudaSetDevice(ctxs[i]->device));
+        BB_CUDA(ctxs[i], ctxs[i]->d_red.ensure(2 * sizeof(long long)));
+    }
+    return BB_OK;
+}
+
+// One process per GPU: every rank passes its local count, all get the sum.
+extern "C" int bb_allreduce_bases(bb_ctx *ctx, int64_t local, int64_t *total) {
+    if (!ctx || !total) return BB_ERR_ARG;
+    if (!ctx->nccl_comm) return set_err(ctx, BB_ERR_STATE, "bb_allreduce_bases: no communicator (bb_comm_init_rank)");
+    BB_CUDA(ctx, cudaSetDevice(ctx->device));
+    long long *d = ctx->d_red.as<long long>();
+    const long long v = local;
+    BB_CUDA(ctx, cudaMemcpyAsync(d, &v, sizeof(v), cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = nccl().AllReduce(d, d + 1, 1, kNcclInt64, kNcclSum, ctx->nccl_comm, ctx->stream);
+    if (rc) return nccl_err(ctx, "ncclAllReduce", rc);
+    long long out = 0;
+    BB_CUDA(ctx, cudaMemcpyAsync(&out, d + 1, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+    BB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *total = out;
+    return BB_OK;
+}
+
+// One process, several GPUs (the CLI's --gpus N): the contexts' counts are summed in one NCCL group call.
+extern "C" int bb_allreduce_bases_all(bb_ctx **ctxs, int n, const int64_t *local, int64_t *total) {
+    if (!ctxs || n <= 0 || !local || !total) return BB_ERR_ARG;
+    for (int i = 0; i < n; i++)
+        if (!ctxs[i] || !ctxs[i]->nccl_comm) return set_err(ctxs[0], BB_ERR_STATE, "bb_allreduce_bases_all: no communicator (bb_comm_init_all)");
+    for (int i = 0; i < n; i++) {
+        BB_CUDA(ctxs[i], cudaSetDevice(ctxs[i]->device));
+        const long long v = local[i];
+        BB_CUDA(ctxs[i], cudaMemcpyAsync(ctxs[i]->d_red.p, &v, sizeof(v), cudaMemcpyHostToDevice, ctxs[i]->stream));
+        BB_CUDA(ctxs[i], cudaStreamSynchronize(ctxs[i]->stream));  // `v` leaves scope
+    }
+    int rc = nccl().GroupStart();
+    for (int i = 0; i < n && !rc; i++) {
+        long long *d = ctxs[i]->d_red.as<long long>();
+        rc = nccl().AllReduce(d, d + 1, 1, kNcclInt64, kNcclSum, ctxs[i]->nccl_comm, ctxs[i]->stream);
+    }
+    const int rc2 = nccl().GroupEnd();
+    if (rc || rc2) return nccl_err(ctxs[0], "ncclAllReduce (group)", rc ? rc : rc2);
+    long long out = 0;
+    BB_CUDA(ctxs[0], cudaSetDevice(ctxs[0]->device));
+    BB_CUDA(ctxs[0], cudaMemcpyAsync(&out, ctxs[0]->d_red.as<long long>() + 1, sizeof(out), cudaMemcpyDeviceToHost, ctxs[0]->stream));
+    for (int i = 0; i < n; i++) {
+        BB_CUDA(ctxs[i], cudaSetDevice(ctxs[i]->device));
+        BB_CUDA(ctxs[i], cudaStreamSynchronize(ctxs[i]->stream));
+    }
+    *total = out;
     return BB_OK;
 }

@@ -524,6 +524,93 @@ bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
     }
 }
 
+// Wide-band nodes by a whole CTA of 8 warps: warps 0-3 run the forward pass over the left half of the target as one
+// 128-lane wavefront (bb_band_pass_mw), warps 4-7 the reverse pass over the right half; warp 0 then picks the split.
+// A quarter of the words per lane of the single-warp wavefront and four schedulers per pass: the dependent chain of
+// columns of the longest reads - what bounds a whole step from below - runs about three times faster.
+#define BB_QUAD_WARPS 4
+#define BB_QUAD_THREADS (2 * BB_QUAD_WARPS * 32)
+#define BB_QUAD_SMEM_BYTES (2 * BB_QUAD_WARPS * bb_esm_words(32) * 4)
+
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
+__global__ void __launch_bounds__(BB_QUAD_THREADS, 1)
+bb_k_node_quad(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
+    __shared__ int s_task;
+    __shared__ uint32_t s_mbox[2][BB_QUAD_WARPS * 2];
+#ifdef BB_EMULATOR
+    static uint32_t s_eq[BB_QUAD_SMEM_BYTES / 4];
+#else
+    extern __shared__ __align__(16) uint32_t s_eq[];  // BB_QUAD_SMEM_BYTES: one match-word cache per warp
+#endif
+    const int lane = threadIdx.x & 31;
+    const int wi = threadIdx.x >> 5;
+    const bool rev = wi >= BB_QUAD_WARPS;
+    const int wg = wi % BB_QUAD_WARPS;
+    BBScratch sc = pool.for_warp(warp_base + blockIdx.x);  // L and R of the CTA's current node
+    const BBNode *list = Q.node[BBQ_NODE_WIDE][parity];
+    const int count = min(Q.count[BBQ_COUNT(BBQ_NODE_WIDE, parity)], Q.cap_node);
+    for (;;) {
+        if (threadIdx.x == 0) s_task = atomicAdd(cursor, 1);
+        __syncthreads();
+        const int w = s_task;
+        __syncthreads();
+        if (w >= count) break;
+        const BBNode nd = list[w];
+        BBReadDev *rd = &B.reads[nd.r];
+        sc.peq = B.speq + rd->speq_off;
+        const uint8_t *q = B.seq + rd->seq_off, *t = B.frag + rd->frag_off;
+        int a, b;
+        bb_task_band(nd, rd->upper, a, b);
+        const int left_w = nd.mm / 2, right_w = nd.mm - left_w;
+        const int loL = max(0, left_w - 1 - a), hiL = min(nd.nn - 1, left_w - 1 + b);
+        const int loR = max(0, right_w - 1 - a), hiR = min(nd.nn - 1, right_w - 1 + b);
+        const int L = bb_pick_L<32>(a, b, 32 * BB_QUAD_WARPS);
+        int err = 0;
+        if (hiL - loL + 1 > sc.lr_cap || hiR - loR + 1 > sc.lr_cap) err = 16;
+        else if (L > 0) {
+            BBProb P;
+            P.n = nd.nn; P.a = a; P.b = b; P.peq = sc.peq; P.hist = nullptr; P.nb_alloc = 0;
+            if (!rev) {
+                P.q = q + nd.q0; P.qs = 1; P.t = t + nd.t0; P.ts = 1; P.ncols = left_w;
+                P.peq_bit0 = nd.q0 + BB_PEQ_BIT0; P.cols_out = sc.L; P.cols_lo = loL;
+            } else {
+                P.q = q + nd.q0 + nd.nn - 1; P.qs = -1; P.t = t + nd.t0 + nd.mm - 1; P.ts = -1; P.ncols = right_w;
+                P.peq_bit0 = nd.q0 + nd.nn - 1 + BB_PEQ_BIT0; P.cols_out = sc.R; P.cols_lo = loR;
+            }
+            P.esm = s_eq + wi * bb_esm_words(32);
+            volatile uint32_t *mb = s_mbox[rev ? 1 : 0];
+            const int bar = rev ? 2 : 1;
+            if (L == 1) bb_band_pass_mw<1, BB_QUAD_WARPS>(P, wg, mb, bar);
+            else if (L == 2) bb_band_pass_mw<2, BB_QUAD_WARPS>(P, wg, mb, bar);
+            else if (L == 4) bb_band_pass_mw<4, BB_QUAD_WARPS>(P, wg, mb, bar);
+            else if (L == 8) bb_band_pass_mw<8, BB_QUAD_WARPS>(P, wg, mb, bar);
+            else if (L == 16) bb_band_pass_mw<16, BB_QUAD_WARPS>(P, wg, mb, bar);
+            else bb_band_pass_mw<32, BB_QUAD_WARPS>(P, wg, mb, bar);
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (wi == 0) {
+            int best = nd.best, split = 0, ls = 0, rs = 0;
+            if (!err) {
+                if (L > 0) err = bb_split_warp(sc, loL, hiL, loR, hiR, nd.nn, left_w, right_w, best, split, ls, rs);
+                else err = bb_node_warp<1>(q, t, nd.q0, nd.nn, nd.t0, nd.mm, a, b, sc, best, split, ls, rs);  // strips
+            }
+            if (lane == 0) {
+                BBAlignOut o;
+                o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
+                if (err) atomicOr(&rd->flags, err << 8);
+                else {
+                    BBNode c0 = {nd.r, nd.q0, split + 1, nd.t0, left_w, ls};
+                    BBNode c1 = {nd.r, nd.q0 + split + 1, nd.nn - split - 1, nd.t0 + left_w, right_w, rs};
+                    bb_push_task(Q, parity ^ 1, o, c0, rd->upper);
+                    bb_push_task(Q, parity ^ 1, o, c1, rd->upper);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // One leaf per warp (bands or lengths beyond the lane kernel's limits).
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 2)

@@ -12,6 +12,13 @@ from . import _lib
 from ._lib import BB_SEG_LITERAL, BB_SEG_REF_FWD, BB_SEG_REF_REV, ReadResult, Segment
 
 
+_RESULT_DTYPE = np.dtype([('out_off', np.int64), ('out_len', np.int32), ('frag_len', np.int32), ('matches', np.int32),
+                          ('columns', np.int32), ('loop_count', np.int32), ('change_count', np.int32),
+                          ('n_alignments', np.int32), ('flags', np.int32), ('loop_kcycles', np.int32),
+                          ('align_kcycles', np.int32)])
+assert _RESULT_DTYPE.itemsize == ctypes.sizeof(ReadResult)
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -98,6 +105,13 @@ class BatchResult(object):
     def identity(self, i):
         r = self.records[i]
         return r.matches / r.columns if r.columns else 0.0
+
+    def table(self):
+        """The records as a numpy structured array (no copy)."""
+        return np.frombuffer(self.records, dtype=_RESULT_DTYPE, count=self.n)
+
+    def total_bases(self):
+        return int(self.table()['out_len'].sum()) if self.n else 0
 
 
 class Engine(object):
@@ -243,6 +257,18 @@ class Engine(object):
         self._check(rc, 'bb_sequence_batch')
         return BatchResult(results, self._seq_buf, self._qual_buf, n), int(total.value)
 
+    # ---- the one collective: SUM of emitted bases over the GPUs (stop condition, simulate.py:63)
+    def comm_init_rank(self, unique_id, rank, world):
+        """One process per GPU: joins the NCCL communicator identified by `unique_id` (128 bytes from
+        `comm_unique_id()` on rank 0, shipped to the other ranks by the host program)."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.bb_comm_init_rank(self._ctx, buf, int(rank), int(world)), 'bb_comm_init_rank')
+
+    def allreduce_bases(self, local):
+        total = ctypes.c_int64(0)
+        self._check(self._lib.bb_allreduce_bases(self._ctx, int(local), ctypes.byref(total)), 'bb_allreduce_bases')
+        return int(total.value)
+
     # ---- single pair helpers
     def get_qscores(self, seq, frag, read_index=0):
         s = np.frombuffer(seq.encode('latin-1'), dtype=np.uint8)
@@ -264,6 +290,40 @@ class Engine(object):
                                      ctypes.byref(n_ops), ctypes.byref(dist))
         self._check(rc, 'bb_align_path')
         return bytes(ops[:n_ops.value]).decode('ascii'), dist.value
+
+
+def nccl_available():
+    return bool(_lib.lib().bb_nccl_available())
+
+
+def comm_unique_id():
+    """128 bytes identifying a new NCCL communicator (ncclGetUniqueId)."""
+    buf = ctypes.create_string_buffer(128)
+    rc = _lib.lib().bb_comm_unique_id(buf)
+    if rc != 0:
+        raise EngineError(f'bb_comm_unique_id failed ({rc}): NCCL not available')
+    return buf.raw
+
+
+def comm_init_all(engines):
+    """One process, several GPUs: one communicator over the engines' devices."""
+    arr = (ctypes.c_void_p * len(engines))(*[e._ctx for e in engines])
+    rc = _lib.lib().bb_comm_init_all(arr, len(engines))
+    if rc != 0:
+        msg = _lib.lib().bb_last_error(engines[0]._ctx)
+        raise EngineError(f'bb_comm_init_all failed ({rc}): {msg.decode() if msg else ""}')
+
+
+def allreduce_bases_all(engines, local):
+    """SUM of the engines' emitted-base counts through one NCCL group call."""
+    arr = (ctypes.c_void_p * len(engines))(*[e._ctx for e in engines])
+    loc = (ctypes.c_int64 * len(engines))(*[int(x) for x in local])
+    total = ctypes.c_int64(0)
+    rc = _lib.lib().bb_allreduce_bases_all(arr, len(engines), loc, ctypes.byref(total))
+    if rc != 0:
+        msg = _lib.lib().bb_last_error(engines[0]._ctx)
+        raise EngineError(f'bb_allreduce_bases_all failed ({rc}): {msg.decode() if msg else ""}')
+    return int(total.value)
 
 
 # ---- module-level default engine for the single-read convenience functions ---------------------------

@@ -37,6 +37,8 @@ from .qscore_model import QScoreModel, qscore_char_to_error_prob
 from .version import __version__
 
 _BASES = np.frombuffer(b'ACGT', dtype=np.uint8)
+import time as _time  # noqa: E402
+_T_IMPORT = _time.perf_counter()
 
 
 # ------------------------------------------------------------------------------------------ single read
@@ -443,8 +445,17 @@ def simulate(args, output=sys.stderr, stdout=None):
     print('', file=output)
 
     n_gpus = max(1, int(getattr(args, 'gpus', 1) or 1))
-    run_batches(args, ref, frag_lengths, identities, error_model, qscore_model, seed, target_size, n_gpus, output, stdout)
+    import os
+    import time
+    t_loop = time.perf_counter()
+    stats = run_batches(args, ref, frag_lengths, identities, error_model, qscore_model, seed, target_size, n_gpus, output,
+                        stdout)
     print('\n', file=output)
+    if os.environ.get('BADREAD_B200_TIMING') == '1':   # one machine-readable line for bench.py's cli_e2e leg
+        import json
+        stats['loop_s'] = time.perf_counter() - t_loop
+        stats['setup_s'] = t_loop - _T_IMPORT
+        print('BADREAD_B200_TIMING ' + json.dumps(stats), file=output, flush=True)
 
 
 def _write_fastq(stdout, buf):
@@ -475,9 +486,18 @@ def run_batches(args, ref, frag_lengths, identities, error_model, qscore_model, 
         engines.append(eng)
         planners.append(NativePlanner(args, ref, frag_lengths, identities, seed, n_threads=threads_each))
 
+    use_nccl = False
+    if n_gpus > 1:   # the stop condition's SUM over the GPUs goes through NCCL when the library can load it
+        from .engine import allreduce_bases_all, comm_init_all, nccl_available
+        if nccl_available():
+            comm_init_all(engines)
+            use_nccl = True
+
     count, total_size, next_index = 0, 0, 0
     mean_len = max(1.0, float(args.mean_frag_length))
     max_batch = int(getattr(args, 'batch_reads', 0) or 16384) * n_gpus
+    import time
+    t_first = time.perf_counter()   # engines, reference and tables are resident: the simulate loop proper starts here
     out_buf = None
     empty = np.zeros(1, dtype=np.uint8)
     print_progress(count, total_size, target_size, output)
@@ -512,10 +532,17 @@ def run_batches(args, ref, frag_lengths, identities, error_model, qscore_model, 
             buf, n_emit, bases, _, out_buf = fastq_format_sharded(planned, recs, seqs, quals, 0, total_size, target_size,
                                                                   out=out_buf)
             _write_fastq(stdout, buf)
+            if use_nccl:
+                # every GPU learns the batch's total from one all-reduce: more than was written means the target was
+                # reached inside this batch (the FASTQ stops after the read that reaches it, simulate.py:63)
+                produced = allreduce_bases_all(engines, [r.total_bases() if r is not None else 0 for r in results])
+                assert produced >= bases and (produced == bases or total_size + bases >= target_size)
             total_size += bases
             count += n_emit
             print_progress(count, total_size, target_size, output)
             next_index += n_batch
+        return {'reads': count, 'bases': total_size, 'gpus': n_gpus, 'batches_s': time.perf_counter() - t_first,
+                'nccl_stop_condition': bool(use_nccl)}
     finally:
         for eng in engines:
             eng.close()

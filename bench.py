@@ -300,6 +300,39 @@ def reference_shim_rate(cfg, n_procs, quantity_bases):
         return {'value': None, 'kind': 'reference', 'sample': f'failed: {e}'}
 
 
+def cli_e2e(cfg, n_gpus=1):
+    """The real command line end to end: `python -m badread_b200 simulate ...` on the config's reference written as FASTA,
+    FASTQ to /dev/null.  Returns wall seconds of the whole process and of its simulate loop (planning + GPU + FASTQ
+    assembly + write; engines, reference and tables already resident), as the tool itself reports them."""
+    try:
+        fd, fasta = tempfile.mkstemp(suffix='.fasta')
+        with os.fdopen(fd, 'wb') as f:
+            for name, n, seed, depth, circ in cfg['contigs']:
+                hdr = f'>{name}' + (f' depth={depth:g}' if depth != 1.0 else '') + (' circular=true' if circ else '')
+                f.write(hdr.encode() + b'\n' + _synth_contig(seed, n).tobytes() + b'\n')
+        env = dict(os.environ)
+        env['BADREAD_B200_TIMING'] = '1'
+        env['PYTHONPATH'] = os.pathsep.join([ROOT, env.get('PYTHONPATH', '')])
+        argv = [sys.executable, '-m', 'badread_b200', 'simulate', '--reference', fasta, '--quantity', cfg['quantity'],
+                '--seed', str(SEED), '--gpus', str(n_gpus)] + cfg['extra']
+        t0 = time.perf_counter()
+        with open(os.devnull, 'wb') as null:
+            p = subprocess.run(argv, env=env, stdout=null, stderr=subprocess.PIPE, timeout=900)
+        wall = time.perf_counter() - t0
+        os.unlink(fasta)
+        if p.returncode != 0:
+            return {'value': None, 'note': f'exit code {p.returncode}: {p.stderr.decode(errors="replace")[-300:]}'}
+        line = [ln for ln in p.stderr.decode(errors='replace').splitlines() if ln.startswith('BADREAD_B200_TIMING ')][-1]
+        st = json.loads(line.split(' ', 1)[1])
+        return {'value': st['bases'] / st['batches_s'] / 1e9, 'unit': 'Gbases/s', 'gpus': n_gpus, 'reads': st['reads'],
+                'bases': st['bases'], 'simulate_loop_s': st['batches_s'], 'process_wall_s': wall, 'setup_s': st['setup_s'],
+                'nccl_stop_condition': st.get('nccl_stop_condition'),
+                'note': '`python -m badread_b200 simulate` > /dev/null; value = bases / simulate loop (native planner + '
+                        'bb_sequence_batch + FASTQ assembly + write), models, reference and engines resident'}
+    except Exception as e:
+        return {'value': None, 'note': f'failed: {e}'}
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -395,7 +428,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
-    from badread_b200.engine import Engine
+    from badread_b200.engine import Engine, comm_unique_id, nccl_available
     wl = Workload(a.config, rank, world, scaling, max_reads=a.reads, batch_reads=a.batch_reads,
                   threads=max(1, n_cores // world))
     eng = Engine(device=local_rank, seed=SEED)
@@ -406,6 +439,13 @@ def main():
     log(f'[rank {rank}] reference + tables uploaded in {time.perf_counter() - t0:.2f} s')
     nb = len(wl.batches)
     config['batches_per_step'] = nb
+    lib_nccl = False
+    if dist is not None and nccl_available():   # the library's own communicator for the SUM of emitted bases
+        import torch
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init_rank(box[0], rank, world)
+        lib_nccl = True
 
     def barrier():
         eng.synchronize()
@@ -502,9 +542,12 @@ def main():
                   'scope': 'whole workload' if limit is None else f'first {limit} read indices (SURVEY.md 8d)',
                   'against': 'oracle/badread_oracle.c (Philox mode), same read indices: seq, qual, matches/columns'}
 
-    ref_shim = None
+    ref_shim, cli = None, None
     if rank == 0 and world == 1 and not a.profile and not a.no_parity and a.ref_shim_bases > 0:
         ref_shim = reference_shim_rate(cfg, n_cores, a.ref_shim_bases)
+    if rank == 0 and world == 1 and not a.profile and not a.no_parity and a.config in (1, 2):
+        eng.close()   # the command line creates its own engine on the same GPU
+        cli = cli_e2e(cfg)
 
     tot_bases, max_elapsed, max_e2e = float(bases), elapsed, e2e_elapsed
     if dist is not None:
@@ -516,6 +559,10 @@ def main():
         tm = torch.tensor([elapsed, e2e_elapsed], device='cuda', dtype=torch.float64)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         tot_bases, max_elapsed, max_e2e = float(tb[0].item()), float(tm[0].item()), float(tm[1].item())
+        if lib_nccl:   # the product's collective: bb_allreduce_bases (must agree with torch's)
+            tot_lib = eng.allreduce_bases(int(bases))
+            assert tot_lib == int(tot_bases), (tot_lib, tot_bases)
+            config['bases_sum'] = 'bb_allreduce_bases (NCCL, in the library)'
         if parity:
             parity['reads_checked'], parity['mismatches'] = int(tb[1].item()), int(tb[2].item())
             parity['bases_checked'] = int(tb[3].item())
@@ -573,7 +620,7 @@ def main():
             'gpu_launches': int(launches),
             'roofline': roofline,
             'cpu_baseline': {'value': cpu_g, 'unit': 'Gbases/s', 'cores': max(1, n_cores // world), 'kind': 'port', 'sample': cpu_desc},
-            'cpu_baseline_reference': ref_shim,
+            'cpu_baseline_reference': ref_shim, 'cli_e2e': cli,
             'parity': parity}
     print(json.dumps(line), flush=True)
     eng.close()

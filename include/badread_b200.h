@@ -159,6 +159,22 @@ BB_API int bb_host_align_path(const uint8_t *query, int32_t q_len, const uint8_t
                        int64_t ops_cap, int64_t *n_ops, int32_t *distance);
 
 
+/* ---- multi-GPU: the one collective of the path ------------------------------------------------------ */
+/* Reads shard over GPUs by read index (GPU g owns indices = g mod G) and never exchange data.  The only value the GPUs
+ * have to agree on is the running total of emitted bases that ends the simulation (simulate.py:63): one NCCL
+ * all-reduce (SUM, one int64) per batch.  NCCL is loaded at run time (dlopen of libnccl.so.2); bb_nccl_available()
+ * says whether that worked.  Two ways to form the communicator:
+ *   one process per GPU (torchrun / mpirun): rank 0 calls bb_comm_unique_id, the host program ships the 128 bytes to
+ *     the other ranks by whatever means it has, every rank calls bb_comm_init_rank, then bb_allreduce_bases;
+ *   one process, several GPUs (`badread simulate --gpus N`): bb_comm_init_all, then bb_allreduce_bases_all. */
+typedef struct bb_nccl_id { char internal[128]; } bb_nccl_id;   /* ncclUniqueId */
+BB_API int bb_nccl_available(void);
+BB_API int bb_comm_unique_id(bb_nccl_id *id);
+BB_API int bb_comm_init_rank(bb_ctx *ctx, const bb_nccl_id *id, int rank, int world);
+BB_API int bb_comm_init_all(bb_ctx **ctxs, int n);
+BB_API int bb_allreduce_bases(bb_ctx *ctx, int64_t local, int64_t *total);
+BB_API int bb_allreduce_bases_all(bb_ctx **ctxs, int n, const int64_t *local, int64_t *total);
+
 /* ---- fragment builder and FASTQ assembly on the host (no GPU needed) -------------------------------- */
 /* The steps either side of the hot path, as native multi-threaded host code.  bb_planner_plan replaces the per-read
  * Python of build_fragment (badread/simulate.py:91-115), get_fragment / get_real_fragment / get_junk_fragment

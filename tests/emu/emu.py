@@ -68,12 +68,14 @@ def lane_align(query, target, k_upper, qabs_pad=0, lw=4):
     return int(out4[0]), int(out4[1]), int(out4[2])
 
 
-def tasks_align(seq, frag, upper):
-    """The level-synchronous alignment task pipeline under the emulator -> expanded ops string."""
+def tasks_align(seq, frag, upper, quad=True):
+    """The level-synchronous alignment task pipeline under the emulator -> expanded ops string.
+    quad: wide nodes by the 8-warp CTA kernel (bb_k_node_quad) instead of warp pairs (bb_k_node_pair)."""
     global _lib
     if _lib is None:
         build()
         _lib = ctypes.CDLL(str(LIB))
+    _lib.emu_set_quad(1 if quad else 0)
     q = seq.encode('latin-1') if isinstance(seq, str) else bytes(seq)
     t = frag.encode('latin-1') if isinstance(frag, str) else bytes(frag)
     n, m = len(q), len(t)

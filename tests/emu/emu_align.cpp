@@ -75,6 +75,9 @@ int emu_lane_align(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper
 }
 
 
+static int use_quad = 1;  // wide nodes by the 8-warp CTA kernel (1) or by warp pairs (0)
+extern "C" __attribute__((visibility("default"))) void emu_set_quad(int v) { use_quad = v; }
+
 // The level-synchronous task pipeline (bb_tasks.cuh) for one read, every kernel as one emulated warp.
 extern "C" __attribute__((visibility("default")))
 int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int upper, uint8_t *ops, unsigned int *dcnt,
@@ -121,7 +124,8 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
         const int p = level & 1;
         for (int c = 0; c < BBQ_NODE_CLASSES; c++) cnt[BBQ_COUNT(c, p ^ 1)] = 0;
         int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++, *c2b = cursor++, *c2c = cursor++;
-        emu::run_block(BB_WARPS_PER_CTA * 32, [&]() { bb_k_node_pair(B, Q, pool, p, c0, 0); });
+        if (use_quad) emu::run_block(BB_QUAD_THREADS, [&]() { bb_k_node_quad(B, Q, pool, p, c0, 0); });
+        else emu::run_block(BB_WARPS_PER_CTA * 32, [&]() { bb_k_node_pair(B, Q, pool, p, c0, 0); });
         emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, p, c1, 0); });
         emu::run_warp([&]() { bb_k_node_warp<2>(B, Q, pool, p, c2, 0); });
         emu::run_warp([&]() { bb_k_node_warp<1>(B, Q, pool, p, c2c, 0); });

@@ -77,8 +77,14 @@ def test_task_pipeline(emu):
     for n, rate in ((2600, 0.05), (9000, 0.06), (15000, 0.05)):
         a = random_dna(rnd, n, 'ACGTN' if n == 9000 else 'ACGT'); b = mutate(rnd, a, rate)
         assert emu.tasks_align(b, a, int(O.align_path(b, a)[1] * 1.2) + 5) == O.align_path(b, a)[0]
-    a = random_dna(rnd, 20000); b = mutate(rnd, a, 0.25)   # wide root: warp pairs
-    assert emu.tasks_align(b, a, int(O.align_path(b, a)[1] * 1.1)) == O.align_path(b, a)[0]
+    a = random_dna(rnd, 20000); b = mutate(rnd, a, 0.25)   # wide root: 8-warp CTAs (128-lane wavefronts) / warp pairs
+    want = O.align_path(b, a)[0]
+    assert emu.tasks_align(b, a, int(O.align_path(b, a)[1] * 1.1)) == want
+    assert emu.tasks_align(b, a, int(O.align_path(b, a)[1] * 1.1), quad=False) == want
+    for n, rate in ((9000, 0.3), (30000, 0.12), (12000, 0.45)):   # wide roots of other chunk widths (1, 2, 4 words per lane)
+        a = random_dna(rnd, n, 'ACGTN' if n == 9000 else 'ACGT'); b = mutate(rnd, a, rate)
+        ops, d = O.align_path(b, a)
+        assert emu.tasks_align(b, a, d + d // 7) == ops, (n, rate)
     # the two-columns-per-step wavefront of the lean warp kernel: odd / even lengths, every register-mask width
     # (L = 1, 2, 4), loose and exact bounds, non-ACGT targets
     for it in range(14):
