@@ -378,11 +378,14 @@ __device__ int bb_band_pass(const BBProb &P, int K) {
 // The wavefront of bb_band_pass spread over the WARPS warps of a CTA group (K = 32 WARPS lane slots, one problem):
 // a band that needs L words per lane on one warp needs L / WARPS here, so a step is WARPS times shorter and the
 // warps issue on different schedulers.  Distance only, column scores out (the node passes of the Hirschberg recursion).
-// Lane 31 of a warp hands its chunk's horizontal deltas to lane 0 of the next warp through a double-buffered mailbox
-// in shared memory; one named barrier (`bar_id`, 32 WARPS threads) per step orders the hand-over.  All warps of the
-// group must call this with the same problem; `wg` is the warp's index in the group.
+// Lane 31 of a warp hands its chunk's horizontal deltas to lane 0 of the next warp through a ring of mailboxes in
+// shared memory: mbox[wg * 8 + (step & 7)] holds warp wg's output of that step and progress[wg] the number of steps it
+// has published.  Lane 0 polls its predecessor's progress (bounded: a warp that waits longer than any correct run can
+// take gives up with an error instead of hanging); no CTA barrier is involved, the warps drift apart by at most WARPS - 1
+// steps because the dependency runs in a ring.  All warps of the group must call this with the same problem; `wg` is
+// the warp's index in the group; progress[] must be zero on entry.  Returns 0, or 256 if the hand-over timed out.
 template <int L, int WARPS>
-__device__ void bb_band_pass_mw(const BBProb &P, int wg, volatile uint32_t *mbox, int bar_id) {
+__device__ int bb_band_pass_mw(const BBProb &P, int wg, volatile uint32_t *mbox, volatile int *progress) {
     constexpr int K = 32 * WARPS;
     constexpr int CH = 32 * L;
     const int lane = threadIdx.x & 31;
@@ -413,16 +416,21 @@ __device__ void bb_band_pass_mw(const BBProb &P, int wg, volatile uint32_t *mbox
     uint32_t tcn = 0;
     const uint8_t *tp = P.t - (long long)u * ts;  // tp + tau*ts is this lane's column at step tau
     if (u <= ulast && 0 - u >= cs && 0 - u <= ce) tcn = *tp;
+    const int src = (wg + WARPS - 1) % WARPS;
+    int failed = 0;
     for (int tau = 0; tau < T; tau++) {
-        // the previous slot's output of step tau - 1: from the lane below, or from the warp before through the mailbox
+        // the previous slot's output of step tau - 1: from the lane below, or from the warp before through its mailbox
         uint32_t in = __shfl_up_sync(BB_FULL, outpack, 1);
-        if (lane == 31) mbox[wg * 2 + (tau & 1)] = outpack;
+        if (lane == 0 && tau > 0) {
+            int spins = 0;
+            while (progress[src] < tau) {
 #ifdef BB_EMULATOR
-        emu::named_barrier(bar_id, K);
-#else
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(K) : "memory");
+                emu::yield();
 #endif
-        if (lane == 0) in = mbox[((wg + WARPS - 1) % WARPS) * 2 + (tau & 1)];
+                if (++spins > (1 << 24)) { failed = 256; break; }
+            }
+            in = mbox[src * 8 + ((tau - 1) & 7)];
+        }
         const int c = tau - u;
         const bool active = (u <= ulast) && c >= cs && c <= ce;
         if (active) {
@@ -536,8 +544,14 @@ __device__ void bb_band_pass_mw(const BBProb &P, int wg, volatile uint32_t *mbox
         }
         const int cn = tau + 1 - u;
         if (u <= ulast && cn >= cs && cn <= ce) tcn = tp[(long long)(tau + 1) * ts];
+        if (lane == 31) {  // publish this step's output for lane 0 of the next warp
+            mbox[wg * 8 + (tau & 7)] = outpack;
+            __threadfence_block();
+            progress[wg] = tau + 1;
+        }
     }
     __syncwarp();
+    return __reduce_or_sync(BB_FULL, (unsigned)failed);
 }
 
 // CB columns per step: the distance-only variant of bb_band_pass for register-resident masks (L <= 4).  Chunk u

@@ -98,7 +98,7 @@ struct bb_ctx {
     int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
     bool head_worker = true;  // worker 0 = the longest reads only (see bb_batch_upload)
     bool is_head = false;     // this worker holds the head batch of the current upload
-    bool use_quad = true;     // wide nodes by 8-warp CTAs (bb_k_node_quad) instead of warp pairs
+    bool use_quad = false;    // wide nodes by 8-warp CTAs (bb_k_node_quad) instead of warp pairs
     int grid_div_env = 0;
     int grid_div = 1;         // persistent grids are launched at 1/grid_div of their full size (the workers of a split batch share the SMs)
     struct QueueBufs { DevBuf node[BBQ_NODE_CLASSES][2], leaf[2], count; } qbuf[2];  // [0] normal, [1] wide-root reads

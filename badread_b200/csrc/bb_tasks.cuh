@@ -536,7 +536,9 @@ template <int BB_TU_ = 0>  // a template: only the translation unit that launche
 __global__ void __launch_bounds__(BB_QUAD_THREADS, 1)
 bb_k_node_quad(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
     __shared__ int s_task;
-    __shared__ uint32_t s_mbox[2][BB_QUAD_WARPS * 2];
+    __shared__ uint32_t s_mbox[2][BB_QUAD_WARPS * 8];
+    __shared__ int s_progress[2][BB_QUAD_WARPS];
+    __shared__ int s_err;
 #ifdef BB_EMULATOR
     static uint32_t s_eq[BB_QUAD_SMEM_BYTES / 4];
 #else
@@ -550,7 +552,8 @@ bb_k_node_quad(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
     const BBNode *list = Q.node[BBQ_NODE_WIDE][parity];
     const int count = min(Q.count[BBQ_COUNT(BBQ_NODE_WIDE, parity)], Q.cap_node);
     for (;;) {
-        if (threadIdx.x == 0) s_task = atomicAdd(cursor, 1);
+        if (threadIdx.x == 0) { s_task = atomicAdd(cursor, 1); s_err = 0; }
+        if (threadIdx.x < 2 * BB_QUAD_WARPS) s_progress[threadIdx.x / BB_QUAD_WARPS][threadIdx.x % BB_QUAD_WARPS] = 0;
         __syncthreads();
         const int w = s_task;
         __syncthreads();
@@ -579,17 +582,20 @@ bb_k_node_quad(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
             }
             P.esm = s_eq + wi * bb_esm_words(32);
             volatile uint32_t *mb = s_mbox[rev ? 1 : 0];
-            const int bar = rev ? 2 : 1;
-            if (L == 1) bb_band_pass_mw<1, BB_QUAD_WARPS>(P, wg, mb, bar);
-            else if (L == 2) bb_band_pass_mw<2, BB_QUAD_WARPS>(P, wg, mb, bar);
-            else if (L == 4) bb_band_pass_mw<4, BB_QUAD_WARPS>(P, wg, mb, bar);
-            else if (L == 8) bb_band_pass_mw<8, BB_QUAD_WARPS>(P, wg, mb, bar);
-            else if (L == 16) bb_band_pass_mw<16, BB_QUAD_WARPS>(P, wg, mb, bar);
-            else bb_band_pass_mw<32, BB_QUAD_WARPS>(P, wg, mb, bar);
+            volatile int *pg = s_progress[rev ? 1 : 0];
+            int e;
+            if (L == 1) e = bb_band_pass_mw<1, BB_QUAD_WARPS>(P, wg, mb, pg);
+            else if (L == 2) e = bb_band_pass_mw<2, BB_QUAD_WARPS>(P, wg, mb, pg);
+            else if (L == 4) e = bb_band_pass_mw<4, BB_QUAD_WARPS>(P, wg, mb, pg);
+            else if (L == 8) e = bb_band_pass_mw<8, BB_QUAD_WARPS>(P, wg, mb, pg);
+            else if (L == 16) e = bb_band_pass_mw<16, BB_QUAD_WARPS>(P, wg, mb, pg);
+            else e = bb_band_pass_mw<32, BB_QUAD_WARPS>(P, wg, mb, pg);
+            if (e && lane == 0) atomicOr(&s_err, e);
         }
         __threadfence_block();
         __syncthreads();
         if (wi == 0) {
+            err |= s_err;
             int best = nd.best, split = 0, ls = 0, rs = 0;
             if (!err) {
                 if (L > 0) err = bb_split_warp(sc, loL, hiL, loR, hiR, nd.nn, left_w, right_w, best, split, ls, rs);

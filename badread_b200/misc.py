@@ -84,6 +84,61 @@ def load_fasta(filename):
     return seqs, depths, circular, hairpin_left, hairpin_right
 
 
+_UPPER = None
+
+
+def load_fasta_arrays(filename):
+    """load_fasta (misc.py:122-153) for large references: the whole file is parsed with numpy (no per-line Python, no
+    3 Gb Python strings).  Returns (names, [uint8 array per contig, upper-cased], depths, circular, hairpin_left,
+    hairpin_right) with the reference's header semantics (`depth=`, `circular=true`, `hairpin_*=true`, name = first
+    token); a repeated name keeps its last sequence, like the reference's dict."""
+    global _UPPER
+    import numpy as np
+    if _UPPER is None:
+        _UPPER = np.arange(256, dtype=np.uint8)
+        _UPPER[ord('a'):ord('z') + 1] -= 32
+    with open(filename, 'rb') as f:
+        magic = f.read(2)
+    if magic == b'\x1f\x8b':
+        with gzip.open(filename, 'rb') as f:
+            raw = f.read()
+    else:
+        with open(filename, 'rb') as f:
+            raw = f.read()
+    data = np.frombuffer(raw, dtype=np.uint8)
+    nl = np.flatnonzero(data == 10)
+    starts = np.concatenate([[0], nl + 1])                       # first byte of every line
+    starts = starts[starts < data.size]
+    ends = np.concatenate([nl, [data.size]])[:starts.size]       # its newline (or the end of the file)
+    is_hdr = data[starts] == ord('>')
+    hdr_lines = np.flatnonzero(is_hdr)
+    names, seqs, depths, circular, hp_left, hp_right = [], {}, {}, {}, {}, {}
+    depth_re = re.compile(r'depth=([\d.]+)')
+    keep = (data != 10) & (data != 13) & (data != 32) & (data != 9)
+    for k, li in enumerate(hdr_lines):
+        header = raw[starts[li] + 1:ends[li]].decode('latin-1').strip()
+        if not header:
+            continue
+        short = header.split()[0]
+        lowered = header.lower()
+        depth = 1.0
+        if 'depth=' in lowered:
+            try:
+                depth = float(depth_re.search(lowered).group(1))
+            except (ValueError, AttributeError):
+                depth = 1.0
+        lo = ends[li] + 1
+        hi = starts[hdr_lines[k + 1]] if k + 1 < hdr_lines.size else data.size
+        body = data[lo:hi]
+        seq = _UPPER[body[keep[lo:hi]]] if hi > lo else np.zeros(0, dtype=np.uint8)
+        if short not in seqs:
+            names.append(short)
+        seqs[short] = seq
+        depths[short], circular[short] = depth, 'circular=true' in lowered
+        hp_left[short], hp_right[short] = 'hairpin_left=true' in lowered, 'hairpin_right=true' in lowered
+    return names, [seqs[n] for n in names], depths, circular, hp_left, hp_right
+
+
 RANDOM_SEQ_DICT = {0: 'A', 1: 'C', 2: 'G', 3: 'T'}
 
 

@@ -32,7 +32,7 @@ from .engine import Engine, FragmentBatch, default_engine, next_read_index
 from .error_model import ErrorModel
 from .fragment_lengths import FragmentLengths
 from .identities import Identities
-from .misc import float_to_str, load_fasta, str_is_int
+from .misc import float_to_str, load_fasta, load_fasta_arrays, str_is_int
 from .qscore_model import QScoreModel, qscore_char_to_error_prob
 from .version import __version__
 
@@ -65,15 +65,14 @@ class Reference(object):
     def __init__(self, filename, output=sys.stderr):
         print('', file=output)
         print(f'Loading reference from {filename}', file=output)
-        seqs, depths, circular, left_hairpin, right_hairpin = load_fasta(filename)
-        self.names = list(seqs.keys())
-        self.lengths = [len(seqs[n]) for n in self.names]
+        self.names, arrays, depths, circular, left_hairpin, right_hairpin = load_fasta_arrays(filename)
+        self.lengths = [int(a.size) for a in arrays]
         self.depths = [depths[n] for n in self.names]
         self.circular = [circular[n] for n in self.names]
         self.left_hairpin = [left_hairpin[n] for n in self.names]
         self.right_hairpin = [right_hairpin[n] for n in self.names]
         self.offsets = np.concatenate([[0], np.cumsum(self.lengths)]).astype(np.int64)
-        self.concat = np.frombuffer(''.join(seqs[n] for n in self.names).encode('latin-1'), dtype=np.uint8)
+        self.concat = np.concatenate(arrays) if arrays else np.zeros(0, dtype=np.uint8)
         plural = '' if len(self.names) == 1 else 's'
         print(f'  {len(self.names):,} contig{plural}:', file=output)
         for i, name in enumerate(self.names):

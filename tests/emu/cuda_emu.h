@@ -174,6 +174,16 @@ inline int __reduce_max_sync(unsigned, int v) {
     emu::barrier();
     return r;
 }
+inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+    emu::Block &w = emu::blk();
+    const int b0 = emu::warp_base();
+    w.xchg[threadIdx.x] = v;
+    emu::barrier();
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) if (b0 + i < w.nthreads && !w.done[b0 + i]) r |= (unsigned)w.xchg[b0 + i];
+    emu::barrier();
+    return r;
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier(); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }

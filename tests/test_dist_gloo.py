@@ -41,6 +41,17 @@ def _worker(rank, world, port, ref_path, out):
     names = [str(pl[3]) for pl in mine]
     gathered = [None] * world
     dist.all_gather_object(gathered, names)
+    # the native planner shards the same way (first index = rank, stride = world) and plans the same reads
+    from badread_b200.planner import NativePlanner
+    nat = NativePlanner(args, ref, fl, Identities(95, 2.5, 99, sink), 9, n_threads=2)
+    pb = nat.plan(rank, len(mine), stride=world)
+    assert [pb.name_str(i) for i in range(len(pb))] == names
+    assert [pb.info_str(i) for i in range(len(pb))] == [' '.join(pl[1]) for pl in mine]
+    assert [float(x) for x in pb.target_identity] == [pl[2] for pl in mine]
+    nat_bases = torch.tensor([float(pb.frag_bases())], dtype=torch.float64)
+    dist.all_reduce(nat_bases, op=dist.ReduceOp.SUM)
+    assert int(nat_bases.item()) == int(t[0].item())
+    nat.close()
     if rank == 0:
         serial = [planner.plan(i) for i in range(64)]
         assert int(t[1].item()) == 64

@@ -231,3 +231,25 @@ def test_library_rebuilds_when_any_device_header_changes():
     assert obj_rules and all('$(HDRS)' in ln for ln in obj_rules)
     assert '$(wildcard bb_tu_*.cu)' in mk and 'bb_api.cu' in mk and 'bb_host.o' in mk and 'bb_planner.o' in mk
     assert [ln for ln in mk.splitlines() if ln.startswith('$(OUT): $(OBJS)')]
+
+
+def test_numpy_fasta_loader_matches_line_parser(tmp_path):
+    """load_fasta_arrays (the loader `simulate` uses; numpy, no per-line Python) against the line-by-line restatement
+    of misc.load_fasta (misc.py:122-153): header flags, depth parsing, upper-casing, blank lines, CRLF, a repeated
+    name, an empty record, gzip."""
+    import gzip
+    import numpy as np
+    from badread_b200.misc import load_fasta, load_fasta_arrays
+    rs = np.random.RandomState(4)
+    body = ''.join('acgtnACGTN'[i] for i in rs.randint(0, 10, 5000))
+    txt = ('>c1 depth=2.5 circular=true extra\n' + '\n'.join(body[i:i + 70] for i in range(0, 3000, 70)) + '\n\n'
+           '>c2 hairpin_left=TRUE hairpin_right=true\r\n' + body[3000:4000] + '\r\n' + body[4000:] + '\n>c3\n>c1 depth=x\nAAAA')
+    for gz in (False, True):
+        p = tmp_path / ('ref.fa' + ('.gz' if gz else ''))
+        with (gzip.open(p, 'wt') if gz else open(p, 'w')) as f:
+            f.write(txt)
+        seqs, depths, circular, left, right = load_fasta(str(p))
+        names, arrays, d2, c2, l2, r2 = load_fasta_arrays(str(p))
+        assert names == list(seqs.keys())
+        assert [a.tobytes().decode() for a in arrays] == [seqs[n] for n in names]
+        assert (depths, circular, left, right) == (d2, c2, l2, r2)
