@@ -423,7 +423,7 @@ __device__ int bb_band_pass_mw(const BBProb &P, int wg, volatile uint32_t *mbox,
         uint32_t in = __shfl_up_sync(BB_FULL, outpack, 1);
         if (lane == 0 && tau > 0) {
             int spins = 0;
-            while (progress[src] < tau) {
+            while (!failed && progress[src] < tau) {  // (after one timeout the pass no longer waits: it ends, flagged)
 #ifdef BB_EMULATOR
                 emu::yield();
 #endif

@@ -91,7 +91,7 @@ struct bb_ctx {
     // scratch
     int n_warps = 0;
     BBScratchPool pool{}, pool_lean{};  // pool_lean: split-score arrays of the single-warp node kernels (bands < 2048 rows)
-    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist, s_lr_lean;
+    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist, s_lr_lean, s_wckpt;
     DevBuf d_ctime, d_chlog, d_wres, d_wtasks, d_wfallback, d_active;
     DevBuf p_q, p_t, p_ops, p_dcnt, p_out, p_qual;  // single-pair entry points (bb_align_path / bb_get_qscores): kept between calls
     int lane8_cols = 4096;  // routing limit of the lane node kernel (tuning knob)
@@ -234,6 +234,7 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed, bool high_prio
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     e = bbl_node_pair_init();
     if (e == cudaSuccess) e = bbl_node_quad_init();
+    if (e == cudaSuccess) e = bbl_window_lane_init();
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     // persistent warps: 4 CTAs of 4 warps per SM for the warp-per-read kernels
     ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
@@ -283,7 +284,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
                       &ctx->d_wtasks, &ctx->d_wfallback, &ctx->d_active,
-                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->s_lr_lean, &ctx->d_scan, &ctx->d_red,
+                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->s_lr_lean, &ctx->s_wckpt, &ctx->d_scan, &ctx->d_red,
                       &ctx->p_q, &ctx->p_t, &ctx->p_ops, &ctx->p_dcnt, &ctx->p_out, &ctx->p_qual};
     for (auto &qb : ctx->qbuf) {
         for (auto &cl : qb.node) for (auto &d : cl) d.release();
@@ -516,7 +517,9 @@ static int w_prepare(bb_ctx *ctx) {
     {   // lane pools shared by the window aligner and the leaf aligner: history of 2048 columns x 8 words per thread
         const size_t lanes = (size_t)lane_ctas * 64;
         BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * lanes * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
-        BB_CUDA(ctx, ctx->s_ltbuf.ensure(2 * lanes * BB_WIN_MAX_COLS));  // the 4-word window kernel runs 2x the lanes
+        BB_CUDA(ctx, ctx->s_ltbuf.ensure(2 * lanes * BB_WIN_MAX_COLS));  // the 4-word window kernel runs up to 1.5x the lanes
+        // window aligners: a checkpoint (2 LW + 2 words) per 16 columns per lane instead of a per-column history
+        BB_CUDA(ctx, ctx->s_wckpt.ensure(2 * lanes * BB_WIN_MAX_TILES * BB_WIN_CKPT_WORDS(BB_WIN_LW) * sizeof(uint32_t)));
     }
     // per-warp scratch: strip carries / bitmaps for the longest joined read; split-score arrays for the widest band
     // (expected: a few times the injected edits; worst case: the whole read)
@@ -636,10 +639,10 @@ static int enqueue_error_loop(bb_ctx *ctx, const BBBatchDev &B) {
         mark(ctx, st, "window_tasks");
         // 4-word windows first (bands up to 64 rows: almost every window); what does not fit falls through to the
         // 8-word build and from there to the warp kernel
-        bbl_window_lane4(pgrid(ctx, 8), st, B, ctx->em, tasks, c + BBC_NTASKS, ctx->seed, ctx->s_leafhist.as<uint2>(),
+        bbl_window_lane4(pgrid(ctx, 6), st, B, ctx->em, tasks, c + BBC_NTASKS, ctx->seed, ctx->s_wckpt.as<uint32_t>(),
                          ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE4, fb1, c + BBC_FB1);
         mark(ctx, st, "window_lane4");
-        bbl_window_lane8(pgrid(ctx, 4), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed, ctx->s_leafhist.as<uint2>(),
+        bbl_window_lane8(pgrid(ctx, 3), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed, ctx->s_wckpt.as<uint32_t>(),
                          ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE8, fb2, c + BBC_FB2);
         mark(ctx, st, "window_lane8");
         bbl_window_warp(pgrid(ctx, 2), st, B, ctx->em, ctx->pool, fb2, c + BBC_FB2, ctx->seed, c + BBC_WARP);

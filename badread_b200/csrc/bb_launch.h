@@ -9,11 +9,12 @@
 
 void bbl_mutate(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter,
                 const int *order, int n_items, bool chain);  // chain: the low-latency build (bb_k_mutate_chain)
+cudaError_t bbl_window_lane_init();
 void bbl_window_lane4(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks,
-                      unsigned long long seed, uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback,
+                      unsigned long long seed, uint32_t *ckpt_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback,
                       int *fallback_count);
 void bbl_window_lane8(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks,
-                      unsigned long long seed, uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback,
+                      unsigned long long seed, uint32_t *ckpt_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback,
                       int *fallback_count);
 void bbl_window_warp(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, const BBWinTask *tasks,
                      const int *n_tasks, unsigned long long seed, int *cursor);

@@ -338,108 +338,154 @@ __device__ __forceinline__ void bb_window_of(int frag_len, unsigned long long se
     }
 }
 
-// One window alignment per thread; persistent lanes, all on the same step of the same phase.
+// One window alignment per thread, 32 at a time per warp in lock step: join -> forward pass -> traceback.
+// The forward pass keeps no per-column history.  It saves the lane's vertical deltas every BB_WIN_TILE columns (a
+// checkpoint: 2 LW + 2 words); the traceback walks the tiles from the last to the first, re-running each tile's columns
+// from its checkpoint into SHARED memory (per-column vertical / horizontal delta words, the two bits per cell edlib's
+// traceback rule needs) and following the path through it.  Round 1 wrote 8 LW bytes per column per window to global
+// memory and read them back along the path - 54 GB per step, with the traceback stalled on those loads 4/5 of the time
+// (ncu: 78 % of the stall cycles on the L1TEX scoreboard, issue slots 18 % busy); now a window moves ~9 KB.
+#define BB_WIN_TILE 16
+#define BB_WIN_CKPT_WORDS(LW) (2 * (LW) + 2)
+#define BB_WIN_MAX_TILES (BB_WIN_MAX_COLS / BB_WIN_TILE)
+#define BB_WIN_SMEM_BYTES(LW) (BB_WIN_TILE * (LW) * 64 * 8)
+
 template <int LW>
-__global__ void __launch_bounds__(64, (LW <= 4 ? 8 : 4))
+__global__ void __launch_bounds__(64, (LW <= 4 ? 6 : 3))
 bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks_ptr, unsigned long long seed,
-                 uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback, int *fallback_count) {
+                 uint32_t *ckpt_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback, int *fallback_count) {
+#ifdef BB_EMULATOR
+    static uint2 s_hist[BB_WIN_TILE * LW * 64];
+#else
+    extern __shared__ __align__(16) uint2 s_hist[];  // [column in tile][word][thread]
+#endif
+    constexpr int CKW = BB_WIN_CKPT_WORDS(LW);
     const int n_tasks = *n_tasks_ptr;
     const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    uint2 *const hist = hist_pool + gl * (long long)(BB_WIN_MAX_COLS * LW);
+    uint32_t *const ckpt = ckpt_pool + gl * (long long)(BB_WIN_MAX_TILES * CKW);
     uint8_t *const tbuf = tbuf_pool + gl * (long long)BB_WIN_MAX_COLS;
-    BBLanePass<LW> S;
-    BBProb P;
-    BBWinTask tk = {0, 0};
-    const uint8_t *frag = nullptr;
-    const uint32_t *state = nullptr;
-    const unsigned int *ctime = nullptr;
-    int phase = 0;  // 0: fetch, 1: join, 2: forward pass, 3: traceback, 4: done
-    int qpos = 0, qn = 0, jx = 0, tm = 0, uw = 0, ti = 0, tj = 0, matches = 0, dels = 0;
-    unsigned int tmax = 0;
+    uint2 *const hs = s_hist + threadIdx.x;
     for (;;) {
-        if (phase == 0) {
-            const int w = atomicAdd(cursor, 1);
-            if (w >= n_tasks) phase = 4;
-            else {
-                tk = tasks[w];
-                const BBReadDev *rd = &B.reads[tk.r];
-                frag = B.frag + rd->frag_off; state = B.state + rd->frag_off; ctime = B.ctime + rd->frag_off;
-                bb_window_of(rd->frag_len, seed, B.read_index[tk.r], tk.a, qpos, qn);
-                tmax = (unsigned int)(BB_ALIGNMENT_INTERVAL * tk.a);
-                jx = 0; tm = 0; uw = 0;
-                phase = 1;
-            }
+        const int w = atomicAdd(cursor, 1);
+        bool active = w < n_tasks;
+        if (!__any_sync(BB_FULL, active)) break;
+        BBWinTask tk = {0, 0};
+        const BBReadDev *rd = nullptr;
+        const uint8_t *frag = nullptr;
+        const uint32_t *state = nullptr;
+        const unsigned int *ctime = nullptr;
+        int qpos = 0, qn = 0;
+        unsigned int tmax = 0;
+        if (active) {
+            tk = tasks[w];
+            rd = &B.reads[tk.r];
+            frag = B.frag + rd->frag_off; state = B.state + rd->frag_off; ctime = B.ctime + rd->frag_off;
+            bb_window_of(rd->frag_len, seed, B.read_index[tk.r], tk.a, qpos, qn);
+            tmax = (unsigned int)(BB_ALIGNMENT_INTERVAL * tk.a);
         }
-        if (__all_sync(BB_FULL, phase == 4)) break;
-        for (int it = 0; it < 64; it++) {  // ''.join(new_fragment_bases[pos:pos2]) as it was after 25*a changes
-            if (phase == 1) {
-                // four slots per iteration: their loads are issued together, the (serial) appends follow
+        // ---- join: ''.join(new_fragment_bases[pos:pos2]) as it was after 25*a changes
+        int tm = 0, uw = 0;
+        const int qn_max = __reduce_max_sync(BB_FULL, qn);
+        for (int j0 = 0; j0 < qn_max; j0 += 4) {
+            if (active && j0 < qn) {
                 unsigned int ct4[4];
                 uint8_t fb4[4];
 #pragma unroll
-                for (int h = 0; h < 4; h++) {
-                    const int j = min(jx + h, qn - 1);
+                for (int h = 0; h < 4; h++) {  // four slots per iteration: their loads are issued together
+                    const int j = min(j0 + h, qn - 1);
                     ct4[h] = ctime[qpos + j];
                     fb4[h] = frag[qpos + j];
                 }
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
-                    if (jx < qn) {
+                    if (j0 + h < qn) {
                         if (ct4[h] == 0u || ct4[h] > tmax) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = fb4[h]; tm++; }
                         else {
-                            const uint32_t st = state[qpos + jx];
+                            const uint32_t st = state[qpos + j0 + h];
                             const int sl = (int)(st & 0xff);
                             for (int c = 0; c < sl; c++) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = bb_slot_char(em, st, c); tm++; }
                             uw += sl < 1 ? 1 : sl;
                         }
-                        jx++;
-                    }
-                }
-                if (jx >= qn) {
-                    const int diff = qn > tm ? qn - tm : tm - qn;
-                    if (uw < diff) uw = diff;
-                    const int mx = qn > tm ? qn : tm;
-                    if (uw > mx) uw = mx;
-                    bb_band(qn, tm, uw, P.a, P.b);
-                    if (tm > BB_WIN_MAX_COLS || bb_lane_words(P.a, P.b) > LW || !bb_uses_traceback(qn, tm)) {
-                        fallback[atomicAdd(fallback_count, 1)] = tk;  // the warp kernel handles this window
-                        phase = 0;
-                    } else {
-                        const BBReadDev *rd = &B.reads[tk.r];
-                        P.n = qn; P.peq = B.fpeq + rd->fpeq_off; P.q = frag + qpos; P.qs = 1;
-                        P.peq_bit0 = qpos + BB_PEQ_BIT0; P.t = tbuf; P.ts = 1;
-                        bb_lane_begin<LW>(S, P);
-                        phase = 2;
                     }
                 }
             }
         }
-        for (int it = 0; it < 128; it++) {  // forward columns with history
-            if (phase == 2) {
-                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
-                if (S.c >= tm) { ti = qn - 1; tj = tm - 1; matches = 0; dels = 0; phase = 3; }
+        BBProb P;
+        P.a = 0; P.b = 1;
+        if (active) {
+            const int diff = qn > tm ? qn - tm : tm - qn;
+            if (uw < diff) uw = diff;
+            const int mx = qn > tm ? qn : tm;
+            if (uw > mx) uw = mx;
+            bb_band(qn, tm, uw, P.a, P.b);
+            if (tm > BB_WIN_MAX_COLS || bb_lane_words(P.a, P.b) > LW || !bb_uses_traceback(qn, tm)) {
+                fallback[atomicAdd(fallback_count, 1)] = tk;  // the next kernel handles this window
+                active = false;
             }
         }
-        for (int it = 0; it < 256; it++) {  // traceback (edlib's rule), counting '=' and 'D' columns
-            if (phase == 3) {
-                if (ti >= 0 && tj >= 0) {
+        if (!active) tm = 0;
+        // ---- forward pass, a checkpoint every BB_WIN_TILE columns
+        BBLanePass<LW> S;
+        if (active) {
+            P.n = qn; P.peq = B.fpeq + rd->fpeq_off; P.q = frag + qpos; P.qs = 1;
+            P.peq_bit0 = qpos + BB_PEQ_BIT0; P.t = tbuf; P.ts = 1;
+            bb_lane_begin<LW>(S, P);
+        }
+        const int tm_max = __reduce_max_sync(BB_FULL, tm);
+        for (int c = 0; c < tm_max; c++) {
+            if (c < tm) {
+                if ((c & (BB_WIN_TILE - 1)) == 0) {
+                    uint32_t *ck = ckpt + (c / BB_WIN_TILE) * CKW;
+#pragma unroll
+                    for (int x = 0; x < LW; x++) { ck[x] = S.Pv[x]; ck[LW + x] = S.Mv[x]; }
+                    ck[2 * LW] = (uint32_t)S.wt; ck[2 * LW + 1] = (uint32_t)S.score;
+                }
+                bb_lane_step<LW, false>(S, P, nullptr);
+            }
+        }
+        // ---- traceback (edlib's rule: 'I' > 'D' > diagonal), tile by tile, counting '=' and 'D' columns
+        int ti = qn - 1, tj = tm - 1, matches = 0, dels = 0;
+        bool walking = active && ti >= 0 && tj >= 0;
+        bool need_tile = walking;
+        int tile_lo = 0;
+        // (every round moves every walking lane at least once: qn + tm rounds bound the loop whatever the data)
+        for (int round = 0; round < 2 * BB_WIN_MAX_COLS + 64 && __any_sync(BB_FULL, walking); round++) {
+            if (walking && need_tile) {  // all walking lanes get here together (see the inner loop's exit)
+                const int tile = tj / BB_WIN_TILE;
+                tile_lo = tile * BB_WIN_TILE;
+                const uint32_t *ck = ckpt + tile * CKW;
+#pragma unroll
+                for (int x = 0; x < LW; x++) { S.Pv[x] = ck[x]; S.Mv[x] = ck[LW + x]; }
+                S.wt = (int)ck[2 * LW]; S.score = (int)ck[2 * LW + 1]; S.c = tile_lo;
+#pragma unroll
+                for (int x = 0; x < LW; x++) bb_fetch_peq(P, 32 * (S.wt + x), S.eA[x], S.eC[x], S.eG[x], S.eT[x]);
+                const int hi = min(tile_lo + BB_WIN_TILE, tm);
+                for (int c = tile_lo; c < hi; c++) bb_lane_step<LW, true, 64>(S, P, hs + ((c - tile_lo) * LW) * 64);
+                need_tile = false;
+            }
+            for (int mv = 0; mv < 64; mv++) {
+                const bool can = walking && !need_tile;
+                if (!__any_sync(BB_FULL, can)) break;
+                if (can) {
                     int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
                     const int x = (ti >> 5) - wt;
                     if (x < 0 || x >= LW) { atomicOr(&B.reads[tk.r].flags, 1); ti = -1; tj = -1; }
                     else {
-                        bb_prefetch_history<LW>(hist, tj);
-                        const uint2 e = hist[(long long)tj * LW + x];
+                        const uint2 e = hs[((tj - tile_lo) * LW + x) * 64];
                         const int bit = ti & 31;
                         if ((e.x >> bit) & 1u) ti--;
                         else if ((e.y >> bit) & 1u) { dels++; tj--; }
                         else { matches += (frag[qpos + ti] == tbuf[tj]) ? 1 : 0; ti--; tj--; }
                     }
-                } else {
-                    if (tj >= 0) dels += tj + 1;
-                    B.wres[B.reads[tk.r].wres_off + tk.a - 1] = make_int2(matches, qn + dels);
-                    phase = 0;
+                    if (ti < 0 || tj < 0) walking = false;
+                    else if (tj < tile_lo) need_tile = true;
                 }
             }
+        }
+        if (active) {
+            if (walking) atomicOr(&B.reads[tk.r].flags, 1);  // cannot happen: the round bound above was hit
+            if (tj >= 0) dels += tj + 1;
+            B.wres[rd->wres_off + tk.a - 1] = make_int2(matches, qn + dels);
         }
     }
 }

@@ -162,8 +162,8 @@ __device__ __forceinline__ void bb_lane_begin(BBLanePass<LW> &S, const BBProb &P
     S.wt = 0; S.score = 32 * LW; S.c = 0;
 }
 
-// One column of the pass. hist (optional): LW entries for this column.
-template <int LW, bool HIST>
+// One column of the pass. hist (optional): LW entries for this column, HSTRIDE apart.
+template <int LW, bool HIST, int HSTRIDE = 1>
 __device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P, uint2 *hist) {
     const int c = S.c;
     if (c - P.a >= 32 * (S.wt + 1)) {  // slide the window down one word
@@ -210,7 +210,7 @@ __device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P,
         const uint32_t raw = Ph[x];
         S.Pv[x] = mhs | ~(Xv[x] | phs);
         S.Mv[x] = phs & Xv[x];
-        if (HIST) hist[x] = make_uint2(S.Pv[x], raw);
+        if (HIST) hist[x * HSTRIDE] = make_uint2(S.Pv[x], raw);
     }
     S.c = c + 1;
 }

@@ -543,7 +543,9 @@ def main():
                   'against': 'oracle/badread_oracle.c (Philox mode), same read indices: seq, qual, matches/columns'}
 
     ref_shim, cli = None, None
-    if rank == 0 and world == 1 and not a.profile and not a.no_parity and a.ref_shim_bases > 0:
+    # (only the 5 Mb configs: the reference's loader turns a 3 Gb FASTA into tens of GB of Python objects PER PROCESS -
+    # running it on all cores at once took the whole box down, twice)
+    if rank == 0 and world == 1 and not a.profile and not a.no_parity and a.ref_shim_bases > 0 and a.config in (1, 2):
         ref_shim = reference_shim_rate(cfg, n_cores, a.ref_shim_bases)
     if rank == 0 and world == 1 and not a.profile and not a.no_parity and a.config in (1, 2):
         eng.close()   # the command line creates its own engine on the same GPU

@@ -122,3 +122,28 @@ def compare_sm(query, target, k, L):
     t = target.encode('latin-1') if isinstance(target, str) else bytes(target)
     rc = _lib.emu_compare_sm(q, len(q), t, len(t), int(k), int(L))
     return None if rc < 0 else int(rc)
+
+
+def window_lane(frag, changes, seed, read_index, lw=4):
+    """bb_k_window_lane<lw> under the emulator for one read: changes = [(position, new string of <= 3 chars)] in the
+    order they were applied -> [(matches, columns)] of the identity re-measurements after 25, 50, ... changes
+    ((-1, -1): the window does not fit lw words and went to the fallback list)."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(LIB))
+    f = frag.encode('latin-1') if isinstance(frag, str) else bytes(frag)
+    pos = np.asarray([p for p, _ in changes], dtype=np.int32)
+    enc = np.zeros(len(changes), dtype=np.uint32)
+    for i, (_, sub) in enumerate(changes):
+        b = sub.encode('latin-1')
+        assert len(b) <= 3
+        enc[i] = len(b) | sum(b[j] << (8 * (j + 1)) for j in range(len(b)))
+    n_meas = len(changes) // 25
+    out = np.full(2 * max(n_meas, 1), -7, dtype=np.int32)
+    flags = _lib.emu_window_lane(f, len(f), pos.ctypes.data_as(ctypes.c_void_p), enc.ctypes.data_as(ctypes.c_void_p),
+                                 len(changes), ctypes.c_uint64(seed), ctypes.c_uint64(read_index), int(lw),
+                                 out.ctypes.data_as(ctypes.c_void_p))
+    if flags:
+        raise RuntimeError(f'window kernel error flags 0x{int(flags):x}')
+    return [(int(out[2 * a]), int(out[2 * a + 1])) for a in range(n_meas)]

@@ -242,3 +242,43 @@ int emu_compare_sm(const uint8_t *q, int n, const uint8_t *t, int m, int k, int 
     if (L == 32) return emu_compare_sm_impl<32>(q, n, t, m, a, b);
     return -1;
 }
+
+
+// The lane-mode window aligner kernel (bb_loop.cuh) on one read: `frag` is the padded fragment, change i (1-based
+// ordinal) rewrites slot pos[i] with the inline-encoded string enc[i] (len | c0 << 8 | c1 << 16 | c2 << 24, len <= 3).
+// Runs identity re-measurements a = 1 .. n_changes / 25 through bb_k_window_lane<LW> as one emulated warp and returns
+// (matches, columns) per measurement; windows that do not fit LW words come back as (-1, -1).
+extern "C" __attribute__((visibility("default")))
+int emu_window_lane(const uint8_t *frag, int frag_len, const int *pos, const uint32_t *enc, int n_changes,
+                    unsigned long long seed, unsigned long long read_index, int lw, int *out_pairs) {
+    std::vector<uint8_t> fr(frag, frag + frag_len);
+    fr.resize((size_t)frag_len + 64, 0);
+    std::vector<uint32_t> state((size_t)frag_len + 64, BB_SLOT_NONE);
+    std::vector<unsigned int> ctime((size_t)frag_len + 64, 0u);
+    for (int i = 0; i < n_changes; i++) { state[(size_t)pos[i]] = enc[i]; ctime[(size_t)pos[i]] = (unsigned int)(i + 1); }
+    std::vector<uint4> fpeq((size_t)bb_peq_words(frag_len) + 8);
+    const int n_meas = n_changes / BB_ALIGNMENT_INTERVAL;
+    std::vector<int2> wres((size_t)n_meas + 4, make_int2(-1, -1));
+    BBReadDev rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.frag_len = frag_len;
+    BBBatchDev B;
+    std::memset(&B, 0, sizeof(B));
+    B.n_reads = 1; B.read_index = &read_index; B.reads = &rd; B.frag = fr.data(); B.state = state.data();
+    B.ctime = ctime.data(); B.fpeq = fpeq.data(); B.wres = wres.data();
+    BBErrorModelDev em;
+    std::memset(&em, 0, sizeof(em));
+    em.k = 7; em.type = 1;
+    std::vector<BBWinTask> tasks, fallback((size_t)n_meas + 4);
+    for (int a = 1; a <= n_meas; a++) tasks.push_back(BBWinTask{0, a});
+    int n_tasks = n_meas, cursor = 0, fb_count = 0;
+    std::vector<uint32_t> ckpt((size_t)64 * BB_WIN_MAX_TILES * BB_WIN_CKPT_WORDS(BB_WIN_LW));
+    std::vector<uint8_t> tbuf((size_t)64 * BB_WIN_MAX_COLS);
+    emu::run_warp([&]() { bb_build_peq(fr.data(), frag_len, fpeq.data()); });
+    emu::run_warp([&]() {
+        if (lw == 4) bb_k_window_lane<4>(B, em, tasks.data(), &n_tasks, seed, ckpt.data(), tbuf.data(), &cursor, fallback.data(), &fb_count);
+        else bb_k_window_lane<BB_WIN_LW>(B, em, tasks.data(), &n_tasks, seed, ckpt.data(), tbuf.data(), &cursor, fallback.data(), &fb_count);
+    });
+    for (int a = 0; a < n_meas; a++) { out_pairs[2 * a] = wres[(size_t)a].x; out_pairs[2 * a + 1] = wres[(size_t)a].y; }
+    return rd.flags;
+}

@@ -136,3 +136,43 @@ def test_shared_memory_match_cache_equals_streamed_words(emu):
                 assert bad == 0, (it, n, len(b), d, L)
                 checked += 1
     assert checked >= 25
+
+
+def test_window_lane_kernel_matches_oracle(emu):
+    """bb_k_window_lane<4> / <8> (checkpoints every 16 columns, tiles re-run into shared memory for the traceback) under
+    the emulator: '=' columns and total columns of every identity re-measurement of a read equal edlib's path between
+    the original 1000-base window (query) and the window as it was after 25 a changes (target) - simulate.py:325-346.
+    Fragments shorter and longer than the window, substitutions / deletions / insertions, 30 ... 250 changes."""
+    from oracle import oracle as O
+    rnd = random.Random(2024)
+    checked = 0
+    for frag_len, n_changes, lw in ((700, 60, 4), (1000, 75, 4), (3000, 250, 4), (2200, 180, 8), (5000, 130, 4), (1800, 260, 8)):
+        frag = random_dna(rnd, frag_len)
+        positions = rnd.sample(range(frag_len), n_changes)
+        changes = []
+        for p in positions:
+            kind = rnd.random()
+            if kind < 0.4:
+                sub = rnd.choice([c for c in 'ACGT' if c != frag[p]])
+            elif kind < 0.7:
+                sub = ''
+            else:
+                sub = frag[p] + rnd.choice('ACGT') if rnd.random() < 0.5 else rnd.choice('ACGT') + frag[p]
+            changes.append((p, sub))
+        seed, read = 77, 5 + frag_len
+        got = emu.window_lane(frag, changes, seed, read, lw=lw)
+        assert len(got) == n_changes // 25
+        for a, (matches, cols) in enumerate(got, start=1):
+            qpos, qn = 0, frag_len
+            if frag_len > 1000:
+                rng = O.Rng(O.RNG_PHILOX, seed, read)
+                rng.stream(4, a - 1)
+                qpos, qn = rng.randbelow(frag_len - 1000 + 1), 1000
+            applied = dict(changes[:25 * a])
+            target = ''.join(applied.get(i, frag[i]) for i in range(qpos, qpos + qn))
+            if (matches, cols) == (-1, -1):
+                continue        # too wide for this build: the next kernel's job
+            ops, _ = O.align_path(frag[qpos:qpos + qn], target)
+            assert (matches, cols) == (ops.count('='), len(ops)), (frag_len, n_changes, lw, a)
+            checked += 1
+    assert checked >= 25
