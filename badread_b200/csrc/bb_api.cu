@@ -235,6 +235,7 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed, bool high_prio
     e = bbl_node_pair_init();
     if (e == cudaSuccess) e = bbl_node_quad_init();
     if (e == cudaSuccess) e = bbl_window_lane_init();
+    if (e == cudaSuccess) e = bbl_leaf_lane_init();
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BB_ERR_CUDA; }
     // persistent warps: 4 CTAs of 4 warps per SM for the warp-per-read kernels
     ctx->n_warps = ctx->sm_count * 4 * BB_WARPS_PER_CTA;
@@ -435,7 +436,7 @@ static int ensure_scratch(bb_ctx *ctx, int hbuf_need, int lr_need, int len_need)
     p.peq = ctx->s_peq.as<uint4>(); p.peq_stride = peq_cap; p.peq_cap = peq_cap;
     // the single-warp node kernels (2 pipelines x 3 widths, all resident at once) only touch the split-score arrays
     constexpr int lean_cap = 2048;  // > a + b + 1 of the widest lean class (bb_pick_L<4>(a, b, 16) > 0: a + b < 1920)
-    const size_t lean_warps = 2 * (size_t)ctx->sm_count * (2 + 3 + 3) * BB_WARPS_PER_CTA;
+    const size_t lean_warps = 2 * (size_t)ctx->sm_count * (4 + 6 + 6) * BB_WARPS_PER_CTA;  // room for the grid knobs' maxima
     BB_CUDA(ctx, ctx->s_lr_lean.ensure(lean_warps * lean_cap * 2 * sizeof(int)));
     ctx->pool_lean = p;
     ctx->pool_lean.lr = ctx->s_lr_lean.as<int>(); ctx->pool_lean.lr_stride = 2ll * lean_cap; ctx->pool_lean.lr_cap = lean_cap;
@@ -514,9 +515,9 @@ static int w_prepare(bb_ctx *ctx) {
     BB_CUDA(ctx, ctx->d_out_seq.ensure((size_t)ctx->out_cap + 16));
     BB_CUDA(ctx, ctx->d_out_qual.ensure((size_t)ctx->out_cap + 16));
     const int lane_ctas = ctx->sm_count * 4;  // 64-thread CTAs of the lane kernels
-    {   // lane pools shared by the window aligner and the leaf aligner: history of 2048 columns x 8 words per thread
+    {   // lane pools of the window aligner and the leaf aligner (the two alignment pipelines each own half)
         const size_t lanes = (size_t)lane_ctas * 64;
-        BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * lanes * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));
+        BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * lanes * BB_LEAF_MAX_TILES * BB_LEAF_CKPT_WORDS * sizeof(uint32_t)));
         BB_CUDA(ctx, ctx->s_ltbuf.ensure(2 * lanes * BB_WIN_MAX_COLS));  // the 4-word window kernel runs up to 1.5x the lanes
         // window aligners: a checkpoint (2 LW + 2 words) per 16 columns per lane instead of a per-column history
         BB_CUDA(ctx, ctx->s_wckpt.ensure(2 * lanes * BB_WIN_MAX_TILES * BB_WIN_CKPT_WORDS(BB_WIN_LW) * sizeof(uint32_t)));
@@ -615,7 +616,12 @@ static int w_batch_upload(bb_ctx *ctx, int32_t n_reads, const uint64_t *read_ind
 // Persistent grids (CTAs that pull work from a queue until it is empty) of `per_sm` CTAs per SM at full size.  The
 // workers of a split batch run side by side: each launches its share, so that their kernels are resident together
 // instead of queueing behind each other's long-running CTAs.
-static int pgrid(const bb_ctx *ctx, int per_sm) {
+static int pgrid(const bb_ctx *ctx, int per_sm, const char *knob = nullptr) {
+    if (knob) {  // tuning: BADREAD_B200_GRID_<KNOB> = CTAs per SM of that kernel
+        static thread_local char name[64];
+        std::snprintf(name, sizeof(name), "BADREAD_B200_GRID_%s", knob);
+        if (const char *e = std::getenv(name)) { const int v = std::atoi(e); if (v > 0) per_sm = v; }
+    }
     return std::max(ctx->sm_count / 2, (ctx->sm_count * per_sm + ctx->grid_div - 1) / ctx->grid_div);
 }
 
@@ -633,16 +639,16 @@ static int enqueue_error_loop(bb_ctx *ctx, const BBBatchDev &B) {
     BBWinTask *fb1 = ctx->d_wfallback.as<BBWinTask>(), *fb2 = fb1 + ctx->wres_total + 8;
     for (int round = 0; round < ctx->n_rounds; round++) {
         int *c = cnt + BB_ROUND_BASE(round);
-        bbl_mutate(std::min(pgrid(ctx, 8), n), st, B, ctx->em, ctx->seed, c + BBC_MUTATE, order, n, ctx->is_head);
+        bbl_mutate(std::min(pgrid(ctx, 8, "MUTATE"), n), st, B, ctx->em, ctx->seed, c + BBC_MUTATE, order, n, ctx->is_head);
         mark(ctx, st, "mutate");
         bb_k_window_tasks<<<(n + 255) / 256, 256, 0, st>>>(B, order, n, tasks, c + BBC_NTASKS);
         mark(ctx, st, "window_tasks");
         // 4-word windows first (bands up to 64 rows: almost every window); what does not fit falls through to the
         // 8-word build and from there to the warp kernel
-        bbl_window_lane4(pgrid(ctx, 6), st, B, ctx->em, tasks, c + BBC_NTASKS, ctx->seed, ctx->s_wckpt.as<uint32_t>(),
+        bbl_window_lane4(std::min(pgrid(ctx, 6, "WIN4"), ctx->sm_count * 8), st, B, ctx->em, tasks, c + BBC_NTASKS, ctx->seed, ctx->s_wckpt.as<uint32_t>(),
                          ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE4, fb1, c + BBC_FB1);
         mark(ctx, st, "window_lane4");
-        bbl_window_lane8(pgrid(ctx, 3), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed, ctx->s_wckpt.as<uint32_t>(),
+        bbl_window_lane8(std::min(pgrid(ctx, 3, "WIN8"), ctx->sm_count * 8), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed, ctx->s_wckpt.as<uint32_t>(),
                          ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE8, fb2, c + BBC_FB2);
         mark(ctx, st, "window_lane8");
         bbl_window_warp(pgrid(ctx, 2), st, B, ctx->em, ctx->pool, fb2, c + BBC_FB2, ctx->seed, c + BBC_WARP);
@@ -662,7 +668,7 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
     const int n = ctx->n_reads;
     const int cap_node = (int)std::min<int64_t>(ctx->seq_cap / 256 + 4ll * n + 1024, 0x7ffffff0);
     const int lane_ctas = ctx->sm_count * 4;
-    const size_t hist_per_pipe = (size_t)lane_ctas * 64 * BB_LEAF_LANE_COLS * BB_LEAF_LW;
+    const size_t hist_per_pipe = (size_t)lane_ctas * 64 * BB_LEAF_MAX_TILES * BB_LEAF_CKPT_WORDS;  // checkpoint words
     BBQueues Q[2];
     int *cnt[2];
     for (int s = 0; s < 2; s++) {
@@ -683,7 +689,7 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
     BB_CUDA(ctx, cudaStreamWaitEvent(stream[1], ctx->ev_fork, 0));
     int *cursor[2] = {cnt[0] + 16, cnt[1] + 16};
     const int warp_base[2] = {0, ctx->n_warps / 2};
-    const int w4 = ctx->sm_count * 2 * BB_WARPS_PER_CTA, w2 = ctx->sm_count * 3 * BB_WARPS_PER_CTA;  // warps of the lean kernels
+    const int w4 = ctx->sm_count * 4 * BB_WARPS_PER_CTA, w2 = ctx->sm_count * 6 * BB_WARPS_PER_CTA;  // scratch slots of the lean kernels (maxima)
     const int lean_base[2] = {0, w4 + 2 * w2};
     // The node classes of a level read the same queues and push into the next level's: they are independent and run
     // side by side on their own streams; the level ends when all of them have finished.
@@ -709,15 +715,15 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
             }
             {
                 cudaStream_t x = on_side();   // the two narrow single-warp classes share a stream
-                bbl_node_warp(2, pgrid(ctx, 3), x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4);
+                bbl_node_warp(2, std::min(pgrid(ctx, 3, "WARP2"), ctx->sm_count * 6), x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4);
                 mark(ctx, x, "node_warp2");
-                bbl_node_warp(1, pgrid(ctx, 3), x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4 + w2);
+                bbl_node_warp(1, std::min(pgrid(ctx, 3, "WARP1"), ctx->sm_count * 6), x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4 + w2);
                 mark(ctx, x, "node_warp1");
                 x = on_side();
-                bbl_node_lane8(pgrid(ctx, 6), x, B, Q[s], p, cursor[s]++);
+                bbl_node_lane8(pgrid(ctx, 6, "LANE8"), x, B, Q[s], p, cursor[s]++);
                 mark(ctx, x, "node_lane8");
             }
-            bbl_node_warp(4, pgrid(ctx, 2), st, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s]);
+            bbl_node_warp(4, std::min(pgrid(ctx, 2, "WARP4"), ctx->sm_count * 4), st, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s]);
             mark(ctx, st, "node_warp4");
             ctx->launches += 4;
             for (int x = 0; x < n_side; x++) {
@@ -730,7 +736,7 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
         cudaStream_t st = stream[s];
         bbl_leaf_warp(ctx->sm_count, st, B, Q[s], ctx->pool, cursor[s]++, warp_base[s]);
         mark(ctx, st, "leaf_warp");
-        bbl_leaf_lane(pgrid(ctx, 4), st, B, Q[s], ctx->s_leafhist.as<uint2>() + s * hist_per_pipe, cursor[s]++);
+        bbl_leaf_lane(std::min(pgrid(ctx, 3, "LEAF"), ctx->sm_count * 4), st, B, Q[s], ctx->s_leafhist.as<uint32_t>() + s * hist_per_pipe, cursor[s]++);
         mark(ctx, st, "leaf_lane");
         ctx->launches += 2;
     }

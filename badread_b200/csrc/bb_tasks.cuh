@@ -306,57 +306,95 @@ bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
 }
 
 // ---------------------------------------------------------------------------------------------- lane leaf kernel
+// One leaf per thread, 32 at a time per warp in lock step: forward pass with a checkpoint of the vertical deltas every
+// BB_LEAF_TILE columns, then the traceback tile by tile out of shared memory (the scheme of bb_k_window_lane; round 1
+// kept 64 bytes of history per column per leaf in global memory: 34 GB per step).
+#define BB_LEAF_TILE 16
+#define BB_LEAF_CKPT_WORDS (2 * BB_LEAF_LW + 2)
+#define BB_LEAF_MAX_TILES (BB_LEAF_LANE_COLS / BB_LEAF_TILE)
+#define BB_LEAF_SMEM_BYTES (BB_LEAF_TILE * BB_LEAF_LW * 64 * 8)
+
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
-__global__ void __launch_bounds__(64)
-bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
-    constexpr int LW = BB_LEAF_LW;
+__global__ void __launch_bounds__(64, 3)
+bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint32_t *ckpt_pool, int *cursor) {
+    constexpr int LW = BB_LEAF_LW, CKW = BB_LEAF_CKPT_WORDS;
+#ifdef BB_EMULATOR
+    static uint2 s_hist[BB_LEAF_TILE * LW * 64];
+#else
+    extern __shared__ __align__(16) uint2 s_hist[];  // [column in tile][word][thread]
+#endif
     const BBNode *list = Q.leaf[0];
     const int count = min(Q.count[BBQ_LEAF_COUNT], Q.cap_leaf);
-    uint2 *const hist = hist_pool + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * (long long)(BB_LEAF_LANE_COLS * LW);
-    BBLanePass<LW> S;
-    BBProb P;
-    BBNode nd;
-    BBAlignOut o;
-    const uint8_t *qp = nullptr, *tp = nullptr;
-    int phase = 0;  // 0: fetch, 1: forward pass, 2: traceback, 3: done
-    int ti = 0, tj = 0, matches = 0, dels = 0;
+    uint32_t *const ckpt = ckpt_pool + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * (long long)(BB_LEAF_MAX_TILES * CKW);
+    uint2 *const hs = s_hist + threadIdx.x;
     for (;;) {
-        if (phase == 0) {
-            const int w = atomicAdd(cursor, 1);
-            if (w >= count) phase = 3;
-            else {
-                nd = list[w];
-                BBReadDev *rd = &B.reads[nd.r];
-                o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
-                bb_task_band(nd, rd->upper, P.a, P.b);
-                P.n = nd.nn; P.peq = B.speq + rd->speq_off;
-                qp = B.seq + rd->seq_off + nd.q0; tp = B.frag + rd->frag_off + nd.t0;
-                P.q = qp; P.qs = 1; P.peq_bit0 = nd.q0 + BB_PEQ_BIT0; P.t = tp; P.ts = 1;
-                bb_lane_begin<LW>(S, P);
-                phase = 1;
-            }
+        const int w = atomicAdd(cursor, 1);
+        const bool active = w < count;
+        if (!__any_sync(BB_FULL, active)) break;
+        BBNode nd = {0, 0, 0, 0, 0, 0};
+        BBAlignOut o = {nullptr, nullptr, nullptr};
+        BBProb P;
+        P.a = 0; P.b = 1;
+        BBLanePass<LW> S;
+        const uint8_t *qp = nullptr, *tp = nullptr;
+        int mm = 0;
+        if (active) {
+            nd = list[w];
+            BBReadDev *rd = &B.reads[nd.r];
+            o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
+            bb_task_band(nd, rd->upper, P.a, P.b);
+            P.n = nd.nn; P.peq = B.speq + rd->speq_off;
+            qp = B.seq + rd->seq_off + nd.q0; tp = B.frag + rd->frag_off + nd.t0;
+            P.q = qp; P.qs = 1; P.peq_bit0 = nd.q0 + BB_PEQ_BIT0; P.t = tp; P.ts = 1;
+            bb_lane_begin<LW>(S, P);
+            mm = nd.mm;
         }
-        if (__all_sync(BB_FULL, phase == 3)) break;
-        for (int it = 0; it < 128; it++) {  // forward columns with history
-            if (phase == 1) {
-                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
-                if (S.c >= nd.mm) {
-                    const int d = bb_lane_column_scores<LW>(S, nd.nn, 0, -1, nullptr);
-                    if (nd.best >= 0 && d != nd.best) atomicOr(&o.rd->flags, 8 << 8);
-                    ti = nd.nn - 1; tj = nd.mm - 1; matches = 0; dels = 0;
-                    phase = 2;
+        // ---- forward pass, a checkpoint every BB_LEAF_TILE columns
+        const int mm_max = __reduce_max_sync(BB_FULL, mm);
+        for (int c = 0; c < mm_max; c++) {
+            if (c < mm) {
+                if ((c & (BB_LEAF_TILE - 1)) == 0) {
+                    uint32_t *ck = ckpt + (c / BB_LEAF_TILE) * CKW;
+#pragma unroll
+                    for (int x = 0; x < LW; x++) { ck[x] = S.Pv[x]; ck[LW + x] = S.Mv[x]; }
+                    ck[2 * LW] = (uint32_t)S.wt; ck[2 * LW + 1] = (uint32_t)S.score;
                 }
+                bb_lane_step<LW, false>(S, P, nullptr);
             }
         }
-        for (int it = 0; it < 256; it++) {  // traceback moves (edlib's rule: 'I' > 'D' > diagonal)
-            if (phase == 2) {
-                if (ti >= 0 && tj >= 0) {
+        if (active) {
+            const int d = bb_lane_column_scores<LW>(S, nd.nn, 0, -1, nullptr);
+            if (nd.best >= 0 && d != nd.best) atomicOr(&o.rd->flags, 8 << 8);
+        }
+        // ---- traceback (edlib's rule: 'I' > 'D' > diagonal), tile by tile
+        int ti = nd.nn - 1, tj = mm - 1, matches = 0, dels = 0;
+        bool walking = active && ti >= 0 && tj >= 0;
+        bool need_tile = walking;
+        int tile_lo = 0;
+        // (every round moves every walking lane at least once: nn + mm rounds bound the loop whatever the data)
+        for (int round = 0; round < (1 << 16) && __any_sync(BB_FULL, walking); round++) {
+            if (walking && need_tile) {  // all walking lanes get here together (see the inner loop's exit)
+                const int tile = tj / BB_LEAF_TILE;
+                tile_lo = tile * BB_LEAF_TILE;
+                const uint32_t *ck = ckpt + tile * CKW;
+#pragma unroll
+                for (int x = 0; x < LW; x++) { S.Pv[x] = ck[x]; S.Mv[x] = ck[LW + x]; }
+                S.wt = (int)ck[2 * LW]; S.score = (int)ck[2 * LW + 1]; S.c = tile_lo;
+#pragma unroll
+                for (int x = 0; x < LW; x++) bb_fetch_peq(P, 32 * (S.wt + x), S.eA[x], S.eC[x], S.eG[x], S.eT[x]);
+                const int hi = min(tile_lo + BB_LEAF_TILE, mm);
+                for (int c = tile_lo; c < hi; c++) bb_lane_step<LW, true, 64>(S, P, hs + ((c - tile_lo) * LW) * 64);
+                need_tile = false;
+            }
+            for (int mv = 0; mv < 64; mv++) {
+                const bool can = walking && !need_tile;
+                if (!__any_sync(BB_FULL, can)) break;
+                if (can) {
                     int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
                     const int x = (ti >> 5) - wt;
                     if (x < 0 || x >= LW) { atomicOr(&o.rd->flags, 1 << 8); ti = -1; tj = -1; }
                     else {
-                        bb_prefetch_history<LW>(hist, tj);
-                        const uint2 e = hist[(long long)tj * LW + x];
+                        const uint2 e = hs[((tj - tile_lo) * LW + x) * 64];
                         const int bit = ti & 31;
                         if ((e.x >> bit) & 1u) { o.ops[nd.q0 + ti] = BB_OP_I; ti--; }
                         else if ((e.y >> bit) & 1u) { bb_add_dels(o, nd.q0 + ti, 1); dels++; tj--; }
@@ -367,14 +405,17 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
                             ti--; tj--;
                         }
                     }
-                } else {
-                    for (int x = 0; x <= ti; x++) o.ops[nd.q0 + x] = BB_OP_I;  // column boundary: insertions remain
-                    if (tj >= 0) { bb_add_dels(o, nd.q0 - 1, tj + 1); dels += tj + 1; }  // row boundary: deletions
-                    atomicAdd(&o.rd->matches, matches);
-                    atomicAdd(&o.rd->dels, dels);
-                    phase = 0;
+                    if (ti < 0 || tj < 0) walking = false;
+                    else if (tj < tile_lo) need_tile = true;
                 }
             }
+        }
+        if (active) {
+            if (walking) atomicOr(&o.rd->flags, 1 << 8);  // cannot happen: the round bound above was hit
+            for (int x = 0; x <= ti; x++) o.ops[nd.q0 + x] = BB_OP_I;  // column boundary: insertions remain
+            if (tj >= 0) { bb_add_dels(o, nd.q0 - 1, tj + 1); dels += tj + 1; }  // row boundary: deletions
+            atomicAdd(&o.rd->matches, matches);
+            atomicAdd(&o.rd->dels, dels);
         }
     }
 }

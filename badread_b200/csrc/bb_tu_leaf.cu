@@ -5,6 +5,10 @@ void bbl_leaf_warp(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, BBScratc
     bb_k_leaf_warp<<<grid, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, pool, cursor, warp_base);
 }
 
-void bbl_leaf_lane(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
-    bb_k_leaf_lane<<<grid, 64, 0, st>>>(B, Q, hist_pool, cursor);
+cudaError_t bbl_leaf_lane_init() {
+    return cudaFuncSetAttribute(bb_k_leaf_lane<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BB_LEAF_SMEM_BYTES);
+}
+
+void bbl_leaf_lane(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, uint32_t *ckpt_pool, int *cursor) {
+    bb_k_leaf_lane<0><<<grid, 64, BB_LEAF_SMEM_BYTES, st>>>(B, Q, ckpt_pool, cursor);
 }

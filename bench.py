@@ -276,6 +276,8 @@ def reference_shim_rate(cfg, n_procs, quantity_bases):
                 f.write(hdr.encode() + b'\n' + _synth_contig(seed, n).tobytes() + b'\n')
         env = dict(os.environ)
         env['PYTHONPATH'] = os.pathsep.join([os.path.join(ROOT, 'oracle', 'edlib_shim'), ref_dir, env.get('PYTHONPATH', '')])
+        for v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+            env[v] = '1'   # one thread per reference process (numpy would start a pool per process)
         runner = ('import sys\nfrom badread.__main__ import main\nmain()\n')
         t0 = time.perf_counter()
         procs = []
@@ -284,14 +286,20 @@ def reference_shim_rate(cfg, n_procs, quantity_bases):
                     '--seed', str(SEED + i)] + cfg['extra']
             procs.append(subprocess.Popen(argv, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL))
         bases = 0
-        for p in procs:
-            out, _ = p.communicate()
-            if p.returncode != 0:
-                raise RuntimeError(f'reference process exited with {p.returncode}')
-            lines = out.split(b'\n')
-            bases += sum(len(lines[j]) for j in range(1, len(lines), 4))
+        deadline = t0 + 240.0   # a reported baseline must not hold the bench up
+        try:
+            for p in procs:
+                out, _ = p.communicate(timeout=max(1.0, deadline - time.perf_counter()))
+                if p.returncode != 0:
+                    raise RuntimeError(f'reference process exited with {p.returncode}')
+                lines = out.split(b'\n')
+                bases += sum(len(lines[j]) for j in range(1, len(lines), 4))
+        finally:
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+            os.unlink(fasta)
         dt = time.perf_counter() - t0
-        os.unlink(fasta)
         return {'value': bases / dt / 1e9, 'unit': 'Gbases/s', 'cores': n_procs, 'kind': 'reference',
                 'sample': f'unmodified badread.simulate (baseline/_ref) + oracle/edlib_shim: {n_procs} processes x --quantity '
                           f'{quantity_bases} with seeds {SEED}..{SEED + n_procs - 1}, {bases} bases in {dt:.1f} s wall of the '
@@ -317,7 +325,7 @@ def cli_e2e(cfg, n_gpus=1):
                 '--seed', str(SEED), '--gpus', str(n_gpus)] + cfg['extra']
         t0 = time.perf_counter()
         with open(os.devnull, 'wb') as null:
-            p = subprocess.run(argv, env=env, stdout=null, stderr=subprocess.PIPE, timeout=900)
+            p = subprocess.run(argv, env=env, stdout=null, stderr=subprocess.PIPE, timeout=240)
         wall = time.perf_counter() - t0
         os.unlink(fasta)
         if p.returncode != 0:
@@ -371,7 +379,7 @@ def main():
     ap.add_argument('--batch_reads', type=int, default=32768, help='reads per device batch')
     ap.add_argument('--profile', action='store_true', help='skip the e2e, parity and CPU legs (for runs under ncu)')
     ap.add_argument('--no_parity', action='store_true', help='skip the parity + CPU baseline leg')
-    ap.add_argument('--ref_shim_bases', type=int, default=1500000,
+    ap.add_argument('--ref_shim_bases', type=int, default=600000,
                     help='bases per process of the reference-with-shim baseline leg (0: skip it)')
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -514,6 +522,7 @@ def main():
         barrier()
         e2e_elapsed = time.perf_counter() - t1
     d2h = 2 * bases_e2e + wl.n_reads * 48
+    log(f'[rank {rank}] timed: {elapsed / a.steps * 1e3:.1f} ms/step resident, {e2e_elapsed / a.steps * 1e3:.1f} ms/step end to end')
 
     # ---- parity + CPU baseline on the same reads
     cpu_g, cpu_desc, parity = None, 'skipped', None
@@ -536,6 +545,7 @@ def main():
             cpu_bases += cb
             cpu_dt += cd
         cpu_g = cpu_bases / cpu_dt / 1e9 if cpu_dt > 0 else None
+        log(f'[rank {rank}] parity leg: {len(picks)} reads, {n_bad} mismatches, oracle {cpu_dt:.1f} s')
         what = 'the whole workload' if limit is None else f'read indices < {limit} of this rank'
         cpu_desc = f'{what}: {len(picks)} reads, {cpu_bases} bases in {cpu_dt:.2f} s on {threads} threads'
         parity = {'reads_checked': len(picks), 'bases_checked': int(cpu_bases), 'mismatches': int(n_bad),
@@ -546,10 +556,14 @@ def main():
     # (only the 5 Mb configs: the reference's loader turns a 3 Gb FASTA into tens of GB of Python objects PER PROCESS -
     # running it on all cores at once took the whole box down, twice)
     if rank == 0 and world == 1 and not a.profile and not a.no_parity and a.ref_shim_bases > 0 and a.config in (1, 2):
+        t_leg = time.perf_counter()
         ref_shim = reference_shim_rate(cfg, n_cores, a.ref_shim_bases)
+        log(f'[rank 0] reference-with-shim leg: {time.perf_counter() - t_leg:.1f} s: {ref_shim.get("value")}')
     if rank == 0 and world == 1 and not a.profile and not a.no_parity and a.config in (1, 2):
         eng.close()   # the command line creates its own engine on the same GPU
+        t_leg = time.perf_counter()
         cli = cli_e2e(cfg)
+        log(f'[rank 0] command-line leg: {time.perf_counter() - t_leg:.1f} s: {cli.get("value")} {cli.get("note", "")[:120]}')
 
     tot_bases, max_elapsed, max_e2e = float(bases), elapsed, e2e_elapsed
     if dist is not None:

@@ -105,6 +105,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     const int big = std::max(n, m) + 64;
     const int NW = BB_WARPS_PER_CTA;  // scratch for every warp of one emulated CTA
     std::vector<uint2> hist((size_t)NW * 106496), lhist((size_t)32 * BB_LEAF_LANE_COLS * BB_LEAF_LW);
+    std::vector<uint32_t> lckpt((size_t)64 * BB_LEAF_MAX_TILES * BB_LEAF_CKPT_WORDS);
     std::vector<int8_t> hbuf((size_t)NW * big);
     std::vector<int> LR((size_t)NW * 2 * big), stack((size_t)NW * 5 * 64);
     std::vector<uint8_t> tbuf(16);
@@ -136,7 +137,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     }
     int *c3 = cursor++, *c4 = cursor++;
     emu::run_warp([&]() { bb_k_leaf_warp(B, Q, pool, c3, 0); });
-    emu::run_warp([&]() { bb_k_leaf_lane(B, Q, lhist.data(), c4); });
+    emu::run_warp([&]() { bb_k_leaf_lane(B, Q, lckpt.data(), c4); });
     out5[0] = rd.matches; out5[1] = rd.dels; out5[2] = cnt[BBQ_OVERFLOW]; out5[3] = rd.lead_del; out5[4] = rd.flags;
     return 0;
 }
