@@ -91,13 +91,14 @@ struct bb_ctx {
     // scratch
     int n_warps = 0;
     BBScratchPool pool{}, pool_lean{};  // pool_lean: split-score arrays of the single-warp node kernels (bands < 2048 rows)
-    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist, s_lr_lean, s_wckpt;
+    DevBuf s_hist, s_hbuf, s_lr, s_stack, s_tbuf, s_peq, s_ltbuf, s_leafhist, s_lr_lean, s_wckpt, s_lanehist;
     DevBuf d_ctime, d_chlog, d_wres, d_wtasks, d_wfallback, d_active;
     DevBuf p_q, p_t, p_ops, p_dcnt, p_out, p_qual;  // single-pair entry points (bb_align_path / bb_get_qscores): kept between calls
     int lane8_cols = 4096;  // routing limit of the lane node kernel (tuning knob)
     int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
     bool head_worker = true;  // worker 0 = the longest reads only (see bb_batch_upload)
     bool is_head = false;     // this worker holds the head batch of the current upload
+    bool lowmem = false;      // window / leaf aligners with checkpoints + shared-memory tiles instead of global history
     bool use_quad = false;    // wide nodes by 8-warp CTAs (bb_k_node_quad) instead of warp pairs
     int grid_div_env = 0;
     int grid_div = 1;         // persistent grids are launched at 1/grid_div of their full size (the workers of a split batch share the SMs)
@@ -245,6 +246,7 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed, bool high_prio
     if (const char *e = std::getenv("BADREAD_B200_HEAD_WORKER")) ctx->head_worker = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_GRID_DIV")) ctx->grid_div_env = std::atoi(e);
     if (const char *e = std::getenv("BADREAD_B200_QUAD")) ctx->use_quad = (e[0] != '0');
+    if (const char *e = std::getenv("BADREAD_B200_LOWMEM")) ctx->lowmem = (e[0] != '0');
     *out = ctx;
     return BB_OK;
 }
@@ -285,7 +287,7 @@ extern "C" int bb_destroy(bb_ctx *ctx) {
                       &ctx->d_qual, &ctx->d_out_seq, &ctx->d_out_qual, &ctx->d_counter, &ctx->s_hist, &ctx->s_hbuf,
                       &ctx->s_lr, &ctx->s_stack, &ctx->s_tbuf, &ctx->s_peq, &ctx->s_ltbuf, &ctx->d_ctime, &ctx->d_chlog, &ctx->d_wres,
                       &ctx->d_wtasks, &ctx->d_wfallback, &ctx->d_active,
-                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->s_lr_lean, &ctx->s_wckpt, &ctx->d_scan, &ctx->d_red,
+                      &ctx->d_fpeq, &ctx->d_speq, &ctx->d_fallback, &ctx->s_leafhist, &ctx->s_lr_lean, &ctx->s_wckpt, &ctx->s_lanehist, &ctx->d_scan, &ctx->d_red,
                       &ctx->p_q, &ctx->p_t, &ctx->p_ops, &ctx->p_dcnt, &ctx->p_out, &ctx->p_qual};
     for (auto &qb : ctx->qbuf) {
         for (auto &cl : qb.node) for (auto &d : cl) d.release();
@@ -517,10 +519,11 @@ static int w_prepare(bb_ctx *ctx) {
     const int lane_ctas = ctx->sm_count * 4;  // 64-thread CTAs of the lane kernels
     {   // lane pools of the window aligner and the leaf aligner (the two alignment pipelines each own half)
         const size_t lanes = (size_t)lane_ctas * 64;
-        BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * lanes * BB_LEAF_MAX_TILES * BB_LEAF_CKPT_WORDS * sizeof(uint32_t)));
+        if (ctx->lowmem) BB_CUDA(ctx, ctx->s_leafhist.ensure(2 * lanes * BB_LEAF_MAX_TILES * BB_LEAF_CKPT_WORDS * sizeof(uint32_t)));
+        else BB_CUDA(ctx, ctx->s_lanehist.ensure(2 * lanes * BB_LEAF_LANE_COLS * BB_LEAF_LW * sizeof(uint2)));  // per-column history
         BB_CUDA(ctx, ctx->s_ltbuf.ensure(2 * lanes * BB_WIN_MAX_COLS));  // the 4-word window kernel runs up to 1.5x the lanes
         // window aligners: a checkpoint (2 LW + 2 words) per 16 columns per lane instead of a per-column history
-        BB_CUDA(ctx, ctx->s_wckpt.ensure(2 * lanes * BB_WIN_MAX_TILES * BB_WIN_CKPT_WORDS(BB_WIN_LW) * sizeof(uint32_t)));
+        if (ctx->lowmem) BB_CUDA(ctx, ctx->s_wckpt.ensure(2 * lanes * BB_WIN_MAX_TILES * BB_WIN_CKPT_WORDS(BB_WIN_LW) * sizeof(uint32_t)));
     }
     // per-warp scratch: strip carries / bitmaps for the longest joined read; split-score arrays for the widest band
     // (expected: a few times the injected edits; worst case: the whole read)
@@ -645,11 +648,19 @@ static int enqueue_error_loop(bb_ctx *ctx, const BBBatchDev &B) {
         mark(ctx, st, "window_tasks");
         // 4-word windows first (bands up to 64 rows: almost every window); what does not fit falls through to the
         // 8-word build and from there to the warp kernel
-        bbl_window_lane4(std::min(pgrid(ctx, 6, "WIN4"), ctx->sm_count * 8), st, B, ctx->em, tasks, c + BBC_NTASKS, ctx->seed, ctx->s_wckpt.as<uint32_t>(),
-                         ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE4, fb1, c + BBC_FB1);
+        if (ctx->lowmem)
+            bbl_window_lane4(std::min(pgrid(ctx, 6, "WIN4"), ctx->sm_count * 8), st, B, ctx->em, tasks, c + BBC_NTASKS, ctx->seed,
+                             ctx->s_wckpt.as<uint32_t>(), ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE4, fb1, c + BBC_FB1);
+        else
+            bbl_window_lane_hist(4, std::min(pgrid(ctx, 8, "WIN4"), ctx->sm_count * 8), st, B, ctx->em, tasks, c + BBC_NTASKS,
+                                 ctx->seed, ctx->s_lanehist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE4, fb1, c + BBC_FB1);
         mark(ctx, st, "window_lane4");
-        bbl_window_lane8(std::min(pgrid(ctx, 3, "WIN8"), ctx->sm_count * 8), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed, ctx->s_wckpt.as<uint32_t>(),
-                         ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE8, fb2, c + BBC_FB2);
+        if (ctx->lowmem)
+            bbl_window_lane8(std::min(pgrid(ctx, 3, "WIN8"), ctx->sm_count * 8), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed,
+                             ctx->s_wckpt.as<uint32_t>(), ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE8, fb2, c + BBC_FB2);
+        else
+            bbl_window_lane_hist(8, std::min(pgrid(ctx, 4, "WIN8"), ctx->sm_count * 4), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed,
+                                 ctx->s_lanehist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE8, fb2, c + BBC_FB2);
         mark(ctx, st, "window_lane8");
         bbl_window_warp(pgrid(ctx, 2), st, B, ctx->em, ctx->pool, fb2, c + BBC_FB2, ctx->seed, c + BBC_WARP);
         mark(ctx, st, "window_warp");
@@ -736,7 +747,11 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
         cudaStream_t st = stream[s];
         bbl_leaf_warp(ctx->sm_count, st, B, Q[s], ctx->pool, cursor[s]++, warp_base[s]);
         mark(ctx, st, "leaf_warp");
-        bbl_leaf_lane(std::min(pgrid(ctx, 3, "LEAF"), ctx->sm_count * 4), st, B, Q[s], ctx->s_leafhist.as<uint32_t>() + s * hist_per_pipe, cursor[s]++);
+        if (ctx->lowmem)
+            bbl_leaf_lane(std::min(pgrid(ctx, 3, "LEAF"), ctx->sm_count * 4), st, B, Q[s], ctx->s_leafhist.as<uint32_t>() + s * hist_per_pipe, cursor[s]++);
+        else
+            bbl_leaf_lane_hist(std::min(pgrid(ctx, 4, "LEAF"), ctx->sm_count * 4), st, B, Q[s],
+                               ctx->s_lanehist.as<uint2>() + s * ((size_t)lane_ctas * 64 * BB_LEAF_LANE_COLS * BB_LEAF_LW), cursor[s]++);
         mark(ctx, st, "leaf_lane");
         ctx->launches += 2;
     }

@@ -490,6 +490,115 @@ bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const
     }
 }
 
+// The DEFAULT window aligner: one window alignment per thread; persistent lanes, all on the same step of the same phase;
+// per-column history (Pv, PhRaw per window word) in global memory, read back along the path by the traceback.  It moves
+// ~64 KB per window through HBM but keeps 4 warps per scheduler resident and overlaps the loads; the checkpoint build
+// above (BADREAD_B200_LOWMEM=1) moves ~9 KB and measured 14 % slower per step.
+template <int LW>
+__global__ void __launch_bounds__(64, (LW <= 4 ? 8 : 4))
+bb_k_window_lane_hist(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks_ptr, unsigned long long seed,
+                 uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback, int *fallback_count) {
+    const int n_tasks = *n_tasks_ptr;
+    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint2 *const hist = hist_pool + gl * (long long)(BB_WIN_MAX_COLS * LW);
+    uint8_t *const tbuf = tbuf_pool + gl * (long long)BB_WIN_MAX_COLS;
+    BBLanePass<LW> S;
+    BBProb P;
+    BBWinTask tk = {0, 0};
+    const uint8_t *frag = nullptr;
+    const uint32_t *state = nullptr;
+    const unsigned int *ctime = nullptr;
+    int phase = 0;  // 0: fetch, 1: join, 2: forward pass, 3: traceback, 4: done
+    int qpos = 0, qn = 0, jx = 0, tm = 0, uw = 0, ti = 0, tj = 0, matches = 0, dels = 0;
+    unsigned int tmax = 0;
+    for (;;) {
+        if (phase == 0) {
+            const int w = atomicAdd(cursor, 1);
+            if (w >= n_tasks) phase = 4;
+            else {
+                tk = tasks[w];
+                const BBReadDev *rd = &B.reads[tk.r];
+                frag = B.frag + rd->frag_off; state = B.state + rd->frag_off; ctime = B.ctime + rd->frag_off;
+                bb_window_of(rd->frag_len, seed, B.read_index[tk.r], tk.a, qpos, qn);
+                tmax = (unsigned int)(BB_ALIGNMENT_INTERVAL * tk.a);
+                jx = 0; tm = 0; uw = 0;
+                phase = 1;
+            }
+        }
+        if (__all_sync(BB_FULL, phase == 4)) break;
+        for (int it = 0; it < 64; it++) {  // ''.join(new_fragment_bases[pos:pos2]) as it was after 25*a changes
+            if (phase == 1) {
+                // four slots per iteration: their loads are issued together, the (serial) appends follow
+                unsigned int ct4[4];
+                uint8_t fb4[4];
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    const int j = min(jx + h, qn - 1);
+                    ct4[h] = ctime[qpos + j];
+                    fb4[h] = frag[qpos + j];
+                }
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    if (jx < qn) {
+                        if (ct4[h] == 0u || ct4[h] > tmax) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = fb4[h]; tm++; }
+                        else {
+                            const uint32_t st = state[qpos + jx];
+                            const int sl = (int)(st & 0xff);
+                            for (int c = 0; c < sl; c++) { if (tm < BB_WIN_MAX_COLS) tbuf[tm] = bb_slot_char(em, st, c); tm++; }
+                            uw += sl < 1 ? 1 : sl;
+                        }
+                        jx++;
+                    }
+                }
+                if (jx >= qn) {
+                    const int diff = qn > tm ? qn - tm : tm - qn;
+                    if (uw < diff) uw = diff;
+                    const int mx = qn > tm ? qn : tm;
+                    if (uw > mx) uw = mx;
+                    bb_band(qn, tm, uw, P.a, P.b);
+                    if (tm > BB_WIN_MAX_COLS || bb_lane_words(P.a, P.b) > LW || !bb_uses_traceback(qn, tm)) {
+                        fallback[atomicAdd(fallback_count, 1)] = tk;  // the warp kernel handles this window
+                        phase = 0;
+                    } else {
+                        const BBReadDev *rd = &B.reads[tk.r];
+                        P.n = qn; P.peq = B.fpeq + rd->fpeq_off; P.q = frag + qpos; P.qs = 1;
+                        P.peq_bit0 = qpos + BB_PEQ_BIT0; P.t = tbuf; P.ts = 1;
+                        bb_lane_begin<LW>(S, P);
+                        phase = 2;
+                    }
+                }
+            }
+        }
+        for (int it = 0; it < 128; it++) {  // forward columns with history
+            if (phase == 2) {
+                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
+                if (S.c >= tm) { ti = qn - 1; tj = tm - 1; matches = 0; dels = 0; phase = 3; }
+            }
+        }
+        for (int it = 0; it < 256; it++) {  // traceback (edlib's rule), counting '=' and 'D' columns
+            if (phase == 3) {
+                if (ti >= 0 && tj >= 0) {
+                    int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
+                    const int x = (ti >> 5) - wt;
+                    if (x < 0 || x >= LW) { atomicOr(&B.reads[tk.r].flags, 1); ti = -1; tj = -1; }
+                    else {
+                        bb_prefetch_history<LW>(hist, tj);
+                        const uint2 e = hist[(long long)tj * LW + x];
+                        const int bit = ti & 31;
+                        if ((e.x >> bit) & 1u) ti--;
+                        else if ((e.y >> bit) & 1u) { dels++; tj--; }
+                        else { matches += (frag[qpos + ti] == tbuf[tj]) ? 1 : 0; ti--; tj--; }
+                    }
+                } else {
+                    if (tj >= 0) dels += tj + 1;
+                    B.wres[B.reads[tk.r].wres_off + tk.a - 1] = make_int2(matches, qn + dels);
+                    phase = 0;
+                }
+            }
+        }
+    }
+}
+
 // Windows beyond the lane limits: one warp each, with the general aligner.
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 4)

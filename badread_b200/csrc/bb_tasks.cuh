@@ -420,6 +420,81 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint32_t *ckpt_pool, int *cursor) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- lane leaf kernel (default)
+// Persistent lanes with per-column history in global memory (see bb_k_window_lane_hist).
+template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
+__global__ void __launch_bounds__(64)
+bb_k_leaf_lane_hist(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
+    constexpr int LW = BB_LEAF_LW;
+    const BBNode *list = Q.leaf[0];
+    const int count = min(Q.count[BBQ_LEAF_COUNT], Q.cap_leaf);
+    uint2 *const hist = hist_pool + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * (long long)(BB_LEAF_LANE_COLS * LW);
+    BBLanePass<LW> S;
+    BBProb P;
+    BBNode nd;
+    BBAlignOut o;
+    const uint8_t *qp = nullptr, *tp = nullptr;
+    int phase = 0;  // 0: fetch, 1: forward pass, 2: traceback, 3: done
+    int ti = 0, tj = 0, matches = 0, dels = 0;
+    for (;;) {
+        if (phase == 0) {
+            const int w = atomicAdd(cursor, 1);
+            if (w >= count) phase = 3;
+            else {
+                nd = list[w];
+                BBReadDev *rd = &B.reads[nd.r];
+                o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
+                bb_task_band(nd, rd->upper, P.a, P.b);
+                P.n = nd.nn; P.peq = B.speq + rd->speq_off;
+                qp = B.seq + rd->seq_off + nd.q0; tp = B.frag + rd->frag_off + nd.t0;
+                P.q = qp; P.qs = 1; P.peq_bit0 = nd.q0 + BB_PEQ_BIT0; P.t = tp; P.ts = 1;
+                bb_lane_begin<LW>(S, P);
+                phase = 1;
+            }
+        }
+        if (__all_sync(BB_FULL, phase == 3)) break;
+        for (int it = 0; it < 128; it++) {  // forward columns with history
+            if (phase == 1) {
+                bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
+                if (S.c >= nd.mm) {
+                    const int d = bb_lane_column_scores<LW>(S, nd.nn, 0, -1, nullptr);
+                    if (nd.best >= 0 && d != nd.best) atomicOr(&o.rd->flags, 8 << 8);
+                    ti = nd.nn - 1; tj = nd.mm - 1; matches = 0; dels = 0;
+                    phase = 2;
+                }
+            }
+        }
+        for (int it = 0; it < 256; it++) {  // traceback moves (edlib's rule: 'I' > 'D' > diagonal)
+            if (phase == 2) {
+                if (ti >= 0 && tj >= 0) {
+                    int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
+                    const int x = (ti >> 5) - wt;
+                    if (x < 0 || x >= LW) { atomicOr(&o.rd->flags, 1 << 8); ti = -1; tj = -1; }
+                    else {
+                        bb_prefetch_history<LW>(hist, tj);
+                        const uint2 e = hist[(long long)tj * LW + x];
+                        const int bit = ti & 31;
+                        if ((e.x >> bit) & 1u) { o.ops[nd.q0 + ti] = BB_OP_I; ti--; }
+                        else if ((e.y >> bit) & 1u) { bb_add_dels(o, nd.q0 + ti, 1); dels++; tj--; }
+                        else {
+                            const bool eq = qp[ti] == tp[tj];
+                            o.ops[nd.q0 + ti] = eq ? BB_OP_EQ : BB_OP_X;
+                            matches += eq ? 1 : 0;
+                            ti--; tj--;
+                        }
+                    }
+                } else {
+                    for (int x = 0; x <= ti; x++) o.ops[nd.q0 + x] = BB_OP_I;  // column boundary: insertions remain
+                    if (tj >= 0) { bb_add_dels(o, nd.q0 - 1, tj + 1); dels += tj + 1; }  // row boundary: deletions
+                    atomicAdd(&o.rd->matches, matches);
+                    atomicAdd(&o.rd->dels, dels);
+                    phase = 0;
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- warp kernels
 // One Hirschberg node per warp: the forward pass over the left half of the target and the reverse pass over the right
 // half run side by side in the warp's two 16-lane groups with exactly L words per lane (class BBQ_NODE_LEAN<L>), several

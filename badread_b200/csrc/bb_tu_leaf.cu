@@ -12,3 +12,7 @@ cudaError_t bbl_leaf_lane_init() {
 void bbl_leaf_lane(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, uint32_t *ckpt_pool, int *cursor) {
     bb_k_leaf_lane<0><<<grid, 64, BB_LEAF_SMEM_BYTES, st>>>(B, Q, ckpt_pool, cursor);
 }
+
+void bbl_leaf_lane_hist(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
+    bb_k_leaf_lane_hist<0><<<grid, 64, 0, st>>>(B, Q, hist_pool, cursor);
+}

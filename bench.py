@@ -286,7 +286,7 @@ def reference_shim_rate(cfg, n_procs, quantity_bases):
                     '--seed', str(SEED + i)] + cfg['extra']
             procs.append(subprocess.Popen(argv, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL))
         bases = 0
-        deadline = t0 + 240.0   # a reported baseline must not hold the bench up
+        deadline = t0 + 180.0   # a reported baseline must not hold the bench up
         try:
             for p in procs:
                 out, _ = p.communicate(timeout=max(1.0, deadline - time.perf_counter()))
@@ -379,7 +379,7 @@ def main():
     ap.add_argument('--batch_reads', type=int, default=32768, help='reads per device batch')
     ap.add_argument('--profile', action='store_true', help='skip the e2e, parity and CPU legs (for runs under ncu)')
     ap.add_argument('--no_parity', action='store_true', help='skip the parity + CPU baseline leg')
-    ap.add_argument('--ref_shim_bases', type=int, default=600000,
+    ap.add_argument('--ref_shim_bases', type=int, default=300000,
                     help='bases per process of the reference-with-shim baseline leg (0: skip it)')
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -557,7 +557,7 @@ def main():
     # running it on all cores at once took the whole box down, twice)
     if rank == 0 and world == 1 and not a.profile and not a.no_parity and a.ref_shim_bases > 0 and a.config in (1, 2):
         t_leg = time.perf_counter()
-        ref_shim = reference_shim_rate(cfg, n_cores, a.ref_shim_bases)
+        ref_shim = reference_shim_rate(cfg, min(n_cores, 32), a.ref_shim_bases)
         log(f'[rank 0] reference-with-shim leg: {time.perf_counter() - t_leg:.1f} s: {ref_shim.get("value")}')
     if rank == 0 and world == 1 and not a.profile and not a.no_parity and a.config in (1, 2):
         eng.close()   # the command line creates its own engine on the same GPU
