@@ -499,7 +499,7 @@ bb_k_leaf_lane_hist(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
 // One Hirschberg node per warp: the forward pass over the left half of the target and the reverse pass over the right
 // half run side by side in the warp's two 16-lane groups with exactly L words per lane (class BBQ_NODE_LEAN<L>), several
 // columns per wavefront step (bb_band_pass_cb); then the split row by edlib's rule.
-template <int L>
+template <int L, int CB = BB_NODE_CB>
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (L == 1 ? 6 : L == 2 ? 5 : 3))
 bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
     constexpr int CLS = L == 1 ? BBQ_NODE_LEAN1 : L == 2 ? BBQ_NODE_LEAN2 : BBQ_NODE_LEAN4;
@@ -536,7 +536,7 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
                 P.q = q + nd.q0 + nd.nn - 1; P.qs = -1; P.t = t + nd.t0 + nd.mm - 1; P.ts = -1; P.ncols = right_w;
                 P.peq_bit0 = nd.q0 + nd.nn - 1 + BB_PEQ_BIT0; P.cols_out = sc.R; P.cols_lo = loR;
             }
-            bb_band_pass_cb<L, true, BB_NODE_CB>(P, 16);
+            bb_band_pass_cb<L, true, CB>(P, 16);
             __syncwarp();
             err = bb_split_warp(sc, loL, hiL, loR, hiR, nd.nn, left_w, right_w, best, split, ls, rs);
         }
