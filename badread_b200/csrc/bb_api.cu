@@ -1260,6 +1260,8 @@ NcclApi &nccl() {
     static bool tried = false;
     if (tried) return api;
     tried = true;
+    // NCCL writes its banner / warnings to stdout unless told otherwise: stdout is where the FASTQ goes
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
@@ -1271,7 +1273,8 @@ NcclApi &nccl() {
     api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
     api.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
     api.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
-    api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommAbort");  // teardown must not wait for peers that already left
+    if (!api.CommDestroy) api.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
     api.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
     nccl_destroy = (void (*)(void *))api.CommDestroy;
     api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.AllReduce && api.GroupStart && api.GroupEnd;

@@ -588,7 +588,9 @@ def main():
             parity['bases_checked'] = int(tb[3].item())
             parity['scope'] += f'; summed over {world} ranks'
     if rank != 0:
+        eng.close()
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
 
@@ -645,6 +647,7 @@ def main():
     print(json.dumps(line), flush=True)
     eng.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     if parity is not None and parity['mismatches']:
         log(f'PARITY FAILURE: {parity}')
