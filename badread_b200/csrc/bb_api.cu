@@ -98,7 +98,7 @@ struct bb_ctx {
     int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
     bool head_worker = true;  // worker 0 = the longest reads only (see bb_batch_upload)
     bool is_head = false;     // this worker holds the head batch of the current upload
-    int head_first = 0;       // 1: the other workers start after the head batch's error loop, 2: after its scan
+    int ring_t = 4;           // columns per traceback tick of the 4-word window aligner (2, 4 or 8)
     int cb_narrow = 2;        // columns per wavefront step of the 1- and 2-word node kernels (2 or 4)
     bool lowmem = false;      // window / leaf aligners with checkpoints + shared-memory tiles instead of global history
     bool use_quad = false;    // wide nodes by 8-warp CTAs (bb_k_node_quad) instead of warp pairs
@@ -250,7 +250,7 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed, bool high_prio
     if (const char *e = std::getenv("BADREAD_B200_QUAD")) ctx->use_quad = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_LOWMEM")) ctx->lowmem = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_CB_NARROW")) ctx->cb_narrow = (e[0] == '4') ? 4 : 2;
-    if (const char *e = std::getenv("BADREAD_B200_HEAD_FIRST")) ctx->head_first = std::atoi(e);
+    if (const char *e = std::getenv("BADREAD_B200_RING_T")) ctx->ring_t = (e[0] == '8') ? 8 : (e[0] == '2') ? 2 : 4;
     *out = ctx;
     return BB_OK;
 }
@@ -656,14 +656,14 @@ static int enqueue_error_loop(bb_ctx *ctx, const BBBatchDev &B) {
             bbl_window_lane4(std::min(pgrid(ctx, 6, "WIN4"), ctx->sm_count * 8), st, B, ctx->em, tasks, c + BBC_NTASKS, ctx->seed,
                              ctx->s_wckpt.as<uint32_t>(), ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE4, fb1, c + BBC_FB1);
         else
-            bbl_window_lane_hist(4, std::min(pgrid(ctx, 8, "WIN4"), ctx->sm_count * 8), st, B, ctx->em, tasks, c + BBC_NTASKS,
+            bbl_window_lane_hist(4, ctx->ring_t, std::min(pgrid(ctx, 8, "WIN4"), ctx->sm_count * 8), st, B, ctx->em, tasks, c + BBC_NTASKS,
                                  ctx->seed, ctx->s_lanehist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE4, fb1, c + BBC_FB1);
         mark(ctx, st, "window_lane4");
         if (ctx->lowmem)
             bbl_window_lane8(std::min(pgrid(ctx, 3, "WIN8"), ctx->sm_count * 8), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed,
                              ctx->s_wckpt.as<uint32_t>(), ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE8, fb2, c + BBC_FB2);
         else
-            bbl_window_lane_hist(8, std::min(pgrid(ctx, 4, "WIN8"), ctx->sm_count * 4), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed,
+            bbl_window_lane_hist(8, 4, std::min(pgrid(ctx, 4, "WIN8"), ctx->sm_count * 4), st, B, ctx->em, fb1, c + BBC_FB1, ctx->seed,
                                  ctx->s_lanehist.as<uint2>(), ctx->s_ltbuf.as<uint8_t>(), c + BBC_LANE8, fb2, c + BBC_FB2);
         mark(ctx, st, "window_lane8");
         bbl_window_warp(pgrid(ctx, 2), st, B, ctx->em, ctx->pool, fb2, c + BBC_FB2, ctx->seed, c + BBC_WARP);
@@ -1028,9 +1028,6 @@ extern "C" int bb_batch_run(bb_ctx *ctx) {
     for (int w = 0; w < S; w++) {
         const int rc = w_enqueue(worker_of(ctx, w));
         if (rc) return w == 0 ? rc : set_err(ctx, rc, worker_of(ctx, w)->err);
-        if (w == 0 && ctx->is_head && ctx->head_first > 0)  // the head batch's short error loop gets the GPU to itself
-            for (int v = 1; v < S; v++)
-                BB_CUDA(ctx, cudaStreamWaitEvent(worker_of(ctx, v)->stream, ctx->ev[ctx->head_first >= 2 ? 3 : 2], 0));
     }
     for (int w = 1; w < S; w++) BB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, worker_of(ctx, w)->ev[BB_N_STAGES - 1], 0));
     BB_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));

@@ -152,3 +152,73 @@ __device__ __forceinline__ void bb_prefetch_history(const uint2 *hist, int tj) {
     if ((e & 15) == 0 && e >= 48) asm volatile("prefetch.global.L2 [%0];" ::"l"(hist + (e - 48)));
 #endif
 }
+
+// ---------------------------------------------------------------------------------------------- traceback staging ring
+// A lane's traceback is a chain of dependent history loads, one per move, out of a per-lane history far too large for
+// any cache: with 3-4 warps per scheduler the kernels sat on that latency (ncu, round 1: 78 % of the stall cycles on the
+// L1TEX scoreboard, issue slots 18 % busy).  The ring stages the history the path is about to walk through in SHARED
+// memory with cp.async: all walking lanes of a warp "tick" at the same loop iteration, every T moves; a tick asks for the
+// columns down to tj - 2T + 1 that are not staged yet and waits only for the copies of the PREVIOUS tick.  A move goes at
+// most one column to the left, so the T columns a lane can reach before the next tick were requested one tick (T moves)
+// earlier and have arrived; the moves themselves read shared memory.  Slot of column c: c mod 2T (the columns a tick
+// overwrites are the ones the path has left behind).  Layout: ring[(slot * LW + word) * 64 + thread] (64 threads per
+// CTA: consecutive threads, consecutive 8-byte entries, no bank conflicts).
+#define BB_RING_BYTES(LW, T) (2 * (T) * (LW) * 64 * 8)
+
+__device__ __forceinline__ void bb_cp_async8(uint2 *smem, const uint2 *gmem) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+#else
+    *smem = *gmem;
+#endif
+}
+__device__ __forceinline__ void bb_cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void bb_cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// One tick of a walking lane at column tj (>= 0).  staged_lo: lowest column requested so far; > tj marks a walk that
+// has not staged anything yet (it then issues two groups, so that the uniform wait below covers its first T columns).
+template <int LW, int T>
+__device__ __forceinline__ void bb_ring_tick(uint2 *ring, const uint2 *hist, int tj, int &staged_lo) {
+    const bool fresh = staged_lo > tj;
+    if (fresh) {
+        const int lo1 = max(0, tj - T + 1);
+        for (int col = tj; col >= lo1; col--) {
+#pragma unroll
+            for (int x = 0; x < LW; x++) bb_cp_async8(ring + ((col & (2 * T - 1)) * LW + x) * 64, hist + (long long)col * LW + x);
+        }
+        bb_cp_async_commit();
+        staged_lo = lo1;
+    }
+    const int want_lo = max(0, tj - 2 * T + 1);
+    for (int col = staged_lo - 1; col >= want_lo; col--) {
+#pragma unroll
+        for (int x = 0; x < LW; x++) bb_cp_async8(ring + ((col & (2 * T - 1)) * LW + x) * 64, hist + (long long)col * LW + x);
+    }
+    bb_cp_async_commit();
+    if (want_lo < staged_lo) staged_lo = want_lo;
+#if defined(__CUDA_ARCH__)
+    // what the tick after the next one will ask for: into L2 now (HBM latency is more than one tick long)
+    {
+        constexpr int LINES = (T * LW * 8 + 127) / 128 + 1;
+        const long long e = ((long long)tj - 4 * T) * LW;
+#pragma unroll
+        for (int x = 0; x < 2 * LINES; x++)
+            if (e + 16 * x >= 0 && (x < LINES || fresh)) asm volatile("prefetch.global.L2 [%0];" ::"l"(hist + e + 16 * x));
+    }
+#endif
+    bb_cp_async_wait<1>();
+}
+
+template <int LW, int T>
+__device__ __forceinline__ uint2 bb_ring_entry(const uint2 *ring, int col, int x) {
+    return ring[((col & (2 * T - 1)) * LW + x) * 64];
+}

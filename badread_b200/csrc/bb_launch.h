@@ -16,7 +16,7 @@ void bbl_window_lane4(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev e
 void bbl_window_lane8(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks,
                       unsigned long long seed, uint32_t *ckpt_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback,
                       int *fallback_count);
-void bbl_window_lane_hist(int words, int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks,
+void bbl_window_lane_hist(int words, int ring_t, int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks,
                           const int *n_tasks, unsigned long long seed, uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor,
                           BBWinTask *fallback, int *fallback_count);
 void bbl_window_warp(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, const BBWinTask *tasks,

@@ -491,17 +491,27 @@ bb_k_window_lane(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const
 }
 
 // The DEFAULT window aligner: one window alignment per thread; persistent lanes, all on the same step of the same phase;
-// per-column history (Pv, PhRaw per window word) in global memory, read back along the path by the traceback.  It moves
-// ~64 KB per window through HBM but keeps 4 warps per scheduler resident and overlaps the loads; the checkpoint build
-// above (BADREAD_B200_LOWMEM=1) moves ~9 KB and measured 14 % slower per step.
-template <int LW>
+// per-column history (Pv, PhRaw per window word) in global memory.  The traceback does not chase it there: the columns
+// ahead of the path are staged in shared memory by cp.async, T columns per tick (bb_ring_tick), so a move costs a
+// shared-memory load instead of an L2 / HBM round trip.  The checkpoint build above (BADREAD_B200_LOWMEM=1) moves ~9 KB
+// per window instead of ~64 KB and measured 14 % slower per step.
+#ifndef BB_WIN_RING_T
+#define BB_WIN_RING_T 4
+#endif
+template <int LW, int T = BB_WIN_RING_T>
 __global__ void __launch_bounds__(64, (LW <= 4 ? 8 : 4))
 bb_k_window_lane_hist(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, const int *n_tasks_ptr, unsigned long long seed,
                  uint2 *hist_pool, uint8_t *tbuf_pool, int *cursor, BBWinTask *fallback, int *fallback_count) {
+#ifdef BB_EMULATOR
+    static uint2 s_ring[BB_RING_BYTES(LW, T) / 8];
+#else
+    extern __shared__ __align__(16) uint2 s_ring[];  // BB_RING_BYTES(LW, T): [column mod 2T][word][thread]
+#endif
     const int n_tasks = *n_tasks_ptr;
     const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     uint2 *const hist = hist_pool + gl * (long long)(BB_WIN_MAX_COLS * LW);
     uint8_t *const tbuf = tbuf_pool + gl * (long long)BB_WIN_MAX_COLS;
+    uint2 *const ring = s_ring + threadIdx.x;
     BBLanePass<LW> S;
     BBProb P;
     BBWinTask tk = {0, 0};
@@ -509,7 +519,7 @@ bb_k_window_lane_hist(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, 
     const uint32_t *state = nullptr;
     const unsigned int *ctime = nullptr;
     int phase = 0;  // 0: fetch, 1: join, 2: forward pass, 3: traceback, 4: done
-    int qpos = 0, qn = 0, jx = 0, tm = 0, uw = 0, ti = 0, tj = 0, matches = 0, dels = 0;
+    int qpos = 0, qn = 0, jx = 0, tm = 0, uw = 0, ti = 0, tj = 0, diags = 0, dels = 0, dist = 0, staged_lo = 0;
     unsigned int tmax = 0;
     for (;;) {
         if (phase == 0) {
@@ -572,25 +582,35 @@ bb_k_window_lane_hist(BBBatchDev B, BBErrorModelDev em, const BBWinTask *tasks, 
         for (int it = 0; it < 128; it++) {  // forward columns with history
             if (phase == 2) {
                 bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
-                if (S.c >= tm) { ti = qn - 1; tj = tm - 1; matches = 0; dels = 0; phase = 3; }
+                if (S.c >= tm) {
+                    // '=' columns without looking at the characters again: the path's 'X' columns are the edit distance
+                    // minus its 'I' and 'D' columns, and the diagonal moves are '=' or 'X'
+                    dist = bb_lane_corner<LW>(S, qn);
+                    ti = qn - 1; tj = tm - 1; diags = 0; dels = 0; staged_lo = tm; phase = 3;
+                }
             }
         }
         for (int it = 0; it < 256; it++) {  // traceback (edlib's rule), counting '=' and 'D' columns
             if (phase == 3) {
                 if (ti >= 0 && tj >= 0) {
+                    // (it is the same for all lanes: the walking lanes of the warp tick together)
+                    if ((it & (T - 1)) == 0) bb_ring_tick<LW, T>(ring, hist, tj, staged_lo);
                     int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
                     const int x = (ti >> 5) - wt;
                     if (x < 0 || x >= LW) { atomicOr(&B.reads[tk.r].flags, 1); ti = -1; tj = -1; }
                     else {
-                        bb_prefetch_history<LW>(hist, tj);
-                        const uint2 e = hist[(long long)tj * LW + x];
+                        const uint2 e = bb_ring_entry<LW, T>(ring, tj, x);
                         const int bit = ti & 31;
                         if ((e.x >> bit) & 1u) ti--;
                         else if ((e.y >> bit) & 1u) { dels++; tj--; }
-                        else { matches += (frag[qpos + ti] == tbuf[tj]) ? 1 : 0; ti--; tj--; }
+                        else { diags++; ti--; tj--; }
                     }
                 } else {
+                    bb_cp_async_wait<0>();  // nothing of this walk may land in the ring after the next walk's copies
                     if (tj >= 0) dels += tj + 1;
+                    // rows = diagonal + 'I' moves, so 'I' = qn - diags; 'X' = dist - 'I' - 'D'
+                    const int matches = diags - (dist - (qn - diags) - dels);
+                    if (dist >= BB_INF) atomicOr(&B.reads[tk.r].flags, 1);
                     B.wres[B.reads[tk.r].wres_off + tk.a - 1] = make_int2(matches, qn + dels);
                     phase = 0;
                 }

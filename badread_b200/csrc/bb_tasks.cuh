@@ -210,7 +210,13 @@ __device__ __forceinline__ void bb_lane_step(BBLanePass<LW> &S, const BBProb &P,
         const uint32_t raw = Ph[x];
         S.Pv[x] = mhs | ~(Xv[x] | phs);
         S.Mv[x] = phs & Xv[x];
-        if (HIST) hist[x * HSTRIDE] = make_uint2(S.Pv[x], raw);
+        if (HIST && (HSTRIDE != 1 || (LW & 1))) hist[x * HSTRIDE] = make_uint2(S.Pv[x], raw);
+        if (HIST && HSTRIDE == 1 && !(LW & 1)) Ph[x] = raw;
+    }
+    if (HIST && HSTRIDE == 1 && !(LW & 1)) {  // a column's entries are contiguous and 16-byte aligned: 128-bit stores
+#pragma unroll
+        for (int x = 0; x < LW; x += 2)
+            reinterpret_cast<uint4 *>(hist)[x >> 1] = make_uint4(S.Pv[x], Ph[x], S.Pv[x + 1], Ph[x + 1]);
     }
     S.c = c + 1;
 }
@@ -231,6 +237,25 @@ __device__ int bb_lane_column_scores(const BBLanePass<LW> &S, int n, int lo, int
                 if (row == n - 1) result = rr;
             }
             rr -= (int)((S.Pv[x] >> r) & 1u) - (int)((S.Mv[x] >> r) & 1u);
+        }
+        run -= __popc(S.Pv[x]) - __popc(S.Mv[x]);
+    }
+    return result;
+}
+
+// D[n-1][last column] of a finished pass (BB_INF if row n-1 is outside the window).
+template <int LW>
+__device__ __forceinline__ int bb_lane_corner(const BBLanePass<LW> &S, int n) {
+    int result = BB_INF;
+    int run = S.score;
+#pragma unroll
+    for (int x = LW - 1; x >= 0; x--) {
+        const int row0 = (S.wt + x) * 32;
+        if (row0 <= n - 1 && n - 1 < row0 + 32) {
+            const int bit = (n - 1) - row0;
+            const uint32_t up = bit == 31 ? 0u : (S.Pv[x] >> (bit + 1));
+            const uint32_t um = bit == 31 ? 0u : (S.Mv[x] >> (bit + 1));
+            result = run - __popc(up) + __popc(um);
         }
         run -= __popc(S.Pv[x]) - __popc(S.Mv[x]);
     }
@@ -421,21 +446,33 @@ bb_k_leaf_lane(BBBatchDev B, BBQueues Q, uint32_t *ckpt_pool, int *cursor) {
 }
 
 // ---------------------------------------------------------------------------------------------- lane leaf kernel (default)
-// Persistent lanes with per-column history in global memory (see bb_k_window_lane_hist).
+// Persistent lanes with per-column history in global memory, walked back through the shared-memory staging ring
+// (see bb_k_window_lane_hist and bb_ring_tick).
+#ifndef BB_LEAF_RING_T
+#define BB_LEAF_RING_T 4
+#endif
+#define BB_LEAF_RING_BYTES BB_RING_BYTES(BB_LEAF_LW, BB_LEAF_RING_T)
+
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(64)
 bb_k_leaf_lane_hist(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
-    constexpr int LW = BB_LEAF_LW;
+    constexpr int LW = BB_LEAF_LW, T = BB_LEAF_RING_T;
+#ifdef BB_EMULATOR
+    static uint2 s_ring[BB_LEAF_RING_BYTES / 8];
+#else
+    extern __shared__ __align__(16) uint2 s_ring[];  // BB_LEAF_RING_BYTES: [column mod 2T][word][thread]
+#endif
     const BBNode *list = Q.leaf[0];
     const int count = min(Q.count[BBQ_LEAF_COUNT], Q.cap_leaf);
     uint2 *const hist = hist_pool + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * (long long)(BB_LEAF_LANE_COLS * LW);
+    uint2 *const ring = s_ring + threadIdx.x;
     BBLanePass<LW> S;
     BBProb P;
     BBNode nd;
     BBAlignOut o;
     const uint8_t *qp = nullptr, *tp = nullptr;
     int phase = 0;  // 0: fetch, 1: forward pass, 2: traceback, 3: done
-    int ti = 0, tj = 0, matches = 0, dels = 0;
+    int ti = 0, tj = 0, matches = 0, dels = 0, staged_lo = 0;
     for (;;) {
         if (phase == 0) {
             const int w = atomicAdd(cursor, 1);
@@ -457,9 +494,9 @@ bb_k_leaf_lane_hist(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
             if (phase == 1) {
                 bb_lane_step<LW, true>(S, P, hist + (long long)S.c * LW);
                 if (S.c >= nd.mm) {
-                    const int d = bb_lane_column_scores<LW>(S, nd.nn, 0, -1, nullptr);
+                    const int d = bb_lane_corner<LW>(S, nd.nn);
                     if (nd.best >= 0 && d != nd.best) atomicOr(&o.rd->flags, 8 << 8);
-                    ti = nd.nn - 1; tj = nd.mm - 1; matches = 0; dels = 0;
+                    ti = nd.nn - 1; tj = nd.mm - 1; matches = 0; dels = 0; staged_lo = nd.mm;
                     phase = 2;
                 }
             }
@@ -467,12 +504,13 @@ bb_k_leaf_lane_hist(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
         for (int it = 0; it < 256; it++) {  // traceback moves (edlib's rule: 'I' > 'D' > diagonal)
             if (phase == 2) {
                 if (ti >= 0 && tj >= 0) {
+                    // (it is the same for all lanes: the walking lanes of the warp tick together)
+                    if ((it & (T - 1)) == 0) bb_ring_tick<LW, T>(ring, hist, tj, staged_lo);
                     int wt = (tj - P.a) >> 5; if (wt < 0) wt = 0;
                     const int x = (ti >> 5) - wt;
                     if (x < 0 || x >= LW) { atomicOr(&o.rd->flags, 1 << 8); ti = -1; tj = -1; }
                     else {
-                        bb_prefetch_history<LW>(hist, tj);
-                        const uint2 e = hist[(long long)tj * LW + x];
+                        const uint2 e = bb_ring_entry<LW, T>(ring, tj, x);
                         const int bit = ti & 31;
                         if ((e.x >> bit) & 1u) { o.ops[nd.q0 + ti] = BB_OP_I; ti--; }
                         else if ((e.y >> bit) & 1u) { bb_add_dels(o, nd.q0 + ti, 1); dels++; tj--; }
@@ -484,6 +522,7 @@ bb_k_leaf_lane_hist(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
                         }
                     }
                 } else {
+                    bb_cp_async_wait<0>();  // nothing of this walk may land in the ring after the next walk's copies
                     for (int x = 0; x <= ti; x++) o.ops[nd.q0 + x] = BB_OP_I;  // column boundary: insertions remain
                     if (tj >= 0) { bb_add_dels(o, nd.q0 - 1, tj + 1); dels += tj + 1; }  // row boundary: deletions
                     atomicAdd(&o.rd->matches, matches);

@@ -14,5 +14,5 @@ void bbl_leaf_lane(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, uint32_t
 }
 
 void bbl_leaf_lane_hist(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
-    bb_k_leaf_lane_hist<0><<<grid, 64, 0, st>>>(B, Q, hist_pool, cursor);
+    bb_k_leaf_lane_hist<0><<<grid, 64, BB_LEAF_RING_BYTES, st>>>(B, Q, hist_pool, cursor);
 }

@@ -249,6 +249,14 @@ def cpu_port_run(wl, picks, n_threads):
     return outs, bases, time.perf_counter() - t0
 
 
+def algorithmic_warp_inst(block_steps):
+    """Integer work the path needs, as warp instructions: the oracle counts the 64-row block updates of the passes a path
+    needs (both passes of every Hirschberg node, the history pass of every leaf and of every identity re-measurement,
+    bands from exact scores; not the distance search in front).  One 64-row update = two 32-row word updates of ~13
+    integer operations each (Myers / Hyyro: 8 logic, 1 add, 2 shifts, 2 for the carries), 32 lanes per warp instruction."""
+    return block_steps * 2 * 13 / 32.0
+
+
 def parity_check(res, picks, outs):
     """GPU reads of one batch (BatchResult) against the oracle's for the same read indices: sequences, quality strings,
     alignment counts.  Returns the mismatching picks."""
@@ -525,7 +533,7 @@ def main():
     log(f'[rank {rank}] timed: {elapsed / a.steps * 1e3:.1f} ms/step resident, {e2e_elapsed / a.steps * 1e3:.1f} ms/step end to end')
 
     # ---- parity + CPU baseline on the same reads
-    cpu_g, cpu_desc, parity = None, 'skipped', None
+    cpu_g, cpu_desc, parity, alg_inst_G = None, 'skipped', None, None
     if not a.profile and not a.no_parity:
         limit = None if cfg['parity'] == 'full' else PARITY_PREFIX
         picks = wl.prefix_reads(limit)
@@ -533,6 +541,8 @@ def main():
             picks = picks[:4096]
         threads = max(1, n_cores // world)
         n_bad, cpu_bases, cpu_dt = 0, 0, 0.0
+        from oracle import oracle as _O
+        _O.block_steps_reset()
         for bi in sorted(set(b for b, _ in picks)):
             # nb == 1: `res` still holds the reads fetched by the last end-to-end step; otherwise the batch is run again
             # (the pinned output buffers are reused by every call, so each batch is compared before the next one runs)
@@ -547,6 +557,8 @@ def main():
             cpu_bases += cb
             cpu_dt += cd
         cpu_g = cpu_bases / cpu_dt / 1e9 if cpu_dt > 0 else None
+        if cpu_bases > 0:   # scaled from the reads the oracle ran to this rank's whole step
+            alg_inst_G = algorithmic_warp_inst(_O.block_steps()) * (bases_e2e / cpu_bases) / 1e9
         log(f'[rank {rank}] parity leg: {len(picks)} reads, {n_bad} mismatches, oracle {cpu_dt:.1f} s')
         what = ('the whole workload' if len(picks) == wl.n_reads else f'the first {len(picks)} reads of this rank') if limit is None \
             else f'read indices < {limit} of this rank'
@@ -621,9 +633,12 @@ def main():
             ach = ginst / (dev_ms / a.steps * 1e-3)
             alu = {'achieved': ach, 'peak': peak_alu, 'unit': 'G warp-inst/s', 'frac': ach / peak_alu,
                    'warp_inst_G_per_step': ginst, 'source': f'{ij_name} (ncu smsp__inst_executed.sum)'}
-            if 'algorithmic_warp_inst_G_per_step' in ij:   # 13 ops per 32-row word update, from the band statistics
-                alu['algorithmic_warp_inst_G_per_step'] = ij['algorithmic_warp_inst_G_per_step']
-                alu['algorithmic_frac'] = float(ij['algorithmic_warp_inst_G_per_step']) / (dev_ms / a.steps * 1e-3) / peak_alu
+            if alg_inst_G is not None:   # what the path needs (oracle's block-update count of this run's reads), not what was issued
+                alu['algorithmic_warp_inst_G_per_step'] = alg_inst_G
+                alu['algorithmic_frac'] = alg_inst_G / (dev_ms / a.steps * 1e-3) / peak_alu
+                alu['issued_over_algorithmic'] = ginst / alg_inst_G
+                alu['algorithmic_source'] = ('oracle block-update count of the parity leg\'s reads (64-row updates of the Hirschberg '
+                                             'node, leaf and window passes with exact bands) x 2 words x 13 ops / 32 lanes')
         except Exception:
             pass
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,

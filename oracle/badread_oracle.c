@@ -297,8 +297,17 @@ static inline int block_step(uint64_t *Pv, uint64_t *Mv, uint64_t Eq, int hin, u
  * hist (optional): (Pv, PhRaw) pairs per (column, block - first_block(column)), nb_alloc pairs per column.
  * colscore (optional): D[i][ncols-1] for all i (SCORE_INF outside the band).
  * Returns D[n-1][ncols-1] (upper bound if the true value exceeds what the band admits). */
+/* Work accounting (bench.py's integer-pipe figure): 64-row block updates of the passes a PATH needs - the two passes
+ * of every Hirschberg node and the history pass of every leaf, with bands from exact scores - not those of the
+ * distance search in front (edlib's k = 64, 128, ... loop; the GPU path has the bound up front and skips it). */
+static __thread int t_count_blocks = 0;
+static int64_t g_block_steps = 0;
+BO_EXPORT void bo_block_steps_reset(void) { __atomic_store_n(&g_block_steps, 0, __ATOMIC_RELAXED); }
+BO_EXPORT int64_t bo_block_steps(void) { return __atomic_load_n(&g_block_steps, __ATOMIC_RELAXED); }
+
 static int64_t banded_nw(const uint8_t *q, int64_t n, const uint8_t *t, int64_t ncols, band_t bd,
                          uint64_t *hist, int64_t nb_alloc, int64_t *colscore) {
+    int64_t n_steps = 0;
     peq_t pq;
     peq_build(&pq, q, n);
     int64_t nblocks = pq.nblocks;
@@ -319,6 +328,7 @@ static int64_t banded_nw(const uint8_t *q, int64_t n, const uint8_t *t, int64_t 
         }
         const uint64_t *eq = peq_row(&pq, t[j]);
         int hin = 1;
+        n_steps += last - first + 1;
         for (int64_t b = first; b <= last; b++) {
             uint64_t ph;
             hin = block_step(&P[b], &M[b], eq[b], hin, &ph);
@@ -348,6 +358,7 @@ static int64_t banded_nw(const uint8_t *q, int64_t n, const uint8_t *t, int64_t 
         }
     }
     free(P); free(M); free(score); peq_free(&pq);
+    if (t_count_blocks) __atomic_fetch_add(&g_block_steps, n_steps, __ATOMIC_RELAXED);
     return result;
 }
 
@@ -439,7 +450,9 @@ static void obtain_alignment(const uint8_t *q, int64_t n, const uint8_t *t, int6
 static void align_path(const uint8_t *q, int64_t n, const uint8_t *t, int64_t m, opbuf *out, int64_t *dist) {
     int64_t best = nw_distance(q, n, t, m);
     if (dist) *dist = best;
+    t_count_blocks = 1;
     obtain_alignment(q, n, t, m, best, out);
+    t_count_blocks = 0;
 }
 
 /* Definitional checker: full-matrix DP + the same traceback / Hirschberg rules on exact scores.

@@ -68,6 +68,9 @@ def lib():
         L.bo_add_errors_to_kmer.restype = c.c_int
         L.bo_add_errors_to_kmer.argtypes = [vp, vp, vp, vp, vp]
         L.bo_sequence_batch.restype = i64
+        L.bo_block_steps_reset.argtypes = []
+        L.bo_block_steps.argtypes = []
+        L.bo_block_steps.restype = i64
         L.bo_sequence_batch.argtypes = [vp, vp, u64, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, c.c_int]
         _lib = L
     return _lib
@@ -216,3 +219,12 @@ class Oracle(object):
             L.bo_free(qual_ptrs[r])
             out.append((s, q, int(matches[r]), int(cols[r])))
         return out, int(total)
+
+
+def block_steps_reset():
+    """Zeroes the counter of 64-row block updates of the path passes (see badread_oracle.c, work accounting)."""
+    lib().bo_block_steps_reset()
+
+
+def block_steps():
+    return int(lib().bo_block_steps())

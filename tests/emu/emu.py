@@ -68,14 +68,16 @@ def lane_align(query, target, k_upper, qabs_pad=0, lw=4):
     return int(out4[0]), int(out4[1]), int(out4[2])
 
 
-def tasks_align(seq, frag, upper, quad=True):
+def tasks_align(seq, frag, upper, quad=True, hist=1):
     """The level-synchronous alignment task pipeline under the emulator -> expanded ops string.
-    quad: wide nodes by the 8-warp CTA kernel (bb_k_node_quad) instead of warp pairs (bb_k_node_pair)."""
+    quad: wide nodes by the 8-warp CTA kernel (bb_k_node_quad) instead of warp pairs (bb_k_node_pair).
+    hist: lane leaves by the default build (global history + shared-memory staging ring) / 0: the checkpoint build."""
     global _lib
     if _lib is None:
         build()
         _lib = ctypes.CDLL(str(LIB))
     _lib.emu_set_quad(1 if quad else 0)
+    _lib.emu_set_hist(int(hist))
     q = seq.encode('latin-1') if isinstance(seq, str) else bytes(seq)
     t = frag.encode('latin-1') if isinstance(frag, str) else bytes(frag)
     n, m = len(q), len(t)
@@ -124,8 +126,9 @@ def compare_sm(query, target, k, L):
     return None if rc < 0 else int(rc)
 
 
-def window_lane(frag, changes, seed, read_index, lw=4):
-    """bb_k_window_lane<lw> under the emulator for one read: changes = [(position, new string of <= 3 chars)] in the
+def window_lane(frag, changes, seed, read_index, lw=4, hist=0):
+    """bb_k_window_lane<lw> (hist = 0: checkpoint build) or bb_k_window_lane_hist<lw> (hist = 1: the default build, 4
+    columns per traceback tick; 2: two columns per tick) under the emulator for one read: changes = [(position, new string of <= 3 chars)] in the
     order they were applied -> [(matches, columns)] of the identity re-measurements after 25, 50, ... changes
     ((-1, -1): the window does not fit lw words and went to the fallback list)."""
     global _lib
@@ -141,6 +144,7 @@ def window_lane(frag, changes, seed, read_index, lw=4):
         enc[i] = len(b) | sum(b[j] << (8 * (j + 1)) for j in range(len(b)))
     n_meas = len(changes) // 25
     out = np.full(2 * max(n_meas, 1), -7, dtype=np.int32)
+    _lib.emu_set_hist(int(hist))
     flags = _lib.emu_window_lane(f, len(f), pos.ctypes.data_as(ctypes.c_void_p), enc.ctypes.data_as(ctypes.c_void_p),
                                  len(changes), ctypes.c_uint64(seed), ctypes.c_uint64(read_index), int(lw),
                                  out.ctypes.data_as(ctypes.c_void_p))

@@ -77,6 +77,8 @@ int emu_lane_align(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper
 
 static int use_quad = 1;  // wide nodes by the 8-warp CTA kernel (1) or by warp pairs (0)
 extern "C" __attribute__((visibility("default"))) void emu_set_quad(int v) { use_quad = v; }
+static int g_use_hist = 0;  // 1: the default lane builds (global history + shared-memory staging ring) instead of the checkpoint builds
+extern "C" __attribute__((visibility("default"))) void emu_set_hist(int v) { g_use_hist = v; }
 
 // The level-synchronous task pipeline (bb_tasks.cuh) for one read, every kernel as one emulated warp.
 extern "C" __attribute__((visibility("default")))
@@ -137,7 +139,8 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     }
     int *c3 = cursor++, *c4 = cursor++;
     emu::run_warp([&]() { bb_k_leaf_warp(B, Q, pool, c3, 0); });
-    emu::run_warp([&]() { bb_k_leaf_lane(B, Q, lckpt.data(), c4); });
+    if (g_use_hist) emu::run_warp([&]() { bb_k_leaf_lane_hist(B, Q, lhist.data(), c4); });
+    else emu::run_warp([&]() { bb_k_leaf_lane(B, Q, lckpt.data(), c4); });
     out5[0] = rd.matches; out5[1] = rd.dels; out5[2] = cnt[BBQ_OVERFLOW]; out5[3] = rd.lead_del; out5[4] = rd.flags;
     return 0;
 }
@@ -276,8 +279,15 @@ int emu_window_lane(const uint8_t *frag, int frag_len, const int *pos, const uin
     std::vector<uint32_t> ckpt((size_t)64 * BB_WIN_MAX_TILES * BB_WIN_CKPT_WORDS(BB_WIN_LW));
     std::vector<uint8_t> tbuf((size_t)64 * BB_WIN_MAX_COLS);
     emu::run_warp([&]() { bb_build_peq(fr.data(), frag_len, fpeq.data()); });
+    std::vector<uint2> whist(g_use_hist ? (size_t)32 * BB_WIN_MAX_COLS * BB_WIN_LW : 1);
     emu::run_warp([&]() {
-        if (lw == 4) bb_k_window_lane<4>(B, em, tasks.data(), &n_tasks, seed, ckpt.data(), tbuf.data(), &cursor, fallback.data(), &fb_count);
+        if (g_use_hist == 2 && lw == 4)  // two columns per tick: the ring wraps every four columns
+            bb_k_window_lane_hist<4, 2>(B, em, tasks.data(), &n_tasks, seed, whist.data(), tbuf.data(), &cursor, fallback.data(), &fb_count);
+        else if (g_use_hist && lw == 4)
+            bb_k_window_lane_hist<4, 4>(B, em, tasks.data(), &n_tasks, seed, whist.data(), tbuf.data(), &cursor, fallback.data(), &fb_count);
+        else if (g_use_hist)
+            bb_k_window_lane_hist<BB_WIN_LW, 4>(B, em, tasks.data(), &n_tasks, seed, whist.data(), tbuf.data(), &cursor, fallback.data(), &fb_count);
+        else if (lw == 4) bb_k_window_lane<4>(B, em, tasks.data(), &n_tasks, seed, ckpt.data(), tbuf.data(), &cursor, fallback.data(), &fb_count);
         else bb_k_window_lane<BB_WIN_LW>(B, em, tasks.data(), &n_tasks, seed, ckpt.data(), tbuf.data(), &cursor, fallback.data(), &fb_count);
     });
     for (int a = 0; a < n_meas; a++) { out_pairs[2 * a] = wres[(size_t)a].x; out_pairs[2 * a + 1] = wres[(size_t)a].y; }

@@ -81,6 +81,7 @@ def test_task_pipeline(emu):
     want = O.align_path(b, a)[0]
     assert emu.tasks_align(b, a, int(O.align_path(b, a)[1] * 1.1)) == want
     assert emu.tasks_align(b, a, int(O.align_path(b, a)[1] * 1.1), quad=False) == want
+    assert emu.tasks_align(b, a, int(O.align_path(b, a)[1] * 1.1), quad=False, hist=0) == want   # checkpoint lane leaves
     for n, rate in ((9000, 0.3), (30000, 0.12), (12000, 0.45)):   # wide roots of other chunk widths (1, 2, 4 words per lane)
         a = random_dna(rnd, n, 'ACGTN' if n == 9000 else 'ACGT'); b = mutate(rnd, a, rate)
         ops, d = O.align_path(b, a)
@@ -138,8 +139,11 @@ def test_shared_memory_match_cache_equals_streamed_words(emu):
     assert checked >= 25
 
 
-def test_window_lane_kernel_matches_oracle(emu):
-    """bb_k_window_lane<4> / <8> (checkpoints every 16 columns, tiles re-run into shared memory for the traceback) under
+@pytest.mark.parametrize('hist', [1, 2, 0])
+def test_window_lane_kernel_matches_oracle(emu, hist):
+    """bb_k_window_lane_hist<4> / <8> (the default: per-column history in global memory, walked back through the
+    shared-memory staging ring, 4 or 2 columns per tick; '=' columns from the move counts and the distance) and
+    bb_k_window_lane<4> / <8> (checkpoints every 16 columns, tiles re-run into shared memory for the traceback) under
     the emulator: '=' columns and total columns of every identity re-measurement of a read equal edlib's path between
     the original 1000-base window (query) and the window as it was after 25 a changes (target) - simulate.py:325-346.
     Fragments shorter and longer than the window, substitutions / deletions / insertions, 30 ... 250 changes."""
@@ -160,7 +164,7 @@ def test_window_lane_kernel_matches_oracle(emu):
                 sub = frag[p] + rnd.choice('ACGT') if rnd.random() < 0.5 else rnd.choice('ACGT') + frag[p]
             changes.append((p, sub))
         seed, read = 77, 5 + frag_len
-        got = emu.window_lane(frag, changes, seed, read, lw=lw)
+        got = emu.window_lane(frag, changes, seed, read, lw=lw, hist=hist)
         assert len(got) == n_changes // 25
         for a, (matches, cols) in enumerate(got, start=1):
             qpos, qn = 0, frag_len

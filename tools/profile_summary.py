@@ -11,11 +11,13 @@ import os
 import re
 import sys
 
-STAGE = {'bb_k_build_fragments': 'build_fragments', 'bb_k_mutate': 'error_loop', 'bb_k_window_lane': 'error_loop',
+STAGE = {'bb_k_build_fragments': 'build_fragments', 'bb_k_mutate': 'error_loop', 'bb_k_mutate_chain': 'error_loop',
+         'bb_k_window_lane': 'error_loop', 'bb_k_window_lane_hist': 'error_loop',
          'bb_k_window_warp': 'error_loop', 'bb_k_replay': 'error_loop', 'bb_k_window_tasks': 'error_loop',
          'bb_k_scan': 'scan', 'bb_k_join': 'join',
          'bb_k_push_roots': 'final_align', 'bb_k_node_warp': 'final_align', 'bb_k_node_lane': 'final_align',
-         'bb_k_node_pair': 'final_align', 'bb_k_leaf_warp': 'final_align', 'bb_k_leaf_lane': 'final_align',
+         'bb_k_node_pair': 'final_align', 'bb_k_node_quad': 'final_align', 'bb_k_leaf_warp': 'final_align',
+         'bb_k_leaf_lane': 'final_align', 'bb_k_leaf_lane_hist': 'final_align',
          'bb_k_qscores': 'qscores', 'bb_k_compact': 'compact'}
 
 
@@ -48,18 +50,18 @@ def load(path):
 
 
 def timed_step(launches):
-    """The launches of the second step: everything from the second bb_k_build_fragments group on."""
-    idx = [i for i, l in enumerate(launches) if l['kernel'].startswith('bb_k_build_fragments')]
-    if not idx:
+    """The launches of the second (timed) step.  A run is pure enqueueing of the same chain of kernels every step, so the
+    profiled run (one warm-up step + one timed step) is two identical halves from the first bb_k_build_fragments on."""
+    first = next((i for i, l in enumerate(launches) if l['kernel'].startswith('bb_k_build_fragments')), None)
+    if first is None:
         return launches
-    # build_fragments launches come in one group per step (one per worker); a new group starts after other kernels ran
-    groups, prev = [], None
-    for i in idx:
-        if prev is None or any(not launches[j]['kernel'].startswith('bb_k_build_fragments') for j in range(prev + 1, i)) and \
-                any(launches[j]['kernel'].startswith('bb_k_compact') for j in range(prev + 1, i)):
-            groups.append(i)
-        prev = i
-    return launches[groups[1]:] if len(groups) > 1 else launches[groups[0]:]
+    rest = launches[first:]
+    half = len(rest) // 2
+    if len(rest) % 2 == 0 and [l['kernel'] for l in rest[:half]] == [l['kernel'] for l in rest[half:]]:
+        return rest[half:]
+    # otherwise: everything from the last launch of the first worker's chain head on (best effort)
+    idx = [i for i, l in enumerate(launches) if l['kernel'].startswith('bb_k_build_fragments')]
+    return launches[idx[len(idx) // 2]:]
 
 
 def main():
