@@ -5,7 +5,7 @@
 // alternative come from the iteration's own random stream, and whether a slot takes the change depends only on
 // the slots changed before.  `errors` (and with it every window alignment) decides one thing only: at the top of
 // which iteration the loop stops.  So the loop is split into three kernels that can each use the whole GPU:
-//   bb_k_mutate        one warp per read runs the k-mer loop AHEAD without any alignment, logging every applied
+//   bb_k_mutate        one CTA per read runs the k-mer loop AHEAD without any alignment, logging every applied
 //                      change (iteration, position) and stamping the slot with the change's ordinal; it stops at
 //                      the loop's own guards (simulate.py:278-286) or when a generous horizon of changes is reached.
 //   bb_k_window_lane   every identity re-measurement of every read is an independent task: "the window as it was
@@ -29,20 +29,28 @@ enum { BB_STOP_HORIZON = 0, BB_STOP_LIMIT = 1, BB_STOP_COUNT = 2, BB_STOP_NOLOOP
 struct BBWinTask { int r, a; };  // read, alignment ordinal (1-based: after 25*a changes)
 
 // ------------------------------------------------------------------------------------------------ mutate
-// One CTA (4 warps) per read: every step the 128 threads evaluate 128 consecutive loop iterations (position, k-mer,
-// model draw: chains of dependent loads, independent across iterations), then warp 0 commits the iterations that
-// change something, in order.
+// One CTA (5 warps) per read.  A step covers 128 consecutive loop iterations: warps 1-4 evaluate them (position, k-mer,
+// model draw: chains of dependent loads, independent across iterations), warp 0 commits the iterations that change
+// something, in order.  The evaluation runs ONE STEP AHEAD of the commit: what an iteration would change depends on its
+// own random stream and on the fragment only, never on earlier commits, and the next step starts at n0 + 128 unless the
+// loop stops - so while warp 0 commits the candidates of step i, warps 1-4 already evaluate step i + 1 into the other
+// half of a double buffer.  A step costs max(evaluate, commit) instead of their sum (the evaluate-then-commit build of
+// round 1 spent 59 % of its warp stall cycles at the CTA barrier between the two: ncu r2s; step 151.4 -> 148.4 ms).  If
+// the loop stops, the speculative step is simply dropped - the resume point is the commit's.
+#define BB_MUTP_THREADS (BB_WARPS_PER_CTA * 32 + 32)
+
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
-__global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(BB_MUTP_THREADS)
 bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work_counter, const int *order,
-            int n_items) {
-    constexpr int NT = BB_WARPS_PER_CTA * 32;
-    __shared__ int s_kind[NT], s_pos[NT], s_rpos[NT];
-    __shared__ uint32_t s_pay[NT];
+                 int n_items) {
+    constexpr int NE = BB_WARPS_PER_CTA * 32;  // evaluator threads = iterations per step
+    __shared__ int s_kind[2][NE], s_pos[2][NE], s_rpos[2][NE];
+    __shared__ uint32_t s_pay[2][NE];
     __shared__ int s_w, s_stop, s_cc;
     __shared__ long long s_n0;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const int ev = threadIdx.x - 32;  // evaluator index (warps 1 ... 4)
     const int k = em.k;
     for (;;) {
         if (threadIdx.x == 0) s_w = atomicAdd(work_counter, 1);
@@ -74,34 +82,35 @@ bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work
             s_stop = stop; s_cc = rd->n_logged; s_n0 = rd->n_resume;
         }
         __syncthreads();
+        // every thread follows n0 in a register: it advances by NE per step for as long as the loop goes on (warp 0
+        // rewrites s_n0 while the evaluators are at work)
+        long long n0 = s_n0;
+        auto evaluate = [&](long long first, int buf) {
+            const long long n = first + ev;
+            int kind = 0, pos_i = 0, rpos = 0;
+            uint32_t payload = 0;
+            if (n < limit) bb_eval_iteration(em, frag, kidx, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
+            s_kind[buf][ev] = kind; s_pos[buf][ev] = pos_i; s_rpos[buf][ev] = rpos; s_pay[buf][ev] = payload;
+        };
+        int cur = 0;
+        if (s_stop < 0 && warp > 0) evaluate(n0, 0);
+        __syncthreads();
         while (s_stop < 0) {
-            const long long n0 = s_n0;
-            if (n0 >= limit) {
-                __syncthreads();
-                if (threadIdx.x == 0) s_stop = BB_STOP_LIMIT;
-                __syncthreads();
-                break;
-            }
-            {
-                const long long n = n0 + threadIdx.x;
-                int kind = 0, pos_i = 0, rpos = 0;
-                uint32_t payload = 0;
-                if (n < limit) bb_eval_iteration(em, frag, kidx, max_kmer_index, seed, read, (unsigned int)n, kind, pos_i, payload, rpos);
-                s_kind[threadIdx.x] = kind; s_pos[threadIdx.x] = pos_i; s_rpos[threadIdx.x] = rpos; s_pay[threadIdx.x] = payload;
-            }
-            __syncthreads();
-            if (warp == 0) {
+            if (warp > 0) evaluate(n0 + NE, cur ^ 1);   // one step ahead
+            else if (n0 >= limit) {
+                if (lane == 0) s_stop = BB_STOP_LIMIT;
+            } else {
                 int change_count = s_cc, stop = -1;
-                long long next_n0 = n0 + NT;
+                long long next_n0 = n0 + NE;
                 for (int g = 0; g < BB_WARPS_PER_CTA && stop < 0; g++) {
-                    uint32_t cmask = __ballot_sync(BB_FULL, s_kind[32 * g + lane] != 0);
+                    uint32_t cmask = __ballot_sync(BB_FULL, s_kind[cur][32 * g + lane] != 0);
                     while (cmask) {
                         const int L = 32 * g + __ffs(cmask) - 1;
                         cmask &= cmask - 1;
                         const long long nL = n0 + L;
                         if (change_count >= horizon) { stop = BB_STOP_HORIZON; next_n0 = nL; break; }  // pause at an iteration top
-                        const int bi = s_pos[L], bkind = s_kind[L], brpos = s_rpos[L];
-                        const uint32_t bpay = s_pay[L];
+                        const int bi = s_pos[cur][L], bkind = s_kind[cur][L], brpos = s_rpos[cur][L];
+                        const uint32_t bpay = s_pay[cur][L];
                         uint32_t enc = 0;
                         bool app = false;
                         if (lane < k) {
@@ -124,10 +133,12 @@ bb_k_mutate(BBBatchDev B, BBErrorModelDev em, unsigned long long seed, int *work
                         if ((double)change_count > cc_limit) { stop = BB_STOP_COUNT; next_n0 = nL + 1; break; }
                     }
                 }
-                __syncwarp();  // every lane has read s_cc / s_n0 before lane 0 replaces them
+                __syncwarp();
                 if (lane == 0) { s_cc = change_count; s_stop = stop; s_n0 = next_n0; }
             }
             __syncthreads();
+            cur ^= 1;
+            n0 += NE;
         }
         if (threadIdx.x == 0) {
             rd->n_logged = s_cc;

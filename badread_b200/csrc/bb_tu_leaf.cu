@@ -1,4 +1,4 @@
-// bb_tu_leaf.cu — compiles the leaf kernels bb_k_leaf_warp and bb_k_leaf_lane (bb_tasks.cuh).
+// bb_tu_leaf.cu — compiles the leaf kernels bb_k_leaf_warp, bb_k_leaf_lane and bb_k_leaf_lane_hist (bb_tasks.cuh).
 #include "bb_launch.h"
 
 void bbl_leaf_warp(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, BBScratchPool pool, int *cursor, int warp_base) {
