@@ -70,6 +70,8 @@ struct BBProb {
     uint2 *hist; int nb_alloc;
     int *cols_out; int cols_lo;
     uint32_t *esm = nullptr;              // SM variant only: the warp's shared-memory match-word cache, bb_esm_words(L)
+    const uint4 *tpeq = nullptr; int tpeq_bit0 = 0;  // bb_band_pass_bp only: match bitmap of the read that holds the target
+                                          // + bit index of column 0 in it (columns ascend for ts > 0, descend for ts < 0)
 };
 
 // Shared-memory match cache of bb_band_pass<L, ., ., true>: lane l keeps the 4 x L match words of its current chunk
@@ -728,6 +730,214 @@ __device__ int bb_band_pass_cb(const BBProb &P, int K) {
 #pragma unroll
             for (int h = 0; h < CB; h++)
                 if (cn + h >= cs && cn + h <= ce) tcn[h] = tp[(long long)(CB * (s + 1) + h) * ts];
+        }
+    }
+    const int owner = (lane & ~(K - 1)) | ((n > 0 ? (n - 1) / CH : 0) & (K - 1));
+    result = __shfl_sync(BB_FULL, result, owner);
+    __syncwarp();
+    return result;
+}
+
+// Bit planes of the 32 target columns [c, c + 32) of a problem, bit j = column c + j: the 2-bit code of the base
+// (A 00, C 01, T 10, G 11 - the code (char >> 1) & 3 of the other passes) and whether it is one of ACGT at all.  Cut out of
+// the match bitmap of the read that holds the target, like bb_fetch_peq cuts the query rows out of theirs.
+__device__ __forceinline__ void bb_fetch_target_planes(const BBProb &P, int c, uint32_t &b0, uint32_t &b1, uint32_t &ok) {
+    const int s = P.ts > 0 ? P.tpeq_bit0 + c : P.tpeq_bit0 - c - 31;
+    const int idx = s >> 5, sh = s & 31;
+    const uint4 lo = P.tpeq[idx], hi = P.tpeq[idx + 1];
+    uint32_t mA = __funnelshift_r(lo.x, hi.x, sh), mC = __funnelshift_r(lo.y, hi.y, sh);
+    uint32_t mG = __funnelshift_r(lo.z, hi.z, sh), mT = __funnelshift_r(lo.w, hi.w, sh);
+    if (P.ts < 0) { mA = __brev(mA); mC = __brev(mC); mG = __brev(mG); mT = __brev(mT); }
+    b0 = mC | mG; b1 = mT | mG; ok = mA | mC | mG | mT;
+}
+
+// bb_band_pass_cb<L, true, 2> on BIT PLANES (the node passes of the lean warp kernels; same outputs).  What a wavefront
+// step spends around the Myers recurrence itself is most of it for narrow chunks (~32 instructions per column against
+// 11 L + 6), so:
+//   * the target is not fetched byte by byte: the codes of 32 columns are two words cut out of the target's match bitmap
+//     (one refill per 16 steps instead of two byte loads with their address arithmetic and ACGT tests per step);
+//   * the chunk keeps its rows as two code planes q0, q1 instead of four letter masks: the match word of a column is
+//     ~((q0 ^ c0) | (q1 ^ c1)) with the column's code bits spread to words - two logic operations per word instead of a
+//     three-way select, 2 L fewer registers;
+//   * rows past the node's last row need no masking (they are rows of 'A' appended to the query: the recurrence only
+//     carries information downwards, and the corner / column scores subtract the vertical deltas below the last row).
+// Exactness for anything that is not ACGT: a target column outside ACGT (its `ok` bit is clear) and a chunk whose rows are
+// not all ACGT (qok) take the per-column path with the letter masks fetched again and exact byte comparison.
+// Requires P.tpeq / P.tpeq_bit0.
+template <int L>
+__device__ int bb_band_pass_bp(const BBProb &P, int K) {
+    constexpr int CB = 2;
+    const int lane = threadIdx.x & 31;
+    const int slot = lane & (K - 1);
+    const int prev = (lane & ~(K - 1)) | ((slot + K - 1) & (K - 1));
+    constexpr int CH = 32 * L;
+    const int n = P.n, ncols = P.ncols, a = P.a, b = P.b;
+    int ulast = -1;
+    if (ncols > 0 && n > 0) {
+        ulast = (ncols - 1 + b) / CH;
+        const int nchunks = (n + CH - 1) / CH;
+        if (ulast > nchunks - 1) ulast = nchunks - 1;
+    }
+    const int T = __reduce_max_sync(BB_FULL, ulast >= 0 ? (ncols - 1) / CB + ulast + 1 : 0);
+    const int cols_hi = min(n - 1, ncols - 1 + b);
+    uint32_t Pv[L], Mv[L], q0[L], q1[L], q0n[L], q1n[L];
+#pragma unroll
+    for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; q0[x] = q1[x] = q0n[x] = q1n[x] = 0u; }
+    bool qok = true;   // every row of the current chunk that exists is one of ACGT
+    bool qokn = true;  // ... of the lane's NEXT chunk, whose planes (q0n, q1n) are fetched a chunk ahead: when a lane
+                       // takes a chunk the other 31 wait for it, so that moment should not begin with loads
+    auto fetch_chunk = [&](int uu) {
+        qokn = true;
+#pragma unroll
+        for (int x = 0; x < L; x++) {
+            uint32_t eA, eC, eG, eT;
+            bb_fetch_peq(P, uu * CH + 32 * x, eA, eC, eG, eT);
+            q0n[x] = eC | eG; q1n[x] = eT | eG;
+            const int v = n - (uu * CH + 32 * x);
+            const uint32_t rows = v >= 32 ? ~0u : (v <= 0 ? 0u : ((1u << v) - 1u));
+            qokn = qokn && (((eA | eC | eG | eT) | ~rows) == ~0u);
+        }
+    };
+    int u = slot;
+    if (u <= ulast) fetch_chunk(u);
+    int cs = max(0, CH * u - b), ce = min(ncols - 1, CH * u + CH - 1 + a);
+    int ce_up = u == 0 ? -1 : min(ncols - 1, CH * u - 1 + a);  // last column of the chunk above (none above chunk 0)
+    int score = 0, result = BB_INF;
+    uint32_t outpack = 0;
+    uint32_t tb0 = 0, tb1 = 0, tok = 0;  // code planes / ACGT flags of the target columns [tbase, tbase + 32)
+    int tbase = -(1 << 28);
+    // one Myers step of the whole chunk on match words Eq with horizontal input hin; returns the horizontal output
+    auto myers = [&](uint32_t (&Eq)[L], int hin) -> int {
+        uint32_t Xv[L], A[L], S[L], Ph[L], Mh[L];
+        const uint32_t hin_neg = hin < 0 ? 1u : 0u;
+#pragma unroll
+        for (int x = 0; x < L; x++) Xv[x] = Eq[x] | Mv[x];
+        Eq[0] |= hin_neg;
+#pragma unroll
+        for (int x = 0; x < L; x++) A[x] = Eq[x] & Pv[x];
+        bb_add_words<L>(A, Pv, S);
+#pragma unroll
+        for (int x = 0; x < L; x++) {
+            const uint32_t Xh = (S[x] ^ Pv[x]) | Eq[x];
+            Ph[x] = Mv[x] | ~(Xh | Pv[x]);
+            Mh[x] = Pv[x] & Xh;
+        }
+        const int hout = (int)(Ph[L - 1] >> 31) - (int)(Mh[L - 1] >> 31);
+#pragma unroll
+        for (int x = L - 1; x >= 0; x--) {
+            const uint32_t ph_lo = x > 0 ? Ph[x - 1] : (hin > 0 ? 0x80000000u : 0u);
+            const uint32_t mh_lo = x > 0 ? Mh[x - 1] : (hin_neg << 31);
+            const uint32_t phs = __funnelshift_l(ph_lo, Ph[x], 1);
+            const uint32_t mhs = __funnelshift_l(mh_lo, Mh[x], 1);
+            Pv[x] = mhs | ~(Xv[x] | phs);
+            Mv[x] = phs & Xv[x];
+        }
+        return hout;
+    };
+    // match words of a column whose code bits are (k0, k1), from the chunk's planes
+    auto planes = [&](uint32_t k0, uint32_t k1, uint32_t (&Eq)[L]) {
+        const uint32_t m0 = 0u - (k0 & 1u), m1 = 0u - (k1 & 1u);
+#pragma unroll
+        for (int x = 0; x < L; x++) Eq[x] = ~((q0[x] ^ m0) | (q1[x] ^ m1));
+    };
+    // any column of the chunk (its first, its last, non-ACGT characters, the last column of the pass)
+    auto column = [&](int c, uint32_t k0, uint32_t k1, bool tplain, int hin, int above) -> int {
+        if (c == cs) {  // a chunk entering the band starts from the all-(+1) upper bound below chunk u-1
+            score = ((u == 0) ? cs : above - hin) + CH;
+            qok = qokn;
+#pragma unroll
+            for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; q0[x] = q0n[x]; q1[x] = q1n[x]; }
+            if (u + K <= ulast) fetch_chunk(u + K);  // not needed before the band has passed this chunk
+        }
+        uint32_t Eq[L];
+        if (qok && tplain) planes(k0, k1, Eq);
+        else {  // exact: the letter masks again; a target character outside ACGT is compared byte by byte
+            const uint32_t code = (k0 & 1u) | ((k1 & 1u) << 1);
+#pragma unroll
+            for (int x = 0; x < L; x++) {
+                uint32_t eA, eC, eG, eT;
+                bb_fetch_peq(P, u * CH + 32 * x, eA, eC, eG, eT);
+                Eq[x] = (code & 2u) ? ((code & 1u) ? eG : eT) : ((code & 1u) ? eC : eA);
+                if (!tplain) {
+                    const uint32_t tc = P.t[(long long)c * P.ts];
+                    Eq[x] = 0u;
+                    const int row0 = u * CH + 32 * x;
+                    for (int r = 0; r < 32; r++)
+                        if (row0 + r < n && P.q[(long long)(row0 + r) * P.qs] == tc) Eq[x] |= 1u << r;
+                }
+            }
+        }
+        const int hout = myers(Eq, hin);
+        score += hout;
+        if (c == ncols - 1) {
+            int run = score;
+#pragma unroll
+            for (int x = L - 1; x >= 0; x--) {
+                const int row0 = u * CH + 32 * x;
+                int rr = run;
+                for (int r = 31; r >= 0; r--) {
+                    const int row = row0 + r;
+                    if (row < n && row >= P.cols_lo && row <= cols_hi) P.cols_out[row - P.cols_lo] = rr;
+                    rr -= (int)((Pv[x] >> r) & 1u) - (int)((Mv[x] >> r) & 1u);
+                }
+                if (row0 <= n - 1 && n - 1 < row0 + 32) {
+                    const int bit = (n - 1) - row0;
+                    const uint32_t up = bit == 31 ? 0u : (Pv[x] >> (bit + 1));
+                    const uint32_t um = bit == 31 ? 0u : (Mv[x] >> (bit + 1));
+                    result = run - __popc(up) + __popc(um);
+                }
+                run -= __popc(Pv[x]) - __popc(Mv[x]);
+            }
+        }
+        return hout;
+    };
+    for (int s = 0; s < T; s++) {
+        const uint32_t in = __shfl_sync(BB_FULL, outpack, prev);
+        const int c0 = CB * (s - u), cl = c0 + CB - 1;
+        if (u <= ulast && cl >= cs && c0 <= ce) {
+            // All lanes cut their next 32 columns out of the bitmap at the same step, every 16th (a lane on its own
+            // would do it whenever ITS window runs out: with the lanes two columns apart that is one lane every step, and
+            // the whole warp waits for that lane's loads); a lane that has just taken a new chunk (32 columns back) or
+            // entered the band between two such steps fetches for itself.
+            int j = c0 - tbase;
+            if ((s & 15) == 0 || (unsigned)j > 30u) { bb_fetch_target_planes(P, c0, tb0, tb1, tok); tbase = c0; j = 0; }
+            const uint32_t k0 = tb0 >> j, k1 = tb1 >> j, kk = tok >> j;  // bits 0, 1: columns c0, c0 + 1
+            const int hin0 = c0 <= ce_up ? (int)((in >> 22) & 3u) - 1 : 1;
+            const int hin1 = cl <= ce_up ? (int)((in >> 24) & 3u) - 1 : 1;
+            int o0, o1, last_score;
+            if (c0 > cs && cl < ce && (kk & 3u) == 3u && qok) {
+                uint32_t Eq[L];
+                planes(k0, k1, Eq);
+                o0 = myers(Eq, hin0);
+                planes(k0 >> 1, k1 >> 1, Eq);
+                o1 = myers(Eq, hin1);
+                score += o0 + o1;
+                last_score = score;
+            } else {
+                int above = (int)(in & BB_MAX_SCORE);  // the chunk above after column c0 + h
+                bool moved = false;
+                o0 = 0; o1 = 0;
+                last_score = score;
+                if (c0 >= cs && c0 <= ce) {
+                    o0 = column(c0, k0, k1, (kk & 1u) != 0u, hin0, above);
+                    last_score = score;
+                    if (c0 == ce) moved = true;
+                }
+                above += (int)((in >> 24) & 3u) - 1;
+                if (!moved && cl >= cs && cl <= ce) {
+                    o1 = column(cl, k0 >> 1, k1 >> 1, (kk & 2u) != 0u, hin1, above);
+                    last_score = score;
+                    if (cl == ce) moved = true;
+                } else o1 = 0;
+                if (moved) {  // the band has moved past this chunk: chunk u + K is next
+                    u += K;
+                    cs = max(0, CH * u - b);
+                    ce = min(ncols - 1, CH * u + CH - 1 + a);
+                    ce_up = min(ncols - 1, CH * u - 1 + a);
+                }
+            }
+            // the score after column c0 and the two horizontal outputs
+            outpack = ((uint32_t)(last_score - o1) & BB_MAX_SCORE) | ((uint32_t)(o0 + 1) << 22) | ((uint32_t)(o1 + 1) << 24);
         }
     }
     const int owner = (lane & ~(K - 1)) | ((n > 0 ? (n - 1) / CH : 0) & (K - 1));

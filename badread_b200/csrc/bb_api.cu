@@ -98,6 +98,7 @@ struct bb_ctx {
     int pair_ctas = 1;   // CTAs per SM of the warp-pair node kernel (tuning knob)
     bool head_worker = true;  // worker 0 = the longest reads only (see bb_batch_upload)
     bool is_head = false;     // this worker holds the head batch of the current upload
+    bool lpt_order = true;    // node queues below the roots walked from the end (longest nodes first)
     int ring_t = 4;           // columns per traceback tick of the 4-word window aligner (2, 4 or 8)
     int cb_narrow = 2;        // columns per wavefront step of the 1- and 2-word node kernels (2 or 4)
     bool lowmem = false;      // window / leaf aligners with checkpoints + shared-memory tiles instead of global history
@@ -250,6 +251,7 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed, bool high_prio
     if (const char *e = std::getenv("BADREAD_B200_QUAD")) ctx->use_quad = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_LOWMEM")) ctx->lowmem = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_CB_NARROW")) ctx->cb_narrow = (e[0] == '4') ? 4 : 2;
+    if (const char *e = std::getenv("BADREAD_B200_LPT")) ctx->lpt_order = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_RING_T")) ctx->ring_t = (e[0] == '8') ? 8 : (e[0] == '2') ? 2 : 4;
     *out = ctx;
     return BB_OK;
@@ -709,10 +711,12 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
     // The node classes of a level read the same queues and push into the next level's: they are independent and run
     // side by side on their own streams; the level ends when all of them have finished.
     for (int level = 0; level < ctx->n_levels; level++) {
-        const int p = level & 1;
+        // (the roots are queued longest read first; every later queue fills in the order the parents finish, longest
+        // last, and is walked from its end)
+        const int p = (level & 1) | (level > 0 && ctx->lpt_order ? BBQ_BACKWARDS : 0);
         for (int s = 0; s < 2; s++) {
             cudaStream_t st = stream[s];
-            BB_CUDA(ctx, cudaMemsetAsync(cnt[s] + BBQ_COUNT(0, p ^ 1), 0, BBQ_NODE_CLASSES * sizeof(int), st));
+            BB_CUDA(ctx, cudaMemsetAsync(cnt[s] + BBQ_COUNT(0, (p & 1) ^ 1), 0, BBQ_NODE_CLASSES * sizeof(int), st));
             BB_CUDA(ctx, cudaEventRecord(ctx->ev_level[s], st));
             int n_side = 0;
             auto on_side = [&]() -> cudaStream_t {

@@ -28,6 +28,10 @@ enum { BBQ_NODE_LANE8 = 0, BBQ_NODE_LEAN1 = 1, BBQ_NODE_LEAN2 = 2, BBQ_NODE_LEAN
 #define BBQ_COUNT(cls, parity) ((parity) * BBQ_NODE_CLASSES + (cls))  // Q.count index of a node queue's length
 #define BBQ_LEAF_COUNT 10  // Q.count index of the leaf counters (lane, warp)
 #define BBQ_OVERFLOW 12
+// Node kernels take `parity | BBQ_BACKWARDS` to walk their queue from its end.  Below the roots a level's queue fills in
+// the order the parents finish - the longest nodes are queued last, and taken in that order they start when everything
+// else is done; from the end, the longest go first.
+#define BBQ_BACKWARDS 2
 
 struct BBNode { int r, q0, nn, t0, mm, best; };  // best < 0: root (band from the read's edit bound)
 
@@ -265,8 +269,10 @@ __device__ __forceinline__ int bb_lane_corner(const BBLanePass<LW> &S, int n) {
 // ---------------------------------------------------------------------------------------------- lane node kernel
 template <int LW>
 __global__ void __launch_bounds__(64, 6)
-bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
+bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity_order, int *cursor) {
     constexpr int CLS = BBQ_NODE_LANE8;
+    const int parity = parity_order & 1;
+    const bool backwards = (parity_order & BBQ_BACKWARDS) != 0;
     const BBNode *list = Q.node[CLS][parity];
     const int count = min(Q.count[BBQ_COUNT(CLS, parity)], Q.cap_node);
     BBLanePass<LW> S;
@@ -281,7 +287,7 @@ bb_k_node_lane(BBBatchDev B, BBQueues Q, int parity, int *cursor) {
             const int w = atomicAdd(cursor, 1);
             if (w >= count) phase = 3;
             else {
-                nd = list[w];
+                nd = list[backwards ? count - 1 - w : w];
                 BBReadDev *rd = &B.reads[nd.r];
                 o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
                 upper = rd->upper;
@@ -540,8 +546,10 @@ bb_k_leaf_lane_hist(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
 // columns per wavefront step (bb_band_pass_cb); then the split row by edlib's rule.
 template <int L, int CB = BB_NODE_CB>
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (L == 1 ? 6 : L == 2 ? 5 : 3))
-bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
+bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity_order, int *cursor, int warp_base) {
     constexpr int CLS = L == 1 ? BBQ_NODE_LEAN1 : L == 2 ? BBQ_NODE_LEAN2 : BBQ_NODE_LEAN4;
+    const int parity = parity_order & 1;
+    const bool backwards = (parity_order & BBQ_BACKWARDS) != 0;
     const int lane = threadIdx.x & 31;
     const int warp = warp_base + blockIdx.x * BB_WARPS_PER_CTA + (threadIdx.x >> 5);
     BBScratch sc = pool.for_warp(warp);
@@ -552,7 +560,7 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
         if (lane == 0) w = atomicAdd(cursor, 1);
         w = __shfl_sync(BB_FULL, w, 0);
         if (w >= count) break;
-        const BBNode nd = list[w];
+        const BBNode nd = list[backwards ? count - 1 - w : w];
         BBReadDev *rd = &B.reads[nd.r];
         BBAlignOut o;
         o.ops = B.ops + rd->seq_off; o.dcnt = B.dcnt + rd->seq_off; o.rd = rd;
@@ -568,14 +576,18 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
         else {
             BBProb P;
             P.n = nd.nn; P.a = a; P.b = b; P.peq = sc.peq; P.hist = nullptr; P.nb_alloc = 0;
+            P.tpeq = B.fpeq + rd->fpeq_off;
             if (lane < 16) {
                 P.q = q + nd.q0; P.qs = 1; P.t = t + nd.t0; P.ts = 1; P.ncols = left_w;
                 P.peq_bit0 = nd.q0 + BB_PEQ_BIT0; P.cols_out = sc.L; P.cols_lo = loL;
+                P.tpeq_bit0 = nd.t0 + BB_PEQ_BIT0;
             } else {
                 P.q = q + nd.q0 + nd.nn - 1; P.qs = -1; P.t = t + nd.t0 + nd.mm - 1; P.ts = -1; P.ncols = right_w;
                 P.peq_bit0 = nd.q0 + nd.nn - 1 + BB_PEQ_BIT0; P.cols_out = sc.R; P.cols_lo = loR;
+                P.tpeq_bit0 = nd.t0 + nd.mm - 1 + BB_PEQ_BIT0;
             }
-            bb_band_pass_cb<L, true, CB>(P, 16);
+            if (CB == 2) bb_band_pass_bp<L>(P, 16);   // the bit-plane build of the 2-column pass
+            else bb_band_pass_cb<L, true, CB>(P, 16);
             __syncwarp();
             err = bb_split_warp(sc, loL, hiL, loR, hiR, nd.nn, left_w, right_w, best, split, ls, rs);
         }
@@ -609,7 +621,9 @@ __device__ __forceinline__ void bb_pair_sync(int id) {
 // the paired single-warp variant, so the steps are half as long); the even warp then picks the split.
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, 2)
-bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
+bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity_order, int *cursor, int warp_base) {
+    const int parity = parity_order & 1;
+    const bool backwards = (parity_order & BBQ_BACKWARDS) != 0;
     __shared__ int s_task[BB_WARPS_PER_CTA / 2];
 #ifdef BB_EMULATOR
     static uint32_t s_eq[BB_PAIR_SMEM_BYTES / 4];
@@ -630,7 +644,7 @@ bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
         const int w = s_task[pair];
         bb_pair_sync(pair + 1);
         if (w >= count) break;
-        const BBNode nd = list[w];
+        const BBNode nd = list[backwards ? count - 1 - w : w];
         BBReadDev *rd = &B.reads[nd.r];
         sc.peq = B.speq + rd->speq_off;
         const uint8_t *q = B.seq + rd->seq_off, *t = B.frag + rd->frag_off;
@@ -689,7 +703,9 @@ bb_k_node_pair(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
 
 template <int BB_TU_ = 0>  // a template: only the translation unit that launches it compiles it
 __global__ void __launch_bounds__(BB_QUAD_THREADS, 1)
-bb_k_node_quad(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor, int warp_base) {
+bb_k_node_quad(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity_order, int *cursor, int warp_base) {
+    const int parity = parity_order & 1;
+    const bool backwards = (parity_order & BBQ_BACKWARDS) != 0;
     __shared__ int s_task;
     __shared__ uint32_t s_mbox[2][BB_QUAD_WARPS * 8];
     __shared__ int s_progress[2][BB_QUAD_WARPS];
@@ -713,7 +729,7 @@ bb_k_node_quad(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cu
         const int w = s_task;
         __syncthreads();
         if (w >= count) break;
-        const BBNode nd = list[w];
+        const BBNode nd = list[backwards ? count - 1 - w : w];
         BBReadDev *rd = &B.reads[nd.r];
         sc.peq = B.speq + rd->speq_off;
         const uint8_t *q = B.seq + rd->seq_off, *t = B.frag + rd->frag_off;

@@ -95,6 +95,8 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     unsigned long long ridx = 0;
     B.n_reads = 1; B.read_index = &ridx; B.reads = &rd; B.frag = fr.data(); B.seq = sq.data(); B.ops = ops; B.dcnt = dcnt;
     B.speq = speq.data();
+    std::vector<uint4> fpeq((size_t)bb_peq_words(m) + 8);
+    B.fpeq = fpeq.data();  // rd.fpeq_off = 0
     std::memset(dcnt, 0, (size_t)n * sizeof(unsigned int));
     const int cap = 8192;
     std::vector<BBNode> qn[BBQ_NODE_CLASSES][2], ql[2];
@@ -120,6 +122,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     pool.tbuf = tbuf.data(); pool.tbuf_stride = 0;
     pool.peq = speq.data(); pool.peq_stride = 0; pool.peq_cap = (int)speq.size();
     emu::run_warp([&]() { bb_build_peq(sq.data(), n, speq.data()); });
+    emu::run_warp([&]() { bb_build_peq(fr.data(), m, fpeq.data()); });
     int order0 = 0;
     emu::run_warp([&]() { bb_k_push_roots(B, Q, Q, &order0); });
     int *cursor = cnt.data() + 16;
@@ -127,12 +130,13 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
         const int p = level & 1;
         for (int c = 0; c < BBQ_NODE_CLASSES; c++) cnt[BBQ_COUNT(c, p ^ 1)] = 0;
         int *c0 = cursor++, *c1 = cursor++, *c2 = cursor++, *c2b = cursor++, *c2c = cursor++;
-        if (use_quad) emu::run_block(BB_QUAD_THREADS, [&]() { bb_k_node_quad(B, Q, pool, p, c0, 0); });
-        else emu::run_block(BB_WARPS_PER_CTA * 32, [&]() { bb_k_node_pair(B, Q, pool, p, c0, 0); });
-        emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, p, c1, 0); });
-        emu::run_warp([&]() { bb_k_node_warp<2>(B, Q, pool, p, c2, 0); });
-        emu::run_warp([&]() { bb_k_node_warp<1>(B, Q, pool, p, c2c, 0); });
-        emu::run_warp([&]() { bb_k_node_lane<BB_NODE_LW_SMALL>(B, Q, p, c2b); });
+        const int po = p | (level > 0 ? BBQ_BACKWARDS : 0);  // as bb_api.cu: queues below the roots are walked from the end
+        if (use_quad) emu::run_block(BB_QUAD_THREADS, [&]() { bb_k_node_quad(B, Q, pool, po, c0, 0); });
+        else emu::run_block(BB_WARPS_PER_CTA * 32, [&]() { bb_k_node_pair(B, Q, pool, po, c0, 0); });
+        emu::run_warp([&]() { bb_k_node_warp<4>(B, Q, pool, po, c1, 0); });
+        emu::run_warp([&]() { bb_k_node_warp<2>(B, Q, pool, po, c2, 0); });
+        emu::run_warp([&]() { bb_k_node_warp<1>(B, Q, pool, po, c2c, 0); });
+        emu::run_warp([&]() { bb_k_node_lane<BB_NODE_LW_SMALL>(B, Q, po, c2b); });
         int pending = 0;
         for (int c = 0; c < BBQ_NODE_CLASSES; c++) pending += cnt[BBQ_COUNT(c, p ^ 1)];
         if (pending == 0) break;
@@ -151,7 +155,7 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
 // (column-score entries + the two corner scores), or -1 if the band does not fit L with K = 16.
 template <int L, int CB>
 static int emu_compare_passes_impl(const uint8_t *q, int n, const uint8_t *t, int m, int a, int b) {
-    std::vector<uint4> peq((size_t)bb_peq_words(n) + 8);
+    std::vector<uint4> peq((size_t)bb_peq_words(n) + 8), tpeq((size_t)bb_peq_words(m) + 8);
     const int left_w = m / 2, right_w = m - left_w;
     const int loL = std::max(0, left_w - 1 - a), loR = std::max(0, right_w - 1 - a);
     std::vector<int> ref((size_t)2 * (n + 64), -7), got((size_t)2 * (n + 64), -7);
@@ -162,17 +166,21 @@ static int emu_compare_passes_impl(const uint8_t *q, int n, const uint8_t *t, in
         emu::run_warp([&]() {
             const int lane = threadIdx.x & 31;
             bb_build_peq(q, n, peq.data());
+            bb_build_peq(t, m, tpeq.data());
             const bool rev = lane >= 16;
             BBProb P;
             P.n = n; P.a = a; P.b = b; P.peq = peq.data(); P.hist = nullptr; P.nb_alloc = 0;
+            P.tpeq = tpeq.data();
             if (!rev) {
                 P.q = q; P.qs = 1; P.t = t; P.ts = 1; P.ncols = left_w; P.peq_bit0 = BB_PEQ_BIT0;
-                P.cols_out = out.data(); P.cols_lo = loL;
+                P.cols_out = out.data(); P.cols_lo = loL; P.tpeq_bit0 = BB_PEQ_BIT0;
             } else {
                 P.q = q + n - 1; P.qs = -1; P.t = t + m - 1; P.ts = -1; P.ncols = right_w; P.peq_bit0 = n - 1 + BB_PEQ_BIT0;
-                P.cols_out = out.data() + n + 64; P.cols_lo = loR;
+                P.cols_out = out.data() + n + 64; P.cols_lo = loR; P.tpeq_bit0 = m - 1 + BB_PEQ_BIT0;
             }
-            const int r = variant ? bb_band_pass_cb<L, true, CB>(P, 16) : bb_band_pass<L, false, true>(P, 16);
+            // CB = 2: the bit-plane build (what the node kernels run); CB = 4: the byte-fetching column-blocked pass
+            const int r = variant ? (CB == 2 ? bb_band_pass_bp<L>(P, 16) : bb_band_pass_cb<L, true, CB>(P, 16))
+                                  : bb_band_pass<L, false, true>(P, 16);
             if (lane == 0) corner[0] = r;
             if (lane == 16) corner[1] = r;
         });
