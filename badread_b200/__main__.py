@@ -22,6 +22,12 @@ def main(output=sys.stderr):
         check_simulate_args(args)
         from .simulate import simulate
         simulate(args, output=output)
+    elif args.subparser_name == 'error_model':
+        from .model_builders import make_error_model
+        make_error_model(args, output=output)
+    elif args.subparser_name == 'qscore_model':
+        from .model_builders import make_qscore_model
+        make_qscore_model(args, output=output)
     else:
         sys.exit(f'Error: the {args.subparser_name} command is not part of badread_b200 (use Badread itself)')
 
@@ -31,13 +37,39 @@ def parse_args(args):
                                      'many types of read problems (B200 build of the simulate command)')
     subparsers = parser.add_subparsers(title='Commands', dest='subparser_name')
     simulate_subparser(subparsers)
-    for other in ('error_model', 'qscore_model', 'plot'):
-        subparsers.add_parser(other, add_help=False)
+    model_subparser(subparsers, 'error_model', 'Build a Badread error model', 7)
+    model_subparser(subparsers, 'qscore_model', 'Build a Badread qscore model', 9)
+    subparsers.add_parser('plot', add_help=False)
     parser.add_argument('--version', action='version', version='Badread v' + __version__)
     if len(args) == 0:
         parser.print_help(file=sys.stderr)
         sys.exit(1)
     return parser.parse_args(args)
+
+
+def model_subparser(subparsers, name, description, default_k):
+    """The arguments of `badread error_model` / `badread qscore_model` (__main__.py:150-208 of the reference)."""
+    group = subparsers.add_parser(name, description=description)
+    required = group.add_argument_group('Required arguments')
+    required.add_argument('--reference', type=str, required=True, help='Reference FASTA file')
+    required.add_argument('--reads', type=str, required=True, help='FASTQ of real reads')
+    required.add_argument('--alignment', type=str, required=True, help='PAF alignment of reads aligned to reference')
+    optional = group.add_argument_group('Optional arguments')
+    what = 'error' if name == 'error_model' else 'qscore'
+    optional.add_argument('--k_size', type=int, default=default_k,
+                          help=f'{what.capitalize()} model k-mer size' + (' (must be odd)' if what == 'qscore' else ''))
+    optional.add_argument('--max_alignments', type=int,
+                          help=f'Only use this many alignments when generating {what} model (default: use all alignments)')
+    if name == 'error_model':
+        optional.add_argument('--max_alt', type=int, default=25, help='Only save up to this many alternatives to each k-mer')
+    else:
+        optional.add_argument('--max_del', type=int, default=6,
+                              help='Deletion runs longer than this will be collapsed to reduce the number of possible alignments')
+        optional.add_argument('--min_occur', type=int, default=100,
+                              help='CIGARs which occur less than this many times will not be included in the model')
+        optional.add_argument('--max_output', type=int, default=10000,
+                              help='The outputted model will be limited to this many lines')
+    group.add_argument('--version', action='version', version='Badread v' + __version__)
 
 
 def simulate_subparser(subparsers):

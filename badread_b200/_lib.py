@@ -113,6 +113,11 @@ def lib():
         'bb_planner_error': (c.c_char_p, [vp]),
         'bb_fastq_format': (c.c_int, [P(PlanView), vp, vp, vp, i32, i64, i64, i32, vp, i64, P(i64), P(i32), P(i64), P(i32)]),
         'bb_fastq_format_sharded': (c.c_int, [i32, vp, vp, vp, vp, i32, i64, i64, i32, vp, i64, P(i64), P(i32), P(i64), P(i32)]),
+        'bb_count_kmer_alternatives': (c.c_int, [c.c_int, c.c_int, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, P(i64),
+                                                 i64, vp, vp, vp, P(i64)]),
+        'bb_count_cigar_qscores': (c.c_int, [c.c_int, c.c_int, c.c_int, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp,
+                                             P(i64), vp, i64, vp, vp, vp, P(i64)]),
+        'bb_model_error': (c.c_char_p, []),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -128,4 +133,5 @@ EXPORTED_SYMBOLS = ['bb_create', 'bb_destroy', 'bb_last_error', 'bb_version', 'b
                     'bb_last_run_ms', 'bb_stage_name', 'bb_launch_count', 'bb_trace_dump', 'bb_get_qscores', 'bb_align_path',
                     'bb_host_align_kmers', 'bb_host_align_path', 'bb_nccl_available', 'bb_comm_unique_id', 'bb_comm_init_rank',
                     'bb_comm_init_all', 'bb_allreduce_bases', 'bb_allreduce_bases_all', 'bb_planner_create', 'bb_planner_destroy',
-                    'bb_planner_plan', 'bb_planner_view', 'bb_planner_error', 'bb_fastq_format', 'bb_fastq_format_sharded']
+                    'bb_planner_plan', 'bb_planner_view', 'bb_planner_error', 'bb_fastq_format', 'bb_fastq_format_sharded',
+                    'bb_count_kmer_alternatives', 'bb_count_cigar_qscores', 'bb_model_error']

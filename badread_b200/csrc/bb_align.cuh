@@ -27,9 +27,6 @@
 #define BB_OP_X 1
 #define BB_OP_I 2
 #define BB_MAX_SCORE 0x3fffff  // scores travel in 22 bits of the shuffle word
-#ifndef BB_NODE_CB
-#define BB_NODE_CB 2           // columns per wavefront step of the lean warp node kernel
-#endif
 #define BB_PEQ_PAD 34          // zero words in front of and behind a read's match bitmap (covers 32-word chunks)
 #define BB_PEQ_BIT0 (32 * BB_PEQ_PAD)  // bit index of the read's first base
 
@@ -556,188 +553,6 @@ __device__ int bb_band_pass_mw(const BBProb &P, int wg, volatile uint32_t *mbox,
     return __reduce_or_sync(BB_FULL, (unsigned)failed);
 }
 
-// CB columns per step: the distance-only variant of bb_band_pass for register-resident masks (L <= 4).  Chunk u
-// works on columns CB (step - u) ... CB (step - u) + CB - 1; one shuffle carries the CB horizontal deltas of the
-// chunk above (2 bits each) and its score after the first of those columns.  A step whose columns are all interior
-// to the chunk (not its first, not its last, all ACGT) runs CB bare Myers steps; everything else takes the general
-// per-column path.  Same outputs as bb_band_pass<L, false, COLS>.  CB <= 4 (22 + 2 CB bits in the shuffle word).
-template <int L, bool COLS, int CB>
-__device__ int bb_band_pass_cb(const BBProb &P, int K) {
-    const int lane = threadIdx.x & 31;
-    const int slot = lane & (K - 1);
-    const int prev = (lane & ~(K - 1)) | ((slot + K - 1) & (K - 1));
-    constexpr int CH = 32 * L;
-    const int n = P.n, ncols = P.ncols, a = P.a, b = P.b, ts = P.ts;
-    int ulast = -1;
-    if (ncols > 0 && n > 0) {
-        ulast = (ncols - 1 + b) / CH;
-        const int nchunks = (n + CH - 1) / CH;
-        if (ulast > nchunks - 1) ulast = nchunks - 1;
-    }
-    const int T = __reduce_max_sync(BB_FULL, ulast >= 0 ? (ncols - 1) / CB + ulast + 1 : 0);
-    const int cols_hi = min(n - 1, ncols - 1 + b);
-    uint32_t Pv[L], Mv[L], eA[L], eC[L], eG[L], eT[L];
-#pragma unroll
-    for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; eA[x] = eC[x] = eG[x] = eT[x] = 0u; }
-    int u = slot;
-    int cs = max(0, CH * u - b), ce = min(ncols - 1, CH * u + CH - 1 + a);
-    int ce_up = min(ncols - 1, CH * u - 1 + a);  // last column of the chunk above
-    int score = 0, result = BB_INF;
-    uint32_t outpack = 0, tcn[CB];
-    const uint8_t *tp = P.t - (long long)CB * u * ts;  // tp + CB*step*ts is the first of this lane's columns
-#pragma unroll
-    for (int h = 0; h < CB; h++) {
-        tcn[h] = 0;
-        const int c = -CB * u + h;
-        if (u <= ulast && c >= cs && c <= ce) tcn[h] = tp[(long long)h * ts];
-    }
-    // one Myers step of the whole chunk on match words Eq with horizontal input hin; returns the horizontal output
-    auto myers = [&](uint32_t (&Eq)[L], int hin) -> int {
-        uint32_t Xv[L], A[L], S[L], Ph[L], Mh[L];
-        const uint32_t hin_neg = hin < 0 ? 1u : 0u;
-#pragma unroll
-        for (int x = 0; x < L; x++) Xv[x] = Eq[x] | Mv[x];
-        Eq[0] |= hin_neg;
-#pragma unroll
-        for (int x = 0; x < L; x++) A[x] = Eq[x] & Pv[x];
-        bb_add_words<L>(A, Pv, S);
-#pragma unroll
-        for (int x = 0; x < L; x++) {
-            const uint32_t Xh = (S[x] ^ Pv[x]) | Eq[x];
-            Ph[x] = Mv[x] | ~(Xh | Pv[x]);
-            Mh[x] = Pv[x] & Xh;
-        }
-        const int hout = (int)(Ph[L - 1] >> 31) - (int)(Mh[L - 1] >> 31);
-#pragma unroll
-        for (int x = L - 1; x >= 0; x--) {
-            const uint32_t ph_lo = x > 0 ? Ph[x - 1] : (hin > 0 ? 0x80000000u : 0u);
-            const uint32_t mh_lo = x > 0 ? Mh[x - 1] : (hin_neg << 31);
-            const uint32_t phs = __funnelshift_l(ph_lo, Ph[x], 1);
-            const uint32_t mhs = __funnelshift_l(mh_lo, Mh[x], 1);
-            Pv[x] = mhs | ~(Xv[x] | phs);
-            Mv[x] = phs & Xv[x];
-        }
-        return hout;
-    };
-    auto select = [&](uint32_t code, uint32_t (&Eq)[L]) {
-#pragma unroll
-        for (int x = 0; x < L; x++) Eq[x] = (code & 2u) ? ((code & 1u) ? eG[x] : eT[x]) : ((code & 1u) ? eC[x] : eA[x]);
-    };
-    // any column of the chunk (its first, its last, non-ACGT targets, the last column of the pass)
-    auto column = [&](int c, uint32_t tc, int hin, int above) -> int {
-        if (c == cs) {  // a chunk entering the band starts from the all-(+1) upper bound below chunk u-1
-            score = ((u == 0) ? cs : above - hin) + CH;
-#pragma unroll
-            for (int x = 0; x < L; x++) {
-                Pv[x] = ~0u; Mv[x] = 0u;
-                bb_fetch_peq(P, u * CH + 32 * x, eA[x], eC[x], eG[x], eT[x]);
-            }
-        }
-        const uint32_t code = (tc >> 1) & 3u;
-        uint32_t Eq[L];
-        select(code, Eq);
-        if (((0x47544341u >> (8 * code)) & 0xffu) != tc) {  // exact byte equality against every row of the chunk
-#pragma unroll
-            for (int x = 0; x < L; x++) {
-                Eq[x] = 0u;
-                const int row0 = u * CH + 32 * x;
-                for (int r = 0; r < 32; r++)
-                    if (row0 + r < n && P.q[(long long)(row0 + r) * P.qs] == tc) Eq[x] |= 1u << r;
-            }
-        }
-        const int hout = myers(Eq, hin);
-        score += hout;
-        if (c == ncols - 1) {
-            int run = score;
-#pragma unroll
-            for (int x = L - 1; x >= 0; x--) {
-                const int row0 = u * CH + 32 * x;
-                if (COLS) {
-                    int rr = run;
-                    for (int r = 31; r >= 0; r--) {
-                        const int row = row0 + r;
-                        if (row < n && row >= P.cols_lo && row <= cols_hi) P.cols_out[row - P.cols_lo] = rr;
-                        rr -= (int)((Pv[x] >> r) & 1u) - (int)((Mv[x] >> r) & 1u);
-                    }
-                }
-                if (row0 <= n - 1 && n - 1 < row0 + 32) {
-                    const int bit = (n - 1) - row0;
-                    const uint32_t up = bit == 31 ? 0u : (Pv[x] >> (bit + 1));
-                    const uint32_t um = bit == 31 ? 0u : (Mv[x] >> (bit + 1));
-                    result = run - __popc(up) + __popc(um);
-                }
-                run -= __popc(Pv[x]) - __popc(Mv[x]);
-            }
-        }
-        return hout;
-    };
-    for (int s = 0; s < T; s++) {
-        const uint32_t in = __shfl_sync(BB_FULL, outpack, prev);
-        const int c0 = CB * (s - u), cl = c0 + CB - 1;
-        if (u <= ulast && cl >= cs && c0 <= ce) {
-            int hin[CB];
-            bool plain = true;
-#pragma unroll
-            for (int h = 0; h < CB; h++) {
-                hin[h] = (u > 0 && c0 + h <= ce_up) ? (int)((in >> (22 + 2 * h)) & 3u) - 1 : 1;
-                const uint32_t code = (tcn[h] >> 1) & 3u;
-                plain = plain && ((0x47544341u >> (8 * code)) & 0xffu) == tcn[h];
-            }
-            int o[CB];
-            int tail = 0;  // sum of the horizontal outputs of columns 1 .. CB-1
-            int last_score;
-            if (c0 > cs && cl < ce && plain) {
-#pragma unroll
-                for (int h = 0; h < CB; h++) {
-                    uint32_t Eq[L];
-                    select((tcn[h] >> 1) & 3u, Eq);
-                    o[h] = myers(Eq, hin[h]);
-                    score += o[h];
-                    if (h > 0) tail += o[h];
-                }
-                last_score = score;
-            } else {
-                int above = (int)(in & BB_MAX_SCORE);  // the chunk above after column c0 + h
-                bool moved = false;
-                last_score = score;
-#pragma unroll
-                for (int h = 0; h < CB; h++) {
-                    const int c = c0 + h;
-                    o[h] = 0;
-                    if (h > 0) above += (int)((in >> (22 + 2 * h)) & 3u) - 1;
-                    if (!moved && c >= cs && c <= ce) {
-                        o[h] = column(c, tcn[h], hin[h], above);
-                        last_score = score;
-                        if (h > 0) tail += o[h];
-                        if (c == ce) {  // the band has moved past this chunk: chunk u + K is next
-                            u += K;
-                            cs = max(0, CH * u - b);
-                            ce = min(ncols - 1, CH * u + CH - 1 + a);
-                            ce_up = min(ncols - 1, CH * u - 1 + a);
-                            tp -= (long long)CB * K * ts;
-                            moved = true;
-                        }
-                    }
-                }
-            }
-            uint32_t pack = (uint32_t)(last_score - tail) & BB_MAX_SCORE;  // the score after column c0
-#pragma unroll
-            for (int h = 0; h < CB; h++) pack |= (uint32_t)(o[h] + 1) << (22 + 2 * h);
-            outpack = pack;
-        }
-        if (u <= ulast) {
-            const int cn = CB * (s + 1 - u);
-#pragma unroll
-            for (int h = 0; h < CB; h++)
-                if (cn + h >= cs && cn + h <= ce) tcn[h] = tp[(long long)(CB * (s + 1) + h) * ts];
-        }
-    }
-    const int owner = (lane & ~(K - 1)) | ((n > 0 ? (n - 1) / CH : 0) & (K - 1));
-    result = __shfl_sync(BB_FULL, result, owner);
-    __syncwarp();
-    return result;
-}
-
 // Bit planes of the 32 target columns [c, c + 32) of a problem, bit j = column c + j: the 2-bit code of the base
 // (A 00, C 01, T 10, G 11 - the code (char >> 1) & 3 of the other passes) and whether it is one of ACGT at all.  Cut out of
 // the match bitmap of the read that holds the target, like bb_fetch_peq cuts the query rows out of theirs.
@@ -751,9 +566,12 @@ __device__ __forceinline__ void bb_fetch_target_planes(const BBProb &P, int c, u
     b0 = mC | mG; b1 = mT | mG; ok = mA | mC | mG | mT;
 }
 
-// bb_band_pass_cb<L, true, 2> on BIT PLANES (the node passes of the lean warp kernels; same outputs).  What a wavefront
-// step spends around the Myers recurrence itself is most of it for narrow chunks (~32 instructions per column against
-// 11 L + 6), so:
+// The node passes of the lean warp kernels: distance only, column scores out (the outputs of bb_band_pass<L, false, true>),
+// TWO columns per wavefront step - chunk u works on columns 2 (step - u) and 2 (step - u) + 1; one shuffle carries the two
+// horizontal deltas of the chunk above (2 bits each) and its score after the first of those columns - on BIT PLANES.  A
+// step whose columns are interior to the chunk (not its first, not its last, all ACGT) runs two bare Myers steps;
+// everything else takes the general per-column path.  What a wavefront step spends around the Myers recurrence itself is
+// most of it for narrow chunks (~32 instructions per column against 11 L + 6), so:
 //   * the target is not fetched byte by byte: the codes of 32 columns are two words cut out of the target's match bitmap
 //     (one refill per 16 steps instead of two byte loads with their address arithmetic and ACGT tests per step);
 //   * the chunk keeps its rows as two code planes q0, q1 instead of four letter masks: the match word of a column is
@@ -1232,7 +1050,7 @@ static __device__ int bb_split_warp(const BBScratch &sc, int loL, int hiL, int l
 // target character, the node is q[q0, q0+nn) x t[t0, t0+mm); band (a, b) must admit every optimal path.
 // best < 0 on entry (root): the minimum of forward + reverse scores over the split column is the edit distance and
 // is returned in best.  Returns 0 or an error code.
-template <int MAXL, bool CB2 = false>
+template <int MAXL>
 __device__ int bb_node_warp(const uint8_t *q, const uint8_t *t, int q0, int nn, int t0, int mm, int a, int b,
                             const BBScratch &sc, int &best, int &split, int &ls, int &rs, int qabs = 0) {
     const int lane = threadIdx.x & 31;
@@ -1256,13 +1074,7 @@ __device__ int bb_node_warp(const uint8_t *q, const uint8_t *t, int q0, int nn, 
         const int L2 = bb_pick_L<MAXL>(a, b, 16);
         if (L2 > 0) {  // forward and reverse pass side by side in two 16-lane groups
             const BBProb PG = make_prob(lane >= 16);
-            if (CB2 && MAXL <= 4) {  // several columns per step (register-resident masks only)
-                if (L2 == 4) bb_band_pass_cb<(MAXL >= 4 ? 4 : 1), true, BB_NODE_CB>(PG, 16);
-                else if (L2 == 2) bb_band_pass_cb<(MAXL >= 2 ? 2 : 1), true, BB_NODE_CB>(PG, 16);
-                else bb_band_pass_cb<1, true, BB_NODE_CB>(PG, 16);
-            } else {
-                bb_band_dispatch<false, true, MAXL>(PG, 16, L2);
-            }
+            bb_band_dispatch<false, true, MAXL>(PG, 16, L2);
         } else {
             const int L1 = bb_pick_L<MAXL>(a, b, 32);
             if (L1 > 0) {

@@ -100,7 +100,6 @@ struct bb_ctx {
     bool is_head = false;     // this worker holds the head batch of the current upload
     bool lpt_order = true;    // node queues below the roots walked from the end (longest nodes first)
     int ring_t = 4;           // columns per traceback tick of the 4-word window aligner (2, 4 or 8)
-    int cb_narrow = 2;        // columns per wavefront step of the 1- and 2-word node kernels (2 or 4)
     bool lowmem = false;      // window / leaf aligners with checkpoints + shared-memory tiles instead of global history
     bool use_quad = false;    // wide nodes by 8-warp CTAs (bb_k_node_quad) instead of warp pairs
     int grid_div_env = 0;
@@ -250,7 +249,6 @@ static int create_worker(bb_ctx **out, int device, uint64_t seed, bool high_prio
     if (const char *e = std::getenv("BADREAD_B200_GRID_DIV")) ctx->grid_div_env = std::atoi(e);
     if (const char *e = std::getenv("BADREAD_B200_QUAD")) ctx->use_quad = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_LOWMEM")) ctx->lowmem = (e[0] != '0');
-    if (const char *e = std::getenv("BADREAD_B200_CB_NARROW")) ctx->cb_narrow = (e[0] == '4') ? 4 : 2;
     if (const char *e = std::getenv("BADREAD_B200_LPT")) ctx->lpt_order = (e[0] != '0');
     if (const char *e = std::getenv("BADREAD_B200_RING_T")) ctx->ring_t = (e[0] == '8') ? 8 : (e[0] == '2') ? 2 : 4;
     *out = ctx;
@@ -734,9 +732,9 @@ static int enqueue_align_tasks(bb_ctx *ctx, const BBBatchDev &B) {
             }
             {
                 cudaStream_t x = on_side();   // the two narrow single-warp classes share a stream
-                bbl_node_warp(2, std::min(pgrid(ctx, 3, "WARP2"), ctx->sm_count * 6), x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4, ctx->cb_narrow);
+                bbl_node_warp(2, std::min(pgrid(ctx, 3, "WARP2"), ctx->sm_count * 6), x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4);
                 mark(ctx, x, "node_warp2");
-                bbl_node_warp(1, std::min(pgrid(ctx, 3, "WARP1"), ctx->sm_count * 6), x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4 + w2, ctx->cb_narrow);
+                bbl_node_warp(1, std::min(pgrid(ctx, 3, "WARP1"), ctx->sm_count * 6), x, B, Q[s], ctx->pool_lean, p, cursor[s]++, lean_base[s] + w4 + w2);
                 mark(ctx, x, "node_warp1");
                 x = on_side();
                 bbl_node_lane8(pgrid(ctx, 6, "LANE8"), x, B, Q[s], p, cursor[s]++);

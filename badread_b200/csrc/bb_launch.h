@@ -22,7 +22,7 @@ void bbl_window_lane_hist(int words, int ring_t, int grid, cudaStream_t st, BBBa
 void bbl_window_warp(int grid, cudaStream_t st, BBBatchDev B, BBErrorModelDev em, BBScratchPool pool, const BBWinTask *tasks,
                      const int *n_tasks, unsigned long long seed, int *cursor);
 void bbl_node_warp(int words, int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor,
-                   int warp_base, int cb = 2);  // words per lane: 1, 2 or 4 (class BBQ_NODE_LEAN1 / 2 / 4); cb: columns per step
+                   int warp_base);  // words per lane: 1, 2 or 4 (class BBQ_NODE_LEAN1 / 2 / 4)
 void bbl_node_lane8(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, int parity, int *cursor);
 cudaError_t bbl_node_quad_init();
 void bbl_node_quad(int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity, int *cursor,

@@ -543,8 +543,8 @@ bb_k_leaf_lane_hist(BBBatchDev B, BBQueues Q, uint2 *hist_pool, int *cursor) {
 // ---------------------------------------------------------------------------------------------- warp kernels
 // One Hirschberg node per warp: the forward pass over the left half of the target and the reverse pass over the right
 // half run side by side in the warp's two 16-lane groups with exactly L words per lane (class BBQ_NODE_LEAN<L>), several
-// columns per wavefront step (bb_band_pass_cb); then the split row by edlib's rule.
-template <int L, int CB = BB_NODE_CB>
+// columns per wavefront step on bit planes (bb_band_pass_bp); then the split row by edlib's rule.
+template <int L>
 __global__ void __launch_bounds__(BB_WARPS_PER_CTA * 32, (L == 1 ? 6 : L == 2 ? 5 : 3))
 bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity_order, int *cursor, int warp_base) {
     constexpr int CLS = L == 1 ? BBQ_NODE_LEAN1 : L == 2 ? BBQ_NODE_LEAN2 : BBQ_NODE_LEAN4;
@@ -586,8 +586,7 @@ bb_k_node_warp(BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity_order, i
                 P.peq_bit0 = nd.q0 + nd.nn - 1 + BB_PEQ_BIT0; P.cols_out = sc.R; P.cols_lo = loR;
                 P.tpeq_bit0 = nd.t0 + nd.mm - 1 + BB_PEQ_BIT0;
             }
-            if (CB == 2) bb_band_pass_bp<L>(P, 16);   // the bit-plane build of the 2-column pass
-            else bb_band_pass_cb<L, true, CB>(P, 16);
+            bb_band_pass_bp<L>(P, 16);
             __syncwarp();
             err = bb_split_warp(sc, loL, hiL, loR, hiR, nd.nn, left_w, right_w, best, split, ls, rs);
         }

@@ -1,14 +1,8 @@
-// bb_tu_node_warp12.cu — compiles bb_k_node_warp<1> and <2> (bb_tasks.cuh): the narrow single-warp node kernels,
-// with 2 and with 4 columns per wavefront step.
+// bb_tu_node_warp12.cu — compiles bb_k_node_warp<1> and <2> (bb_tasks.cuh): the narrow single-warp node kernels.
 #include "bb_launch.h"
 
 void bbl_node_warp_12(int words, int grid, cudaStream_t st, BBBatchDev B, BBQueues Q, BBScratchPool pool, int parity,
-                      int *cursor, int warp_base, int cb) {
-    if (words == 2) {
-        if (cb == 4) bb_k_node_warp<2, 4><<<grid, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, pool, parity, cursor, warp_base);
-        else bb_k_node_warp<2, 2><<<grid, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, pool, parity, cursor, warp_base);
-    } else {
-        if (cb == 4) bb_k_node_warp<1, 4><<<grid, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, pool, parity, cursor, warp_base);
-        else bb_k_node_warp<1, 2><<<grid, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, pool, parity, cursor, warp_base);
-    }
+                      int *cursor, int warp_base) {
+    if (words == 2) bb_k_node_warp<2><<<grid, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, pool, parity, cursor, warp_base);
+    else bb_k_node_warp<1><<<grid, BB_WARPS_PER_CTA * 32, 0, st>>>(B, Q, pool, parity, cursor, warp_base);
 }

@@ -243,6 +243,39 @@ BB_API int bb_fastq_format_sharded(int32_t n_shards, const bb_plan_view *const *
                             int64_t target_bases, int32_t n_threads, uint8_t *out, int64_t out_cap, int64_t *out_len,
                             int32_t *n_emitted, int64_t *bases_emitted, int32_t *next_read);
 
+/* ---- Model builders: the counting passes of `badread error_model` (badread/error_model.py:31-83) and `badread
+ * qscore_model` (badread/qscore_model.py:78-161) on the GPU.  The caller has parsed the inputs and chosen the alignments
+ * (badread/alignment.py:79-105) and hands them over flat: for alignment a = 0 .. n_aln-1 the aligned slice of the read
+ * read[read_off[a] .. read_off[a+1]) (and its qualities), the aligned slice of the reference ref[ref_off[a] .. ref_off[a+1])
+ * already on the read's strand, and the CIGAR runs ops[ops_off[a] .. ops_off[a+1]) in read orientation, each
+ * (length << 2) | type with type 0 = M, 1 = I, 2 = D, starting at read offset op_read0[] / reference offset op_ref0[] within
+ * the alignment.  A window's content is a 64-bit key; the library returns every distinct key with its count(s) and the first
+ * window it occurred in (the reference's dicts keep insertion order and its stable sorts break ties by it), in arbitrary order:
+ *   bb_count_kmer_alternatives  key = reference k-mer (2k bits from bit 63 down, A C G T = 0 1 2 3) | read k-mer length
+ *                               (6 bits) | read k-mer (2 bits a base from bit 0 up); counts_out: one per key;
+ *                               first_out = (alignment << 32) | reference offset of the window.  k <= 12.
+ *   bb_count_cigar_qscores      key = CIGAR length (6 bits from bit 63 down) | symbols (2 bits each from bit 0 up, = X I D =
+ *                               0 1 2 3, runs of 'D' cut to max_del); counts_out: 94 per key (quality 0 .. 93 of the window's
+ *                               middle base); first_out = (alignment << 36) | ((window size - 1) / 2 << 32) | read offset;
+ *                               overall_out[94]: the qualities of all bases.  Odd k <= 13: every odd size up to k is counted.
+ * Windows that do not fit a key (and quality characters outside '!' .. '~') are not counted but listed: alignment, offset and
+ * window size (negative for a bad quality character) in ovf_*; the caller evaluates those itself.  table_cap (a power of two)
+ * slots are used on the device and bound the number of distinct keys; BB_ERR_CAPACITY if the table or the overflow list is
+ * too small (*n_ovf then holds the required overflow capacity).  bb_model_error() describes the last failure of the calling
+ * thread.  No bb_ctx is involved: the calls allocate and release what they need on `device`. */
+BB_API int bb_count_kmer_alternatives(int device, int k, int32_t n_aln, const uint8_t *read, const int64_t *read_off,
+                               const uint8_t *ref, const int64_t *ref_off, const uint32_t *ops, const int32_t *op_read0,
+                               const int32_t *op_ref0, const int64_t *ops_off, int64_t table_cap, uint64_t *keys_out,
+                               uint64_t *first_out, uint32_t *counts_out, int64_t *n_entries, int64_t ovf_cap,
+                               int32_t *ovf_aln, int32_t *ovf_pos, int32_t *ovf_k, int64_t *n_ovf);
+BB_API int bb_count_cigar_qscores(int device, int k, int max_del, int32_t n_aln, const uint8_t *read, const uint8_t *qual,
+                           const int64_t *read_off, const uint8_t *ref, const int64_t *ref_off, const uint32_t *ops,
+                           const int32_t *op_read0, const int32_t *op_ref0, const int64_t *ops_off, int64_t table_cap,
+                           uint64_t *keys_out, uint64_t *first_out, uint32_t *counts_out, int64_t *n_entries,
+                           uint64_t *overall_out, int64_t ovf_cap, int32_t *ovf_aln, int32_t *ovf_pos, int32_t *ovf_k,
+                           int64_t *n_ovf);
+BB_API const char *bb_model_error(void);
+
 #ifdef __cplusplus
 }
 #endif

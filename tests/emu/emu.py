@@ -100,16 +100,17 @@ def tasks_align(seq, frag, upper, quad=True, hist=1):
     return s
 
 
-def compare_passes(query, target, k, cb=2):
-    """Mismatch count between the column-blocked (cb columns per step) and the single-column distance pass, both
-    directions of a Hirschberg node side by side; None if the band does not fit the lean kernel."""
+def compare_passes(query, target, k):
+    """Mismatch count between the two-column bit-plane pass of the lean node kernels (bb_band_pass_bp) and the
+    single-column distance pass, both directions of a Hirschberg node side by side; None if the band does not fit the
+    lean kernels."""
     global _lib
     if _lib is None:
         build()
         _lib = ctypes.CDLL(str(LIB))
     q = query.encode('latin-1') if isinstance(query, str) else bytes(query)
     t = target.encode('latin-1') if isinstance(target, str) else bytes(target)
-    rc = _lib.emu_compare_passes(q, len(q), t, len(t), int(k), int(cb))
+    rc = _lib.emu_compare_passes(q, len(q), t, len(t), int(k))
     return None if rc < 0 else int(rc)
 
 

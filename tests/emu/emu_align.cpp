@@ -150,10 +150,10 @@ int emu_tasks_align(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
 }
 
 
-// The column-blocked distance pass against the single-column one on the same problem: both directions side by side in
+// The two-column bit-plane distance pass (bb_band_pass_bp) against the single-column one on the same problem: both directions side by side in
 // two 16-lane groups (K = 16), as the lean warp node kernel runs them.  Returns the number of mismatching outputs
 // (column-score entries + the two corner scores), or -1 if the band does not fit L with K = 16.
-template <int L, int CB>
+template <int L>
 static int emu_compare_passes_impl(const uint8_t *q, int n, const uint8_t *t, int m, int a, int b) {
     std::vector<uint4> peq((size_t)bb_peq_words(n) + 8), tpeq((size_t)bb_peq_words(m) + 8);
     const int left_w = m / 2, right_w = m - left_w;
@@ -178,9 +178,7 @@ static int emu_compare_passes_impl(const uint8_t *q, int n, const uint8_t *t, in
                 P.q = q + n - 1; P.qs = -1; P.t = t + m - 1; P.ts = -1; P.ncols = right_w; P.peq_bit0 = n - 1 + BB_PEQ_BIT0;
                 P.cols_out = out.data() + n + 64; P.cols_lo = loR; P.tpeq_bit0 = m - 1 + BB_PEQ_BIT0;
             }
-            // CB = 2: the bit-plane build (what the node kernels run); CB = 4: the byte-fetching column-blocked pass
-            const int r = variant ? (CB == 2 ? bb_band_pass_bp<L>(P, 16) : bb_band_pass_cb<L, true, CB>(P, 16))
-                                  : bb_band_pass<L, false, true>(P, 16);
+            const int r = variant ? bb_band_pass_bp<L>(P, 16) : bb_band_pass<L, false, true>(P, 16);
             if (lane == 0) corner[0] = r;
             if (lane == 16) corner[1] = r;
         });
@@ -193,19 +191,14 @@ static int emu_compare_passes_impl(const uint8_t *q, int n, const uint8_t *t, in
 }
 
 extern "C" __attribute__((visibility("default")))
-int emu_compare_passes(const uint8_t *q, int n, const uint8_t *t, int m, int k, int cb) {
+int emu_compare_passes(const uint8_t *q, int n, const uint8_t *t, int m, int k) {
     int a, b;
     bb_band(n, m, k, a, b);
     const int L = bb_pick_L<4>(a, b, 16);
     if (L <= 0) return -1;
-    if (cb == 2) {
-        if (L == 4) return emu_compare_passes_impl<4, 2>(q, n, t, m, a, b);
-        if (L == 2) return emu_compare_passes_impl<2, 2>(q, n, t, m, a, b);
-        return emu_compare_passes_impl<1, 2>(q, n, t, m, a, b);
-    }
-    if (L == 4) return emu_compare_passes_impl<4, 4>(q, n, t, m, a, b);
-    if (L == 2) return emu_compare_passes_impl<2, 4>(q, n, t, m, a, b);
-    return emu_compare_passes_impl<1, 4>(q, n, t, m, a, b);
+    if (L == 4) return emu_compare_passes_impl<4>(q, n, t, m, a, b);
+    if (L == 2) return emu_compare_passes_impl<2>(q, n, t, m, a, b);
+    return emu_compare_passes_impl<1>(q, n, t, m, a, b);
 }
 
 
