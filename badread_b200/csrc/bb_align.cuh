@@ -598,6 +598,7 @@ __device__ int bb_band_pass_bp(const BBProb &P, int K) {
     }
     const int T = __reduce_max_sync(BB_FULL, ulast >= 0 ? (ncols - 1) / CB + ulast + 1 : 0);
     const int cols_hi = min(n - 1, ncols - 1 + b);
+    const bool even_band = ((a | b) & 1) == 0;
     uint32_t Pv[L], Mv[L], q0[L], q1[L], q0n[L], q1n[L];
 #pragma unroll
     for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; q0[x] = q1[x] = q0n[x] = q1n[x] = 0u; }
@@ -659,14 +660,16 @@ __device__ int bb_band_pass_bp(const BBProb &P, int K) {
         for (int x = 0; x < L; x++) Eq[x] = ~((q0[x] ^ m0) | (q1[x] ^ m1));
     };
     // any column of the chunk (its first, its last, non-ACGT characters, the last column of the pass)
-    auto column = [&](int c, uint32_t k0, uint32_t k1, bool tplain, int hin, int above) -> int {
-        if (c == cs) {  // a chunk entering the band starts from the all-(+1) upper bound below chunk u-1
-            score = ((u == 0) ? cs : above - hin) + CH;
-            qok = qokn;
+    // a chunk entering the band (at its column cs) starts from the all-(+1) upper bound below chunk u-1
+    auto enter_chunk = [&](int hin, int above) {
+        score = ((u == 0) ? cs : above - hin) + CH;
+        qok = qokn;
 #pragma unroll
-            for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; q0[x] = q0n[x]; q1[x] = q1n[x]; }
-            if (u + K <= ulast) fetch_chunk(u + K);  // not needed before the band has passed this chunk
-        }
+        for (int x = 0; x < L; x++) { Pv[x] = ~0u; Mv[x] = 0u; q0[x] = q0n[x]; q1[x] = q1n[x]; }
+        if (u + K <= ulast) fetch_chunk(u + K);  // not needed before the band has passed this chunk
+    };
+    auto column = [&](int c, uint32_t k0, uint32_t k1, bool tplain, int hin, int above, bool entered) -> int {
+        if (c == cs && !entered) enter_chunk(hin, above);
         uint32_t Eq[L];
         if (qok && tplain) planes(k0, k1, Eq);
         else {  // exact: the letter masks again; a target character outside ACGT is compared byte by byte
@@ -723,7 +726,14 @@ __device__ int bb_band_pass_bp(const BBProb &P, int K) {
             const int hin0 = c0 <= ce_up ? (int)((in >> 22) & 3u) - 1 : 1;
             const int hin1 = cl <= ce_up ? (int)((in >> 24) & 3u) - 1 : 1;
             int o0, o1, last_score;
-            if (c0 > cs && cl < ce && (kk & 3u) == 3u && qok) {
+            // With a and b even (bb_task_band makes them so) a chunk's columns are whole pairs - cs is even, ce odd unless
+            // it is the pass's last column - and taking or leaving a chunk does not leave the common path: the lanes that
+            // do either run a few extra instructions around the same two Myers steps as everybody else.  (Handled column
+            // by column, as any odd band still is, every entry and exit made the whole warp run the general path for one
+            // lane: a third of the warp instructions of a narrow pass.)
+            const bool entered = even_band && c0 == cs;
+            if (entered) enter_chunk(hin0, (int)(in & BB_MAX_SCORE));
+            if ((even_band ? c0 >= cs : c0 > cs) && cl < ce + (even_band ? 1 : 0) && cl < ncols - 1 && (kk & 3u) == 3u && qok) {
                 uint32_t Eq[L];
                 planes(k0, k1, Eq);
                 o0 = myers(Eq, hin0);
@@ -731,19 +741,25 @@ __device__ int bb_band_pass_bp(const BBProb &P, int K) {
                 o1 = myers(Eq, hin1);
                 score += o0 + o1;
                 last_score = score;
+                if (cl == ce) {  // (even band) the band has moved past this chunk: chunk u + K is next
+                    u += K;
+                    cs = max(0, CH * u - b);
+                    ce = min(ncols - 1, CH * u + CH - 1 + a);
+                    ce_up = min(ncols - 1, CH * u - 1 + a);
+                }
             } else {
                 int above = (int)(in & BB_MAX_SCORE);  // the chunk above after column c0 + h
                 bool moved = false;
                 o0 = 0; o1 = 0;
                 last_score = score;
                 if (c0 >= cs && c0 <= ce) {
-                    o0 = column(c0, k0, k1, (kk & 1u) != 0u, hin0, above);
+                    o0 = column(c0, k0, k1, (kk & 1u) != 0u, hin0, above, entered);
                     last_score = score;
                     if (c0 == ce) moved = true;
                 }
                 above += (int)((in >> 24) & 3u) - 1;
                 if (!moved && cl >= cs && cl <= ce) {
-                    o1 = column(cl, k0 >> 1, k1 >> 1, (kk & 2u) != 0u, hin1, above);
+                    o1 = column(cl, k0 >> 1, k1 >> 1, (kk & 2u) != 0u, hin1, above, false);
                     last_score = score;
                     if (cl == ce) moved = true;
                 } else o1 = 0;

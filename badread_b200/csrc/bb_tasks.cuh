@@ -65,6 +65,9 @@ __device__ __forceinline__ void bb_task_band(const BBNode &nd, int upper, int &a
     const int mx = nd.nn > nd.mm ? nd.nn : nd.mm;
     if (k > mx) k = mx;
     bb_band(nd.nn, nd.mm, k, a, b);
+    // an even band (a wider band is always valid): the chunks of the two-column wavefront then begin and end on whole
+    // column pairs (bb_band_pass_bp)
+    a += a & 1; b += b & 1;
 }
 
 // Queue a child (or finish it on the spot when one side is empty, edlib.cpp obtainAlignment).

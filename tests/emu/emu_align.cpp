@@ -194,11 +194,17 @@ extern "C" __attribute__((visibility("default")))
 int emu_compare_passes(const uint8_t *q, int n, const uint8_t *t, int m, int k) {
     int a, b;
     bb_band(n, m, k, a, b);
-    const int L = bb_pick_L<4>(a, b, 16);
-    if (L <= 0) return -1;
-    if (L == 4) return emu_compare_passes_impl<4>(q, n, t, m, a, b);
-    if (L == 2) return emu_compare_passes_impl<2>(q, n, t, m, a, b);
-    return emu_compare_passes_impl<1>(q, n, t, m, a, b);
+    int bad = 0, done = 0;
+    for (int even = 0; even < 2; even++) {   // the band as it is (odd bands: chunks handled column by column at their ends) and
+        if (even) { a += a & 1; b += b & 1; }  // made even as bb_task_band does (entry / exit on the common path)
+        const int L = bb_pick_L<4>(a, b, 16);
+        if (L <= 0) continue;
+        done++;
+        if (L == 4) bad += emu_compare_passes_impl<4>(q, n, t, m, a, b);
+        else if (L == 2) bad += emu_compare_passes_impl<2>(q, n, t, m, a, b);
+        else bad += emu_compare_passes_impl<1>(q, n, t, m, a, b);
+    }
+    return done ? bad : -1;
 }
 
 
