@@ -2,6 +2,7 @@
 // orchestration. All hot-path work is done by the kernels in bb_kernels.cuh; there is no CPU path here.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -1294,6 +1295,22 @@ int nccl_err(bb_ctx *ctx, const char *what, int rc) {
 
 extern "C" int bb_nccl_available(void) { return nccl().ok ? 1 : 0; }
 
+// NCCL prints its version banner with a plain printf to stdout when NCCL_DEBUG=VERSION (init.cc showVersion; the debug
+// file setting does not apply to it) - and stdout is where `badread simulate` writes the FASTQ (measured: 29 bytes that
+// made the 2-GPU output differ from the 1-GPU one).  While a communicator is created, file descriptor 1 points at stderr.
+struct StdoutToStderr {
+    int saved = -1;
+    StdoutToStderr() {
+        fflush(stdout);
+        saved = dup(1);
+        if (saved >= 0) dup2(2, 1);
+    }
+    ~StdoutToStderr() {
+        fflush(stdout);
+        if (saved >= 0) { dup2(saved, 1); close(saved); }
+    }
+};
+
 extern "C" int bb_comm_unique_id(bb_nccl_id *id) {
     if (!id) return BB_ERR_ARG;
     if (!nccl().ok) return BB_ERR_STATE;
@@ -1305,7 +1322,11 @@ extern "C" int bb_comm_init_rank(bb_ctx *ctx, const bb_nccl_id *id, int rank, in
     if (!nccl().ok) return set_err(ctx, BB_ERR_STATE, "libnccl.so.2 could not be loaded");
     BB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ctx->nccl_comm && nccl().CommDestroy) { nccl().CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
-    const int rc = nccl().CommInitRank(&ctx->nccl_comm, world, *id, rank);
+    int rc;
+    {
+        StdoutToStderr guard;
+        rc = nccl().CommInitRank(&ctx->nccl_comm, world, *id, rank);
+    }
     if (rc) return nccl_err(ctx, "ncclCommInitRank", rc);
     BB_CUDA(ctx, ctx->d_red.ensure(2 * sizeof(long long)));
     return BB_OK;
@@ -1317,7 +1338,11 @@ extern "C" int bb_comm_init_all(bb_ctx **ctxs, int n) {
     std::vector<int> devs((size_t)n);
     std::vector<void *> comms((size_t)n, nullptr);
     for (int i = 0; i < n; i++) { if (!ctxs[i]) return BB_ERR_ARG; devs[(size_t)i] = ctxs[i]->device; }
-    const int rc = nccl().CommInitAll(comms.data(), n, devs.data());
+    int rc;
+    {
+        StdoutToStderr guard;
+        rc = nccl().CommInitAll(comms.data(), n, devs.data());
+    }
     if (rc) return nccl_err(ctxs[0], "ncclCommInitAll", rc);
     for (int i = 0; i < n; i++) {
         ctxs[i]->nccl_comm = comms[(size_t)i];
