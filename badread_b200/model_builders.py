@@ -238,38 +238,65 @@ def make_error_model(args, output=sys.stderr, dot_interval=1000):
     k = args.k_size
     flat = FlatAlignments(alignments, reads, refs, output, dot_interval)
     keys, first, counts, _, ovf = _count('kmers', flat, k)
-    shift_ref = 64 - 2 * k
-    shift_len = shift_ref - 6
-    table = collections.defaultdict(dict)    # ref k-mer -> {read k-mer: [count, first occurrence]}
-    for key, stamp, cnt in zip(keys.tolist(), first.tolist(), counts[:, 0].tolist()):
-        ref_kmer = ''.join('ACGT'[(key >> (62 - 2 * j)) & 3] for j in range(k))
-        n = (key >> shift_len) & 63
-        read_kmer = ''.join('ACGT'[(key >> (2 * j)) & 3] for j in range(n))
-        table[ref_kmer][read_kmer] = [cnt, stamp]
-    cache = {}
-    for a, r, _ in zip(*(o.tolist() for o in ovf)):     # read k-mers too long for a key: exact, here
+    counts = counts[:, 0].astype(np.int64)
+    shift_ref, shift_len = np.uint64(64 - 2 * k), np.uint64(58 - 2 * k)
+    # read k-mers too long for a key (the overflow list): counted here, exactly; {reference k-mer: {read k-mer: [count, first]}}
+    long_alts, cache = collections.defaultdict(dict), {}
+    for a, r, _ in zip(*(o.tolist() for o in ovf)):
         if a not in cache:
             cache[a] = flat.columns(a)
         read, ref, _, _, rp_at, is_m, _ = cache[a]
         p_lo = 0 if r == 0 else int(rp_at[r])
         p_hi = int(rp_at[r + k - 1]) + int(is_m[r + k - 1])
-        ref_kmer = bytes(ref[r:r + k]).decode('latin-1')
         read_kmer = bytes(read[p_lo:p_hi]).decode('latin-1')
         if set(read_kmer) <= set('ACGT'):
-            entry = table[ref_kmer].setdefault(read_kmer, [0, (a << 32) | r])
+            code = 0
+            for c in bytes(ref[r:r + k]):
+                code = code * 4 + b'ACGT'.index(c)
+            entry = long_alts[code].setdefault(read_kmer, [0, (a << 32) | r])
             entry[0] += 1
             entry[1] = min(entry[1], (a << 32) | r)
+    # per reference k-mer: total, the count of the unchanged k-mer, and the alternatives by (count, first occurrence) -
+    # the order of the reference's stable sort by fraction over its insertion-ordered dict
+    refcode = (keys >> shift_ref).astype(np.int64)
+    totals = np.bincount(refcode, weights=counts, minlength=4 ** k).astype(np.int64)
+    for code, alts in long_alts.items():
+        totals[code] += sum(c for c, _ in alts.values())
+    same = np.zeros(4 ** k, dtype=np.uint64)        # the read part of the key of an unchanged k-mer: base j at bits 2j
+    codes = np.arange(4 ** k, dtype=np.uint64)
+    for j in range(k):
+        same |= ((codes >> np.uint64(2 * (k - 1 - j))) & np.uint64(3)) << np.uint64(2 * j)
+    identity_key = (codes << shift_ref) | (np.uint64(k) << shift_len) | same
+    is_identity = keys == identity_key[refcode]
+    unchanged = np.zeros(4 ** k, dtype=np.int64)
+    unchanged[refcode[is_identity]] = counts[is_identity]
+    alt = np.flatnonzero(~is_identity)
+    order = alt[np.lexsort((first[alt], -counts[alt], refcode[alt]))]
+    group = refcode[order]
+    starts = np.flatnonzero(np.concatenate([[True], group[1:] != group[:-1]])) if order.size else np.zeros(0, dtype=np.int64)
+    rank = np.arange(order.size) - np.repeat(starts, np.diff(np.concatenate([starts, [order.size]])))
+    # (a reference k-mer with alternatives in the overflow list keeps all of its entries: they are merged below)
+    crowded = np.zeros(4 ** k, dtype=bool)
+    crowded[list(long_alts)] = True
+    kept = order[(rank < args.max_alt) | crowded[group]]
+    lens = ((keys[kept] >> shift_len) & np.uint64(63)).astype(np.int64)
+    width = int(lens.max()) if kept.size else 1
+    letters = np.frombuffer(b'ACGT', dtype=np.uint8)[((keys[kept][:, None] >> (np.uint64(2) * np.arange(width, dtype=np.uint64))) &
+                                                   np.uint64(3)).astype(np.int64)].tobytes()
+    kept_code, kept_count, kept_first = refcode[kept].tolist(), counts[kept].tolist(), first[kept].tolist()
+    per_code = collections.defaultdict(list)
+    for i, n in enumerate(lens.tolist()):
+        per_code[kept_code[i]].append((letters[i * width:i * width + n].decode(), kept_count[i], kept_first[i]))
     out = []
-    for idx in range(4 ** k):
-        kmer = ''.join('ACGT'[(idx >> (2 * (k - 1 - j))) & 3] for j in range(k))
-        alts = table.get(kmer)
-        if not alts:
-            continue
-        total = sum(c for c, _ in alts.values())
-        line = [f'{kmer},{alts.get(kmer, [0])[0] / total:.6f};']
-        others = sorted(((s, a, c / total) for a, (c, s) in alts.items() if a != kmer))      # by first occurrence ...
-        others.sort(key=lambda x: x[2], reverse=True)                                      # ... then stably by fraction
-        line.extend(f'{a},{frac:.6f};' for _, a, frac in others[:args.max_alt])
+    totals_l, unchanged_l = totals.tolist(), unchanged.tolist()
+    for code in np.flatnonzero(totals).tolist():
+        kmer = ''.join('ACGT'[(code >> (2 * (k - 1 - j))) & 3] for j in range(k))
+        total = totals_l[code]
+        alts = per_code.get(code, [])
+        if code in long_alts:
+            alts = sorted(alts + [(a, c, s) for a, (c, s) in long_alts[code].items()], key=lambda x: (-x[1], x[2]))
+        line = [f'{kmer},{unchanged_l[code] / total:.6f};']
+        line.extend(f'{a},{c / total:.6f};' for a, c, _ in alts[:args.max_alt])
         out.append(''.join(line))
     print('\n'.join(out))
 
