@@ -193,11 +193,15 @@ def test_long_reads_in_a_split_batch_match_oracle(engine):
     assert not bad, [(i, lens[i], idents[i]) for i in bad[:10]]
 
 
-def test_checkpoint_window_and_leaf_builds_match_oracle(monkeypatch):
-    """BADREAD_B200_LOWMEM=1 selects the window / leaf aligners that keep checkpoints and re-run tiles into shared
-    memory instead of a per-column history in global memory (7x less DRAM traffic, measured slower): same reads."""
+@pytest.mark.parametrize('knob,value', [('BADREAD_B200_LOWMEM', '1'), ('BADREAD_B200_RING_T', '2'), ('BADREAD_B200_RING_T', '8'),
+                                        ('BADREAD_B200_LPT', '0')])
+def test_alternative_builds_match_oracle(monkeypatch, knob, value):
+    """The builds behind the tuning knobs write the same reads as the defaults: BADREAD_B200_LOWMEM=1 (window / leaf
+    aligners that keep checkpoints and re-run tiles into shared memory instead of a per-column history in global memory:
+    7x less DRAM traffic, measured slower), BADREAD_B200_RING_T=2 / 8 (columns per tick of the traceback's staging ring),
+    BADREAD_B200_LPT=0 (node queues walked in push order)."""
     from badread_b200.engine import Engine, FragmentBatch
-    monkeypatch.setenv('BADREAD_B200_LOWMEM', '1')
+    monkeypatch.setenv(knob, value)
     eng = Engine(device=0, seed=99)
     try:
         em, qm = load_models('nanopore2023', 'nanopore2023')
