@@ -300,3 +300,109 @@ int emu_window_lane(const uint8_t *frag, int frag_len, const int *pos, const uin
     for (int a = 0; a < n_meas; a++) { out_pairs[2 * a] = wres[(size_t)a].x; out_pairs[2 * a + 1] = wres[(size_t)a].y; }
     return rd.flags;
 }
+
+
+// The error loop (bb_loop.cuh) of ONE read under the emulator, as bb_api.cu enqueues it: bb_k_mutate -> bb_k_window_tasks ->
+// bb_k_window_lane_hist<4> -> <8> -> bb_k_window_warp -> bb_k_replay, round after round until the read is done.  The
+// fragment comes unpadded; the pads are drawn like bb_k_build_fragments draws them.  The error model comes as the flat
+// tables bb_upload_error_model takes.  out8: loop_count, change_count, n_align, seq_len, start_trim, end_trim, upper, flags;
+// joined_out: ''.join(new_fragment_bases) after the loop (cut to joined_cap).  Returns the number of rounds, or -1.
+extern "C" __attribute__((visibility("default")))
+int emu_error_loop(const uint8_t *fragment, int n, double target, unsigned long long seed, unsigned long long read_index,
+                   int k, const int32_t *kmer_to_row, int32_t n_rows, const int32_t *row_off, const double *cum,
+                   const uint8_t *flags, const uint32_t *slots, const uint8_t *pool_bytes, int *out8, uint8_t *joined_out,
+                   int joined_cap) {
+    const int frag_len = n + 2 * k;
+    std::vector<BBRowInfo> info((size_t)n_rows);
+    for (int32_t r = 0; r < n_rows; r++) {
+        const int32_t e0 = row_off[r], ne = row_off[r + 1] - e0;
+        BBRowInfo &ri = info[(size_t)r];
+        ri.cum_last = cum[e0 + ne - 1]; ri.cum0 = cum[e0]; ri.e0 = e0; ri.ne = ne;
+        ri.first_is_identity = flags[e0] == 1 ? 1 : 0; ri.pad = 0;
+    }
+    BBErrorModelDev em;
+    std::memset(&em, 0, sizeof(em));
+    em.k = k; em.type = 1; em.kmer_to_row = kmer_to_row; em.row_off = row_off; em.cum = cum; em.flags = flags; em.slots = slots;
+    em.pool = pool_bytes; em.rowinfo = info.data();
+    std::vector<uint8_t> fr((size_t)frag_len + 64, 0);
+    {
+        BBRng rng;
+        rng.init(seed, read_index);
+        rng.stream(BB_PURPOSE_PAD, 0);
+        for (int j = 0; j < k; j++) fr[(size_t)j] = rng.random_base();
+        for (int j = 0; j < k; j++) fr[(size_t)(frag_len - k + j)] = rng.random_base();
+        std::memcpy(fr.data() + k, fragment, (size_t)n);
+    }
+    std::vector<uint32_t> state((size_t)frag_len + 64, BB_SLOT_NONE);
+    std::vector<unsigned int> ctime((size_t)frag_len + 64, 0u);
+    std::vector<int> kidx((size_t)frag_len + 64, -1);
+    for (int x = 0; x + k <= frag_len; x++) {
+        int idx = 0;
+        bool ok = true;
+        for (int j = 0; j < k; j++) {
+            const uint8_t c = fr[(size_t)(x + j)];
+            const int code = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+            if (code < 0) ok = false;
+            idx = idx * 4 + (code & 3);
+        }
+        kidx[(size_t)x] = ok ? kmer_to_row[idx] : -1;
+    }
+    std::vector<uint4> fpeq((size_t)bb_peq_words(frag_len) + 8);
+    const int cap = (int)(0.9 * (double)frag_len) + k + 2;
+    std::vector<uint2> chlog((size_t)cap + 8);
+    std::vector<int2> wres((size_t)cap / BB_ALIGNMENT_INTERVAL + 8, make_int2(-1, -1));
+    BBReadDev rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.frag_len = frag_len;
+    const double need = (double)frag_len * (1.0 - target);
+    rd.horizon = (int)std::min<double>((double)cap, std::max(0.0, 1.25 * need) + 48.0);
+    rd.status = BB_READ_PENDING;
+    BBBatchDev B;
+    std::memset(&B, 0, sizeof(B));
+    int order0 = 0;
+    B.n_reads = 1; B.read_index = &read_index; B.target = &target; B.order = &order0; B.reads = &rd; B.frag = fr.data();
+    B.state = state.data(); B.ctime = ctime.data(); B.kidx = kidx.data(); B.fpeq = fpeq.data(); B.chlog = chlog.data();
+    B.wres = wres.data();
+    emu::run_warp([&]() { bb_build_peq(fr.data(), frag_len, fpeq.data()); });
+    // scratch of the warp window kernel (warp 0 of one CTA) and of the lane kernels (one warp)
+    const int big = 2 * BB_WIN_MAX_COLS + frag_len + 64;
+    const int NW = BB_WARPS_PER_CTA;
+    std::vector<uint2> hist((size_t)NW * 106496), whist((size_t)32 * BB_WIN_MAX_COLS * BB_WIN_LW);
+    std::vector<int8_t> hbuf((size_t)NW * big);
+    std::vector<int> LR((size_t)NW * 2 * big), stack((size_t)NW * 5 * 64);
+    std::vector<uint8_t> wtbuf((size_t)NW * big), ltbuf((size_t)64 * BB_WIN_MAX_COLS);
+    std::vector<uint4> wpeq((size_t)NW * (bb_peq_words(big) + 8));
+    BBScratchPool pool;
+    std::memset(&pool, 0, sizeof(pool));
+    pool.hist = hist.data(); pool.hist_stride = 106496; pool.hist_cap = 106496;
+    pool.hbuf = hbuf.data(); pool.hbuf_stride = big; pool.hbuf_cap = big;
+    pool.lr = LR.data(); pool.lr_stride = 2 * (long long)big; pool.lr_cap = big;
+    pool.stack = stack.data(); pool.stack_cap = 64;
+    pool.tbuf = wtbuf.data(); pool.tbuf_stride = big;
+    pool.peq = wpeq.data(); pool.peq_stride = bb_peq_words(big) + 8; pool.peq_cap = bb_peq_words(big) + 8;
+    std::vector<BBWinTask> tasks((size_t)cap / BB_ALIGNMENT_INTERVAL + 8), fb1(tasks.size()), fb2(tasks.size());
+    int rounds = 0;
+    for (; rounds < 12 && rd.status != BB_READ_DONE; rounds++) {
+        int c_mut = 0, n_tasks = 0, c4 = 0, n_fb1 = 0, c8 = 0, n_fb2 = 0, cw = 0, pending = 0;
+        emu::run_block(BB_MUTP_THREADS, [&]() { bb_k_mutate(B, em, seed, &c_mut, &order0, 1); });
+        emu::run_warp([&]() { bb_k_window_tasks(B, &order0, 1, tasks.data(), &n_tasks); });
+        emu::run_warp([&]() {
+            bb_k_window_lane_hist<4, 4>(B, em, tasks.data(), &n_tasks, seed, whist.data(), ltbuf.data(), &c4, fb1.data(), &n_fb1);
+        });
+        emu::run_warp([&]() {
+            bb_k_window_lane_hist<BB_WIN_LW, 4>(B, em, fb1.data(), &n_fb1, seed, whist.data(), ltbuf.data(), &c8, fb2.data(), &n_fb2);
+        });
+        emu::run_block(BB_WARPS_PER_CTA * 32, [&]() { bb_k_window_warp(B, em, pool, fb2.data(), &n_fb2, seed, &cw); });
+        emu::run_warp([&]() { bb_k_replay(B, &order0, 1, k, &pending); });
+    }
+    if (rd.status != BB_READ_DONE) return -1;
+    out8[0] = rd.loop_count; out8[1] = rd.change_count; out8[2] = rd.n_align; out8[3] = rd.seq_len;
+    out8[4] = rd.start_trim; out8[5] = rd.end_trim; out8[6] = rd.upper; out8[7] = rd.flags;
+    int w = 0;
+    for (int x = 0; x < frag_len; x++) {
+        const uint32_t st = state[(size_t)x];
+        if (st == BB_SLOT_NONE) { if (w < joined_cap) joined_out[w] = fr[(size_t)x]; w++; }
+        else for (int c = 0; c < (int)(st & 0xff); c++) { if (w < joined_cap) joined_out[w] = bb_slot_char(em, st, c); w++; }
+    }
+    return w == rd.seq_len ? rounds : -2;
+}

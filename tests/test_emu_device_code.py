@@ -183,3 +183,28 @@ def test_window_lane_kernel_matches_oracle(emu, hist):
             assert (matches, cols) == (ops.count('='), len(ops)), (frag_len, n_changes, lw, a)
             checked += 1
     assert checked >= 25
+
+
+@pytest.mark.parametrize('model', ['nanopore2023', 'pacbio2021', 'nanopore2020'])
+def test_error_loop_kernels_match_oracle(emu, model):
+    """The error loop as the GPU runs it - bb_k_mutate (evaluation one step ahead of the ordered commit), the window task
+    list, the lane window aligners with the staging ring and their fall-backs, bb_k_replay, round after round - under the
+    emulator: loop_count, change_count, the number of identity re-measurements, the trims and the mutated read itself
+    equal the oracle's sequential loop (simulate.py:256-358), for fragments below and above the 1000-base window, low and
+    high target identities, and a read that needs more than one round."""
+    from conftest import load_models
+    from oracle import oracle as O
+    em, qm = load_models(model, model)
+    orc = O.Oracle(em, qm)
+    rnd = random.Random(101)
+    most_rounds = 0
+    for n, ident in ((40, 0.9), (300, 0.8), (986, 0.93), (1500, 0.97), (2500, 0.65), (6000, 0.9), (3000, 1.0), (500, 0.999)):
+        frag = random_dna(rnd, n, 'ACGTN' if n == 1500 else 'ACGT')
+        seed, read = 1000 + n, 7 * n
+        joined, st = emu.error_loop(frag, ident, seed, read, em)
+        seq, _, _, want = orc.sequence_fragment(frag, ident, seed, read, with_stats=True)
+        assert {k: st[k] for k in ('loop_count', 'change_count', 'n_alignments', 'untrimmed_len')} == \
+            {k: want[k] for k in ('loop_count', 'change_count', 'n_alignments', 'untrimmed_len')}, (model, n, ident)
+        assert joined[st['start_trim']:len(joined) - st['end_trim']] == seq, (model, n, ident)
+        most_rounds = max(most_rounds, st['rounds'])
+    assert most_rounds >= (2 if model == 'nanopore2020' else 1)     # (2500 bases at 0.65: the horizon is hit, the loop resumes)
