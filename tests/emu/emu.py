@@ -185,3 +185,30 @@ def error_loop(fragment, target_identity, seed, read_index, error_model):
              'untrimmed_len': int(out8[3]), 'start_trim': int(out8[4]), 'end_trim': int(out8[5]), 'upper': int(out8[6]),
              'rounds': int(rounds)}
     return bytes(joined[:out8[3]]).decode('latin-1'), stats
+
+
+def get_qscores(seq, frag, upper, qscore_model, seed, read_index):
+    """get_qscores on the device code under the emulator: alignment task pipeline + bb_k_qscores_pair -> (quality
+    string, '=' columns, alignment columns)."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(LIB))
+    _lib.emu_set_quad(0)
+    _lib.emu_set_hist(1)
+    t = qscore_model.to_device_tables()
+    q = seq.encode('latin-1') if isinstance(seq, str) else bytes(seq)
+    f = frag.encode('latin-1') if isinstance(frag, str) else bytes(frag)
+    qual = np.zeros(len(q), dtype=np.uint8)
+    out5 = np.zeros(5, dtype=np.int32)
+    arr = {name: np.ascontiguousarray(t[name]) for name in ('keys', 'row_off', 'scores', 'cum')}
+    _lib.emu_get_qscores.restype = ctypes.c_int
+    _lib.emu_get_qscores.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int32] + [ctypes.c_void_p] * 4 + [ctypes.c_uint64, ctypes.c_uint64,
+                                                                               ctypes.c_void_p, ctypes.c_void_p]
+    rc = _lib.emu_get_qscores(q, len(q), f, len(f), int(upper), int(t['kmer_size']), int(t['n_keys']),
+                              *(arr[n].ctypes.data_as(ctypes.c_void_p) for n in ('keys', 'row_off', 'scores', 'cum')),
+                              seed, read_index, qual.ctypes.data_as(ctypes.c_void_p), out5.ctypes.data_as(ctypes.c_void_p))
+    if rc:
+        raise RuntimeError(f'get_qscores under the emulator failed (flags 0x{int(out5[4]):x}, overflow {int(out5[2])})')
+    return bytes(qual).decode('latin-1'), int(out5[0]), len(q) + int(out5[1])

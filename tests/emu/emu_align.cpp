@@ -406,3 +406,33 @@ int emu_error_loop(const uint8_t *fragment, int n, double target, unsigned long 
     }
     return w == rd.seq_len ? rounds : -2;
 }
+
+
+// get_qscores (qscore_model.py:32-75) under the emulator: the alignment task pipeline of emu_tasks_align, then
+// bb_k_qscores_pair with the hash table bb_upload_qscore_model builds from the packed keys.  qual_out: n quality characters;
+// out5 as emu_tasks_align.
+extern "C" __attribute__((visibility("default")))
+int emu_get_qscores(const uint8_t *seq, int n, const uint8_t *frag, int m, int upper, int kmer_size, int32_t n_keys,
+                    const uint64_t *keys, const int32_t *row_off, const uint8_t *scores, const double *cum,
+                    unsigned long long seed, unsigned long long read_index, uint8_t *qual_out, int *out5) {
+    std::vector<uint8_t> ops((size_t)n + 8);
+    std::vector<unsigned int> dcnt((size_t)n + 8);
+    const int rc = emu_tasks_align(seq, n, frag, m, upper, ops.data(), dcnt.data(), out5);
+    if (rc || out5[4] || out5[2]) return 1;
+    uint32_t bits = 6;
+    while ((1ull << bits) < 2ull * (uint64_t)n_keys) bits++;
+    const size_t hsize = (size_t)1 << bits;
+    std::vector<uint64_t> hk(hsize, 0);
+    std::vector<int32_t> hv(hsize, -1);
+    for (int32_t i = 0; i < n_keys; i++) {
+        uint32_t h = (uint32_t)((keys[i] * 0x9E3779B97F4A7C15ull) >> (64 - bits));
+        while (hk[h] != 0 && hk[h] != keys[i]) h = (h + 1) & (uint32_t)(hsize - 1);
+        hk[h] = keys[i]; hv[h] = i;
+    }
+    BBQScoreModelDev qm;
+    std::memset(&qm, 0, sizeof(qm));
+    qm.kmer_size = kmer_size; qm.hkeys = hk.data(); qm.hvals = hv.data(); qm.hbits = bits; qm.row_off = row_off;
+    qm.scores = scores; qm.cum = cum;
+    emu::run_block(256, [&]() { bb_k_qscores_pair(ops.data(), dcnt.data(), n, qm, seed, read_index, qual_out); });
+    return 0;
+}

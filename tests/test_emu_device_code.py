@@ -208,3 +208,21 @@ def test_error_loop_kernels_match_oracle(emu, model):
         assert joined[st['start_trim']:len(joined) - st['end_trim']] == seq, (model, n, ident)
         most_rounds = max(most_rounds, st['rounds'])
     assert most_rounds >= (2 if model == 'nanopore2020' else 1)     # (2500 bases at 0.65: the horizon is hit, the loop resumes)
+
+
+@pytest.mark.parametrize('qscore_model', ['nanopore2023', 'pacbio2021', 'ideal', 'random'])
+def test_get_qscores_kernels_match_oracle(emu, qscore_model):
+    """get_qscores (qscore_model.py:32-75) as the GPU computes it - the alignment task pipeline, then per base the CIGAR
+    window, the hash look-up with the trim-by-one fall-back and `choices` on the base's own Philox stream
+    (bb_k_qscores_pair) - under the emulator: quality string, '=' columns and alignment columns equal the oracle's."""
+    from conftest import load_models
+    from oracle import oracle as O
+    em, qm = load_models('nanopore2023', qscore_model)
+    orc = O.Oracle(em, qm)
+    rnd = random.Random(9)
+    for n, rate in ((1, 0.0), (50, 0.1), (800, 0.05), (3000, 0.08), (2200, 0.25), (1200, 0.0)):
+        frag = random_dna(rnd, n, 'ACGTN' if n == 800 else 'ACGT')
+        seq = mutate(rnd, frag, rate) or 'A'
+        d = O.align_path(seq, frag)[1]
+        assert emu.get_qscores(seq, frag, d + rnd.choice([0, 5, 40]), qm, 321, 17 + n) == orc.get_qscores(seq, frag, 321, 17 + n), \
+            (qscore_model, n, rate)
