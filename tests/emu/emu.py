@@ -156,7 +156,8 @@ def window_lane(frag, changes, seed, read_index, lw=4, hist=0):
 
 def error_loop(fragment, target_identity, seed, read_index, error_model):
     """The error loop kernels (bb_k_mutate, bb_k_window_tasks, bb_k_window_lane_hist<4> / <8>, bb_k_window_warp,
-    bb_k_replay) of one read under the emulator, round after round as bb_api.cu enqueues them.  error_model: a
+    bb_k_replay) of one read under the emulator, round after round as bb_api.cu enqueues them, then bb_k_join (its read,
+    match bitmap and distance bound are checked inside the harness).  error_model: a
     badread_b200.error_model.ErrorModel with tables.  Returns (joined read, stats dict)."""
     global _lib
     if _lib is None:
@@ -167,23 +168,25 @@ def error_loop(fragment, target_identity, seed, read_index, error_model):
     k = int(t['k'])
     cap = 2 * (len(f) + 2 * k) + 64
     joined = np.zeros(cap, dtype=np.uint8)
+    padded = np.zeros(len(f) + 2 * k, dtype=np.uint8)
     out8 = np.zeros(8, dtype=np.int32)
     arr = {name: np.ascontiguousarray(t[name]) for name in ('kmer_to_row', 'row_off', 'cum', 'flags', 'slots', 'pool')}
     _lib.emu_error_loop.restype = ctypes.c_int
     _lib.emu_error_loop.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int,
                                     ctypes.c_void_p, ctypes.c_int32] + [ctypes.c_void_p] * 5 + [ctypes.c_void_p, ctypes.c_void_p,
-                                                                                                 ctypes.c_int]
+                                                                                                 ctypes.c_int, ctypes.c_void_p]
     rounds = _lib.emu_error_loop(f, len(f), float(target_identity), seed, read_index, k,
                                  arr['kmer_to_row'].ctypes.data_as(ctypes.c_void_p), len(arr['row_off']) - 1,
                                  *(arr[n].ctypes.data_as(ctypes.c_void_p) for n in ('row_off', 'cum', 'flags', 'slots', 'pool')),
-                                 out8.ctypes.data_as(ctypes.c_void_p), joined.ctypes.data_as(ctypes.c_void_p), cap)
+                                 out8.ctypes.data_as(ctypes.c_void_p), joined.ctypes.data_as(ctypes.c_void_p), cap,
+                                 padded.ctypes.data_as(ctypes.c_void_p))
     if rounds < 0:
         raise RuntimeError(f'error loop under the emulator failed ({rounds})')
     if out8[7]:
         raise RuntimeError(f'error loop flags 0x{int(out8[7]):x}')
     stats = {'loop_count': int(out8[0]), 'change_count': int(out8[1]), 'n_alignments': int(out8[2]),
              'untrimmed_len': int(out8[3]), 'start_trim': int(out8[4]), 'end_trim': int(out8[5]), 'upper': int(out8[6]),
-             'rounds': int(rounds)}
+             'rounds': int(rounds), 'padded_fragment': bytes(padded).decode('latin-1')}
     return bytes(joined[:out8[3]]).decode('latin-1'), stats
 
 

@@ -306,12 +306,13 @@ int emu_window_lane(const uint8_t *frag, int frag_len, const int *pos, const uin
 // bb_k_window_lane_hist<4> -> <8> -> bb_k_window_warp -> bb_k_replay, round after round until the read is done.  The
 // fragment comes unpadded; the pads are drawn like bb_k_build_fragments draws them.  The error model comes as the flat
 // tables bb_upload_error_model takes.  out8: loop_count, change_count, n_align, seq_len, start_trim, end_trim, upper, flags;
-// joined_out: ''.join(new_fragment_bases) after the loop (cut to joined_cap).  Returns the number of rounds, or -1.
+// joined_out: ''.join(new_fragment_bases) after the loop (cut to joined_cap), checked against bb_k_join's output (read,
+// match bitmap, distance bound); padded_out (optional): the fragment with its pads.  Returns the number of rounds, or < 0.
 extern "C" __attribute__((visibility("default")))
 int emu_error_loop(const uint8_t *fragment, int n, double target, unsigned long long seed, unsigned long long read_index,
                    int k, const int32_t *kmer_to_row, int32_t n_rows, const int32_t *row_off, const double *cum,
                    const uint8_t *flags, const uint32_t *slots, const uint8_t *pool_bytes, int *out8, uint8_t *joined_out,
-                   int joined_cap) {
+                   int joined_cap, uint8_t *padded_out) {
     const int frag_len = n + 2 * k;
     std::vector<BBRowInfo> info((size_t)n_rows);
     for (int32_t r = 0; r < n_rows; r++) {
@@ -396,6 +397,12 @@ int emu_error_loop(const uint8_t *fragment, int n, double target, unsigned long 
         emu::run_warp([&]() { bb_k_replay(B, &order0, 1, k, &pending); });
     }
     if (rd.status != BB_READ_DONE) return -1;
+    // K3: bb_k_join writes the read, its match bitmap and the tighter bound on its distance to the fragment
+    std::vector<uint8_t> seq((size_t)rd.seq_len + 64, 0);
+    std::vector<uint4> speq((size_t)bb_peq_words(rd.seq_len) + 8), speq_want(speq.size());
+    B.seq = seq.data(); B.speq = speq.data();
+    const int loop_upper = rd.upper;
+    emu::run_block(256, [&]() { bb_k_join(B, em); });
     out8[0] = rd.loop_count; out8[1] = rd.change_count; out8[2] = rd.n_align; out8[3] = rd.seq_len;
     out8[4] = rd.start_trim; out8[5] = rd.end_trim; out8[6] = rd.upper; out8[7] = rd.flags;
     int w = 0;
@@ -404,7 +411,13 @@ int emu_error_loop(const uint8_t *fragment, int n, double target, unsigned long 
         if (st == BB_SLOT_NONE) { if (w < joined_cap) joined_out[w] = fr[(size_t)x]; w++; }
         else for (int c = 0; c < (int)(st & 0xff); c++) { if (w < joined_cap) joined_out[w] = bb_slot_char(em, st, c); w++; }
     }
-    return w == rd.seq_len ? rounds : -2;
+    if (w != rd.seq_len) return -2;
+    if (std::memcmp(seq.data(), joined_out, (size_t)std::min(w, joined_cap)) != 0) return -3;   // the kernel's join
+    emu::run_warp([&]() { bb_build_peq(seq.data(), rd.seq_len, speq_want.data()); });
+    if (std::memcmp(speq.data(), speq_want.data(), (size_t)bb_peq_words(rd.seq_len) * sizeof(uint4)) != 0) return -4;
+    if (rd.upper > loop_upper) return -5;
+    if (padded_out) std::memcpy(padded_out, fr.data(), (size_t)frag_len);
+    return rounds;
 }
 
 

@@ -226,3 +226,24 @@ def test_get_qscores_kernels_match_oracle(emu, qscore_model):
         d = O.align_path(seq, frag)[1]
         assert emu.get_qscores(seq, frag, d + rnd.choice([0, 5, 40]), qm, 321, 17 + n) == orc.get_qscores(seq, frag, 321, 17 + n), \
             (qscore_model, n, rate)
+
+
+@pytest.mark.parametrize('models', [('nanopore2023', 'nanopore2023'), ('pacbio2021', 'pacbio2021'), ('nanopore2020', 'ideal')])
+def test_whole_read_on_device_code_matches_oracle(emu, models):
+    """simulate.sequence_fragment (simulate.py:256-358) end to end on the DEVICE code, without a GPU: error loop -> bb_k_join
+    -> alignment task pipeline -> quality scores, with the bound and the trims the kernels computed; sequence, quality
+    string and matches / columns equal the oracle's for the same seed and read index."""
+    from conftest import load_models
+    from oracle import oracle as O
+    em, qm = load_models(*models)
+    orc = O.Oracle(em, qm)
+    rnd = random.Random(515)
+    for n, ident in ((60, 0.9), (700, 0.88), (1800, 0.95), (5200, 0.8), (2600, 1.0)):
+        frag = random_dna(rnd, n)
+        seed, read = 31 + n, 3 * n + 1
+        joined, st = emu.error_loop(frag, ident, seed, read, em)
+        qual, matches, columns = emu.get_qscores(joined, st['padded_fragment'], st['upper'], qm, seed, read)
+        lo, hi = st['start_trim'], len(joined) - st['end_trim']
+        seq, want_qual, _, want = orc.sequence_fragment(frag, ident, seed, read, with_stats=True)
+        assert (joined[lo:hi], qual[lo:hi]) == (seq, want_qual), (models, n, ident)
+        assert (matches, columns) == (want['matches'], want['columns']), (models, n, ident)
