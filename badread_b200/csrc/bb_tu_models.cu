@@ -44,10 +44,14 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     return x;
 }
 
-// Slot of `key` (claimed if new), or -1 if the table is full.
+// Slot of `key` (claimed if new), or -1 if the table is (as good as) full: a probe sequence of 1024 slots does not
+// happen below a load of ~0.95, and once one thread has given up the others stop at their next key instead of walking the
+// whole table each - the caller doubles the table and counts again.
 __device__ long long table_slot(const Table &T, unsigned long long key) {
+    if (*(volatile int *)&T.status[0]) return -1;
     unsigned long long h = mix64(key) & (unsigned long long)(T.cap - 1);
-    for (long long probe = 0; probe < T.cap; probe++) {
+    const long long limit = T.cap < 1024 ? T.cap : 1024;
+    for (long long probe = 0; probe < limit; probe++) {
         const unsigned long long prev = atomicCAS(&T.keys[h], BBM_EMPTY, key);
         if (prev == BBM_EMPTY || prev == key) return (long long)h;
         h = (h + 1) & (unsigned long long)(T.cap - 1);

@@ -197,7 +197,7 @@ def _count(which, flat, k, max_del=0, device=0):
     """Runs bb_count_kmer_alternatives / bb_count_cigar_qscores, growing the table until it fits."""
     L = _lib.lib()
     per_slot = 1 if which == 'kmers' else N_Q
-    cap = 1 << 16       # slots; doubled until the distinct keys fit (k-mer pairs: at most one per window)
+    cap = 1 << 18       # slots; doubled until the distinct keys fit (k-mer pairs: at most one per window)
     while which == 'kmers' and cap < min(2 * int(flat.ref_off[-1]) + 16, 1 << 22):
         cap <<= 1
     ovf_cap = 1 << 16
