@@ -214,6 +214,13 @@ inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p =
 inline int atomicOr(int *p, int v) { const int o = *p; *p = o | v; return o; }
 inline int atomicExch(int *p, int v) { const int o = *p; *p = v; return o; }
 inline int atomicMax(int *p, int v) { const int o = *p; if (v > o) *p = v; return o; }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v < o) *p = v; return o; }
+inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long v) {
+    const unsigned long long o = *p;
+    if (o == cmp) *p = v;
+    return o;
+}
 inline long long clock64() { return 0; }
 inline void __syncthreads() { emu::block_barrier(); }
 inline void __threadfence_block() {}

@@ -215,3 +215,44 @@ def get_qscores(seq, frag, upper, qscore_model, seed, read_index):
     if rc:
         raise RuntimeError(f'get_qscores under the emulator failed (flags 0x{int(out5[4]):x}, overflow {int(out5[2])})')
     return bytes(qual).decode('latin-1'), int(out5[0]), len(q) + int(out5[1])
+
+
+def count_windows(which, flat, k, max_del=0, device=0, cap=None):
+    """The counting kernels of the model builders (csrc/bb_models.cuh) under the emulator, in place of
+    badread_b200.model_builders._count: same arguments, same return value."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(LIB))
+    kind = 0 if which == 'kmers' else 1
+    per_slot = 1 if kind == 0 else 94
+    if cap is None:
+        cap = 1 << 12
+        while kind == 0 and cap < 2 * int(flat.ref_off[-1]) + 16:
+            cap <<= 1
+    ovf_cap = 1 << 16
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    _lib.emu_count_windows.restype = ctypes.c_int
+    _lib.emu_count_windows.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int32] + [ctypes.c_void_p] * 9 + \
+        [ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p,
+         ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+    while True:
+        keys = np.empty(cap, dtype=np.uint64); first = np.empty(cap, dtype=np.uint64)
+        counts = np.empty(cap * per_slot, dtype=np.uint32)
+        ovf = [np.empty(ovf_cap, dtype=np.int32) for _ in range(3)]
+        overall = np.zeros(94, dtype=np.uint64)
+        n, m = ctypes.c_int64(0), ctypes.c_int64(0)
+        rc = _lib.emu_count_windows(kind, k, max_del, flat.n, p(flat.read), p(flat.qual), p(flat.read_off), p(flat.ref),
+                                    p(flat.ref_off), p(flat.ops), p(flat.op_read0), p(flat.op_ref0), p(flat.ops_off), cap, p(keys),
+                                    p(first), p(counts), ctypes.byref(n), p(overall), ovf_cap, p(ovf[0]), p(ovf[1]), p(ovf[2]),
+                                    ctypes.byref(m))
+        if rc == -4:          # table (or overflow list) full: the same retry as model_builders._count
+            if m.value > ovf_cap:
+                ovf_cap = int(m.value) + 16
+            else:
+                cap <<= 1
+            continue
+        if rc:
+            raise RuntimeError(f'emu_count_windows failed ({rc})')
+        return keys[:n.value], first[:n.value], counts[:n.value * per_slot].reshape(n.value, per_slot), overall, \
+            [o[:m.value] for o in ovf]

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../badread_b200/csrc/bb_kernels.cuh"
+#include "../../badread_b200/csrc/bb_models.cuh"
 
 extern "C" __attribute__((visibility("default")))
 int emu_align_path(const uint8_t *q, int n, const uint8_t *t, int m, int k_upper, int qabs_pad, int maxl, uint8_t *ops,
@@ -447,5 +448,48 @@ int emu_get_qscores(const uint8_t *seq, int n, const uint8_t *frag, int m, int u
     qm.kmer_size = kmer_size; qm.hkeys = hk.data(); qm.hvals = hv.data(); qm.hbits = bits; qm.row_off = row_off;
     qm.scores = scores; qm.cum = cum;
     emu::run_block(256, [&]() { bb_k_qscores_pair(ops.data(), dcnt.data(), n, qm, seed, read_index, qual_out); });
+    return 0;
+}
+
+
+// The counting kernels of the model builders (bb_models.cuh) under the emulator, with the interface of
+// bb_count_kmer_alternatives / bb_count_cigar_qscores (include/badread_b200.h; which = 0 / 1): one emulated CTA per alignment.
+extern "C" __attribute__((visibility("default")))
+int emu_count_windows(int which, int k, int max_del, int32_t n_aln, const uint8_t *read, const uint8_t *qual,
+                      const int64_t *read_off, const uint8_t *ref, const int64_t *ref_off, const uint32_t *ops,
+                      const int32_t *op_read0, const int32_t *op_ref0, const int64_t *ops_off, int64_t table_cap,
+                      uint64_t *keys_out, uint64_t *first_out, uint32_t *counts_out, int64_t *n_entries, uint64_t *overall_out,
+                      int64_t ovf_cap, int32_t *ovf_aln, int32_t *ovf_pos, int32_t *ovf_k, int64_t *n_ovf) {
+    const int per_slot = which ? BBM_NQ : 1;
+    BBMAln A;
+    A.read = read; A.qual = qual; A.ref = ref; A.read_off = read_off; A.ref_off = ref_off; A.ops_off = ops_off; A.ops = ops;
+    A.op_read0 = op_read0; A.op_ref0 = op_ref0;
+    std::vector<unsigned long long> keys((size_t)table_cap, BBM_EMPTY), first((size_t)table_cap, BBM_EMPTY);
+    std::vector<unsigned int> counts((size_t)table_cap * per_slot, 0u);
+    int status[4] = {0, 0, 0, 0};
+    unsigned long long novf = 0, n = 0;
+    std::vector<unsigned long long> overall(BBM_NQ, 0ull);
+    BBMTable T;
+    T.keys = keys.data(); T.first = first.data(); T.counts = counts.data(); T.cap = table_cap; T.status = status;
+    T.ovf_aln = ovf_aln; T.ovf_pos = ovf_pos; T.ovf_k = ovf_k; T.n_ovf = &novf; T.ovf_cap = ovf_cap;
+    std::vector<int> rp((size_t)ref_off[n_aln] + 8), dc((size_t)read_off[n_aln] + 8), lead((size_t)n_aln + 8);
+    std::vector<uint8_t> ism((size_t)ref_off[n_aln] + 8), sym((size_t)read_off[n_aln] + 8);
+    for (int a = 0; a < n_aln; a++) {
+        blockIdx.x = (unsigned)a;
+        if (which) emu::run_block(256, [&]() { bbm_k_cigar_qscores(A, n_aln, k, max_del, sym.data(), dc.data(), lead.data(), T, overall.data()); });
+        else emu::run_block(256, [&]() { bbm_k_kmer_alternatives(A, n_aln, k, rp.data(), ism.data(), T); });
+    }
+    blockIdx.x = 0;
+    *n_ovf = (int64_t)novf;
+    if (status[0] || status[1]) { *n_entries = 0; return -4; }
+    for (long long b = 0; b < (table_cap + 255) / 256; b++) {
+        blockIdx.x = (unsigned)b;
+        emu::run_block(256, [&]() {
+            bbm_k_compact(T, per_slot, (unsigned long long *)keys_out, (unsigned long long *)first_out, counts_out, &n, table_cap);
+        });
+    }
+    blockIdx.x = 0;
+    *n_entries = (int64_t)n;
+    if (which) for (int q = 0; q < BBM_NQ; q++) overall_out[q] = overall[(size_t)q];
     return 0;
 }
