@@ -256,3 +256,29 @@ def count_windows(which, flat, k, max_del=0, device=0, cap=None):
             raise RuntimeError(f'emu_count_windows failed ({rc})')
         return keys[:n.value], first[:n.value], counts[:n.value * per_slot].reshape(n.value, per_slot), overall, \
             [o[:m.value] for o in ovf]
+
+
+def build_fragment(ref, literals, segments, k, kmer_to_row, seed, read_index):
+    """bb_k_build_fragments (+ bb_k_compact on its output) for one read under the emulator.  segments: [(kind, src, len)]
+    with kind 0 = reference slice, 1 = reverse complement of a reference slice, 2 = literal bytes.  Returns (padded
+    fragment, k-mer row index per position, status: 0 = slots reset, bitmap and compaction right)."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(str(LIB))
+    r = np.frombuffer(ref.encode('latin-1') if isinstance(ref, str) else bytes(ref), dtype=np.uint8)
+    lit = np.frombuffer((literals.encode('latin-1') if isinstance(literals, str) else bytes(literals)) or b'\0', dtype=np.uint8)
+    kind = np.asarray([s[0] for s in segments], dtype=np.int32)
+    src = np.asarray([s[1] for s in segments], dtype=np.int64)
+    ln = np.asarray([s[2] for s in segments], dtype=np.int32)
+    n = int(ln.sum()) + 2 * k
+    frag = np.zeros(n + 8, dtype=np.uint8)
+    kidx = np.full(n + 8, -9, dtype=np.int32)
+    k2r = np.ascontiguousarray(kmer_to_row, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    _lib.emu_build_fragment.restype = ctypes.c_int
+    _lib.emu_build_fragment.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
+                                                                ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+    status = _lib.emu_build_fragment(p(r), p(lit), p(kind), p(src), p(ln), len(segments), k, p(k2r), seed, read_index, p(frag),
+                                     p(kidx))
+    return bytes(frag[:n]).decode('latin-1'), kidx[:max(0, n - k + 1)].tolist(), int(status)

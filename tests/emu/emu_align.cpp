@@ -493,3 +493,55 @@ int emu_count_windows(int which, int k, int max_del, int32_t n_aln, const uint8_
     if (which) for (int q = 0; q < BBM_NQ; q++) overall_out[q] = overall[(size_t)q];
     return 0;
 }
+
+
+// K1 bb_k_build_fragments and K6 bb_k_compact for ONE read under the emulator.  The read is described like in
+// bb_batch_upload: n_segs segments (kind, src, len) over the reference `ref` and the literal pool `lit`.  Outputs: the
+// padded fragment, the k-mer row index per position, and a status that is 0 iff state / ctime were reset, the fragment's
+// match bitmap equals bb_build_peq of the fragment, and bb_k_compact copies seq[start_trim : start_trim + out_len).
+extern "C" __attribute__((visibility("default")))
+int emu_build_fragment(const uint8_t *ref, const uint8_t *lit, const int32_t *seg_kind, const int64_t *seg_src,
+                       const int32_t *seg_len, int n_segs, int k, const int32_t *kmer_to_row, unsigned long long seed,
+                       unsigned long long read_index, uint8_t *frag_out, int32_t *kidx_out) {
+    uint8_t comp[256];
+    std::memset(comp, 'N', sizeof(comp));
+    const char *from = "ATGCatgcRYSWKMBVDHNryswkmbvdhn.-?";
+    const char *to = "TACGtacgYRSWMKVBHDNyrswmkvbhdn.-?";
+    for (int i = 0; from[i]; i++) comp[(uint8_t)from[i]] = (uint8_t)to[i];
+    std::memcpy(bb_c_comp, comp, 256);        // (the library: cudaMemcpyToSymbol in create_worker)
+    std::vector<bb_segment> segs((size_t)n_segs);
+    int len = 0;
+    for (int s = 0; s < n_segs; s++) { segs[(size_t)s] = bb_segment{seg_src[s], seg_len[s], seg_kind[s]}; len += seg_len[s]; }
+    const int frag_len = len + 2 * k;
+    int seg_off[2] = {0, n_segs};
+    BBReadDev rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.frag_len = frag_len;
+    std::vector<uint8_t> fr((size_t)frag_len + 64, 0);
+    std::vector<uint32_t> state((size_t)frag_len + 64, 7u);
+    std::vector<unsigned int> ctime((size_t)frag_len + 64, 7u);
+    std::vector<int> kidx((size_t)frag_len + 64, -7);
+    std::vector<uint4> fpeq((size_t)bb_peq_words(frag_len) + 8), want(fpeq.size());
+    BBBatchDev B;
+    std::memset(&B, 0, sizeof(B));
+    B.n_reads = 1; B.read_index = &read_index; B.seg_off = seg_off; B.segs = segs.data(); B.lit = lit; B.reads = &rd;
+    B.frag = fr.data(); B.state = state.data(); B.ctime = ctime.data(); B.kidx = kidx.data(); B.fpeq = fpeq.data();
+    blockIdx.x = 0;
+    emu::run_block(256, [&]() { bb_k_build_fragments(B, ref, k, seed, kmer_to_row); });
+    std::memcpy(frag_out, fr.data(), (size_t)frag_len);
+    for (int x = 0; x + k <= frag_len; x++) kidx_out[x] = kidx[(size_t)x];
+    int status = 0;
+    for (int x = 0; x < frag_len; x++) if (state[(size_t)x] != BB_SLOT_NONE || ctime[(size_t)x] != 0u) status |= 1;
+    emu::run_warp([&]() { bb_build_peq(fr.data(), frag_len, want.data()); });
+    if (std::memcmp(fpeq.data(), want.data(), (size_t)bb_peq_words(frag_len) * sizeof(uint4)) != 0) status |= 2;
+    // K6 on the same buffers: out = seq[start_trim : start_trim + out_len), qualities likewise
+    std::vector<uint8_t> qual((size_t)frag_len + 64), out_seq((size_t)frag_len + 64, 0), out_qual((size_t)frag_len + 64, 0);
+    for (int x = 0; x < frag_len; x++) qual[(size_t)x] = (uint8_t)(33 + x % 60);
+    rd.seq_len = frag_len; rd.start_trim = std::min(k, frag_len); rd.end_trim = std::min(k, frag_len - rd.start_trim);
+    rd.out_len = frag_len - rd.start_trim - rd.end_trim;
+    B.seq = fr.data(); B.qual = qual.data(); B.out_seq = out_seq.data(); B.out_qual = out_qual.data();
+    emu::run_block(256, [&]() { bb_k_compact(B); });
+    if (std::memcmp(out_seq.data(), fr.data() + rd.start_trim, (size_t)rd.out_len) != 0 ||
+        std::memcmp(out_qual.data(), qual.data() + rd.start_trim, (size_t)rd.out_len) != 0) status |= 4;
+    return status;
+}

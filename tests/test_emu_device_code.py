@@ -247,3 +247,44 @@ def test_whole_read_on_device_code_matches_oracle(emu, models):
         seq, want_qual, _, want = orc.sequence_fragment(frag, ident, seed, read, with_stats=True)
         assert (joined[lo:hi], qual[lo:hi]) == (seq, want_qual), (models, n, ident)
         assert (matches, columns) == (want['matches'], want['columns']), (models, n, ident)
+
+
+def test_fragment_builder_and_compaction_kernels(emu):
+    """bb_k_build_fragments under the emulator: reference slices of either strand (misc.reverse_complement with its IUPAC
+    table, misc.py:56-71) and literal bytes gathered behind each other, the 2k pad bases from the read's Philox stream
+    (the oracle pads the same way), slots reset, the k-mer row of every position, the fragment's match bitmap; and
+    bb_k_compact's trim."""
+    from conftest import load_models
+    from badread_b200.misc import reverse_complement
+    from oracle import oracle as O
+    em, _ = load_models('nanopore2023', 'nanopore2023')
+    t = em.to_device_tables()
+    k = int(t['k'])
+    rnd = random.Random(64)
+    ref = random_dna(rnd, 5000, 'ACGTNRY')
+    lit = 'AATGTACTTCGTTCAGTTACGTATTGCT' + random_dna(rnd, 300)
+    for it in range(6):
+        segs, want = [], []
+        for _ in range(rnd.randrange(1, 6)):
+            kind = rnd.randrange(3)
+            pool = lit if kind == 2 else ref
+            n = rnd.randrange(1, 700 if kind != 2 else 120)
+            src = rnd.randrange(0, len(pool) - n)
+            segs.append((kind, src, n))
+            piece = pool[src:src + n]
+            want.append(reverse_complement(piece) if kind == 1 else piece)
+        body = ''.join(want)
+        seed, read = 900 + it, 17 * it + 2
+        frag, kidx, status = emu.build_fragment(ref, lit, segs, k, t['kmer_to_row'], seed, read)
+        assert status == 0
+        assert frag[k:len(frag) - k] == body
+        rng = O.Rng(O.RNG_PHILOX, seed, read)
+        rng.stream(2, 0)                                    # BB_PURPOSE_PAD
+        pads = ''.join('ACGT'[rng.randbelow(4)] for _ in range(2 * k))
+        assert frag[:k] + frag[len(frag) - k:] == pads
+        for x in (0, 1, len(frag) // 2, len(frag) - k):
+            kmer = frag[x:x + k]
+            code = 0
+            for c in kmer:
+                code = code * 4 + 'ACGT'.find(c)
+            assert kidx[x] == (int(t['kmer_to_row'][code]) if set(kmer) <= set('ACGT') else -1)
